@@ -1,0 +1,166 @@
+/*
+ * pgx.h -- C ABI of libpgx.so, the B200 (sm_100a) device path for pygmu2's
+ * ConvolvePE / SpatialHRTF / MixPE hot path.
+ *
+ * pygmu2 is pure Python and has no FFI of its own: its only
+ * plugin surface is the ProcessingElement protocol.  The entry points below are
+ * therefore what a maintainer-added binding for this path would call; each one
+ * cites the reference code it replaces (paths relative to the reference tree).
+ * The ctypes stub that binds them is shown in INTEGRATION.md and shipped as
+ * pygmu2_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: pointers, ints, no torch / numpy types in any signature;
+ *   - every function returns PGX_OK (0) or a negative pgx_status; the message is
+ *     available per thread from pgx_last_error();
+ *   - a handle may be used by one thread at a time, from any thread (the library
+ *     calls cudaSetDevice itself: reference audio_renderer.py:214-236 pulls from
+ *     PortAudio's thread);
+ *   - "stream" below means an audio stream (one ConvolvePE / one HRTF source),
+ *     "cuda_stream" is a cudaStream_t passed as void* (NULL = the bank's own).
+ */
+#ifndef PGX_H_
+#define PGX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PGX_API __attribute__((visibility("default")))
+#else
+#define PGX_API
+#endif
+
+typedef enum pgx_status {
+  PGX_OK = 0,
+  PGX_ERR_INVALID = -1, /* contract violation  -> Python ValueError   */
+  PGX_ERR_CUDA = -2,    /* CUDA runtime failure -> Python RuntimeError */
+  PGX_ERR_NO_DEVICE = -3,
+  PGX_ERR_NOMEM = -4
+} pgx_status;
+
+/* flags for pgx_bank_config.flags */
+#define PGX_FLAG_MIXDOWN_INPUT 1u /* mean over c_in channels -> 1 internal channel (spatial_pe.py:483) */
+
+typedef struct pgx_bank pgx_bank; /* opaque: device-resident state of N lock-stepped audio streams */
+
+/*
+ * Element (stream s, channel c, sample i) of a caller buffer lives at
+ *   base[s*stream + c*chan + i*samp]   (strides in floats).
+ * Snippet data (samples, channels) of one PE is {0, 1, C}; a planar bank buffer
+ * [N][C][n] is {C*n, n, 1}.  The addressed elements must tile one dense block.
+ */
+typedef struct pgx_layout {
+  int64_t stream;
+  int64_t chan;
+  int64_t samp;
+} pgx_layout;
+
+typedef struct pgx_bank_config {
+  int32_t device;          /* CUDA device ordinal */
+  int32_t n_streams;       /* N >= 1 independent streams processed in lockstep */
+  int32_t c_in;            /* source channels per stream */
+  int32_t c_out;           /* output channels per stream (convolve_pe.py:114-144, :207-223) */
+  int32_t filter_len;      /* L >= 1 taps */
+  int32_t filter_channels; /* 1 (mono filter on every channel) or c_out */
+  int32_t n_filters;       /* F distinct filters resident on the device (1 = shared) */
+  int32_t block;           /* partition size B: power of two in [16, 8192]; FFT size is 2B */
+  int32_t max_pull;        /* largest n accepted by one process call (staging size) */
+  uint32_t flags;          /* PGX_FLAG_* */
+} pgx_bank_config;
+
+typedef struct pgx_bank_info {
+  int32_t n_streams, c_in, c_x, c_out, filter_len, filter_channels, n_filters;
+  int32_t block, partitions, max_pull, device;
+  int32_t head, fill;       /* ring position: current delay-line slot, samples in the open block */
+  int64_t state_bytes;      /* device bytes held (delay line + filter spectra + staging) */
+  int64_t kernel_launches;  /* kernels launched by this handle since creation */
+  int64_t block_steps;      /* FFT->MAC->IFFT steps executed since creation */
+} pgx_bank_info;
+
+/* ---- library ------------------------------------------------------------ */
+PGX_API int pgx_abi_version(void);
+PGX_API const char* pgx_last_error(void);
+PGX_API int pgx_device_count(int* count);
+/* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
+PGX_API int pgx_host_alloc(void** ptr, int64_t bytes);
+PGX_API int pgx_host_free(void* ptr);
+
+/* ---- bank: replaces ConvolvePE state + _render (convolve_pe.py:185-342) and
+ *      SpatialHRTF.render (spatial_pe.py:465-518) for N streams at once ------ */
+
+/*
+ * Prepare filters and allocate state.  Replaces ConvolvePE._ensure_filter_prepared
+ * (convolve_pe.py:185-248: render the FIR once, rfft it, zero the tail) with a
+ * uniformly partitioned spectrum set per filter.
+ *   h                 host, [n_filters][filter_channels][filter_len] float32
+ *   filter_of_stream  host, [n_streams] indices into the filter set, or NULL for
+ *                     stream s -> filter (s % n_filters)
+ */
+PGX_API int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h,
+                    const int32_t* filter_of_stream);
+PGX_API int pgx_bank_destroy(pgx_bank* bank);
+PGX_API int pgx_bank_get_info(pgx_bank* bank, pgx_bank_info* info);
+
+/*
+ * History := 0.  k == 0 resets every stream and re-anchors the block grid
+ * (ConvolvePE._reset_state / non-contiguous pull, convolve_pe.py:146-154,255-256;
+ * SpatialHRTF._reset_tail_if_noncontiguous, spatial_pe.py:461-463); k > 0 clears
+ * only the listed streams' history.
+ */
+PGX_API int pgx_bank_reset(pgx_bank* bank, const int32_t* stream_ids, int32_t k);
+
+/*
+ * Replace resident filter `filter_index` by new taps h [filter_channels][filter_len]
+ * (host) and re-derive its partition spectra.  A per-PE SpatialHRTF whose azimuth /
+ * elevation attributes were mutated between pulls uses this (spatial_pe.py:446-459).
+ */
+PGX_API int pgx_bank_load_filter(pgx_bank* bank, int32_t filter_index, const float* h);
+
+/*
+ * Re-select the filter of every stream for the following pulls (a moving HRTF
+ * source: spatial_pe.py:446-449 re-resolves the IR on every render).
+ */
+PGX_API int pgx_bank_set_filter_map(pgx_bank* bank, const int32_t* filter_of_stream);
+
+/*
+ * One pull of n samples for all streams: y = x * h with carried history.
+ * Replaces ConvolvePE._render (convolve_pe.py:250-342) / SpatialHRTF.render
+ * (spatial_pe.py:465-518).  Host buffers; H2D and D2H copies happen inside and the
+ * call returns when y is complete.  1 <= n <= max_pull.
+ */
+PGX_API int pgx_bank_process(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y,
+                     pgx_layout y_layout, int32_t n);
+
+/*
+ * Same pull, fused with the MixPE sum over streams (mix_pe.py:92-94):
+ * y_mix[c*chan + i*samp] = sum_s y[s][c][i]  (y_layout.stream is ignored).
+ */
+PGX_API int pgx_bank_process_mix(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y_mix,
+                         pgx_layout y_layout, int32_t n);
+
+/* Device-resident variants: x / y are device pointers; work is enqueued on
+ * cuda_stream (NULL = the bank's stream) and NOT synchronised. */
+PGX_API int pgx_bank_process_device(pgx_bank* bank, const float* x_dev, pgx_layout x_layout, float* y_dev,
+                            pgx_layout y_layout, int32_t n, int32_t mix, void* cuda_stream);
+PGX_API int pgx_bank_synchronize(pgx_bank* bank);
+
+/* ---- MixPE: replaces the float32 left-to-right sum of mix_pe.py:92-94 ------ */
+/*
+ * out[e] = ((in_0[e] + in_1[e]) + in_2[e]) + ...  in float32, in input order, for
+ * e in [0, n_elems).  inputs: host, [n_inputs][n_elems] dense.  Bit-exact with
+ * numpy's sequential "+=".
+ */
+PGX_API int pgx_mix_sum(int32_t device, const float* inputs, int32_t n_inputs, int64_t n_elems, float* out);
+PGX_API int pgx_mix_sum_device(int32_t device, const float* inputs_dev, int32_t n_inputs, int64_t n_elems,
+                       float* out_dev, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGX_H_ */

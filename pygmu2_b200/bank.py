@@ -1,0 +1,219 @@
+"""
+ConvolveBank / HrtfMixBank: Python owners of a device-resident ``pgx_bank``.
+
+A bank is N independent audio streams advanced in lockstep by one C-ABI call per
+pull: the batched form of the reference's one-PE-one-FFT loop (SURVEY.md §1:
+"N streams = N Python objects each doing its own FFTs").  Bank-level arrays are
+planar float32: x is (N, C_in, n), y is (N, C_out, n), a fused mix is (C_out, n).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BankConfig, BankInfo, Layout, check, lib
+
+
+def next_pow2(n: int) -> int:
+    n = int(n)
+    return 1 if n <= 1 else 1 << (n - 1).bit_length()
+
+
+def choose_block(filter_len: int, pull_hint: int | None) -> int:
+    """Partition size B for a filter of ``filter_len`` taps pulled ``pull_hint`` samples at a time.
+
+    Delay-line traffic per second is ~ L*sr/B rows and every pull costs at least one block step
+    (three launches), so B = next_pow2(pull) is the sweet spot whatever L is: a longer filter just
+    has more partitions, a shorter one a single zero-padded partition.
+    """
+    want = next_pow2(int(pull_hint)) if pull_hint else 512
+    return int(min(max(16, want), 4096))
+
+
+class ConvolveBank:
+    """N lock-stepped streams, each convolved with one of F resident filters.
+
+    filters : (F, L) or (F, L, C_f) float32 (a single (L,) / (L, C_f) filter is F = 1)
+    c_in    : source channels per stream
+    Channel rules are ConvolvePE's (reference convolve_pe.py:207-223): mono filter ->
+    every source channel; multi-channel filter -> fan-out of a mono source or one filter
+    channel per source channel.
+    """
+
+    def __init__(self, filters, n_streams: int, c_in: int = 1, *, block: int | None = None,
+                 pull_hint: int | None = None, max_pull: int | None = None, filter_of_stream=None,
+                 device: int = 0, mixdown_input: bool = False, single_filter_dims: bool = False):
+        h = np.asarray(filters, dtype=np.float32)
+        if single_filter_dims:  # (L,) or (L, C_f)
+            h = h[None] if h.ndim >= 1 else h
+        if h.ndim == 2:  # (F, L)
+            h = h[:, :, None]
+        if h.ndim != 3:
+            raise ValueError(f"filters must be (F, L) or (F, L, C_f), got shape {h.shape}")
+        F, L, c_f = h.shape
+        if L < 1:
+            raise ValueError("ConvolvePE filter must be non-empty")
+        c_x = 1 if mixdown_input else int(c_in)
+        if c_f == 1:
+            c_out = c_x
+        elif c_x == 1 or c_x == c_f:
+            c_out = c_f
+        else:
+            raise ValueError(
+                f"ConvolvePE filter channels ({c_f}) must match src channels ({c_x}), "
+                f"or be mono, or be multi-channel with a mono source."
+            )
+        B = int(block) if block else choose_block(L, pull_hint)
+        self.n_streams, self.c_in, self.c_out, self.c_f = int(n_streams), int(c_in), int(c_out), int(c_f)
+        self.filter_len, self.n_filters, self.block = int(L), int(F), B
+        self.partitions = -(-L // B)
+        self.max_pull = int(max_pull) if max_pull else max(8 * B, 4096)
+        self.device = int(device)
+        _lib.require_device()
+        cfg = BankConfig(device=self.device, n_streams=self.n_streams, c_in=self.c_in, c_out=self.c_out,
+                         filter_len=L, filter_channels=c_f, n_filters=F, block=B, max_pull=self.max_pull,
+                         flags=_lib.PGX_FLAG_MIXDOWN_INPUT if mixdown_input else 0)
+        h_planar = np.ascontiguousarray(np.transpose(h, (0, 2, 1)))  # [F][C_f][L]
+        fmap = None
+        if filter_of_stream is not None:
+            fmap = np.ascontiguousarray(filter_of_stream, dtype=np.int32)
+            if fmap.shape != (self.n_streams,):
+                raise ValueError("filter_of_stream must have one entry per stream")
+        self._h = C.c_void_p()
+        check(lib().pgx_bank_create(C.byref(self._h), C.byref(cfg),
+                                    h_planar.ctypes.data_as(C.POINTER(C.c_float)),
+                                    fmap.ctypes.data_as(C.POINTER(C.c_int32)) if fmap is not None else None))
+        self.sources = None
+
+    # -- lifetime ------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().pgx_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> BankInfo:
+        out = BankInfo()
+        check(lib().pgx_bank_get_info(self._h, C.byref(out)))
+        return out
+
+    # -- state ---------------------------------------------------------------
+    def reset(self, streams=None) -> None:
+        """History := 0 for all streams (and re-anchor the block grid), or for the listed ones."""
+        if streams is None:
+            check(lib().pgx_bank_reset(self._h, None, 0))
+        else:
+            ids = np.ascontiguousarray(streams, dtype=np.int32)
+            check(lib().pgx_bank_reset(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), int(ids.size)))
+
+    def load_filter(self, filter_index: int, h) -> None:
+        """Replace one resident filter: h is (L,) or (L, C_f) float32."""
+        h = np.asarray(h, dtype=np.float32)
+        if h.ndim == 1:
+            h = h[:, None]
+        if h.shape != (self.filter_len, self.c_f):
+            raise ValueError(f"filter must be ({self.filter_len}, {self.c_f}), got {h.shape}")
+        hp = np.ascontiguousarray(h.T)
+        check(lib().pgx_bank_load_filter(self._h, int(filter_index), hp.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def set_filter_map(self, filter_of_stream) -> None:
+        fmap = np.ascontiguousarray(filter_of_stream, dtype=np.int32)
+        if fmap.shape != (self.n_streams,):
+            raise ValueError("filter_of_stream must have one entry per stream")
+        check(lib().pgx_bank_set_filter_map(self._h, fmap.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    # -- pulls (host buffers; copies inside) ------------------------------------
+    def _chunks(self, n):
+        pos = 0
+        while pos < n:
+            d = min(self.max_pull, n - pos)
+            yield pos, d
+            pos += d
+
+    def process(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """x (N, C_in, n) float32 -> y (N, C_out, n) float32."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 3 or x.shape[0] != self.n_streams or x.shape[1] != self.c_in:
+            raise ValueError(f"x must be ({self.n_streams}, {self.c_in}, n), got {x.shape}")
+        n = x.shape[2]
+        y = out if out is not None else np.empty((self.n_streams, self.c_out, n), dtype=np.float32)
+        if n <= self.max_pull:
+            check(lib().pgx_bank_process(self._h, _lib.f32_ptr(x), Layout(self.c_in * n, n, 1),
+                                         _lib.f32_ptr(y), Layout(self.c_out * n, n, 1), n))
+            return y
+        for pos, d in self._chunks(n):
+            xc = np.ascontiguousarray(x[:, :, pos:pos + d])
+            yc = np.empty((self.n_streams, self.c_out, d), dtype=np.float32)
+            check(lib().pgx_bank_process(self._h, _lib.f32_ptr(xc), Layout(self.c_in * d, d, 1),
+                                         _lib.f32_ptr(yc), Layout(self.c_out * d, d, 1), d))
+            y[:, :, pos:pos + d] = yc
+        return y
+
+    def process_mix(self, x: np.ndarray) -> np.ndarray:
+        """x (N, C_in, n) -> fused MixPE sum over streams (C_out, n)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 3 or x.shape[0] != self.n_streams or x.shape[1] != self.c_in:
+            raise ValueError(f"x must be ({self.n_streams}, {self.c_in}, n), got {x.shape}")
+        n = x.shape[2]
+        y = np.empty((self.c_out, n), dtype=np.float32)
+        for pos, d in self._chunks(n):
+            xc = x if d == n else np.ascontiguousarray(x[:, :, pos:pos + d])
+            yc = y if d == n else np.empty((self.c_out, d), dtype=np.float32)
+            check(lib().pgx_bank_process_mix(self._h, _lib.f32_ptr(xc), Layout(self.c_in * d, d, 1),
+                                             _lib.f32_ptr(yc), Layout(0, d, 1), d))
+            if d != n:
+                y[:, pos:pos + d] = yc
+        return y
+
+    def process_interleaved(self, x: np.ndarray) -> np.ndarray:
+        """Single-stream Snippet layout: x (n, C_in) -> y (n, C_out). Used by the PE shims."""
+        if self.n_streams != 1:
+            raise ValueError("process_interleaved is for single-stream banks")
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        y = np.empty((n, self.c_out), dtype=np.float32)
+        for pos, d in self._chunks(n):
+            xc, yc = x[pos:pos + d], y[pos:pos + d]  # row slices of C-contiguous arrays stay dense
+            check(lib().pgx_bank_process(self._h, _lib.f32_ptr(xc), Layout(0, 1, self.c_in),
+                                         _lib.f32_ptr(yc), Layout(0, 1, self.c_out), d))
+        return y
+
+    # -- device-resident pulls (pointers from torch / cuda-python; not synchronised) ------------
+    def process_device(self, x_ptr: int, y_ptr: int, n: int, *, mix: bool = False, cuda_stream: int = 0,
+                       x_layout: Layout | None = None, y_layout: Layout | None = None) -> None:
+        xl = x_layout or Layout(self.c_in * n, n, 1)
+        yl = y_layout or Layout(0 if mix else self.c_out * n, n, 1)
+        check(lib().pgx_bank_process_device(self._h, C.c_void_p(x_ptr), xl, C.c_void_p(y_ptr), yl, int(n),
+                                            1 if mix else 0, C.c_void_p(cuda_stream)))
+
+    def synchronize(self) -> None:
+        check(lib().pgx_bank_synchronize(self._h))
+
+    # -- batched renderer support ------------------------------------------------
+    def attach_sources(self, sources) -> None:
+        """N host PEs feeding the N streams; enables ``render`` for BankRenderer."""
+        sources = list(sources)
+        if len(sources) != self.n_streams:
+            raise ValueError("need one source PE per stream")
+        self.sources = sources
+        self._pos = None
+        self.mix_output = False
+
+    def render(self, start: int, duration: int) -> np.ndarray:
+        """One lockstep pull of every attached source: (N, C_out, n), or (C_out, n) when mix_output."""
+        if self.sources is None:
+            raise RuntimeError("no sources attached")
+        if self._pos is None or start != self._pos:
+            self.reset()  # non-contiguous pull: history := 0 (convolve_pe.py:255-256)
+        x = np.empty((self.n_streams, self.c_in, duration), dtype=np.float32)
+        for s, pe in enumerate(self.sources):
+            x[s] = pe.render(start, duration).data.T
+        self._pos = start + duration
+        return self.process_mix(x) if self.mix_output else self.process(x)

@@ -1,0 +1,149 @@
+"""
+ConvolvePE -- drop-in for pygmu2's streaming FIR convolution PE, on the GPU.
+
+Same constructor, properties, channel rules, extent, exceptions and statefulness as
+the reference (src/pygmu2/convolve_pe.py:41-348); ``render(start, duration)`` returns a
+host Snippet of (duration, channels) float32.  What changes is underneath: instead of
+one float64 numpy rfft/irfft pair of size ``fft_size`` per hop (:289-339), the PE keeps
+a device-resident uniformly partitioned overlap-save state (``ConvolveBank`` with one
+stream) and advances it with three sm_100a kernels per block step.  ``fft_size`` keeps
+its meaning as a schedule hint only -- it never changed the result in the reference
+ -- but is validated and reported exactly as before.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .bank import ConvolveBank, choose_block, next_pow2
+from .core import Extent, ProcessingElement, Snippet
+
+
+class ConvolvePE(ProcessingElement):
+    """Streaming convolution y = x * h (filter finite, starting at 0).
+
+    Args:
+        src: source PE
+        fir: filter PE, extent Extent(0, L)
+        fft_size: reference-compatible hint; must be >= L when given
+        block_size: (extension) partition size B of the device path; default picks
+            next_pow2(first pull) clamped to [16, 4096]
+        device: (extension) CUDA device ordinal, default 0
+    """
+
+    def __init__(self, src: ProcessingElement, fir: ProcessingElement, *, fft_size: int | None = None,
+                 block_size: int | None = None, device: int = 0):
+        self._src = src
+        self._fir = fir
+        self._fft_size = int(fft_size) if fft_size is not None else None
+        self._block_size = int(block_size) if block_size is not None else None
+        self._device = int(device)
+        self._fir_len = None
+        self._bank = None
+        self._last_render_end = None
+
+    src = property(lambda self: self._src)
+    fir = property(lambda self: self._fir)
+    fft_size = property(lambda self: self._fft_size)
+
+    def inputs(self) -> list:
+        return [self._src, self._fir]
+
+    @staticmethod
+    def ir_energy_norm(filter_pe: ProcessingElement) -> float:
+        """sqrt(sum h^2) over all channels in float64; 1.0 if unbounded or ~0 (convolve_pe.py:86-108)."""
+        ext = filter_pe.extent()
+        if ext.start is None or ext.end is None:
+            return 1.0
+        data = filter_pe.render(ext.start, ext.end - ext.start).data
+        norm = float(np.sqrt(np.sum(data.astype(np.float64) ** 2)))
+        return norm if norm > 1e-10 else 1.0
+
+    def is_pure(self) -> bool:
+        return False  # carries overlap state
+
+    def channel_count(self):
+        # convolve_pe.py:114-144
+        src_ch, filt_ch = self._src.channel_count(), self._fir.channel_count()
+        if src_ch is None and filt_ch is None:
+            return None
+        if src_ch is None:
+            return filt_ch
+        if filt_ch is None or int(filt_ch) == 1:
+            return src_ch
+        if int(src_ch) == 1:
+            return int(filt_ch)
+        return src_ch
+
+    def _on_start(self) -> None:
+        self._reset_state()
+
+    def _on_stop(self) -> None:
+        self._reset_state()
+
+    def _reset_state(self) -> None:
+        # The reference drops _tail here but keeps _H, which makes a restart assert
+        # (convolve_pe.py:152-154,186-187,252; SURVEY.md §7 "bugs not to copy").  Here the
+        # prepared filter stays resident and the history is cleared on the next pull.
+        self._last_render_end = None
+
+    def _compute_extent(self) -> Extent:
+        # convolve_pe.py:156-183
+        src_ext, filt_ext = self._src.extent(), self._fir.extent()
+        if filt_ext.start is not None and filt_ext.start != 0:
+            raise ValueError(f"ConvolvePE filter extent must start at 0, got {filt_ext}")
+        if filt_ext.start is None:
+            raise ValueError(f"ConvolvePE filter extent must be finite and start at 0, got {filt_ext}")
+        if filt_ext.end is None:
+            raise ValueError(f"ConvolvePE filter extent must be finite, got {filt_ext}")
+        filt_len = int(filt_ext.end - filt_ext.start)
+        if filt_len < 1:
+            return Extent(0, 0)
+        if src_ext.end is None:
+            return Extent(src_ext.start, None)
+        return Extent(src_ext.start, int(src_ext.end + (filt_len - 1)))
+
+    def _ensure_filter_prepared(self, pull_hint: int) -> None:
+        if self._bank is not None:
+            return
+        filt_ext = self._fir.extent()
+        if filt_ext.start != 0 or filt_ext.end is None:
+            raise ValueError(f"ConvolvePE filter must have extent Extent(0, N), got {filt_ext}")
+        filt_len = int(filt_ext.end)
+        if filt_len < 1:
+            raise ValueError("ConvolvePE filter must be non-empty")
+        h = self._fir.render(0, filt_len).data  # rendered once, float32 (convolve_pe.py:198)
+        if h.ndim != 2 or h.shape[0] != filt_len:
+            raise ValueError(f"ConvolvePE filter returned invalid shape {getattr(h, 'shape', None)}")
+        src_ch = self._src.channel_count()
+        if src_ch is None:
+            src_ch = self._src.render(0, 1).channels  # convolve_pe.py:203-205
+        if self._fft_size is None:
+            self._fft_size = next_pow2(max(2048, filt_len))  # convolve_pe.py:226-229
+        if self._fft_size < filt_len:
+            raise ValueError(f"fft_size ({self._fft_size}) must be >= filter length ({filt_len})")
+        block = self._block_size or choose_block(filt_len, pull_hint)
+        # channel-rule violations raise ValueError inside ConvolveBank (convolve_pe.py:219-223)
+        self._bank = ConvolveBank(h, 1, int(src_ch), block=block, device=self._device, single_filter_dims=True)
+        self._fir_len = filt_len
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        self._ensure_filter_prepared(duration)
+        if self._last_render_end is None or start != self._last_render_end:
+            self._bank.reset()  # non-contiguous pull: prior samples are zeros (convolve_pe.py:255-256)
+        x = self._src.render(start, duration).data
+        if x.ndim != 2:
+            raise ValueError(f"ConvolvePE src returned invalid shape {getattr(x, 'shape', None)}")
+        if x.shape[1] != self._bank.c_in:
+            raise ValueError(f"ConvolvePE src returned {x.shape[1]} channels, prepared for {self._bank.c_in}")
+        y = self._bank.process_interleaved(x)
+        self._last_render_end = start + duration
+        return Snippet(start, y)
+
+    @property
+    def bank(self):
+        """The device state (None before the first render)."""
+        return self._bank
+
+    def __repr__(self) -> str:
+        return (f"ConvolvePE(src={self._src.__class__.__name__}, "
+                f"fir={self._fir.__class__.__name__}, fft_size={self._fft_size})")

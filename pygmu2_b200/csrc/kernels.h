@@ -1,0 +1,61 @@
+// kernels.h -- launch interfaces of the sm_100a kernels behind libpgx.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pgx {
+
+// K1: ingest new samples, window [prev block | open block | 0], real FFT, write one delay-line row.
+struct R2CArgs {
+  const float* x;        // device samples: element (s, c, i) at x[s*xs + c*xc + (x_off+i)*xi]
+  int64_t xs, xc, xi;
+  int32_t x_off;
+  float* hist;           // [n_fft][2][B] time-domain halves (previous block / open block)
+  float2* fdl;           // [n_fft][P][B] packed input spectra (frequency-domain delay line)
+  const float2* tw;      // [2B] exp(-2*pi*i*k/2B)
+  int32_t n_fft;         // N * c_x transforms
+  int32_t c_in, c_x, B, P;
+  int32_t slot, half, fill, take;
+  int32_t mixdown;
+};
+void launch_r2c_ingest(const R2CArgs& a, cudaStream_t st);
+
+// Filter preparation: partition p of filter row f -> spectrum rows (P-1-p) and (2P-1-p), scaled 1/B.
+struct FilterPrepArgs {
+  const float* h;        // device [n_rows][L]
+  float2* Hd;            // [n_rows][2P][B]
+  const float2* tw;
+  int32_t n_rows, L, B, P;
+};
+void launch_filter_prep(const FilterPrepArgs& a, cudaStream_t st);
+
+// K3/K4: complex multiply-accumulate over delay-line rows x filter-spectrum rows.
+struct MacArgs {
+  const float4* fdl;     // rows of W4 float4
+  const float4* Hd;
+  float4* yspec;         // [n_split][n_out][W4]
+  const int32_t* fmap;   // [N] filter of stream
+  int32_t N, c_x, c_out, c_f, P, W4, q0;
+  int32_t n_out, n_terms, terms_per_split, n_split;
+  int32_t mix;           // 0: out o=(s,c), terms j<P.  1: out o=c, terms (s,j) (fused MixPE / HRTF stereo mix)
+};
+void launch_fdl_mac(const MacArgs& a, cudaStream_t st);
+
+// K2: sum split partials, inverse real FFT, emit the new output samples.
+struct C2RArgs {
+  const float2* yspec;   // [n_split][n_out][B]
+  int32_t n_split, n_out;
+  float* y;              // element (s, c, i) at y[s*ys + c*yc + (y_off+i)*yi]; o = s*c_out + c
+  int64_t ys, yc, yi;
+  int32_t y_off;
+  int32_t c_out, B, fill, take;
+  const float2* tw;
+};
+void launch_c2r_emit(const C2RArgs& a, cudaStream_t st);
+
+// K5: MixPE left-to-right float32 sum of n_inputs dense arrays.
+void launch_mix_sum(const float* in, int32_t n_inputs, int64_t n_elems, float* out, cudaStream_t st);
+
+int fft_smem_bytes(int B);
+
+}  // namespace pgx

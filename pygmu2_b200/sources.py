@@ -1,0 +1,184 @@
+"""
+Host-side input vehicles around the hot path: the few trivial pygmu2 PEs that
+the reference's own hot-path tests, examples and the BASELINE configs use to
+feed ConvolvePE / SpatialPE / MixPE.  They are *not* accelerated (SURVEY.md §2b:
+out of scope) and exist so graphs can be built on a machine without pygmu2.
+
+ArrayPE   array_pe.py:17-133     ConstantPE constant_pe.py:15-72
+SinePE    sine_pe.py:119-175 (constant parameters only)
+GainPE    gain_pe.py:92-127 (constant gain only)   DelayPE delay_pe.py:153-160 (integer delay)
+CropPE    crop_pe.py:18-96       CachePE    cache_pe.py:17-84
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .core import Extent, ExtendMode, ProcessingElement, Snippet, SourcePE
+
+
+class ArrayPE(SourcePE):
+    def __init__(self, data, extend_mode: ExtendMode = ExtendMode.ZERO):
+        arr = np.asarray(data, dtype=np.float32)
+        if arr.ndim == 1:
+            arr = arr.reshape(-1, 1)
+        elif arr.ndim > 2:
+            raise ValueError(f"ArrayPE data must be 1D or 2D, got {arr.ndim}D")
+        if arr.shape[0] == 0:
+            raise ValueError("ArrayPE data cannot be empty")
+        self._data = arr
+        self._extend_mode = extend_mode
+
+    data = property(lambda self: self._data)
+
+    def channel_count(self) -> int:
+        return self._data.shape[1]
+
+    def _compute_extent(self) -> Extent:
+        return Extent(0, self._data.shape[0])
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        n, ch = self._data.shape
+        out = np.zeros((duration, ch), dtype=np.float32)
+        lo, hi = max(0, start), min(n, start + duration)
+        if lo < hi:
+            out[lo - start:hi - start] = self._data[lo:hi]
+        mode = self._extend_mode
+        if mode in (ExtendMode.HOLD_FIRST, ExtendMode.HOLD_BOTH) and start < 0:
+            out[:min(duration, -start)] = self._data[0]
+        if mode in (ExtendMode.HOLD_LAST, ExtendMode.HOLD_BOTH) and start + duration > n:
+            first = max(0, n - start)
+            if first < duration:
+                out[first:] = self._data[-1]
+        return Snippet(start, out)
+
+    def __repr__(self):
+        return f"ArrayPE(shape={self._data.shape})"
+
+
+class ConstantPE(SourcePE):
+    def __init__(self, value: float, channels: int = 1):
+        self._value, self._channels = value, channels
+
+    value = property(lambda self: self._value)
+
+    def channel_count(self) -> int:
+        return self._channels
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        return Snippet(start, np.full((duration, self._channels), self._value, dtype=np.float32))
+
+    def __repr__(self):
+        return f"ConstantPE(value={self._value}, channels={self._channels})"
+
+
+class SinePE(SourcePE):
+    """Constant-parameter sine: float64 phase straight from the sample index, float32 out."""
+
+    def __init__(self, frequency: float = 440.0, amplitude: float = 1.0, phase: float = 0.0, channels: int = 1):
+        self._frequency, self._amplitude = float(frequency), float(amplitude)
+        self._phase, self._channels = float(phase), int(channels)
+
+    def channel_count(self) -> int:
+        return self._channels
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        t = np.arange(start, start + duration, dtype=np.float64) / self.sample_rate
+        ph = self._phase + 2.0 * np.pi * self._frequency * t
+        s = (self._amplitude * np.sin(ph)).reshape(-1, 1)
+        if self._channels > 1:
+            s = np.tile(s, (1, self._channels))
+        return Snippet(start, s.astype(np.float32))
+
+    def __repr__(self):
+        return f"SinePE(frequency={self._frequency}, amplitude={self._amplitude})"
+
+
+class _Unary(ProcessingElement):
+    def __init__(self, source: ProcessingElement):
+        self._source = source
+
+    source = property(lambda self: self._source)
+
+    def inputs(self) -> list:
+        return [self._source]
+
+    def is_pure(self) -> bool:
+        return True
+
+    def channel_count(self):
+        return self._source.channel_count()
+
+    def _compute_extent(self) -> Extent:
+        return self._source.extent()
+
+
+class GainPE(_Unary):
+    def __init__(self, source: ProcessingElement, gain: float = 1.0):
+        if isinstance(gain, ProcessingElement):
+            raise NotImplementedError("pygmu2_b200.GainPE supports constant gain only (out of scope: gain_pe.py:104-121)")
+        super().__init__(source)
+        self._gain = gain
+
+    gain = property(lambda self: self._gain)
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        return Snippet(start, self._source.render(start, duration).data * np.float32(self._gain))
+
+
+class DelayPE(_Unary):
+    def __init__(self, source: ProcessingElement, delay: int):
+        if int(delay) != delay:
+            raise NotImplementedError("pygmu2_b200.DelayPE supports integer delays only")
+        super().__init__(source)
+        self._delay = int(delay)
+
+    delay = property(lambda self: self._delay)
+
+    def _compute_extent(self) -> Extent:
+        e = self._source.extent()
+        return Extent(None if e.start is None else e.start + self._delay,
+                      None if e.end is None else e.end + self._delay)
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        return Snippet(start, self._source.render(start - self._delay, duration).data)
+
+
+class CropPE(_Unary):
+    """Zero outside [start, start+duration) of the source's timeline."""
+
+    def __init__(self, source: ProcessingElement, start: int, duration: int):
+        super().__init__(source)
+        self._crop = Extent(int(start), int(start) + int(duration))
+
+    def _compute_extent(self) -> Extent:
+        return self._source.extent().intersection(self._crop)
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        ch = self.channel_count() or 1
+        out = np.zeros((duration, ch), dtype=np.float32)
+        ov = self.extent().intersection(Extent(start, start + duration))
+        if not ov.is_empty() and ov.start is not None and ov.end is not None and ov.end > ov.start:
+            seg = self._source.render(ov.start, ov.end - ov.start).data
+            out[ov.start - start:ov.end - start] = seg
+        return Snippet(start, out)
+
+
+class CachePE(_Unary):
+    """Memoises the last (start, duration) pull so two sinks cost one source render."""
+
+    def __init__(self, source: ProcessingElement):
+        super().__init__(source)
+        self._key = None
+        self._snip = None
+
+    def _reset_state(self) -> None:
+        self._key = self._snip = None
+
+    _on_start = _on_stop = _reset_state
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        if self._snip is not None and self._key == (start, duration):
+            return self._snip
+        self._snip = self._source.render(start, duration)
+        self._key = (start, duration)
+        return self._snip

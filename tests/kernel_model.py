@@ -1,0 +1,163 @@
+"""
+Numpy model of the device algorithms in pygmu2_b200/csrc (index-for-index):
+Stockham radix-4/2 passes, the packed real-FFT pre/post-processing, the
+reversed+doubled filter-spectrum layout and the ring / partial-block schedule of
+the bank.  CPU-only test aid: it lets the host-side schedule and the kernels'
+index math be checked against the oracle without a GPU.  Not a product path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def twiddle_table(M: int) -> np.ndarray:
+    """tw[k] = exp(-2*pi*i*k/M), k in [0, M): the device table (computed in double, stored float)."""
+    k = np.arange(M, dtype=np.float64)
+    return np.exp(-2j * np.pi * k / M).astype(np.complex64)
+
+
+def stockham(z: np.ndarray, twM: np.ndarray, inverse: bool) -> np.ndarray:
+    """n-point complex FFT, n = len(z) power of two >= 2, radix-4 passes then one radix-2 if needed.
+    twM is the table for M = 2n, so exp(-2*pi*i*m/n) = twM[2m]."""
+    n = z.shape[0]
+    a = z.astype(np.complex64).copy()
+    b = np.empty_like(a)
+    Ns = 1
+    while Ns < n:
+        R = 4 if n // Ns >= 4 else 2
+        nj = n // R
+        for j in range(nj):
+            k = j % Ns
+            m = k * (n // (Ns * R))
+            v = [a[j + r * nj] for r in range(R)]
+            for r in range(1, R):
+                w = twM[2 * m * r]
+                if inverse:
+                    w = np.conj(w)
+                v[r] = np.complex64(v[r] * w)
+            if R == 4:
+                s = 1j if inverse else -1j
+                t0, t1 = v[0] + v[2], v[0] - v[2]
+                t2, t3 = v[1] + v[3], (v[1] - v[3]) * s
+                o = [t0 + t2, t1 + t3, t0 - t2, t1 - t3]
+            else:
+                o = [v[0] + v[1], v[0] - v[1]]
+            j0 = (j // Ns) * Ns * R + k
+            for r in range(R):
+                b[j0 + r * Ns] = np.complex64(o[r])
+        a, b = b, a
+        Ns *= R
+    return a
+
+
+def r2c_packed(w: np.ndarray, twM: np.ndarray) -> np.ndarray:
+    """Real window w (2B floats) -> packed half spectrum (B complex): slot[0] = (X[0].re, X[B].re)."""
+    B = w.shape[0] // 2
+    z = (w[0::2] + 1j * w[1::2]).astype(np.complex64)
+    Z = stockham(z, twM, inverse=False)
+    out = np.empty(B, np.complex64)
+    out[0] = (Z[0].real + Z[0].imag) + 1j * (Z[0].real - Z[0].imag)
+    for k in range(1, B):
+        zk, zc = Z[k], np.conj(Z[B - k])
+        e = 0.5 * (zk + zc)
+        o = -0.5j * (zk - zc)
+        out[k] = np.complex64(e + twM[k] * o)
+    return out
+
+
+def c2r_packed(Y: np.ndarray, twM: np.ndarray) -> np.ndarray:
+    """Packed half spectrum (B complex) -> 2B real samples, UNSCALED by 1/B (folded into the filter)."""
+    B = Y.shape[0]
+    Z = np.empty(B, np.complex64)
+    x0, xn = Y[0].real, Y[0].imag
+    Z[0] = 0.5 * (x0 + xn) + 0.5j * (x0 - xn)
+    for k in range(1, B):
+        xk, xc = Y[k], np.conj(Y[B - k])
+        e = 0.5 * (xk + xc)
+        o = 0.5 * np.conj(twM[k]) * (xk - xc)
+        Z[k] = np.complex64(e + 1j * o)
+    z = stockham(Z, twM, inverse=True)
+    out = np.empty(2 * B, np.float32)
+    out[0::2] = z.real
+    out[1::2] = z.imag
+    return out
+
+
+def mac_packed(acc, x, h):
+    """acc += x*h on packed spectra: bin 0 carries two independent real bins."""
+    acc[1:] += x[1:] * h[1:]
+    acc[0] += (x[0].real * h[0].real) + 1j * (x[0].imag * h[0].imag)
+
+
+class ModelBank:
+    """One stream, one channel pair; same state machine as csrc/pgx_engine (ring head, fill, halves)."""
+
+    def __init__(self, h: np.ndarray, B: int, vectorized: bool = True):
+        self.B, self.L = B, h.shape[0]
+        self.P = -(-self.L // B)
+        self.tw = twiddle_table(2 * B)
+        self.vec = vectorized
+        P = self.P
+        self.Hd = np.zeros((2 * P, B), np.complex64)
+        for p in range(P):
+            w = np.zeros(2 * B, np.float32)
+            seg = h[p * B:(p + 1) * B]
+            w[:seg.shape[0]] = seg
+            Hp = self._r2c(w) / np.float32(B)
+            q = P - 1 - p
+            self.Hd[q] = Hp
+            self.Hd[q + P] = Hp
+        self.reset()
+
+    def _r2c(self, w):
+        if not self.vec:
+            return r2c_packed(w, self.tw)
+        B = self.B
+        X = np.fft.rfft(w.astype(np.float64))
+        out = X[:B].astype(np.complex64)
+        out[0] = X[0].real + 1j * X[B].real
+        return out
+
+    def _c2r(self, Y):
+        if not self.vec:
+            return c2r_packed(Y, self.tw)
+        B = self.B
+        X = np.empty(B + 1, np.complex128)
+        X[:B] = Y
+        X[0] = Y[0].real
+        X[B] = Y[0].imag
+        return (np.fft.irfft(X, n=2 * B) * B).astype(np.float32)
+
+    def reset(self):
+        self.fdl = np.zeros((self.P, self.B), np.complex64)
+        self.hist = np.zeros((2, self.B), np.float32)
+        self.half = 0      # which half is "cur"
+        self.fill = 0
+        self.head = 0
+
+    def process(self, x: np.ndarray) -> np.ndarray:
+        B, P = self.B, self.P
+        y = np.empty_like(x)
+        pos, n = 0, x.shape[0]
+        while pos < n:
+            take = min(B - self.fill, n - pos)
+            cur, prev = self.hist[self.half], self.hist[self.half ^ 1]
+            cur[self.fill:self.fill + take] = x[pos:pos + take]
+            m_new = self.fill + take
+            w = np.zeros(2 * B, np.float32)
+            w[:B] = prev
+            w[B:B + m_new] = cur[:m_new]
+            self.fdl[self.head] = self._r2c(w)
+            acc = np.zeros(B, np.complex64)
+            q0 = P - 1 - self.head
+            for j in range(P):
+                mac_packed(acc, self.fdl[j], self.Hd[q0 + j])
+            yt = self._c2r(acc)
+            y[pos:pos + take] = yt[B + self.fill:B + m_new]
+            self.fill = m_new
+            pos += take
+            if self.fill == B:
+                self.head = (self.head + 1) % P
+                self.half ^= 1
+                self.fill = 0
+        return y
