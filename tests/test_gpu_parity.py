@@ -1,0 +1,363 @@
+"""
+Parity of the CUDA path (through the C ABI: ctypes -> libpgx.so) against the oracle and
+against golden outputs of the real reference.  Needs a B200: run with ``-m gpu``.
+
+Tolerance (BASELINE.json north_star): max-abs error <= 1e-5 of full scale of the reference
+output, fp32 device arithmetic vs the reference's float64 (ConvolvePE) / float32 (HRTF).
+MixPE's K5 sum is bit-exact.
+"""
+import numpy as np
+import pytest
+
+import pygmu2_b200 as pg
+import pygmu2_oracle as orc
+from pygmu2_b200 import workloads as wl
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _pull_pe(pe, pulls, start=0):
+    out, pos = [], start
+    for d in pulls:
+        out.append(pe.render(pos, int(d)).data.copy())
+        pos += int(d)
+    return np.concatenate(out, axis=0)
+
+
+def _oracle_pulls(conv, x, pulls):
+    out, pos = [], 0
+    for d in pulls:
+        d = int(d)
+        seg = x[pos:pos + d]
+        if seg.shape[0] < d:
+            seg = np.concatenate([seg, np.zeros((d - seg.shape[0],) + seg.shape[1:], np.float32)])
+        out.append(conv.render(seg))
+        pos += d
+    return np.concatenate(out, axis=0)
+
+
+# ---------------------------------------------------------------------------
+# the reference's own hot-path tests, run against the device PEs
+# (reference tests/test_convolve_pe.py:49-162)
+class TestReferenceConvolveCases:
+    def setup_method(self):
+        self.renderer = pg.NullRenderer(sample_rate=10_000)
+
+    def test_matches_numpy_convolve_mono(self):
+        x = np.array([1, 2, 3, 4], dtype=np.float32)
+        h = np.array([1, 0.5, -1], dtype=np.float32)
+        pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h), fft_size=16)
+        self.renderer.set_source(pe)
+        y_expected = np.convolve(x, h, mode="full").astype(np.float32)
+        y = pe.render(0, len(y_expected)).data[:, 0]
+        np.testing.assert_allclose(y, y_expected, atol=1e-5, rtol=0.0)
+
+    def test_dirac_impulse_is_identity(self):
+        x = np.random.default_rng(0).normal(size=64).astype(np.float32)
+        pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE([1.0]), fft_size=64)
+        self.renderer.set_source(pe)
+        y = pe.render(0, len(x)).data[:, 0]
+        np.testing.assert_allclose(y, x, atol=1e-6, rtol=0.0)
+
+    def test_filter_mono_applies_to_all_channels(self):
+        x = np.array([[1, 10], [2, 20], [3, 30], [4, 40]], dtype=np.float32)
+        h = np.array([1, -1], dtype=np.float32)
+        pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h), fft_size=16)
+        self.renderer.set_source(pe)
+        y = pe.render(0, 5).data
+        np.testing.assert_allclose(y[:, 0], np.convolve(x[:, 0], h), atol=1e-5, rtol=0.0)
+        np.testing.assert_allclose(y[:, 1], np.convolve(x[:, 1], h), atol=1e-5, rtol=0.0)
+
+    def test_mono_src_multi_channel_filter_fans_out(self):
+        x = np.array([1.0, 2.0, 3.0, 4.0], dtype=np.float32)
+        h = np.stack([np.array([1.0, 0.5], np.float32), np.array([-1.0, 0.5], np.float32)], axis=1)
+        pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h), fft_size=16)
+        self.renderer.set_source(pe)
+        y = pe.render(0, 5).data
+        assert y.shape[1] == 2
+        np.testing.assert_allclose(y[:, 0], np.convolve(x, h[:, 0]), atol=1e-5, rtol=0.0)
+        np.testing.assert_allclose(y[:, 1], np.convolve(x, h[:, 1]), atol=1e-5, rtol=0.0)
+
+    def test_chunked_render_matches_full(self):
+        x = np.random.default_rng(0).normal(size=200).astype(np.float32)
+        h = np.array([0.25, 0.5, 0.25], dtype=np.float32)
+        full = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h), fft_size=64)
+        self.renderer.set_source(full)
+        total = len(x) + len(h) - 1
+        y_full = full.render(0, total).data[:, 0]
+        chunked = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h), fft_size=64)
+        self.renderer.set_source(chunked)
+        y_chunk = _pull_pe(chunked, (17, 23, 19, 41, 7, 93, 2))[:, 0]
+        np.testing.assert_allclose(y_chunk[:total], y_full, atol=1e-5, rtol=0.0)
+
+    def test_fft_size_smaller_than_filter_raises(self):
+        pe = pg.ConvolvePE(pg.ArrayPE(np.ones(8)), pg.ArrayPE(np.ones(20)), fft_size=16)
+        with pytest.raises(ValueError):
+            pe.render(0, 4)
+
+    def test_channel_mismatch_raises(self):
+        pe = pg.ConvolvePE(pg.ArrayPE(np.ones((8, 2))), pg.ArrayPE(np.ones((4, 3))))
+        with pytest.raises(ValueError):
+            pe.render(0, 4)
+
+    def test_default_fft_size_reported(self):
+        pe = pg.ConvolvePE(pg.ArrayPE(np.ones(8)), pg.ArrayPE(np.ones(3000)))
+        pe.render(0, 4)
+        assert pe.fft_size == 4096
+
+    def test_restart_after_stop_works(self):
+        # the reference asserts here; the device PE simply starts a new run
+        x = np.arange(1, 9, dtype=np.float32)
+        pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE([1.0, 1.0]))
+        r = pg.NullRenderer(sample_rate=10_000)
+        r.set_source(pe)
+        r.start()
+        a = pe.render(0, 8).data.copy()
+        r.stop()
+        r.start()
+        b = pe.render(0, 8).data
+        np.testing.assert_allclose(a, b, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------
+# golden outputs of the real reference
+def test_golden_unit_vectors():
+    g = golden("convolve_unit.npz")
+    pg.set_sample_rate(10_000)
+    x = np.array([1, 2, 3, 4], dtype=np.float32)
+    y = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(np.array([1, 0.5, -1], np.float32)), fft_size=16).render(0, 6).data
+    np.testing.assert_allclose(y, g["mono_small"], atol=1e-5)
+    xs = np.array([[1, 10], [2, 20], [3, 30], [4, 40]], dtype=np.float32)
+    y = pg.ConvolvePE(pg.ArrayPE(xs), pg.ArrayPE(np.array([1, -1], np.float32)), fft_size=16).render(0, 5).data
+    np.testing.assert_allclose(y, g["stereo_monofilter"], atol=1e-5)
+    h2 = np.stack([np.array([1.0, 0.5], np.float32), np.array([-1.0, 0.5], np.float32)], axis=1)
+    y = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h2), fft_size=16).render(0, 5).data
+    np.testing.assert_allclose(y, g["fanout"], atol=1e-5)
+    xr = np.random.default_rng(0).normal(size=200).astype(np.float32)
+    pe = pg.ConvolvePE(pg.ArrayPE(xr), pg.ArrayPE(np.array([0.25, 0.5, 0.25], np.float32)), fft_size=64)
+    np.testing.assert_allclose(_pull_pe(pe, (17, 23, 19, 41, 7, 93, 2)), g["chunked"], atol=1e-5)
+
+
+@pytest.mark.parametrize("block", [None, 16, 64, 256, 1024])
+def test_golden_ragged_pulls_and_reset(block):
+    g = golden("convolve_ragged.npz")
+    pe = pg.ConvolvePE(pg.ArrayPE(g["x"]), pg.ArrayPE(g["h"]), block_size=block)
+    ya = _pull_pe(pe, g["pulls_a"])
+    assert rel_err(ya, g["ya"]) <= TOL
+    yb = _pull_pe(pe, g["pulls_b"], start=int(g["start_b"]))  # jump back: history must be cleared
+    assert rel_err(yb, g["yb"]) <= TOL
+
+
+def test_golden_c1_sine_fir4096():
+    g = golden("c1_sine_fir4096.npz")
+    n = int(g["n"])
+    pe = pg.ConvolvePE(pg.SinePE(frequency=440.0), pg.ArrayPE(wl.c1_fir()))
+    with pg.NullRenderer(sample_rate=wl.SR_441) as r:
+        r.set_source(pe)
+        r.start()
+        y = pe.render(0, n).data
+    assert pe.fft_size == 4096
+    assert rel_err(y, g["y"]) <= TOL
+
+
+def test_golden_c2_stereo_reverb():
+    g = golden("c2_stereo_reverb.npz")
+    pg.set_sample_rate(wl.SR_48)
+    npull = int(g["n_pulls"])
+    pe = pg.ConvolvePE(pg.ArrayPE(wl.c2_input(npull * wl.C2_PULL)), pg.ArrayPE(wl.c2_ir()))
+    y = _pull_pe(pe, (wl.C2_PULL,) * npull)
+    assert pe.bank.block == 512 and pe.bank.partitions == 259
+    assert rel_err(y, g["y"]) <= TOL
+
+
+def test_golden_c3_hrtf_mix_fused_and_per_pe():
+    g = golden("c3_hrtf_mix.npz")
+    ns, npull = int(g["n_sources"]), int(g["n_pulls"])
+    n = npull * wl.C3_PULL
+    el = wl.c3_elevations()[:ns]
+    for fuse in (True, False):
+        methods = [pg.SpatialHRTF(azimuth=wl.c3_azimuth(s, 0, npull, ns), elevation=float(el[s])) for s in range(ns)]
+        pes = [pg.SpatialPE(pg.ArrayPE(wl.c3_source(n, s, ns)), method=m) for s, m in enumerate(methods)]
+        mix = pg.MixPE(*pes, fuse=fuse)
+        outs = []
+        for b in range(npull):
+            for s, m in enumerate(methods):
+                m.azimuth = wl.c3_azimuth(s, b, npull, ns)
+            outs.append(mix.render(b * wl.C3_PULL, wl.C3_PULL).data.copy())
+        assert rel_err(np.concatenate(outs), g["y"]) <= TOL, f"fuse={fuse}"
+
+
+def test_golden_c3_single_source_ragged_swap_reset():
+    g = golden("c3_hrtf_mix.npz")
+    m = pg.SpatialHRTF(azimuth=-37.0, elevation=12.0)
+    sp = pg.SpatialPE(pg.ArrayPE(wl.c3_source(4000, 3, 1)), method=m)
+    segs, pos = [], 0
+    for i, d in enumerate(g["single_pulls"]):
+        if i == 3:
+            m.azimuth = 100.0
+        if i == 5:
+            m.elevation = -35.0
+        segs.append(sp.render(pos, int(d)).data.copy())
+        pos += int(d)
+    segs.append(sp.render(3000, 400).data.copy())
+    assert rel_err(np.concatenate(segs), g["single"]) <= TOL
+    st = np.stack([wl.c3_source(1500, 1, 1), wl.c3_source(1500, 2, 1)], axis=1)
+    sp2 = pg.SpatialPE(pg.ArrayPE(st), method=pg.SpatialHRTF(azimuth=60.0, elevation=-20.0))
+    assert rel_err(_pull_pe(sp2, (512, 512, 476)), g["stereo_src"]) <= TOL
+
+
+def test_hrtf_sample_rate_mismatch_raises_in_strict():
+    pg.set_sample_rate(48_000)
+    sp = pg.SpatialPE(pg.ArrayPE(np.ones(64)), method=pg.SpatialHRTF(azimuth=10.0))
+    with pytest.raises(RuntimeError):
+        sp.render(0, 32)
+
+
+def test_golden_c4_streams_and_fused_mix():
+    g = golden("c4_streams_mix.npz")
+    ns, npull, L = int(g["n_streams"]), int(g["n_pulls"]), int(g["L"])
+    n = npull * wl.C4_PULL
+    irs = np.stack([wl.c4_ir(s, L) for s in range(ns)])
+    x = np.stack([wl.c4_input(n, s) for s in range(ns)])[:, None, :]
+    bank = pg.ConvolveBank(irs, ns, 1, block=512)
+    ys = np.concatenate([bank.process(x[:, :, b * 512:(b + 1) * 512]) for b in range(npull)], axis=2)
+    assert rel_err(ys[:, 0, :], g["per_stream"]) <= TOL
+    # the drop-in graph: MixPE over ConvolvePEs is adopted into one bank and mixed on the device
+    pes = [pg.ConvolvePE(pg.ArrayPE(wl.c4_input(n, s)), pg.ArrayPE(wl.c4_ir(s, L))) for s in range(ns)]
+    mix = pg.MixPE(*pes)
+    y = _pull_pe(mix, (wl.C4_PULL,) * npull)
+    assert mix._fused not in (None, False)
+    assert rel_err(y, g["mix"]) <= TOL
+    pes = [pg.ConvolvePE(pg.ArrayPE(wl.c4_input(n, s)), pg.ArrayPE(wl.c4_ir(s, L))) for s in range(ns)]
+    y2 = _pull_pe(pg.MixPE(*pes, fuse=False), (wl.C4_PULL,) * npull)
+    assert rel_err(y2, g["mix"]) <= TOL
+
+
+def test_golden_c5_voicebank_long_ir_64_blocks():
+    g = golden("c5_voicebank_longir.npz")
+    nv, npull, L = int(g["n_voices"]), int(g["n_pulls"]), int(g["L"])
+    n = npull * wl.C5_PULL
+    v = wl.c5_voices(n, nv)
+    vm = pg.MixPE(*[pg.ArrayPE(v[i]) for i in range(nv)])
+    assert np.array_equal(vm.render(0, n).data, g["voice_mix"])  # K5 is bit-exact
+    pe = pg.ConvolvePE(pg.MixPE(*[pg.ArrayPE(v[i]) for i in range(nv)]), pg.ArrayPE(wl.c5_ir(L)))
+    y = _pull_pe(pe, (wl.C5_PULL,) * npull)
+    assert pe.bank.block == 64 and pe.bank.partitions == 6891
+    assert rel_err(y, g["y"]) <= TOL
+
+
+def test_golden_mix_extents_bit_exact():
+    g = golden("mix_extents.npz")
+    a = [g[f"a{i}"] for i in range(7)]
+    pes = [pg.ArrayPE(a[0]), pg.DelayPE(pg.ArrayPE(a[1]), 100), pg.ArrayPE(a[2][:50]),
+           pg.DelayPE(pg.ArrayPE(a[3]), 250)] + [pg.ArrayPE(t) for t in a[4:]]
+    assert np.array_equal(pg.MixPE(*pes).render(0, 600).data, g["y"])
+    assert np.array_equal(pg.MixPE(*pes).render(560, 100).data, g["y_late"])
+
+
+# ---------------------------------------------------------------------------
+# seeded random cases against the oracle
+@pytest.mark.parametrize("L,B,c_src,c_f", [
+    (1, 16, 1, 1), (15, 16, 2, 1), (16, 16, 1, 2), (17, 16, 2, 2), (100, 32, 1, 1), (1000, 128, 3, 3),
+    (5000, 512, 2, 1), (4096, 4096, 1, 1), (9000, 2048, 1, 2), (20000, 8192, 1, 1),
+])
+def test_oracle_parity_shapes(L, B, c_src, c_f):
+    rng = np.random.default_rng(1000 + L + B)
+    h = (rng.standard_normal((L, c_f)) / np.sqrt(L)).astype(np.float32)
+    n = max(3 * B + 37, 2 * L + 11)
+    x = rng.uniform(-1, 1, (n, c_src)).astype(np.float32)
+    pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h), block_size=B)
+    pulls = []
+    left = n + L  # run past the source end to flush the tail
+    for d in (1, B - 1, B, B + 1, 7, 2 * B + 3):
+        if left <= 0:
+            break
+        pulls.append(min(d, left))
+        left -= pulls[-1]
+    if left > 0:
+        pulls.append(left)
+    y = _pull_pe(pe, pulls)
+    ref = _oracle_pulls(orc.OracleConvolve(h, c_src), x, pulls)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) <= TOL
+
+
+def test_bank_many_streams_distinct_and_shared_filters():
+    rng = np.random.default_rng(5)
+    N, L, B, n = 37, 3000, 256, 1500
+    x = rng.uniform(-1, 1, (N, 2, n)).astype(np.float32)
+    for shared in (True, False):
+        F = 1 if shared else N
+        h = (rng.standard_normal((F, L, 2)) / np.sqrt(L)).astype(np.float32)
+        bank = pg.ConvolveBank(h, N, 2, block=B)
+        pulls = (100, 256, 300, 844)
+        ys = np.concatenate([bank.process(np.ascontiguousarray(x[:, :, a:a + d]))
+                             for a, d in zip(np.cumsum((0,) + pulls[:-1]), pulls)], axis=2)
+        for s in (0, 1, N // 2, N - 1):
+            ref = orc.OracleConvolve(h[0 if shared else s], 2).render(x[s].T)
+            assert rel_err(ys[s].T, ref) <= TOL
+        # fused mix == sum of per-stream outputs
+        bank2 = pg.ConvolveBank(h, N, 2, block=B)
+        ymix = bank2.process_mix(x)
+        ref_mix = np.sum(ys.astype(np.float64), axis=0)
+        assert rel_err(ymix, ref_mix) <= TOL
+
+
+def test_bank_per_stream_reset():
+    rng = np.random.default_rng(6)
+    N, L, B = 4, 700, 64
+    h = (rng.standard_normal((N, L)) / np.sqrt(L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (N, 1, 1000)).astype(np.float32)
+    bank = pg.ConvolveBank(h, N, 1, block=B)
+    bank.process(np.ascontiguousarray(x[:, :, :333]))
+    bank.reset(streams=[1, 3])
+    y = bank.process(np.ascontiguousarray(x[:, :, 333:]))
+    for s in range(N):
+        o = orc.OracleConvolve(h[s], 1)
+        if s in (1, 3):
+            ref = o.render(x[s, 0, 333:])
+        else:
+            o.render(x[s, 0, :333])
+            ref = o.render(x[s, 0, 333:])
+        assert rel_err(y[s, 0], ref[:, 0]) <= TOL, s
+
+
+def test_mix_sum_bit_exact_random():
+    rng = np.random.default_rng(9)
+    a = [rng.standard_normal((1000, 2)).astype(np.float32) * 10 ** rng.uniform(-3, 3) for _ in range(33)]
+    assert np.array_equal(pg.device_mix_sum(a), orc.oracle_mix(a))
+
+
+# ---------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes (the oracle would take minutes there)
+def test_full_size_c2_impulse_and_linearity():
+    """C2 at the named size (L=132300, B=512, P=259): a unit impulse reproduces the IR exactly
+    (to fp32 FFT rounding), and the response is linear in the input."""
+    pg.set_sample_rate(wl.SR_48)
+    ir = wl.c2_ir()
+    L = ir.shape[0]
+    bank = pg.ConvolveBank(ir, 3, 2, block=512, single_filter_dims=True, max_pull=8192)
+    n = 8192 * 17  # > L
+    rng = np.random.default_rng(12)
+    a = rng.uniform(-1, 1, (2, 4096)).astype(np.float32)
+    x = np.zeros((3, 2, n), np.float32)
+    x[0, :, 0] = 1.0                     # impulse
+    x[1, :, :4096] = a                   # signal
+    x[2, :, :4096] = 0.5 * a
+    x[2, :, 0] += 0.25                   # 0.5*signal + 0.25*impulse
+    y = bank.process(x)
+    assert rel_err(y[0, :, :L].T, ir) <= TOL
+    assert np.max(np.abs(y[0, :, L:])) <= TOL * np.max(np.abs(ir))
+    lin = 0.5 * y[1].astype(np.float64) + 0.25 * y[0].astype(np.float64)
+    assert rel_err(y[2], lin) <= TOL
+
+
+def test_full_size_c5_impulse_response():
+    ir = wl.c5_ir()
+    L = ir.shape[0]
+    pe = pg.ConvolvePE(pg.ArrayPE(np.array([1.0], np.float32)), pg.ArrayPE(ir), block_size=64)
+    y = _pull_pe(pe, (64,) * 40)[:, 0]   # 40 low-latency pulls through P = 6891 partitions
+    assert rel_err(y, ir[:y.shape[0]]) <= TOL
+    del L
