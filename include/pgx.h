@@ -81,6 +81,7 @@ typedef struct pgx_bank_info {
   int64_t state_bytes;      /* device bytes held (delay line + filter spectra + staging) */
   int64_t kernel_launches;  /* kernels launched by this handle since creation */
   int64_t block_steps;      /* FFT->MAC->IFFT steps executed since creation */
+  int32_t mac_grid, mac_split, mac_stream_tile, mac_occupancy; /* launch plan of the accumulate kernel */
 } pgx_bank_info;
 
 /* ---- library ------------------------------------------------------------ */
@@ -149,6 +150,16 @@ PGX_API int pgx_bank_process_mix(pgx_bank* bank, const float* x, pgx_layout x_la
 PGX_API int pgx_bank_process_device(pgx_bank* bank, const float* x_dev, pgx_layout x_layout, float* y_dev,
                             pgx_layout y_layout, int32_t n, int32_t mix, void* cuda_stream);
 PGX_API int pgx_bank_synchronize(pgx_bank* bank);
+
+/* ---- measurement: per-kernel device time, CUDA events on the launching stream ---- */
+typedef struct pgx_profile {
+  double ms_r2c, ms_mac, ms_c2r; /* summed durations of K1 / K3 / K2 launches */
+  int64_t steps;                 /* block steps covered */
+} pgx_profile;
+/* begin: every following block step records events around each of its three kernels.
+ * end: synchronise, sum the durations into *out, stop recording. */
+PGX_API int pgx_bank_profile_begin(pgx_bank* bank);
+PGX_API int pgx_bank_profile_end(pgx_bank* bank, pgx_profile* out);
 
 /* ---- MixPE: replaces the float32 left-to-right sum of mix_pe.py:92-94 ------ */
 /*

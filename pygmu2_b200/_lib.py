@@ -32,7 +32,12 @@ class BankInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_streams", "c_in", "c_x", "c_out", "filter_len", "filter_channels",
                                           "n_filters", "block", "partitions", "max_pull", "device", "head",
                                           "fill")] + \
-               [(n, C.c_int64) for n in ("state_bytes", "kernel_launches", "block_steps")]
+               [(n, C.c_int64) for n in ("state_bytes", "kernel_launches", "block_steps")] + \
+               [(n, C.c_int32) for n in ("mac_grid", "mac_split", "mac_stream_tile", "mac_occupancy")]
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms_r2c", C.c_double), ("ms_mac", C.c_double), ("ms_c2r", C.c_double), ("steps", C.c_int64)]
 
 
 _f32p = C.POINTER(C.c_float)
@@ -56,6 +61,8 @@ PROTOTYPES = {
     "pgx_bank_process_device": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32,
                                           C.c_int32, C.c_void_p]),
     "pgx_bank_synchronize": (C.c_int, [C.c_void_p]),
+    "pgx_bank_profile_begin": (C.c_int, [C.c_void_p]),
+    "pgx_bank_profile_end": (C.c_int, [C.c_void_p, C.POINTER(Profile)]),
     "pgx_mix_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pgx_mix_sum_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
 }

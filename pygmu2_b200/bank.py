@@ -196,6 +196,16 @@ class ConvolveBank:
     def synchronize(self) -> None:
         check(lib().pgx_bank_synchronize(self._h))
 
+    # -- measurement ---------------------------------------------------------------
+    def profile_begin(self) -> None:
+        check(lib().pgx_bank_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> _lib.Profile(ms_r2c, ms_mac, ms_c2r, steps): summed per-kernel CUDA-event durations."""
+        out = _lib.Profile()
+        check(lib().pgx_bank_profile_end(self._h, C.byref(out)))
+        return out
+
     # -- batched renderer support ------------------------------------------------
     def attach_sources(self, sources) -> None:
         """N host PEs feeding the N streams; enables ``render`` for BankRenderer."""

@@ -10,13 +10,15 @@
 //   and the per-source HRTF multiply (spatial_pe.py:503-504) are the same accumulation.
 //
 // HBM-bound: each term streams one B*8-byte row of X (and of H when filters are distinct) exactly
-// once, as 16-byte vector loads with U rows in flight per thread; 8 flop per 16 bytes.
+// once, as 16-byte vector loads with U rows in flight per thread; 8 flop per 16 bytes.  When all
+// streams share one filter (ST > 1) a CTA covers ST streams so each filter row is fetched once per
+// ST delay-line rows.  The work list (out tile x bin tile x term split) is a flat 1-D grid whose
+// size the host picks as a near-integer number of full waves (see mac_plan()).
 #include "kernels.h"
 
 namespace pgx {
 
 static constexpr int kMacThreads = 128;
-static constexpr int kMacUnroll = 8;
 
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 r;
@@ -37,88 +39,171 @@ __device__ __forceinline__ void cmac2(float4& acc, const float4 x, const float4 
   acc.w = fmaf(x.w, h.z, acc.w);
 }
 
-template <bool MIX>
+// ST = streams per CTA that share the filter rows (conv mode, one resident filter); U = rows in flight.
+template <bool MIX, int ST, int U>
 __global__ void __launch_bounds__(kMacThreads) k_fdl_mac(const MacArgs a) {
   __shared__ float4 red[kMacThreads];
-  __shared__ float2 red0[kMacThreads];
   const int lanes = a.W4 < kMacThreads ? a.W4 : kMacThreads;  // threads covering one row segment
   const int G = kMacThreads / lanes;                          // term-parallel groups
   const int g = threadIdx.x / lanes, lane = threadIdx.x - g * lanes;
-  const int kv = blockIdx.y * lanes + lane;                   // float4 index within the row
-  const int o = blockIdx.x, sp = blockIdx.z;
+  // flat work index -> (split, out tile, bin tile)
+  const int ktiles = a.W4 / lanes;
+  int w = blockIdx.x;
+  const int kt = w % ktiles;
+  w /= ktiles;
+  const int ot = w % a.n_otiles;
+  const int sp = w / a.n_otiles;
+  const int kv = kt * lanes + lane;  // float4 index within the row
   const int r0 = sp * a.terms_per_split;
   const int r1 = min(r0 + a.terms_per_split, a.n_terms);
-  const int c = MIX ? o : o % a.c_out;
-  const int s_fixed = MIX ? 0 : o / a.c_out;
+  // out tile -> channel c and first stream
+  int c, s0;
+  if (MIX) {
+    c = ot;
+    s0 = 0;
+  } else if (ST == 1) {
+    c = ot % a.c_out;
+    s0 = ot / a.c_out;
+  } else {
+    c = ot % a.c_out;
+    s0 = (ot / a.c_out) * ST;
+  }
   const int gx = (a.c_x == 1) ? 0 : c;
   const int fc = (a.c_f == 1) ? 0 : c;
   const bool bin0 = (kv == 0);  // packed bin 0 = two independent real bins (DC, Nyquist)
-  const size_t xrow_stride = (size_t)a.W4;
-  const float4* hbase_fixed = a.Hd + ((size_t)(a.fmap[s_fixed] * a.c_f + fc) * 2 * a.P + a.q0) * xrow_stride + kv;
-  const float4* xbase_fixed = a.fdl + ((size_t)(s_fixed * a.c_x + gx) * a.P) * xrow_stride + kv;
+  const size_t rs = (size_t)a.W4;
+  const size_t stream_stride = (size_t)a.c_x * a.P * rs;  // delay-line rows of one stream
+  const float4* hbase = a.Hd + ((size_t)(a.fmap[s0] * a.c_f + fc) * 2 * a.P + a.q0) * rs + kv;
+  const float4* xbase = a.fdl + ((size_t)(s0 * a.c_x + gx) * a.P) * rs + kv;
 
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 acc0 = make_float2(0.f, 0.f);
-
-  for (int r = r0 + g; r < r1; r += G * kMacUnroll) {
-    float4 xv[kMacUnroll], hv[kMacUnroll];
+  float4 acc[ST];
+  float2 acc0[ST];
 #pragma unroll
-    for (int u = 0; u < kMacUnroll; ++u) {
+  for (int t = 0; t < ST; ++t) {
+    acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc0[t] = make_float2(0.f, 0.f);
+  }
+  int nst = ST;
+  if (ST > 1) nst = min(ST, a.N - s0);
+
+  for (int r = r0 + g; r < r1; r += G * U) {
+    float4 xv[U][ST], hv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       const int rr = r + u * G;
       if (rr < r1) {
         const float4 *xp, *hp;
         if (MIX) {
           const int s = rr / a.P, j = rr - s * a.P;
-          xp = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + j) * xrow_stride + kv;
-          hp = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + a.q0 + j) * xrow_stride + kv;
+          xp = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + j) * rs + kv;
+          hp = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + a.q0 + j) * rs + kv;
         } else {
-          xp = xbase_fixed + (size_t)rr * xrow_stride;
-          hp = hbase_fixed + (size_t)rr * xrow_stride;
+          xp = xbase + (size_t)rr * rs;
+          hp = hbase + (size_t)rr * rs;
         }
-        xv[u] = ld_stream(xp);
-        hv[u] = __ldg(hp);
+        hv[u] = (ST > 1) ? __ldg(hp) : ld_stream(hp);
+#pragma unroll
+        for (int t = 0; t < ST; ++t)
+          xv[u][t] = (t < nst) ? ld_stream(xp + (size_t)t * stream_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
-        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < ST; ++t) xv[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kMacUnroll; ++u) {
-      cmac2(acc, xv[u], hv[u]);
-      if (bin0) {
-        acc0.x = fmaf(xv[u].x, hv[u].x, acc0.x);
-        acc0.y = fmaf(xv[u].y, hv[u].y, acc0.y);
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int t = 0; t < ST; ++t) {
+        cmac2(acc[t], xv[u][t], hv[u]);
+        if (bin0) {
+          acc0[t].x = fmaf(xv[u][t].x, hv[u].x, acc0[t].x);
+          acc0[t].y = fmaf(xv[u][t].y, hv[u].y, acc0[t].y);
+        }
       }
     }
   }
-  if (bin0) {
-    acc.x = acc0.x;
-    acc.y = acc0.y;
-  }
-  if (G > 1) {  // rows narrower than the CTA: groups took interleaved terms, fold them
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    if (g == 0) {
-      for (int gg = 1; gg < G; ++gg) {
-        const float4 v = red[gg * lanes + lane];
-        acc.x += v.x;
-        acc.y += v.y;
-        acc.z += v.z;
-        acc.w += v.w;
+#pragma unroll
+  for (int t = 0; t < ST; ++t) {
+    if (bin0) {
+      acc[t].x = acc0[t].x;
+      acc[t].y = acc0[t].y;
+    }
+    if (G > 1) {  // rows narrower than the CTA: groups took interleaved terms, fold them
+      __syncthreads();
+      red[threadIdx.x] = acc[t];
+      __syncthreads();
+      if (g == 0) {
+        for (int gg = 1; gg < G; ++gg) {
+          const float4 v = red[gg * lanes + lane];
+          acc[t].x += v.x;
+          acc[t].y += v.y;
+          acc[t].z += v.z;
+          acc[t].w += v.w;
+        }
       }
     }
+    if (g == 0 && t < nst) {
+      const int o = MIX ? c : (s0 + t) * a.c_out + c;
+      a.yspec[((size_t)sp * a.n_out + o) * rs + kv] = acc[t];
+    }
   }
-  if (g == 0) a.yspec[((size_t)sp * a.n_out + o) * xrow_stride + kv] = acc;
-  (void)red0;
+}
+
+template <bool MIX, int ST, int U>
+static int mac_occupancy() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fdl_mac<MIX, ST, U>, kMacThreads, 0);
+  return nb > 0 ? nb : 1;
+}
+
+// Pick the stream tile and the term split so the flat grid is a near-integer number of full waves.
+MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count) {
+  MacPlan p{};
+  const int lanes = W4 < kMacThreads ? W4 : kMacThreads;
+  const int groups = kMacThreads / lanes, ktiles = W4 / lanes;
+  p.st = (!mix && shared_filter && N >= 4) ? 4 : 1;
+  int occ;
+  if (mix) occ = mac_occupancy<true, 1, 8>();
+  else if (p.st == 4) occ = mac_occupancy<false, 4, 4>();
+  else occ = mac_occupancy<false, 1, 8>();
+  p.n_otiles = mix ? c_out : ((N + p.st - 1) / p.st) * c_out;
+  const long resident = (long)sm_count * occ;
+  const long base = (long)p.n_otiles * ktiles;
+  const int min_terms = 16 * groups;  // at least two unrolled batches per group and split
+  int max_split = n_terms / min_terms;
+  if (max_split < 1) max_split = 1;
+  if (max_split > 1024) max_split = 1024;
+  // cost model: waves x (terms per CTA + fixed per-CTA overhead expressed in row-terms)
+  double best = 1e300;
+  int best_s = 1;
+  for (int s = 1; s <= max_split; ++s) {
+    const long items = base * s;
+    const long waves = (items + resident - 1) / resident;
+    const int tps = (n_terms + s - 1) / s;
+    const double cost = (double)waves * (double)(tps + 6 * groups);
+    if (cost < best * 0.995) {
+      best = cost;
+      best_s = s;
+    }
+  }
+  p.n_split = best_s;
+  p.terms_per_split = (n_terms + best_s - 1) / best_s;
+  p.n_split = (n_terms + p.terms_per_split - 1) / p.terms_per_split;
+  p.grid = (int)(base * p.n_split);
+  p.occupancy = occ;
+  return p;
 }
 
 void launch_fdl_mac(const MacArgs& a, cudaStream_t st) {
   const int lanes = a.W4 < kMacThreads ? a.W4 : kMacThreads;
-  dim3 grid(a.n_out, a.W4 / lanes, a.n_split);
+  const int grid = a.n_otiles * (a.W4 / lanes) * a.n_split;
   if (a.mix)
-    k_fdl_mac<true><<<grid, kMacThreads, 0, st>>>(a);
+    k_fdl_mac<true, 1, 8><<<grid, kMacThreads, 0, st>>>(a);
+  else if (a.st == 4)
+    k_fdl_mac<false, 4, 4><<<grid, kMacThreads, 0, st>>>(a);
   else
-    k_fdl_mac<false><<<grid, kMacThreads, 0, st>>>(a);
+    k_fdl_mac<false, 1, 8><<<grid, kMacThreads, 0, st>>>(a);
 }
 
 // K5 -- MixPE: out = ((in0 + in1) + in2) + ... per element, float32, input order (bit-exact with

@@ -37,8 +37,13 @@ struct MacArgs {
   const int32_t* fmap;   // [N] filter of stream
   int32_t N, c_x, c_out, c_f, P, W4, q0;
   int32_t n_out, n_terms, terms_per_split, n_split;
+  int32_t n_otiles, st;  // out tiles in the flat grid; streams per CTA sharing the filter rows (1 or 4)
   int32_t mix;           // 0: out o=(s,c), terms j<P.  1: out o=c, terms (s,j) (fused MixPE / HRTF stereo mix)
 };
+struct MacPlan {
+  int32_t st, n_otiles, n_split, terms_per_split, grid, occupancy;
+};
+MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count);
 void launch_fdl_mac(const MacArgs& a, cudaStream_t st);
 
 // K2: sum split partials, inverse real FFT, emit the new output samples.

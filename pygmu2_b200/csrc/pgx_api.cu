@@ -78,24 +78,15 @@ struct pgx_bank {
   float* y_stage = nullptr;
   size_t hist_bytes = 0, fdl_bytes = 0, Hd_bytes = 0, yspec_bytes = 0, xs_bytes = 0, ys_bytes = 0;
   int head = 0, fill = 0, half = 0;
-  int split_conv = 1, split_mix = 1;
+  pgx::MacPlan plan_conv{}, plan_mix{};
+  int sm_count = 148;
   int64_t launches = 0, steps = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // 4 per block step: before K1, K1|K3, K3|K2, after K2
+  size_t prof_used = 0;
 };
 
 namespace {
-
-int choose_split(int n_out, int ktiles, int n_terms, int groups) {
-  const int64_t target = 148 * 8;  // CTAs wanted in flight: 148 SMs x 8 resident 128-thread CTAs
-  const int64_t base = (int64_t)n_out * ktiles;
-  if (base >= target) return 1;
-  int64_t want = (target + base - 1) / base;
-  const int min_terms = 8 * groups;  // keep at least one unrolled batch of rows per group
-  int64_t most = (n_terms + min_terms - 1) / min_terms;
-  if (most < 1) most = 1;
-  if (want > most) want = most;
-  if (want > 4096) want = 4096;
-  return (int)want;
-}
 
 void free_bank(pgx_bank* b) {
   if (!b) return;
@@ -109,6 +100,7 @@ void free_bank(pgx_bank* b) {
   cudaFree(b->fmap);
   cudaFree(b->x_stage);
   cudaFree(b->y_stage);
+  for (cudaEvent_t e : b->prof_events) cudaEventDestroy(e);
   if (b->fmap_pinned) cudaFreeHost(b->fmap_pinned);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -131,7 +123,21 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     r.n_fft = c.n_streams * b->c_x; r.c_in = c.c_in; r.c_x = b->c_x; r.B = B; r.P = P;
     r.slot = b->head; r.half = b->half; r.fill = b->fill; r.take = take;
     r.mixdown = (c.flags & PGX_FLAG_MIXDOWN_INPUT) ? 1 : 0;
+    cudaEvent_t* ev = nullptr;
+    if (b->profiling) {
+      if (b->prof_used + 4 > b->prof_events.size()) {
+        for (int i = 0; i < 4; ++i) {
+          cudaEvent_t e;
+          PGX_CUDA(cudaEventCreate(&e));
+          b->prof_events.push_back(e);
+        }
+      }
+      ev = &b->prof_events[b->prof_used];
+      b->prof_used += 4;
+      cudaEventRecord(ev[0], st);
+    }
     pgx::launch_r2c_ingest(r, st);
+    if (ev) cudaEventRecord(ev[1], st);
 
     pgx::MacArgs m{};
     m.fdl = reinterpret_cast<const float4*>(b->fdl);
@@ -143,16 +149,18 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     m.mix = mix ? 1 : 0;
     m.n_out = mix ? c.c_out : c.n_streams * c.c_out;
     m.n_terms = mix ? c.n_streams * P : P;
-    m.n_split = mix ? b->split_mix : b->split_conv;
-    m.terms_per_split = (m.n_terms + m.n_split - 1) / m.n_split;
+    const pgx::MacPlan& pl = mix ? b->plan_mix : b->plan_conv;
+    m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
     (void)lanes;
     pgx::launch_fdl_mac(m, st);
+    if (ev) cudaEventRecord(ev[2], st);
 
     pgx::C2RArgs k{};
     k.yspec = b->yspec; k.n_split = m.n_split; k.n_out = m.n_out;
     k.y = y_dev; k.ys = mix ? 0 : yl.stream; k.yc = yl.chan; k.yi = yl.samp; k.y_off = pos;
     k.c_out = c.c_out; k.B = B; k.fill = b->fill; k.take = take; k.tw = b->tw;
     pgx::launch_c2r_emit(k, st);
+    if (ev) cudaEventRecord(ev[3], st);
 
     b->launches += 3;
     b->steps += 1;
@@ -258,11 +266,15 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
   b->hist_bytes = n_fft * 2 * B * sizeof(float);
   b->fdl_bytes = n_fft * P * B * sizeof(float2);
   b->Hd_bytes = h_rows * 2 * P * B * sizeof(float2);
-  const int W4 = B / 2, lanes = W4 < 128 ? W4 : 128, groups = 128 / lanes, ktiles = W4 / lanes;
-  b->split_conv = choose_split(c.n_streams * c.c_out, ktiles, P, groups);
-  b->split_mix = choose_split(c.c_out, ktiles, c.n_streams * P, groups);
-  const size_t y_conv = (size_t)b->split_conv * c.n_streams * c.c_out;
-  const size_t y_mix = (size_t)b->split_mix * c.c_out;
+  {
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess && prop.multiProcessorCount > 0)
+      b->sm_count = prop.multiProcessorCount;
+  }
+  b->plan_conv = pgx::mac_plan(c.n_streams, c.c_out, B / 2, P, false, c.n_filters == 1, b->sm_count);
+  b->plan_mix = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams * P, true, c.n_filters == 1, b->sm_count);
+  const size_t y_conv = (size_t)b->plan_conv.n_split * c.n_streams * c.c_out;
+  const size_t y_mix = (size_t)b->plan_mix.n_split * c.c_out;
   b->yspec_bytes = (y_conv > y_mix ? y_conv : y_mix) * B * sizeof(float2);
   b->xs_bytes = (size_t)c.n_streams * c.c_in * c.max_pull * sizeof(float);
   b->ys_bytes = (size_t)c.n_streams * c.c_out * c.max_pull * sizeof(float);
@@ -341,6 +353,8 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + b->yspec_bytes + b->xs_bytes + b->ys_bytes);
   info->kernel_launches = b->launches;
   info->block_steps = b->steps;
+  info->mac_grid = b->plan_conv.grid; info->mac_split = b->plan_conv.n_split;
+  info->mac_stream_tile = b->plan_conv.st; info->mac_occupancy = b->plan_conv.occupancy;
   return PGX_OK;
 }
 
@@ -446,6 +460,33 @@ int pgx_bank_synchronize(pgx_bank* b) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   PGX_CUDA(cudaStreamSynchronize(b->stream));
+  return PGX_OK;
+}
+
+int pgx_bank_profile_begin(pgx_bank* b) {
+  if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  b->profiling = true;
+  b->prof_used = 0;
+  return PGX_OK;
+}
+
+int pgx_bank_profile_end(pgx_bank* b, pgx_profile* out) {
+  if (!b || !out) return fail(PGX_ERR_INVALID, "NULL argument");
+  PGX_CUDA(cudaSetDevice(b->cfg.device));
+  b->profiling = false;
+  out->ms_r2c = out->ms_mac = out->ms_c2r = 0.0;
+  out->steps = (int64_t)(b->prof_used / 4);
+  if (b->prof_used) PGX_CUDA(cudaEventSynchronize(b->prof_events[b->prof_used - 1]));
+  for (size_t i = 0; i + 3 < b->prof_used; i += 4) {
+    float a = 0.f, m = 0.f, c = 0.f;
+    PGX_CUDA(cudaEventElapsedTime(&a, b->prof_events[i], b->prof_events[i + 1]));
+    PGX_CUDA(cudaEventElapsedTime(&m, b->prof_events[i + 1], b->prof_events[i + 2]));
+    PGX_CUDA(cudaEventElapsedTime(&c, b->prof_events[i + 2], b->prof_events[i + 3]));
+    out->ms_r2c += a;
+    out->ms_mac += m;
+    out->ms_c2r += c;
+  }
+  b->prof_used = 0;
   return PGX_OK;
 }
 
