@@ -152,10 +152,26 @@ __global__ void __launch_bounds__(kFftThreads) k_c2r_emit(const C2RArgs a) {
   float2* bufA = sm + (size_t)g * 2 * n;
   float2* bufB = bufA + n;
   if (active) {
+    const float2 *xrow = nullptr, *hrow = nullptr;
+    if (a.fdl) {  // conv mode: present term = delay-line slot `head` x filter partition 0 (row P-1 of Hd)
+      const int s = o / a.c_out, c = o - s * a.c_out;
+      const int gx = (a.c_x == 1) ? 0 : c, fc = (a.c_f == 1) ? 0 : c;
+      xrow = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + a.head) * n;
+      hrow = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + (a.P - 1)) * n;
+    }
     for (int k = t; k < n; k += T) {
       float2 acc = make_float2(0.f, 0.f);
+      if (xrow) {
+        const float2 x = xrow[k], h = __ldg(hrow + k);
+        acc = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);
+      }
       for (int sp = 0; sp < a.n_split; ++sp) {
         const float2 v = a.yspec[((size_t)sp * a.n_out + o) * n + k];
+        acc.x += v.x;
+        acc.y += v.y;
+      }
+      for (int sp = 0; sp < a.n_split_now; ++sp) {
+        const float2 v = a.ynow[((size_t)sp * a.n_out + o) * n + k];
         acc.x += v.x;
         acc.y += v.y;
       }

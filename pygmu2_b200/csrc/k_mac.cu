@@ -94,12 +94,14 @@ __global__ void __launch_bounds__(kMacThreads) k_fdl_mac(const MacArgs a) {
       if (rr < r1) {
         const float4 *xp, *hp;
         if (MIX) {
-          const int s = rr / a.P, j = rr - s * a.P;
+          const int s = rr / a.Pt, jj = rr - s * a.Pt;
+          const int j = (a.jfix >= 0) ? a.jfix : jj + (jj >= a.skip ? 1 : 0);
           xp = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + j) * rs + kv;
           hp = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + a.q0 + j) * rs + kv;
         } else {
-          xp = xbase + (size_t)rr * rs;
-          hp = hbase + (size_t)rr * rs;
+          const int j = (a.jfix >= 0) ? a.jfix : rr + (rr >= a.skip ? 1 : 0);
+          xp = xbase + (size_t)j * rs;
+          hp = hbase + (size_t)j * rs;
         }
         hv[u] = (ST > 1) ? __ldg(hp) : ld_stream(hp);
 #pragma unroll

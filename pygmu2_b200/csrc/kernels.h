@@ -39,6 +39,10 @@ struct MacArgs {
   int32_t n_out, n_terms, terms_per_split, n_split;
   int32_t n_otiles, st;  // out tiles in the flat grid; streams per CTA sharing the filter rows (1 or 4)
   int32_t mix;           // 0: out o=(s,c), terms j<P.  1: out o=c, terms (s,j) (fused MixPE / HRTF stereo mix)
+  // which delay-line slots are terms: Pt slots per stream; slot = jfix if jfix >= 0 (only that slot),
+  // else jj + (jj >= skip) for jj in [0, Pt) (skip = the open slot `head` for the background pass, or a
+  // value >= P for "all slots").  n_terms = Pt (conv) or N*Pt (mix).
+  int32_t Pt, skip, jfix;
 };
 struct MacPlan {
   int32_t st, n_otiles, n_split, terms_per_split, grid, occupancy;
@@ -48,8 +52,15 @@ void launch_fdl_mac(const MacArgs& a, cudaStream_t st);
 
 // K2: sum split partials, inverse real FFT, emit the new output samples.
 struct C2RArgs {
-  const float2* yspec;   // [n_split][n_out][B]
+  const float2* yspec;   // [n_split][n_out][B]   partial sums of the background (past-partition) pass
   int32_t n_split, n_out;
+  const float2* ynow;    // [n_split_now][n_out][B] partial sums of the present pass (mix mode), or NULL
+  int32_t n_split_now;
+  // conv mode: the present term X[slot head] * H[partition 0] is folded in here (one row pair per out)
+  const float2* fdl;     // NULL when ynow carries the present term
+  const float2* Hd;
+  const int32_t* fmap;
+  int32_t c_x, c_f, P, head;
   float* y;              // element (s, c, i) at y[s*ys + c*yc + (y_off+i)*yi]; o = s*c_out + c
   int64_t ys, yc, yi;
   int32_t y_off;

@@ -5,11 +5,18 @@
 //   fdl   [N*c_x][P][B]      float2  frequency-domain delay line: packed spectra of the last P windows
 //   Hd    [F*c_f][2P][B]     float2  filter partition spectra, reversed + doubled, scaled 1/B
 //   yspec [n_split][n_out][B] float2 split partial sums of the multiply-accumulate
-// and advances them one "block step" at a time: K1 (ingest + R2C) -> K3 (MAC over P) -> K2 (C2R + emit).
-// A pull of n samples is cut at block boundaries; a partially filled block is transformed with
-// zeros in the not-yet-known positions (causality makes the emitted samples exact) and re-transformed
-// when more samples arrive, so any (start, duration) pull pattern is zero-latency like the reference
-// (convolve_pe.py:250-342), while the block grid stays aligned for the partitioned filter.
+// and advances them one "block step" at a time.  A pull of n samples is cut at block boundaries; a
+// partially filled block is transformed with zeros in the not-yet-known positions (causality makes the
+// emitted samples exact) and re-transformed when more samples arrive, so any (start, duration) pull
+// pattern is zero-latency like the reference (convolve_pe.py:250-342), while the block grid stays
+// aligned for the partitioned filter.
+//
+// Schedule of one block step (two CUDA streams):
+//   critical stream : K1 ingest + R2C of the open block  ->  [mix mode: K3 over the open slot of every
+//                     stream]  ->  K2: past partial sums + present term, C2R, emit
+//   background      : K3 over the P-1 *past* partitions of the open block.  It depends only on rows
+//                     committed before the block opened, so it is launched as soon as the previous
+//                     block's K1 has run, overlaps K1/K2, and is reused by every partial pull of the block.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -66,11 +73,15 @@ bool layout_dense(const pgx_layout& l, int64_t S, int64_t C, int64_t n) {
 struct pgx_bank {
   pgx_bank_config cfg{};
   int c_x = 1, P = 1, B = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // default critical stream
+  cudaStream_t bg = nullptr;      // background stream for the past-partition pass
+  cudaEvent_t ev_fork = nullptr, ev_past = nullptr;
+  bool ev_past_recorded = false;
   float* hist = nullptr;
   float2* fdl = nullptr;
   float2* Hd = nullptr;
-  float2* yspec = nullptr;
+  float2* ypast[2] = {nullptr, nullptr};  // past-partition partial sums, double buffered by block parity
+  float2* ynow = nullptr;                 // present-slot partial sums (mix mode)
   float2* tw = nullptr;
   int32_t* fmap = nullptr;
   int32_t* fmap_pinned = nullptr;
@@ -78,12 +89,18 @@ struct pgx_bank {
   float* y_stage = nullptr;
   size_t hist_bytes = 0, fdl_bytes = 0, Hd_bytes = 0, yspec_bytes = 0, xs_bytes = 0, ys_bytes = 0;
   int head = 0, fill = 0, half = 0;
-  pgx::MacPlan plan_conv{}, plan_mix{};
+  int par = 0;               // which ypast buffer belongs to the open block
+  bool past_valid = false;   // ypast[par] holds the past sum of the open block ...
+  int past_mode = -1;        // ... for this mode (0 conv, 1 mix)
+  pgx::MacPlan plan_conv{}, plan_mix{}, plan_now{};
   int sm_count = 148;
   int64_t launches = 0, steps = 0;
   bool profiling = false;
-  std::vector<cudaEvent_t> prof_events;  // 4 per block step: before K1, K1|K3, K3|K2, after K2
-  size_t prof_used = 0;
+  struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3, 2 = K2
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_pool_used = 0;
+  int64_t prof_steps = 0;
 };
 
 namespace {
@@ -95,15 +112,84 @@ void free_bank(pgx_bank* b) {
   cudaFree(b->hist);
   cudaFree(b->fdl);
   cudaFree(b->Hd);
-  cudaFree(b->yspec);
+  cudaFree(b->ypast[0]);
+  cudaFree(b->ypast[1]);
+  cudaFree(b->ynow);
   cudaFree(b->tw);
   cudaFree(b->fmap);
   cudaFree(b->x_stage);
   cudaFree(b->y_stage);
-  for (cudaEvent_t e : b->prof_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : b->prof_pool) cudaEventDestroy(e);
+  if (b->bg) cudaStreamSynchronize(b->bg);
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_past) cudaEventDestroy(b->ev_past);
+  if (b->bg) cudaStreamDestroy(b->bg);
   if (b->fmap_pinned) cudaFreeHost(b->fmap_pinned);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
+}
+
+cudaEvent_t prof_event(pgx_bank* b) {
+  if (b->prof_pool_used == b->prof_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    b->prof_pool.push_back(e);
+  }
+  return b->prof_pool[b->prof_pool_used++];
+}
+
+struct ProfScope {  // records a CUDA-event pair around one launch when profiling is on
+  pgx_bank* b;
+  cudaStream_t st;
+  int kind;
+  cudaEvent_t e0 = nullptr;
+  ProfScope(pgx_bank* b_, cudaStream_t st_, int kind_) : b(b_), st(st_), kind(kind_) {
+    if (b->profiling) {
+      e0 = prof_event(b);
+      cudaEventRecord(e0, st);
+    }
+  }
+  ~ProfScope() {
+    if (e0) {
+      cudaEvent_t e1 = prof_event(b);
+      cudaEventRecord(e1, st);
+      b->prof_spans.push_back({kind, e0, e1});
+    }
+  }
+};
+
+void fill_mac_common(pgx_bank* b, pgx::MacArgs& m, bool mix) {
+  const pgx_bank_config& c = b->cfg;
+  m.fdl = reinterpret_cast<const float4*>(b->fdl);
+  m.Hd = reinterpret_cast<const float4*>(b->Hd);
+  m.fmap = b->fmap;
+  m.N = c.n_streams; m.c_x = b->c_x; m.c_out = c.c_out; m.c_f = c.filter_channels; m.P = b->P; m.W4 = b->B / 2;
+  m.q0 = b->P - 1 - b->head;
+  m.mix = mix ? 1 : 0;
+  m.n_out = mix ? c.c_out : c.n_streams * c.c_out;
+}
+
+// Background pass: sum over the P-1 committed partitions of the open block into ypast[par].
+// Forked from `after` (an event on the critical stream after which every committed row is written).
+void launch_past(pgx_bank* b, bool mix, cudaStream_t crit) {
+  cudaEventRecord(b->ev_fork, crit);
+  cudaStreamWaitEvent(b->bg, b->ev_fork, 0);
+  pgx::MacArgs m{};
+  fill_mac_common(b, m, mix);
+  const pgx::MacPlan& pl = mix ? b->plan_mix : b->plan_conv;
+  m.yspec = reinterpret_cast<float4*>(b->ypast[b->par]);
+  m.Pt = b->P - 1; m.skip = b->head; m.jfix = -1;
+  m.n_terms = mix ? b->cfg.n_streams * (b->P - 1) : (b->P - 1);
+  m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
+  {
+    ProfScope ps(b, b->bg, 1);
+    pgx::launch_fdl_mac(m, b->bg);
+  }
+  cudaEventRecord(b->ev_past, b->bg);
+  b->ev_past_recorded = true;
+  b->launches += 1;
+  b->past_valid = true;
+  b->past_mode = mix ? 1 : 0;
 }
 
 // One pull on device buffers, enqueued on st (no synchronisation).
@@ -111,8 +197,6 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
              bool mix, cudaStream_t st) {
   const pgx_bank_config& c = b->cfg;
   const int B = b->B, P = b->P;
-  const int W4 = B / 2;
-  const int lanes = W4 < 128 ? W4 : 128;
   int pos = 0;
   while (pos < n) {
     const int take = (B - b->fill < n - pos) ? (B - b->fill) : (n - pos);
@@ -123,57 +207,78 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     r.n_fft = c.n_streams * b->c_x; r.c_in = c.c_in; r.c_x = b->c_x; r.B = B; r.P = P;
     r.slot = b->head; r.half = b->half; r.fill = b->fill; r.take = take;
     r.mixdown = (c.flags & PGX_FLAG_MIXDOWN_INPUT) ? 1 : 0;
-    cudaEvent_t* ev = nullptr;
-    if (b->profiling) {
-      if (b->prof_used + 4 > b->prof_events.size()) {
-        for (int i = 0; i < 4; ++i) {
-          cudaEvent_t e;
-          PGX_CUDA(cudaEventCreate(&e));
-          b->prof_events.push_back(e);
-        }
-      }
-      ev = &b->prof_events[b->prof_used];
-      b->prof_used += 4;
-      cudaEventRecord(ev[0], st);
+    {
+      ProfScope ps(b, st, 0);
+      pgx::launch_r2c_ingest(r, st);
     }
-    pgx::launch_r2c_ingest(r, st);
-    if (ev) cudaEventRecord(ev[1], st);
+    b->launches += 1;
 
-    pgx::MacArgs m{};
-    m.fdl = reinterpret_cast<const float4*>(b->fdl);
-    m.Hd = reinterpret_cast<const float4*>(b->Hd);
-    m.yspec = reinterpret_cast<float4*>(b->yspec);
-    m.fmap = b->fmap;
-    m.N = c.n_streams; m.c_x = b->c_x; m.c_out = c.c_out; m.c_f = c.filter_channels; m.P = P; m.W4 = W4;
-    m.q0 = P - 1 - b->head;
-    m.mix = mix ? 1 : 0;
-    m.n_out = mix ? c.c_out : c.n_streams * c.c_out;
-    m.n_terms = mix ? c.n_streams * P : P;
-    const pgx::MacPlan& pl = mix ? b->plan_mix : b->plan_conv;
-    m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
-    (void)lanes;
-    pgx::launch_fdl_mac(m, st);
-    if (ev) cudaEventRecord(ev[2], st);
+    const bool completes = (b->fill + take == B);
+    int n_split_past = 0;
+    if (P > 1) {
+      if (!b->past_valid || b->past_mode != (mix ? 1 : 0)) launch_past(b, mix, st);
+      cudaStreamWaitEvent(st, b->ev_past, 0);
+      n_split_past = (mix ? b->plan_mix : b->plan_conv).n_split;
+    }
 
     pgx::C2RArgs k{};
-    k.yspec = b->yspec; k.n_split = m.n_split; k.n_out = m.n_out;
+    k.yspec = b->ypast[b->par]; k.n_split = n_split_past;
+    k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
+    if (mix) {  // present term of every stream: K3 restricted to the open slot
+      pgx::MacArgs m{};
+      fill_mac_common(b, m, true);
+      m.yspec = reinterpret_cast<float4*>(b->ynow);
+      m.Pt = 1; m.skip = P; m.jfix = b->head;
+      m.n_terms = c.n_streams;
+      m.n_split = b->plan_now.n_split; m.terms_per_split = b->plan_now.terms_per_split;
+      m.n_otiles = b->plan_now.n_otiles; m.st = b->plan_now.st;
+      {
+        ProfScope ps(b, st, 1);
+        pgx::launch_fdl_mac(m, st);
+      }
+      b->launches += 1;
+      k.ynow = b->ynow; k.n_split_now = m.n_split;
+      k.fdl = nullptr;
+    } else {
+      k.ynow = nullptr; k.n_split_now = 0;
+      k.fdl = b->fdl;
+    }
+    k.Hd = b->Hd; k.fmap = b->fmap; k.c_x = b->c_x; k.c_f = c.filter_channels; k.P = P; k.head = b->head;
     k.y = y_dev; k.ys = mix ? 0 : yl.stream; k.yc = yl.chan; k.yi = yl.samp; k.y_off = pos;
     k.c_out = c.c_out; k.B = B; k.fill = b->fill; k.take = take; k.tw = b->tw;
-    pgx::launch_c2r_emit(k, st);
-    if (ev) cudaEventRecord(ev[3], st);
-
-    b->launches += 3;
+    if (completes && P > 1) {
+      // the block commits with this step: its row is final once K1 has run, so the next block's past
+      // pass can start now and overlap this step's K2 (and the next step's K1)
+      b->head = (b->head + 1) % P;
+      b->par ^= 1;
+      launch_past(b, mix, st);
+      b->head = (b->head + P - 1) % P;
+      b->par ^= 1;
+    }
+    {
+      ProfScope ps(b, st, 2);
+      pgx::launch_c2r_emit(k, st);
+    }
+    b->launches += 1;
     b->steps += 1;
+    if (b->profiling) b->prof_steps += 1;
     b->fill += take;
     pos += take;
-    if (b->fill == B) {  // block complete: commit the row, advance the ring
+    if (completes) {  // block complete: commit the row, advance the ring
       b->head = (b->head + 1) % P;
       b->half ^= 1;
       b->fill = 0;
+      if (P > 1) b->par ^= 1;  // past sum of the new open block was launched above
     }
   }
   PGX_CUDA(cudaGetLastError());
   return PGX_OK;
+}
+
+// state changes outside run_pull invalidate the cached past sum and must not race the background pass
+void quiesce_background(pgx_bank* b) {
+  if (b->ev_past_recorded) cudaStreamWaitEvent(b->stream, b->ev_past, 0);
+  b->past_valid = false;
 }
 
 int check_pull_args(pgx_bank* b, const void* x, const void* y, int n) {
@@ -271,11 +376,17 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess && prop.multiProcessorCount > 0)
       b->sm_count = prop.multiProcessorCount;
   }
-  b->plan_conv = pgx::mac_plan(c.n_streams, c.c_out, B / 2, P, false, c.n_filters == 1, b->sm_count);
-  b->plan_mix = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams * P, true, c.n_filters == 1, b->sm_count);
-  const size_t y_conv = (size_t)b->plan_conv.n_split * c.n_streams * c.c_out;
-  const size_t y_mix = (size_t)b->plan_mix.n_split * c.c_out;
+  size_t y_conv = 0, y_mix = 0;
+  if (P > 1) {  // background pass over the P-1 committed partitions
+    b->plan_conv = pgx::mac_plan(c.n_streams, c.c_out, B / 2, P - 1, false, c.n_filters == 1, b->sm_count);
+    b->plan_mix = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams * (P - 1), true, c.n_filters == 1, b->sm_count);
+    y_conv = (size_t)b->plan_conv.n_split * c.n_streams * c.c_out;
+    y_mix = (size_t)b->plan_mix.n_split * c.c_out;
+  }
+  b->plan_now = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams, true, c.n_filters == 1, b->sm_count);
   b->yspec_bytes = (y_conv > y_mix ? y_conv : y_mix) * B * sizeof(float2);
+  if (b->yspec_bytes == 0) b->yspec_bytes = sizeof(float2);
+  const size_t ynow_bytes = (size_t)b->plan_now.n_split * c.c_out * B * sizeof(float2);
   b->xs_bytes = (size_t)c.n_streams * c.c_in * c.max_pull * sizeof(float);
   b->ys_bytes = (size_t)c.n_streams * c.c_out * c.max_pull * sizeof(float);
 
@@ -284,11 +395,20 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     if (e != cudaSuccess && rc == PGX_OK)
       rc = fail(e == cudaErrorMemoryAllocation ? PGX_ERR_NOMEM : PGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   };
-  guard(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  {
+    int lo = 0, hi = 0;  // the critical path (K1/K2) outranks the background pass when both want an SM
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    guard(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, hi), "cudaStreamCreate");
+    guard(cudaStreamCreateWithPriority(&b->bg, cudaStreamNonBlocking, lo), "cudaStreamCreate(bg)");
+  }
+  guard(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+  guard(cudaEventCreateWithFlags(&b->ev_past, cudaEventDisableTiming), "cudaEventCreate");
   guard(cudaMalloc(&b->hist, b->hist_bytes), "cudaMalloc(hist)");
   guard(cudaMalloc(&b->fdl, b->fdl_bytes), "cudaMalloc(fdl)");
   guard(cudaMalloc(&b->Hd, b->Hd_bytes), "cudaMalloc(Hd)");
-  guard(cudaMalloc(&b->yspec, b->yspec_bytes), "cudaMalloc(yspec)");
+  guard(cudaMalloc(&b->ypast[0], b->yspec_bytes), "cudaMalloc(ypast0)");
+  guard(cudaMalloc(&b->ypast[1], b->yspec_bytes), "cudaMalloc(ypast1)");
+  guard(cudaMalloc(&b->ynow, ynow_bytes), "cudaMalloc(ynow)");
   guard(cudaMalloc(&b->tw, (size_t)2 * B * sizeof(float2)), "cudaMalloc(tw)");
   guard(cudaMalloc(&b->fmap, (size_t)c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
   guard(cudaMalloc(&b->x_stage, b->xs_bytes), "cudaMalloc(x_stage)");
@@ -350,7 +470,7 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->filter_len = c.filter_len; info->filter_channels = c.filter_channels; info->n_filters = c.n_filters;
   info->block = b->B; info->partitions = b->P; info->max_pull = c.max_pull; info->device = c.device;
   info->head = b->head; info->fill = b->fill;
-  info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + b->yspec_bytes + b->xs_bytes + b->ys_bytes);
+  info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + 2 * b->yspec_bytes + b->xs_bytes + b->ys_bytes);
   info->kernel_launches = b->launches;
   info->block_steps = b->steps;
   info->mac_grid = b->plan_conv.grid; info->mac_split = b->plan_conv.n_split;
@@ -361,10 +481,12 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
 int pgx_bank_reset(pgx_bank* b, const int32_t* stream_ids, int32_t k) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
+  quiesce_background(b);
   if (k <= 0 || !stream_ids) {
     PGX_CUDA(cudaMemsetAsync(b->hist, 0, b->hist_bytes, b->stream));
     PGX_CUDA(cudaMemsetAsync(b->fdl, 0, b->fdl_bytes, b->stream));
     b->head = b->fill = b->half = 0;
+    b->par = 0;
     return PGX_OK;
   }
   const size_t hs = (size_t)b->c_x * 2 * b->B * sizeof(float);
@@ -384,6 +506,7 @@ int pgx_bank_load_filter(pgx_bank* b, int32_t filter_index, const float* h) {
   if (filter_index < 0 || filter_index >= c.n_filters)
     return fail(PGX_ERR_INVALID, "filter_index %d outside [0,%d)", filter_index, c.n_filters);
   PGX_CUDA(cudaSetDevice(c.device));
+  quiesce_background(b);
   float* h_dev = nullptr;
   const size_t hb = (size_t)c.filter_channels * c.filter_len * sizeof(float);
   PGX_CUDA(cudaMalloc(&h_dev, hb));
@@ -409,6 +532,7 @@ int pgx_bank_set_filter_map(pgx_bank* b, const int32_t* filter_of_stream) {
   for (int s = 0; s < b->cfg.n_streams; ++s)
     if (filter_of_stream[s] < 0 || filter_of_stream[s] >= b->cfg.n_filters)
       return fail(PGX_ERR_INVALID, "filter_of_stream[%d]=%d outside [0,%d)", s, filter_of_stream[s], b->cfg.n_filters);
+  quiesce_background(b);
   PGX_CUDA(cudaStreamSynchronize(b->stream));  // the pinned staging copy may still be in flight
   memcpy(b->fmap_pinned, filter_of_stream, (size_t)b->cfg.n_streams * sizeof(int32_t));
   PGX_CUDA(cudaMemcpyAsync(b->fmap, b->fmap_pinned, (size_t)b->cfg.n_streams * sizeof(int32_t), cudaMemcpyHostToDevice,
@@ -460,13 +584,16 @@ int pgx_bank_synchronize(pgx_bank* b) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   PGX_CUDA(cudaStreamSynchronize(b->stream));
+  PGX_CUDA(cudaStreamSynchronize(b->bg));
   return PGX_OK;
 }
 
 int pgx_bank_profile_begin(pgx_bank* b) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   b->profiling = true;
-  b->prof_used = 0;
+  b->prof_spans.clear();
+  b->prof_pool_used = 0;
+  b->prof_steps = 0;
   return PGX_OK;
 }
 
@@ -475,18 +602,17 @@ int pgx_bank_profile_end(pgx_bank* b, pgx_profile* out) {
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   b->profiling = false;
   out->ms_r2c = out->ms_mac = out->ms_c2r = 0.0;
-  out->steps = (int64_t)(b->prof_used / 4);
-  if (b->prof_used) PGX_CUDA(cudaEventSynchronize(b->prof_events[b->prof_used - 1]));
-  for (size_t i = 0; i + 3 < b->prof_used; i += 4) {
-    float a = 0.f, m = 0.f, c = 0.f;
-    PGX_CUDA(cudaEventElapsedTime(&a, b->prof_events[i], b->prof_events[i + 1]));
-    PGX_CUDA(cudaEventElapsedTime(&m, b->prof_events[i + 1], b->prof_events[i + 2]));
-    PGX_CUDA(cudaEventElapsedTime(&c, b->prof_events[i + 2], b->prof_events[i + 3]));
-    out->ms_r2c += a;
-    out->ms_mac += m;
-    out->ms_c2r += c;
+  out->steps = b->prof_steps;
+  PGX_CUDA(cudaDeviceSynchronize());
+  for (const pgx_bank::ProfSpan& sp : b->prof_spans) {
+    float ms = 0.f;
+    PGX_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    if (sp.kind == 0) out->ms_r2c += ms;
+    else if (sp.kind == 1) out->ms_mac += ms;
+    else out->ms_c2r += ms;
   }
-  b->prof_used = 0;
+  b->prof_spans.clear();
+  b->prof_pool_used = 0;
   return PGX_OK;
 }
 
