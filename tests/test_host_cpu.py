@@ -1,0 +1,319 @@
+"""
+CPU-side tests (-m "not gpu"): the C-ABI library loads and exports every symbol include/pgx.h
+declares (no compute calls), the host-side mirror of the PE protocol behaves like the reference
+(restated reference tests: tests/test_extent.py, test_snippet.py, test_mix_pe.py, test_spatial_pe.py,
+test_renderer.py, test_convolve_pe.py:30-42), the product path fails loudly without a CUDA device,
+the numpy model of the device schedule agrees with the oracle, and world_size-2 gloo sharding works.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pygmu2_b200 as pg
+from pygmu2_b200 import _lib, dist as pdist, kemar
+from conftest import ROOT, golden
+
+
+# ---- C ABI -------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pgx.h")).read()
+    declared = set(re.findall(r"PGX_API\s+(?:const\s+char\*|int)\s+(pgx_\w+)\s*\(", hdr))
+    assert declared, "no prototypes parsed from pgx.h"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    h = _lib.lib()
+    for name in declared:
+        assert hasattr(h, name), name
+    assert h.pgx_abi_version() == _lib.ABI_VERSION
+    assert isinstance(h.pgx_last_error(), bytes)
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    assert C.sizeof(_lib.Layout) == 24
+    assert C.sizeof(_lib.BankConfig) == 40
+    assert C.sizeof(_lib.Profile) == 32
+
+
+def test_no_silent_cpu_path():
+    """Without a CUDA device the device-backed PEs raise; nothing falls back to numpy."""
+    if _lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    pe = pg.ConvolvePE(pg.ArrayPE([1.0, 2.0, 3.0]), pg.ArrayPE([1.0, 1.0]))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        pe.render(0, 3)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        pg.device_mix_sum([np.zeros((4, 1), np.float32)] * 2)
+    sp = pg.SpatialPE(pg.ArrayPE(np.ones(16)), method=pg.SpatialHRTF(30.0))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        sp.render(0, 8)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pygmu2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pygmu2_oracle" not in src and "import oracle" not in src, f
+
+
+# ---- Extent / Snippet (reference tests/test_extent.py, tests/test_snippet.py) ---------------------
+def test_extent_algebra():
+    E = pg.Extent
+    with pytest.raises(ValueError):
+        E(5, 2)
+    assert E(0, 10).contains(0) and not E(0, 10).contains(10)
+    assert E(None, None).contains(-10 ** 9)
+    assert E(0, 10).spans(2, 8) and not E(0, 10).spans(2, 9)
+    assert E(0, 10).intersects(E(9, 20)) and not E(0, 10).intersects(E(10, 20))
+    assert not E(5, 5).intersects(E(0, 10)) and not E(5, 5).intersects(E(5, 5))
+    assert E(0, 10).intersection(E(5, 20)) == E(5, 10)
+    assert E(0, 10).intersection(E(20, 30)).is_empty()
+    assert E(0, 100).union(E(50, 200)) == E(0, 200)
+    assert E(0, 100).union(E(None, None)) == E(None, None)
+    assert E(0, 10).union(E(3, 3)) == E(0, 10)
+    assert E(None, 5).duration is None and E(2, 5).duration == 3
+    assert not E(3, 3) and E(0, 1)
+
+
+def test_snippet_rules():
+    s = pg.Snippet(7, np.arange(4, dtype=np.float64))
+    assert s.data.shape == (4, 1) and s.data.dtype == np.float32 and (s.start, s.end, s.duration) == (7, 11, 4)
+    with pytest.raises(ValueError):
+        pg.Snippet(0, np.zeros((2, 2, 2)))
+    z = pg.Snippet.from_zeros(3, 0, 2)
+    assert z.duration == 0 and z.channels == 2
+    assert pg.Snippet(0, np.ones((3, 2))) == pg.Snippet(0, np.ones((3, 2)) + 1e-9)
+
+
+def test_sample_rate_required_before_construction():
+    pg.core._state["sample_rate"] = None
+    with pytest.raises(RuntimeError):
+        pg.ArrayPE([1.0])
+    pg.set_sample_rate(44100)
+
+
+def test_render_wrapper_contract():
+    a = pg.ArrayPE([1.0, 2.0, 3.0])
+    with pytest.raises(ValueError):
+        a.render(0, -1)
+    assert a.render(5, 0).data.shape == (0, 1)
+    np.testing.assert_array_equal(a.render(-1, 5).data[:, 0], [0, 1, 2, 3, 0])  # zero fill outside extent
+
+
+# ---- ConvolvePE host logic (reference tests/test_convolve_pe.py:30-42,165-185) ---------------------
+def test_convolve_filter_extent_contract():
+    src = pg.ArrayPE([1, 2, 3, 4])
+    with pytest.raises(ValueError):
+        pg.ConvolvePE(src, pg.CropPE(pg.ArrayPE([1, 0, 0]), 1, 2)).extent()   # start != 0
+    with pytest.raises(ValueError):
+        pg.ConvolvePE(src, pg.ConstantPE(1.0)).extent()                        # infinite
+
+
+def test_convolve_extent_channels_props():
+    pe = pg.ConvolvePE(pg.ArrayPE(np.zeros((10, 1))), pg.ArrayPE(np.zeros((4, 2))), fft_size=64)
+    assert pe.extent() == pg.Extent(0, 13)
+    assert pe.channel_count() == 2 and pe.fft_size == 64 and not pe.is_pure()
+    assert pe.inputs() == [pe.src, pe.fir]
+    assert pg.ConvolvePE(pg.ArrayPE(np.zeros((10, 2))), pg.ArrayPE(np.zeros(4))).channel_count() == 2
+    assert pg.ConvolvePE(pg.SinePE(), pg.ArrayPE(np.zeros(4))).extent() == pg.Extent(None, None)
+    assert "ConvolvePE(src=ArrayPE, fir=ArrayPE, fft_size=64)" == repr(pe)
+
+
+def test_ir_energy_norm():
+    assert pg.ConvolvePE.ir_energy_norm(pg.ArrayPE([3.0, 4.0])) == pytest.approx(5.0, rel=1e-5)
+    assert pg.ConvolvePE.ir_energy_norm(pg.ArrayPE([1.0])) == pytest.approx(1.0, rel=1e-5)
+    assert pg.ConvolvePE.ir_energy_norm(pg.ArrayPE([0.0, 0.0])) == 1.0
+    assert pg.ConvolvePE.ir_energy_norm(pg.ArrayPE(np.ones((2, 2)))) == pytest.approx(2.0, rel=1e-5)
+    assert pg.ConvolvePE.ir_energy_norm(pg.ConstantPE(1.0)) == 1.0
+
+
+# ---- MixPE host logic (reference tests/test_mix_pe.py:17-64,161-227) --------------------------------
+def test_mix_construction_extent_channels():
+    with pytest.raises(ValueError, match="at least 2 inputs"):
+        pg.MixPE(pg.ConstantPE(1.0))
+    m = pg.MixPE([pg.ConstantPE(0.3), pg.ConstantPE(0.4)])
+    assert len(m.inputs()) == 2 and m.is_pure() and repr(m) == "MixPE(ConstantPE, ConstantPE)"
+    assert m.extent() == pg.Extent(None, None)
+    assert pg.MixPE(pg.ArrayPE(np.zeros(100)), pg.DelayPE(pg.ArrayPE(np.zeros(150)), 50)).extent() == pg.Extent(0, 200)
+    assert pg.MixPE(pg.ArrayPE(np.zeros(100)), pg.ConstantPE(0.0)).extent() == pg.Extent(None, None)
+    assert pg.MixPE(pg.ConstantPE(0, 2), pg.ConstantPE(0, 2)).channel_count() == 2
+    with pytest.raises(ValueError, match="channel mismatch"):
+        m.resolve_channel_count([1, 2])
+    out = pg.MixPE(pg.ArrayPE(np.ones(4)), pg.ArrayPE(np.ones(4))).render(100, 8)   # every input misses
+    assert out.data.shape == (8, 1) and not out.data.any()
+
+
+# ---- Spatial host logic (reference tests/test_spatial_pe.py) ------------------------------------------
+def test_spatial_methods_host():
+    mono = pg.Snippet(0, np.arange(1, 5, dtype=np.float32))
+    st = pg.Snippet(0, np.array([[1, 3], [2, 4]], dtype=np.float32))
+    assert np.array_equal(pg.SpatialAdapter(2).render(mono, 0, 4, 44100), np.repeat(mono.data, 2, axis=1))
+    assert np.array_equal(pg.SpatialAdapter(1).render(st, 0, 2, 44100)[:, 0], [2, 3])
+    q = pg.SpatialAdapter(4).render(st, 0, 2, 44100)
+    assert np.array_equal(q, [[1, 3, 2, 2], [2, 4, 3, 3]])
+    with pytest.raises(ValueError):
+        pg.SpatialAdapter(0)
+    lin = pg.SpatialLinear(azimuth=0.0).render(mono, 0, 4, 44100)
+    np.testing.assert_allclose(lin[:, 0], 0.5 * mono.data[:, 0], atol=1e-6)
+    cp = pg.SpatialConstantPower(azimuth=200.0).render(mono, 0, 4, 44100)     # clamped to +90: hard right
+    np.testing.assert_allclose(cp[:, 0], 0.0, atol=1e-6)
+    np.testing.assert_allclose(cp[:, 1], mono.data[:, 0], atol=1e-6)
+    c0 = pg.SpatialConstantPower(azimuth=0.0).render(mono, 0, 4, 44100)
+    np.testing.assert_allclose(c0[:, 0] ** 2 + c0[:, 1] ** 2, mono.data[:, 0] ** 2, rtol=1e-5)
+
+
+def test_spatial_pe_contract():
+    with pytest.raises(ValueError):
+        pg.SpatialPE(pg.SinePE(), method=None)
+    az = pg.ConstantPE(10.0)
+    sp = pg.SpatialPE(pg.ArrayPE(np.zeros(10)), method=pg.SpatialLinear(azimuth=az))
+    assert sp.inputs()[1] is az and sp.extent() == pg.Extent(0, 10) and sp.is_pure() and sp.channel_count() == 2
+    with pytest.raises(ValueError, match="must be static"):
+        pg.SpatialHRTF(azimuth=az)
+    with pytest.raises(ValueError, match="must be static"):
+        pg.SpatialHRTF(azimuth=0.0, elevation=az)
+    m = pg.SpatialHRTF(azimuth=45, elevation=10)
+    assert m.azimuth == 45.0 and m.output_channels == 2 and repr(m) == "SpatialHRTF(azimuth=45.0, elevation=10.0)"
+
+
+def test_hrtf_filename_lookup_and_table():
+    f = pg.SpatialHRTF.hrtf_filename_for
+    assert f(0, 0) == "H0e000a.wav" and f(45, 0) == "H0e045a.wav" and f(-45, 0) == f(45, 0)
+    assert f(90, 0) == "H0e090a.wav" and f(0, 30).startswith("H30")
+    names = {e[2] for e in pg.SpatialHRTF.KEMAR_HRTF_ENTRIES}
+    assert len(pg.SpatialHRTF.KEMAR_HRTF_ENTRIES) == 368 and f(123.4, 56.7) in names
+    g = golden("hrtf_lookup.npz")    # picks of the real reference, incl. ties and clamping
+    idx = np.array([kemar.nearest_index(a, e) for a, e in zip(g["az"], g["el"])])
+    assert np.array_equal(idx, g["idx"])
+    table, sr = kemar.load_table()
+    assert table.shape == (368, 128, 2) and table.dtype == np.float32 and sr == 44100
+
+
+# ---- Renderer (reference tests/test_renderer.py) -----------------------------------------------------
+class _Stateful(pg.ProcessingElement):
+    def __init__(self, src):
+        self._src, self.log = src, []
+
+    def inputs(self):
+        return [self._src]
+
+    def _on_start(self):
+        self.log.append("start")
+
+    def _on_stop(self):
+        self.log.append("stop")
+
+    def _render(self, start, duration):
+        return self._src.render(start, duration)
+
+
+def test_renderer_contract():
+    r = pg.NullRenderer(sample_rate=44100)
+    with pytest.raises(RuntimeError):
+        r.start()
+    pe = _Stateful(pg.ConstantPE(0.5))
+    r.set_source(pe)
+    with pytest.raises(RuntimeError):
+        r.render(0, 10)
+    r.start()
+    with pytest.raises(ValueError):
+        r.render(0, 0)
+    r.render(0, 16)
+    with pytest.raises(RuntimeError):
+        r.set_source(pe)
+    r.stop()
+    r.stop()
+    assert pe.log == ["start", "stop"] and r.channel_count == 1
+    shared = _Stateful(pg.ConstantPE(0.1))
+    with pytest.raises(ValueError, match="not pure"):
+        pg.NullRenderer().set_source(pg.MixPE(shared, shared, fuse=False))
+    with pg.NullRenderer() as r2:
+        r2.set_source(pe)
+        r2.start()
+    assert not r2.started
+
+
+# ---- device schedule model vs oracle ---------------------------------------------------------------
+def test_kernel_model_matches_oracle():
+    import kernel_model as km
+    import pygmu2_oracle as orc
+    rng = np.random.default_rng(3)
+    for L, B, vec in ((3, 16, False), (70, 16, False), (900, 64, True)):
+        h = (rng.standard_normal(L) / np.sqrt(L)).astype(np.float32)
+        x = rng.uniform(-1, 1, 260 if not vec else 2500).astype(np.float32)
+        mb, o = km.ModelBank(h, B, vec), orc.OracleConvolve(h, 1)
+        ys, yr, pos = [], [], 0
+        for d in (1, 17, B - 1, B, B + 1, 3 * B + 5, 10 ** 6):
+            d = min(d, len(x) - pos)
+            if d <= 0:
+                break
+            ys.append(mb.process(x[pos:pos + d]))
+            yr.append(o.render(x[pos:pos + d])[:, 0])
+            pos += d
+        ys, yr = np.concatenate(ys), np.concatenate(yr)
+        assert np.max(np.abs(ys - yr)) <= 1e-5 * np.max(np.abs(yr))
+
+
+def test_choose_block_and_workload_bytes():
+    from pygmu2_b200 import workloads as wl
+    assert pg.choose_block(132300, 512) == 512 and pg.choose_block(441000, 64) == 64
+    assert pg.choose_block(3, 6) == 16 and pg.choose_block(4096, 441000) == 4096
+    # bytes per output sample.channel
+    assert round(wl.bytes_per_block_step(256, 2, 2, 132300, 512, False) / (256 * 2 * 512)) == 2092
+    assert round(wl.bytes_per_block_step(256, 2, 2, 132300, 512, True) / (256 * 2 * 512)) == 4168
+    assert round(wl.bytes_per_block_step(512, 1, 1, 88200, 512, True) / (512 * 512)) == 2789
+
+
+# ---- multi-process sharding over gloo (world_size 2) -----------------------------------------------
+def test_shard_bounds_partition():
+    for n, w in ((4096, 8), (10, 3), (2, 4), (7, 7)):
+        spans = [pdist.shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, ret):
+    import sys
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import pygmu2_oracle as orc
+    from pygmu2_b200 import dist as pd, workloads as wl
+    pd.init_process_group("gloo")
+    N, L, n = 6, 700, 1024
+    sm = None
+
+    def local_mix(x_local):  # oracle stands in for the device bank: this test covers the host plumbing
+        parts = [orc.OracleConvolve(wl.c4_ir(sm.lo + i, L), 1).render(x_local[i, 0])[:, 0] for i in range(x_local.shape[0])]
+        return np.sum(np.stack(parts), axis=0, dtype=np.float32)[None, :]
+
+    sm = pd.ShardedMix(N, local_mix=local_mix, root=0)
+    x_local = np.stack([wl.c4_input(n, s) for s in range(sm.lo, sm.hi)])[:, None, :]
+    y = sm.render_mix_host(x_local)
+    if rank == 0:
+        ret["y"] = y.copy()
+        ret["span0"] = (sm.lo, sm.hi)
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_mix_gloo_world2():
+    import torch.multiprocessing as mp
+    import pygmu2_oracle as orc
+    from pygmu2_b200 import workloads as wl
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29600 + (os.getpid() % 300)
+    mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
+    N, L, n = 6, 700, 1024
+    full = np.sum(np.stack([orc.OracleConvolve(wl.c4_ir(s, L), 1).render(wl.c4_input(n, s))[:, 0] for s in range(N)]),
+                  axis=0, dtype=np.float64)
+    assert ret["span0"] == (0, 3)
+    assert np.max(np.abs(ret["y"][0] - full)) <= 1e-5 * np.max(np.abs(full))
