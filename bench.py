@@ -204,10 +204,10 @@ def _config(args, cores_note=None):
     P = -(-L // B)
     c = {
         "workload": "C2 stereo convolution reverb: 3 s IR (132300 taps) @48 kHz, 512-sample blocks, uniform partitions",
-        "streams_per_gpu": args.streams, "channels": CH, "filter": args.variant, "filter_len": L, "block": B,
-        "partitions": P, "pull": PULL, "sample_rate": SR,
+        "streams_per_gpu": args.streams or STREAMS_PER_GPU, "channels": CH, "filter": args.variant, "filter_len": L,
+        "block": B, "partitions": P, "pull": PULL, "sample_rate": SR,
         "l2": "inputs larger than L2: the delay-line state streamed every step is "
-              f"{args.streams * CH * P * B * 8 / 1e6:.0f} MB (+ filter spectra) vs 126 MB L2",
+              f"{(args.streams or STREAMS_PER_GPU) * CH * P * B * 8 / 1e6:.0f} MB (+ filter spectra) vs 126 MB L2",
     }
     if cores_note:
         c["host"] = cores_note
@@ -215,6 +215,67 @@ def _config(args, cores_note=None):
 
 
 # ---------------------------------------------------------------------------
+# Workloads.  c2 is the headline (BASELINE.json configs[1]); the others are the remaining BASELINE
+# configs at their SURVEY.md §8d roofline-run sizes, selectable with --workload for profiling.
+def make_workload(args, rank, local):
+    import pygmu2_b200 as pg
+    from pygmu2_b200 import kemar
+    w = args.workload
+    distinct = args.variant == "distinct"
+    if w == "c2":
+        N = args.streams or STREAMS_PER_GPU
+        if distinct:
+            irs = np.stack([wl.c2_ir(stream=rank * N + s) for s in range(N)])
+            bank = pg.ConvolveBank(irs, N, CH, block=B, max_pull=PULL, device=local)
+        else:
+            bank = pg.ConvolveBank(wl.c2_ir(), N, CH, block=B, max_pull=PULL, device=local, single_filter_dims=True)
+        return dict(bank=bank, N=N, c_in=CH, c_out=CH, L=L, B=B, pull=PULL, sr=SR, distinct=distinct, mix=False,
+                    config=_config(args), fill_steps=bank.partitions)
+    if w == "c1":   # 4096 mono streams x distinct 4096-tap FIRs, B = 4096 (P = 1): FFT-stage bound
+        N = args.streams or 4096
+        rng = np.random.default_rng(1234 + rank)
+        irs = (rng.standard_normal((N, 4096)) / 64.0).astype(np.float32)
+        bank = pg.ConvolveBank(irs, N, 1, block=4096, max_pull=4096, device=local)
+        cfg = {"workload": "C1 4096-tap FIR, mono, 44.1 kHz: N independent streams x distinct filters, B=4096, P=1",
+               "streams_per_gpu": N, "block": 4096, "partitions": 1, "pull": 4096, "sample_rate": wl.SR_441,
+               "l2": f"per-step footprint {N * (4097 * 8 * 3 + 4096 * 8) / 1e6:.0f} MB vs 126 MB L2"}
+        return dict(bank=bank, N=N, c_in=1, c_out=1, L=4096, B=4096, pull=4096, sr=wl.SR_441, distinct=True, mix=False,
+                    config=cfg, fill_steps=2)
+    if w == "c3":   # 256 moving mono sources x 512-tap HRTF pairs -> one stereo mix (fused)
+        N = args.streams or wl.C3_SOURCES
+        table = wl.c3_synthetic_hrtf_table(512)
+        both = np.concatenate([table, table[:, :, ::-1]], axis=0)
+        bank = pg.ConvolveBank(both, N, 1, block=512, max_pull=512, device=local, mixdown_input=True,
+                               filter_of_stream=np.zeros(N, np.int32))
+        cfg = {"workload": "C3 SpatialPE HRTF: 256 moving sources x 512-tap per ear (synthetic table, 736 resident "
+                           "filter pairs), fused MixPE stereo sum, 512-sample pulls @44.1 kHz, filter re-selected every pull",
+               "sources_per_gpu": N, "block": 512, "partitions": 1, "pull": 512, "sample_rate": wl.SR_441,
+               "l2": "L2-resident by nature (5.8 MB per step): launch/FFT-bound, reported as such"}
+        return dict(bank=bank, N=N, c_in=1, c_out=2, L=512, B=512, pull=512, sr=wl.SR_441, distinct=True, mix=True,
+                    config=cfg, fill_steps=2, moving=True, n_filters=both.shape[0])
+    if w == "c4":   # 512 mono streams per GPU x distinct 2 s IRs, fused mix (+ one NCCL reduce per pull when sharded)
+        N = args.streams or 512
+        irs = np.stack([wl.c4_ir(rank * N + s) for s in range(N)])
+        bank = pg.ConvolveBank(irs, N, 1, block=512, max_pull=512, device=local)
+        cfg = {"workload": "C4 independent streams x 2 s random IRs (88200 taps) @44.1 kHz, 512-sample pulls, fused MixPE "
+                           "sum, sharded across GPUs with one NCCL reduce of the mix per pull",
+               "streams_per_gpu": N, "block": 512, "partitions": bank.partitions, "pull": 512, "sample_rate": wl.SR_441,
+               "l2": f"delay line + filter spectra streamed per step: {2 * N * bank.partitions * 512 * 8 / 1e6:.0f} MB vs 126 MB L2"}
+        return dict(bank=bank, N=N, c_in=1, c_out=1, L=wl.C4_L, B=512, pull=512, sr=wl.SR_441, distinct=True, mix=True,
+                    config=cfg, fill_steps=bank.partitions, reduce=True)
+    if w == "c5":   # 10 s IR at 64-sample blocks: N=1 is the named latency case, N=256 replicas give an HBM figure
+        N = args.streams or 1
+        bank = pg.ConvolveBank(wl.c5_ir(), N, 1, block=64, max_pull=64, device=local, single_filter_dims=True)
+        cfg = {"workload": "C5 10 s IR (441000 taps) @44.1 kHz at 64-sample pulls (6891 uniform partitions), "
+                           f"{N} stream(s); voice generation excluded",
+               "streams_per_gpu": N, "block": 64, "partitions": bank.partitions, "pull": 64, "sample_rate": wl.SR_441,
+               "l2": ("state 7 MB: L2-resident, latency-bound" if N == 1 else
+                      f"delay line streamed per step: {N * bank.partitions * 64 * 8 / 1e6:.0f} MB vs 126 MB L2")}
+        return dict(bank=bank, N=N, c_in=1, c_out=1, L=wl.C5_L, B=64, pull=64, sr=wl.SR_441, distinct=False, mix=False,
+                    config=cfg, fill_steps=min(bank.partitions, 400))
+    raise SystemExit(f"unknown workload {w}")
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -231,39 +292,51 @@ def run_gpu(args):
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    pg.set_sample_rate(SR)
 
-    N, K, W = args.streams, args.steps, args.warmup
-    distinct = args.variant == "distinct"
-    P = -(-L // B)
-    if distinct:
-        irs = np.stack([wl.c2_ir(stream=rank * N + s) for s in range(N)])
-        bank = pg.ConvolveBank(irs, N, CH, block=B, max_pull=PULL, device=local)
-    else:
-        bank = pg.ConvolveBank(wl.c2_ir(), N, CH, block=B, max_pull=PULL, device=local, single_filter_dims=True)
+    K, W = args.steps, max(args.warmup, 3)
+    spec = make_workload(args, rank, local)
+    bank, N, c_in, c_out = spec["bank"], spec["N"], spec["c_in"], spec["c_out"]
+    Lw, Bw, pull, sr = spec["L"], spec["B"], spec["pull"], spec["sr"]
+    mix, distinct = spec["mix"], spec["distinct"]
+    pg.set_sample_rate(sr)
+    P = bank.partitions
+    n_out_ch = c_out if mix else N * c_out            # output channels produced per GPU per step
+    do_reduce = bool(spec.get("reduce")) and world > 1
 
-    # synthetic inputs, resident in HBM: N_INPUT_BLOCKS pulls of uniform(-1,1), planar [blk][N][CH][PULL]
+    # synthetic inputs, resident in HBM: N_INPUT_BLOCKS pulls of uniform(-1,1), planar [blk][N][c_in][pull]
     rng = np.random.default_rng(1000 + rank)
-    x_host = rng.uniform(-1.0, 1.0, (N_INPUT_BLOCKS, N, CH, PULL)).astype(np.float32)
+    x_host = rng.uniform(-1.0, 1.0, (N_INPUT_BLOCKS, N, c_in, pull)).astype(np.float32)
+    if args.workload in ("c3", "c4"):
+        x_host /= np.float32(N)
     x_dev = torch.from_numpy(x_host).to(dev)
-    y_dev = torch.empty((N, CH, PULL), dtype=torch.float32, device=dev)
+    y_dev = torch.empty((n_out_ch, pull), dtype=torch.float32, device=dev)
     stream = torch.cuda.Stream(device=dev)
     sh = stream.cuda_stream
-    blk_bytes = N * CH * PULL * 4
+    blk_bytes = N * c_in * pull * 4
+    out_bytes = n_out_ch * pull * 4
+    traj = traj_dev = None
+    if spec.get("moving"):  # per-pull filter choice of every source, resident as one int32 row per pull
+        traj = np.random.default_rng(6).integers(0, spec["n_filters"], (64, N)).astype(np.int32)
+        traj_dev = torch.from_numpy(traj).to(dev)
 
     def step(i):
-        bank.process_device(x_dev.data_ptr() + (i % N_INPUT_BLOCKS) * blk_bytes, y_dev.data_ptr(), PULL,
-                            cuda_stream=sh)
+        if traj_dev is not None:
+            bank.use_filter_map_device(traj_dev.data_ptr() + (i % 64) * N * 4)
+        bank.process_device(x_dev.data_ptr() + (i % N_INPUT_BLOCKS) * blk_bytes, y_dev.data_ptr(), pull,
+                            mix=mix, cuda_stream=sh)
+        if do_reduce:
+            with torch.cuda.stream(stream):
+                dist.reduce(y_dev, dst=0, op=dist.ReduceOp.SUM)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # fill the delay line so the timed steps stream real (non-zero) spectra: P pulls, then W warm-up steps
-    for i in range(P):
+    # fill the delay line so the timed steps stream real (non-zero) spectra, then W warm-up steps
+    for i in range(spec["fill_steps"]):
         step(i)
-    for i in range(max(W, 3)):
+    for i in range(W):
         step(i)
     barrier()
 
@@ -273,8 +346,10 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
+    th0 = time.perf_counter()
     for i in range(K):
         step(i)
+    host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / K
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -292,19 +367,34 @@ def run_gpu(args):
         step(i)
     prof = bank.profile_end()
     clocks = sampler.finish()
+    if traj_dev is not None:
+        bank.use_filter_map_device(None)
 
     # e2e: public host API, pinned host buffers, H2D + step + D2H every step
     from pygmu2_b200._lib import PinnedArray
-    xp = PinnedArray((N_INPUT_BLOCKS, N, CH, PULL))
-    yp = PinnedArray((N, CH, PULL))
+    xp = PinnedArray((N_INPUT_BLOCKS, N, c_in, pull))
+    yp = PinnedArray((c_out, pull) if mix else (N, c_out, pull))
     xp.array[...] = x_host
     ke = min(K, 400)
+
+    def e2e_step(i):
+        if traj is not None:
+            bank.set_filter_map(traj[i % 64])
+        if mix:
+            yp.array[...] = bank.process_mix(xp.array[i % N_INPUT_BLOCKS])
+            if do_reduce:
+                tt = torch.from_numpy(yp.array).to(dev)
+                dist.reduce(tt, dst=0, op=dist.ReduceOp.SUM)
+                tt.cpu()
+        else:
+            bank.process(xp.array[i % N_INPUT_BLOCKS], out=yp.array)
+
     for i in range(3):
-        bank.process(xp.array[i % N_INPUT_BLOCKS], out=yp.array)
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(ke):
-        bank.process(xp.array[i % N_INPUT_BLOCKS], out=yp.array)
+        e2e_step(i)
     torch.cuda.synchronize(dev)
     dt_e2e = time.perf_counter() - t0
     te = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
@@ -313,52 +403,55 @@ def run_gpu(args):
     dt_e2e = float(te.item())
     checksum = float(np.abs(yp.array).mean())
 
-    audio_per_step = world * N * CH * PULL / SR            # audio-seconds x channels, all ranks
-    value = audio_per_step * K / (ms_max * 1e-3)
-    e2e_value = audio_per_step * ke / dt_e2e
+    # audio-seconds x channels per step: every rank's streams for independent outputs, ONE mix when mixed
+    units = (c_out if (mix and (do_reduce or world == 1)) else world * n_out_ch) * pull / sr
+    value = units * K / (ms_max * 1e-3)
+    e2e_value = units * ke / dt_e2e
 
     peak, peak_src = measured_hbm_peak()
-    Kbins = B + 1
-    mac_bytes = N * CH * P * Kbins * 8 * (2 if distinct else 1) + N * CH * Kbins * 8   # rows streamed + Y written
-    step_bytes = wl.bytes_per_block_step(N, CH, CH, L, B, distinct)
-    mac_ms = prof.ms_mac / max(prof.steps, 1)
-    step_ms_prof = (prof.ms_r2c + prof.ms_mac + prof.ms_c2r) / max(prof.steps, 1)
-    achieved = mac_bytes / (mac_ms * 1e-3) / 1e9
+    Kbins = Bw + 1
+    xrows = N * (1 if bank.info().c_x == 1 else c_in)
+    mac_bytes = xrows * P * Kbins * 8 + (N * c_out * P * Kbins * 8 if distinct else 0) + n_out_ch * Kbins * 8
+    step_bytes = wl.bytes_per_block_step(N, c_in, c_out, Lw, Bw, distinct)
+    nprof = max(prof.steps, 1)
+    mac_ms = prof.ms_mac / nprof
+    ksum = prof.ms_r2c + prof.ms_mac + prof.ms_c2r
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "mac_traffic.json")
-    if os.path.exists(tr_path):
+    if args.workload == "c2" and os.path.exists(tr_path):
         try:
             traffic = json.load(open(tr_path)).get(args.variant)
         except Exception:
             traffic = None
 
     if rank == 0:
+        achieved = mac_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": _config(args),
+            "config": spec["config"],
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": blk_bytes, "d2h_bytes_per_step": blk_bytes,
-                    "steps": ke, "api": "ConvolveBank.process (pgx_bank_process, pinned host buffers)",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": blk_bytes, "d2h_bytes_per_step": out_bytes,
+                    "steps": ke, "api": "ConvolveBank.process[_mix] (pgx_bank_process[_mix], pinned host buffers)",
                     "checksum_mean_abs_y": checksum},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": {"bound": "hbm", "kernel": "k_fdl_mac", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": mac_bytes, "mean_launch_ms": mac_ms,
                          "launch_plan": {"grid": info.mac_grid, "term_splits": info.mac_split,
                                          "streams_per_cta": info.mac_stream_tile, "ctas_per_sm": info.mac_occupancy},
-                         "share_of_step": prof.ms_mac / max(prof.ms_r2c + prof.ms_mac + prof.ms_c2r, 1e-12),
-                         "timing": f"CUDA events around each kernel on the launching stream, {prof.steps} steps "
-                                   "(instrumented pass of the same loop)",
+                         "share_of_step": prof.ms_mac / max(ksum, 1e-12),
+                         "timing": f"CUDA events around each kernel on its launching stream, {prof.steps} steps "
+                                   "(instrumented pass of the same loop; K3 overlaps K1/K2 on a second stream, "
+                                   "so the per-kernel times add up to more than the step)",
                          "step": {"algorithmic_bytes": step_bytes, "ms": ms_max / K,
                                   "achieved": step_bytes / (ms_max / K * 1e-3) / 1e9,
                                   "frac": step_bytes / (ms_max / K * 1e-3) / 1e9 / peak,
-                                  "kernel_ms": {"k_r2c_ingest": prof.ms_r2c / max(prof.steps, 1), "k_fdl_mac": mac_ms,
-                                                "k_c2r_emit": prof.ms_c2r / max(prof.steps, 1),
-                                                "sum": step_ms_prof}}},
+                                  "kernel_ms": {"k_r2c_ingest": prof.ms_r2c / nprof, "k_fdl_mac": mac_ms,
+                                                "k_c2r_emit": prof.ms_c2r / nprof, "sum": ksum / nprof}}},
         }
-        if not args.no_cpu and world == 1:
+        if not args.no_cpu and world == 1 and args.workload == "c2":
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_seconds)
         else:
             line["cpu_baseline"] = None
@@ -379,7 +472,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="shared", choices=["shared", "distinct"],
                     help="one IR shared by all streams (the named reverb) or one IR per stream")
-    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="stereo streams per GPU")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's named size)")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="c2 = BASELINE.json configs[1] (headline); the others are the remaining configs, for profiling")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

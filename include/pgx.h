@@ -128,6 +128,9 @@ PGX_API int pgx_bank_load_filter(pgx_bank* bank, int32_t filter_index, const flo
  * source: spatial_pe.py:446-449 re-resolves the IR on every render).
  */
 PGX_API int pgx_bank_set_filter_map(pgx_bank* bank, const int32_t* filter_of_stream);
+/* Same, but the [n_streams] map already lives on the device (e.g. one row of a resident
+ * trajectory table); NULL switches back to the bank's own map.  No copy, no synchronisation. */
+PGX_API int pgx_bank_use_filter_map_device(pgx_bank* bank, const int32_t* filter_of_stream_dev);
 
 /*
  * One pull of n samples for all streams: y = x * h with carried history.

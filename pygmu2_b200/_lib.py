@@ -56,6 +56,7 @@ PROTOTYPES = {
     "pgx_bank_reset": (C.c_int, [C.c_void_p, _i32p, C.c_int32]),
     "pgx_bank_load_filter": (C.c_int, [C.c_void_p, C.c_int32, _f32p]),
     "pgx_bank_set_filter_map": (C.c_int, [C.c_void_p, _i32p]),
+    "pgx_bank_use_filter_map_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgx_bank_process": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32]),
     "pgx_bank_process_mix": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32]),
     "pgx_bank_process_device": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32,

@@ -129,6 +129,10 @@ class ConvolveBank:
             raise ValueError("filter_of_stream must have one entry per stream")
         check(lib().pgx_bank_set_filter_map(self._h, fmap.ctypes.data_as(C.POINTER(C.c_int32))))
 
+    def use_filter_map_device(self, ptr: int | None) -> None:
+        """Point the bank at an int32 [n_streams] map already resident on the device (None: its own)."""
+        check(lib().pgx_bank_use_filter_map_device(self._h, C.c_void_p(ptr) if ptr else None))
+
     # -- pulls (host buffers; copies inside) ------------------------------------
     def _chunks(self, n):
         pos = 0

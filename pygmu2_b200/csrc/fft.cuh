@@ -1,10 +1,17 @@
-// fft.cuh -- shared-memory Stockham FFT building blocks (sm_100a).
+// fft.cuh -- register-resident Stockham FFT building blocks (sm_100a).
 //
 // A real transform of 2B samples is computed as a B-point complex transform of
 // z[n] = w[2n] + i*w[2n+1] plus an O(B) split step, and stored as a *packed*
 // half spectrum of exactly B complex bins: bin 0 carries (Re X[0], Re X[B]) (both
 // purely real), bins 1..B-1 are X[k].  One delay-line row is therefore B*8 bytes,
 // a power of two, 16-byte aligned for float4 / bulk-copy streaming.
+//
+// The complex transform: N = 2^LOG2N points, N/8 threads per transform, each thread owning the
+// 8 elements at positions j + m*N/8.  Passes are radix 8 (in-register 8-point butterflies) with one
+// final radix-4 / radix-2 pass when LOG2N is not a multiple of 3; between passes the data is
+// exchanged through padded, ping-pong shared-memory buffers (Stockham autosort order, one
+// __syncthreads per pass).  The first pass takes its inputs straight from registers (loaded from
+// global by the caller) and the last pass leaves its outputs in registers, again at j + m*N/8.
 //
 // Replaces numpy.fft.rfft / irfft at reference convolve_pe.py:237-239,313,318.
 #pragma once
@@ -17,97 +24,151 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
+// multiply by -i (forward) / +i (inverse)
 template <bool INV>
-__device__ __forceinline__ float2 tw_load(const float2* __restrict__ tw, int idx) {
-  float2 w = __ldg(tw + idx);
+__device__ __forceinline__ float2 mul_mi(float2 d) {
+  return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+}
+template <bool INV>
+__device__ __forceinline__ float2 tw_get(const float2* tw, int idx) {
+  float2 w = tw[idx];
   if (INV) w.y = -w.y;
   return w;
 }
 
-// Autosort Stockham passes, radix 4 while the remaining factor allows, then one radix 2.
-// n = number of complex points (power of two >= 2); threads t in [0, T) of one transform
-// cooperate; `a` holds the input, `b` is scratch; returns the buffer holding the result.
-// twM[k] = exp(-2*pi*i*k/(2n)), so exp(-2*pi*i*m/n) = twM[2m].
-// Every thread of the CTA must call this (it contains __syncthreads()).
+// padded shared-memory index: one pad element per 16 keeps both the contiguous reads and the
+// stride-8 writes of the first pass free of 8-byte bank conflicts
+__device__ __forceinline__ int phys(int i) { return i + (i >> 4); }
+
+template <int LOG2N>
+struct FftCfg {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int T8 = N / 8;                   // threads per transform
+  static constexpr int NP8 = LOG2N / 3;              // radix-8 passes
+  static constexpr int RLAST = 1 << (LOG2N % 3);     // 1 = none, else a final radix-2 / radix-4 pass
+  static constexpr int PADN = N + N / 16;            // padded buffer length (elements)
+  static constexpr int CTA = T8 < 256 ? 256 : T8;    // threads per CTA
+  static constexpr int FPB = CTA / T8;               // transforms per CTA
+  static constexpr bool SMEM_TW = N <= 1024;         // stage the 2N-entry twiddle table in shared memory
+  static constexpr int SMEM_BYTES = (SMEM_TW ? 2 * N : 0) * 8 + FPB * 2 * PADN * 8;
+};
+
 template <bool INV>
-__device__ __forceinline__ float2* stockham_passes(float2* a, float2* b, const int n, const int t, const int T,
-                                                   const float2* __restrict__ twM) {
-  int Ns = 1;
-  while (Ns < n) {
-    if (n / Ns >= 4) {
-      const int nj = n >> 2;
-      const int tws = 2 * (n / (Ns * 4));
-      for (int j = t; j < nj; j += T) {
-        const int k = j & (Ns - 1);
-        float2 v0 = a[j], v1 = a[j + nj], v2 = a[j + 2 * nj], v3 = a[j + 3 * nj];
-        if (k != 0) {
-          const int m = k * tws;
-          v1 = cmul(v1, tw_load<INV>(twM, m));
-          v2 = cmul(v2, tw_load<INV>(twM, 2 * m));
-          v3 = cmul(v3, tw_load<INV>(twM, 3 * m));
-        }
-        const float2 t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3);
-        const float2 d = csub(v1, v3);
-        const float2 t3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);  // (v1-v3) * (+/- i)
-        const int j0 = ((j - k) << 2) + k;
-        b[j0] = cadd(t0, t2);
-        b[j0 + Ns] = cadd(t1, t3);
-        b[j0 + 2 * Ns] = csub(t0, t2);
-        b[j0 + 3 * Ns] = csub(t1, t3);
-      }
-      Ns <<= 2;
-    } else {
-      const int nj = n >> 1;  // here Ns == n/2
-      for (int j = t; j < nj; j += T) {
-        const float2 v0 = a[j];
-        float2 v1 = a[j + nj];
-        if (j != 0) v1 = cmul(v1, tw_load<INV>(twM, 2 * j));
-        b[j] = cadd(v0, v1);
-        b[j + Ns] = csub(v0, v1);
-      }
-      Ns <<= 1;
-    }
-    __syncthreads();
-    float2* tmp = a;
-    a = b;
-    b = tmp;
-  }
-  return a;
+__device__ __forceinline__ void bfly2(float2& a, float2& b) {
+  const float2 t = csub(a, b);
+  a = cadd(a, b);
+  b = t;
 }
 
-// Split step after the forward transform: Z (n complex) -> packed half spectrum bin k.
-__device__ __forceinline__ float2 r2c_bin(const float2* Z, const int n, const int k,
-                                          const float2* __restrict__ twM) {
-  if (k == 0) {
-    const float2 z0 = Z[0];
-    return make_float2(z0.x + z0.y, z0.x - z0.y);
+// 4-point DFT, natural order in and out
+template <bool INV>
+__device__ __forceinline__ void bfly4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  const float2 c0 = cadd(v0, v2), c1 = csub(v0, v2), c2 = cadd(v1, v3), c3 = mul_mi<INV>(csub(v1, v3));
+  v0 = cadd(c0, c2);
+  v1 = cadd(c1, c3);
+  v2 = csub(c0, c2);
+  v3 = csub(c1, c3);
+}
+
+// 8-point DFT, natural order in and out
+template <bool INV>
+__device__ __forceinline__ void bfly8(float2 (&v)[8]) {
+  constexpr float kH = 0.70710678118654752440f;
+  float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+  float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+  // b1 *= w8, b2 *= w8^2 = -+i, b3 *= w8^3 with w8 = exp(-+ i pi/4)
+  b1 = INV ? make_float2(kH * (b1.x - b1.y), kH * (b1.x + b1.y)) : make_float2(kH * (b1.x + b1.y), kH * (b1.y - b1.x));
+  b2 = mul_mi<INV>(b2);
+  b3 = INV ? make_float2(-kH * (b3.x + b3.y), kH * (b3.x - b3.y)) : make_float2(kH * (b3.y - b3.x), -kH * (b3.x + b3.y));
+  bfly4<INV>(a0, a1, a2, a3);
+  bfly4<INV>(b0, b1, b2, b3);
+  v[0] = a0; v[1] = b0; v[2] = a1; v[3] = b1; v[4] = a2; v[5] = b2; v[6] = a3; v[7] = b3;
+}
+
+// All passes of one N-point transform.  v[m] = element j + m*T8 on entry and on exit.
+// sA / sB: this transform's two padded buffers; `first` selects which one the first exchange uses
+// (the other may still be read by the caller's pre-processing).  tw[k] = exp(-2*pi*i*k/(2N)).
+// Every thread of the CTA must call this (it contains __syncthreads()).
+template <int LOG2N, bool INV>
+__device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* sB, const int first, const int j,
+                                           const float2* tw) {
+  using C = FftCfg<LOG2N>;
+  constexpr int N = C::N, T8 = C::T8;
+  float2* cur = nullptr;
+  int Ns = 1;
+#pragma unroll
+  for (int p = 0; p < C::NP8; ++p) {
+    const int k = j & (Ns - 1);
+    if (p > 0) {
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = cur[phys(j + r * T8)];
+      const int m = 2 * k * (N / (8 * Ns));
+      const float2 w1 = tw_get<INV>(tw, m), w2 = tw_get<INV>(tw, 2 * m), w4 = tw_get<INV>(tw, 4 * m);
+      const float2 w3 = cmul(w1, w2);
+      v[1] = cmul(v[1], w1);
+      v[2] = cmul(v[2], w2);
+      v[3] = cmul(v[3], w3);
+      v[4] = cmul(v[4], w4);
+      v[5] = cmul(v[5], cmul(w4, w1));
+      v[6] = cmul(v[6], cmul(w4, w2));
+      v[7] = cmul(v[7], cmul(w4, w3));
+    }
+    bfly8<INV>(v);
+    if (p < C::NP8 - 1 || C::RLAST > 1) {
+      float2* d = ((p + first) & 1) ? sB : sA;
+      const int j0 = (j - k) * 8 + k;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) d[phys(j0 + r * Ns)] = v[r];
+      cur = d;
+    }
+    Ns *= 8;
   }
-  const float2 zk = Z[k];
-  float2 zc = Z[n - k];
-  zc.y = -zc.y;
+  if (C::RLAST == 4) {
+    __syncthreads();
+    constexpr int NB = N / 4;  // butterflies in this pass; Ns == NB, so k == jj
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int jj = j + u * T8;
+      float2 t0 = cur[phys(jj)], t1 = cur[phys(jj + NB)], t2 = cur[phys(jj + 2 * NB)], t3 = cur[phys(jj + 3 * NB)];
+      const int m = 2 * jj;  // 2*k*(N/(4*Ns)) with Ns = N/4
+      const float2 w1 = tw_get<INV>(tw, m), w2 = tw_get<INV>(tw, 2 * m);
+      t1 = cmul(t1, w1);
+      t2 = cmul(t2, w2);
+      t3 = cmul(t3, cmul(w1, w2));
+      bfly4<INV>(t0, t1, t2, t3);
+      v[u] = t0; v[u + 2] = t1; v[u + 4] = t2; v[u + 6] = t3;  // position jj + r*NB = j + (u + 2r)*T8
+    }
+  } else if (C::RLAST == 2) {
+    __syncthreads();
+    constexpr int NB = N / 2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + u * T8;
+      float2 t0 = cur[phys(jj)], t1 = cur[phys(jj + NB)];
+      t1 = cmul(t1, tw_get<INV>(tw, 2 * jj));
+      bfly2<INV>(t0, t1);
+      v[u] = t0; v[u + 4] = t1;  // position jj + r*NB = j + (u + 4r)*T8
+    }
+  }
+}
+
+// Split step after the forward transform: packed half-spectrum bin k from Z[k] and Z[N-k].
+__device__ __forceinline__ float2 r2c_bin(const float2 zk, const float2 znk, const float2 w) {
+  const float2 zc = make_float2(znk.x, -znk.y);
   const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
   const float2 d = csub(zk, zc);
   const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // -i/2 * d
-  const float2 w = __ldg(twM + k);
   return cadd(e, cmul(w, o));
 }
 
-// Merge step before the inverse transform: packed half spectrum Y -> Z bin k (unscaled).
-__device__ __forceinline__ float2 c2r_bin(const float2* Y, const int n, const int k,
-                                          const float2* __restrict__ twM) {
-  if (k == 0) {
-    const float2 y0 = Y[0];
-    return make_float2(0.5f * (y0.x + y0.y), 0.5f * (y0.x - y0.y));
-  }
-  const float2 xk = Y[k];
-  float2 xc = Y[n - k];
-  xc.y = -xc.y;
+// Merge step before the inverse transform: Z[k] (unscaled) from packed bins Y[k], Y[N-k].
+__device__ __forceinline__ float2 c2r_bin(const float2 xk, const float2 xnk, const float2 w) {
+  const float2 xc = make_float2(xnk.x, -xnk.y);
   const float2 e = make_float2(0.5f * (xk.x + xc.x), 0.5f * (xk.y + xc.y));
   const float2 d = csub(xk, xc);
-  float2 w = __ldg(twM + k);
-  w.y = -w.y;
-  const float2 o = cmul(make_float2(0.5f * w.x, 0.5f * w.y), d);
-  return make_float2(e.x - o.y, e.y + o.x);  // e + i*o
+  const float2 o = cmul(make_float2(0.5f * w.x, -0.5f * w.y), d);  // conj(w)/2 * d
+  return make_float2(e.x - o.y, e.y + o.x);                        // e + i*o
 }
 
 }  // namespace pgx

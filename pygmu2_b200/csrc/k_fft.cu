@@ -2,208 +2,282 @@
 //
 // K1/K2 replace np.fft.rfft / np.fft.irfft in the reference's overlap-save loop
 // (convolve_pe.py:294-322): K1 also does what :294-310 (build [tail | segment | zeros]) and
-// :325-336 (tail update) do, K2 what :321-322 (keep the valid output samples) does.
+// :325-336 (tail update) do, K2 what :321-322 (keep the valid output samples) does, plus the
+// present-partition product X_t * H_0 of :314-317.
+//
+// One transform per N/8 threads (see fft.cuh); a CTA hosts FPB transforms.  K1 loads its window
+// straight from global memory into registers (first pass needs no staging), K2 leaves its result in
+// registers and writes only the samples that are new.  Kernels are instantiated per LOG2N = 4..13.
 #include "fft.cuh"
 #include "kernels.h"
 
 namespace pgx {
 
-static constexpr int kFftThreads = 256;
-
-// threads per transform: one radix-4 butterfly per thread per pass when the CTA allows it
-__host__ __device__ inline int threads_per_fft(int B) { return (B / 4 < kFftThreads) ? B / 4 : kFftThreads; }
-
-int fft_smem_bytes(int B) {
-  const int T = threads_per_fft(B);
-  const int fpb = kFftThreads / T;
-  return fpb * 2 * B * (int)sizeof(float2);
+template <int LOG2N>
+__device__ __forceinline__ const float2* stage_twiddles(float2* smem, const float2* __restrict__ tw_global) {
+  using C = FftCfg<LOG2N>;
+  if constexpr (!C::SMEM_TW) {
+    return tw_global;
+  } else {
+  for (int i = threadIdx.x; i < 2 * C::N; i += C::CTA) smem[i] = __ldg(tw_global + i);
+    return smem;  // visible after the first __syncthreads(); the first pass uses no twiddles
+  }
 }
 
-__global__ void __launch_bounds__(kFftThreads) k_r2c_ingest(const R2CArgs a) {
+// MODE 0: stream ingest -> one delay-line row.  MODE 1: filter partition -> two (reversed, doubled) rows.
+template <int LOG2N, int MODE>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, const FilterPrepArgs fp) {
+  using C = FftCfg<LOG2N>;
+  constexpr int N = C::N, T8 = C::T8;
   extern __shared__ float2 sm[];
-  const int n = a.B;
-  const int T = threads_per_fft(n);
-  const int fpb = kFftThreads / T;
-  const int g = threadIdx.x / T, t = threadIdx.x % T;
-  const int f = blockIdx.x * fpb + g;
-  const bool active = f < a.n_fft;
-  float2* bufA = sm + (size_t)g * 2 * n;
-  float2* bufB = bufA + n;
-
-  float* cur = nullptr;
-  const float* prev = nullptr;
-  const int m_new = a.fill + a.take;
-  if (active) {
-    const int s = f / a.c_x, cx = f - s * a.c_x;
-    cur = a.hist + ((size_t)f * 2 + a.half) * n;
-    prev = a.hist + ((size_t)f * 2 + (a.half ^ 1)) * n;
-    // ingest: open block [fill, fill+take) := new samples (optionally the mean over source channels)
-    for (int i = t; i < a.take; i += T) {
-      const int64_t base = (int64_t)s * a.xs + (int64_t)(a.x_off + i) * a.xi;
-      float v;
-      if (a.mixdown) {
-        float acc = 0.f;
-        for (int c = 0; c < a.c_in; ++c) acc += a.x[base + c * a.xc];
-        v = acc / (float)a.c_in;
-      } else {
-        v = a.x[base + cx * a.xc];
-      }
-      cur[a.fill + i] = v;
-    }
-  }
-  __syncthreads();
-  if (active) {
-    // z[q] = w[2q] + i*w[2q+1] over the window w = [prev (B) | cur[0:m_new) | zeros]
-    for (int q = t; q < n; q += T) {
-      const int i0 = 2 * q;
-      float2 z;
-      if (i0 < n) {
-        z = *reinterpret_cast<const float2*>(prev + i0);
-      } else {
-        const int c0 = i0 - n;
-        z.x = (c0 < m_new) ? cur[c0] : 0.f;
-        z.y = (c0 + 1 < m_new) ? cur[c0 + 1] : 0.f;
-      }
-      bufA[q] = z;
-    }
-  }
-  __syncthreads();
-  const float2* Z = stockham_passes<false>(bufA, bufB, n, t, T, a.tw);
-  if (active) {
-    float2* row = a.fdl + ((size_t)f * a.P + a.slot) * n;
-    for (int k = t; k < n; k += T) row[k] = r2c_bin(Z, n, k, a.tw);
-  }
-}
-
-void launch_r2c_ingest(const R2CArgs& a, cudaStream_t st) {
-  const int T = threads_per_fft(a.B);
-  const int fpb = kFftThreads / T;
-  const int grid = (a.n_fft + fpb - 1) / fpb;
-  const int smem = fft_smem_bytes(a.B);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(k_r2c_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k_r2c_ingest<<<grid, kFftThreads, smem, st>>>(a);
-}
-
-__global__ void __launch_bounds__(kFftThreads) k_filter_prep(const FilterPrepArgs a) {
-  extern __shared__ float2 sm[];
-  const int n = a.B;
-  const int T = threads_per_fft(n);
-  const int fpb = kFftThreads / T;
-  const int g = threadIdx.x / T, t = threadIdx.x % T;
-  const int64_t f = (int64_t)blockIdx.x * fpb + g;  // (row, partition)
-  const int64_t total = (int64_t)a.n_rows * a.P;
+  const float2* tw = stage_twiddles<LOG2N>(sm, MODE == 0 ? a.tw : fp.tw);
+  float2* bufs = sm + (C::SMEM_TW ? 2 * N : 0);
+  const int g = threadIdx.x / T8, j = threadIdx.x - g * T8;
+  float2* sA = bufs + (size_t)g * 2 * C::PADN;
+  float2* sB = sA + C::PADN;
+  const int64_t f = (int64_t)blockIdx.x * C::FPB + g;
+  const int64_t total = (MODE == 0) ? (int64_t)a.n_fft : (int64_t)fp.n_rows * fp.P;
   const bool active = f < total;
-  float2* bufA = sm + (size_t)g * 2 * n;
-  float2* bufB = bufA + n;
-  int row = 0, p = 0;
+
+  float2 v[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
+  int frow = 0, fpart = 0;
   if (active) {
-    row = (int)(f / a.P);
-    p = (int)(f - (int64_t)row * a.P);
-    const float* h = a.h + (size_t)row * a.L;
-    const int base = p * n;
-    for (int q = t; q < n; q += T) {
-      const int i0 = 2 * q;  // window = [partition (B taps) | zeros (B)]
-      float2 z = make_float2(0.f, 0.f);
-      if (i0 < n) {
-        if (base + i0 < a.L) z.x = h[base + i0];
-        if (base + i0 + 1 < a.L) z.y = h[base + i0 + 1];
+    if (MODE == 0) {
+      // window w = [prev block (N) | open block cur[0:m_new) | zeros]; element q is (w[2q], w[2q+1])
+      const int s = (int)f / a.c_x, cx = (int)f - s * a.c_x;
+      float* cur = a.hist + ((size_t)f * 2 + a.half) * N;
+      const float* prev = a.hist + ((size_t)f * 2 + (a.half ^ 1)) * N;
+      const int m_new = a.fill + a.take;
+      const float* xs = a.x + (int64_t)s * a.xs + (a.mixdown ? 0 : (int64_t)cx * a.xc);
+      const float inv_c = 1.0f / (float)a.c_in;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int i0 = 2 * (j + m * T8);
+        if (i0 < N) {
+          v[m] = *reinterpret_cast<const float2*>(prev + i0);
+        } else {
+          const int c0 = i0 - N;
+          float e[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = c0 + h;
+            float val = 0.f;
+            if (c < a.fill) {
+              val = cur[c];                               // already ingested by an earlier partial pull
+            } else if (c < m_new) {
+              const int64_t off = (int64_t)(a.x_off + c - a.fill) * a.xi;
+              if (a.mixdown) {
+                float acc = 0.f;
+                for (int ch = 0; ch < a.c_in; ++ch) acc += xs[off + (int64_t)ch * a.xc];
+                val = acc / (float)a.c_in;
+              } else {
+                val = xs[off];
+              }
+              cur[c] = val;                               // each sample has exactly one owner thread
+            }
+            e[h] = val;
+          }
+          v[m] = make_float2(e[0], e[1]);
+        }
       }
-      bufA[q] = z;
+      (void)inv_c;
+    } else {
+      frow = (int)(f / fp.P);
+      fpart = (int)(f - (int64_t)frow * fp.P);
+      const float* h = fp.h + (size_t)frow * fp.L;
+      const int base = fpart * N;  // window = [partition (N taps) | zeros (N)]
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int i0 = 2 * (j + m * T8);
+        if (i0 < N) {
+          if (base + i0 < fp.L) v[m].x = h[base + i0];
+          if (base + i0 + 1 < fp.L) v[m].y = h[base + i0 + 1];
+        }
+      }
     }
   }
+
+  fft_passes<LOG2N, false>(v, sA, sB, 0, j, tw);
+
+  // split step needs Z[N-k]: exchange through shared memory (natural order, padded)
   __syncthreads();
-  const float2* Z = stockham_passes<false>(bufA, bufB, n, t, T, a.tw);
+#pragma unroll
+  for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+  __syncthreads();
   if (active) {
-    // reversed + doubled layout: partition p at rows P-1-p and 2P-1-p, so that the rows paired with
-    // delay-line slots 0..P-1 are the contiguous run starting at P-1-head (see k_mac.cu).
-    const float scale = 1.0f / (float)n;  // the inverse transform's 1/B, folded in here
-    float2* r0 = a.Hd + ((size_t)row * 2 * a.P + (a.P - 1 - p)) * n;
-    float2* r1 = r0 + (size_t)a.P * n;
-    for (int k = t; k < n; k += T) {
-      float2 v = r2c_bin(Z, n, k, a.tw);
-      v.x *= scale;
-      v.y *= scale;
-      r0[k] = v;
-      r1[k] = v;
+    float2 *row0, *row1 = nullptr;
+    float scale = 1.f;
+    if (MODE == 0) {
+      row0 = a.fdl + ((size_t)f * a.P + a.slot) * N;
+    } else {
+      // reversed + doubled layout: partition p at rows P-1-p and 2P-1-p (see k_mac.cu); 1/N of the inverse
+      // transform is folded in here
+      row0 = fp.Hd + ((size_t)frow * 2 * fp.P + (fp.P - 1 - fpart)) * N;
+      row1 = row0 + (size_t)fp.P * N;
+      scale = 1.0f / (float)N;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int k = j + m * T8;
+      float2 o;
+      if (k == 0) {
+        o = make_float2(v[m].x + v[m].y, v[m].x - v[m].y);
+      } else {
+        o = r2c_bin(v[m], sA[phys(N - k)], tw[k]);
+      }
+      if (MODE == 1) {
+        o.x *= scale;
+        o.y *= scale;
+        row1[k] = o;
+      }
+      row0[k] = o;
     }
   }
 }
 
-void launch_filter_prep(const FilterPrepArgs& a, cudaStream_t st) {
-  const int T = threads_per_fft(a.B);
-  const int fpb = kFftThreads / T;
-  const int64_t total = (int64_t)a.n_rows * a.P;
-  const int grid = (int)((total + fpb - 1) / fpb);
-  const int smem = fft_smem_bytes(a.B);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(k_filter_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k_filter_prep<<<grid, kFftThreads, smem, st>>>(a);
-}
-
-__global__ void __launch_bounds__(kFftThreads) k_c2r_emit(const C2RArgs a) {
+template <int LOG2N>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
+  using C = FftCfg<LOG2N>;
+  constexpr int N = C::N, T8 = C::T8;
   extern __shared__ float2 sm[];
-  const int n = a.B;
-  const int T = threads_per_fft(n);
-  const int fpb = kFftThreads / T;
-  const int g = threadIdx.x / T, t = threadIdx.x % T;
-  const int o = blockIdx.x * fpb + g;
+  const float2* tw = stage_twiddles<LOG2N>(sm, a.tw);
+  float2* bufs = sm + (C::SMEM_TW ? 2 * N : 0);
+  const int g = threadIdx.x / T8, j = threadIdx.x - g * T8;
+  float2* sA = bufs + (size_t)g * 2 * C::PADN;
+  float2* sB = sA + C::PADN;
+  const int o = blockIdx.x * C::FPB + g;
   const bool active = o < a.n_out;
-  float2* bufA = sm + (size_t)g * 2 * n;
-  float2* bufB = bufA + n;
+
+  float2 v[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
   if (active) {
     const float2 *xrow = nullptr, *hrow = nullptr;
     if (a.fdl) {  // conv mode: present term = delay-line slot `head` x filter partition 0 (row P-1 of Hd)
       const int s = o / a.c_out, c = o - s * a.c_out;
       const int gx = (a.c_x == 1) ? 0 : c, fc = (a.c_f == 1) ? 0 : c;
-      xrow = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + a.head) * n;
-      hrow = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + (a.P - 1)) * n;
+      xrow = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + a.head) * N;
+      hrow = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + (a.P - 1)) * N;
     }
-    for (int k = t; k < n; k += T) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int k = j + m * T8;
       float2 acc = make_float2(0.f, 0.f);
       if (xrow) {
         const float2 x = xrow[k], h = __ldg(hrow + k);
         acc = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);
       }
       for (int sp = 0; sp < a.n_split; ++sp) {
-        const float2 v = a.yspec[((size_t)sp * a.n_out + o) * n + k];
-        acc.x += v.x;
-        acc.y += v.y;
+        const float2 t = a.yspec[((size_t)sp * a.n_out + o) * N + k];
+        acc.x += t.x;
+        acc.y += t.y;
       }
       for (int sp = 0; sp < a.n_split_now; ++sp) {
-        const float2 v = a.ynow[((size_t)sp * a.n_out + o) * n + k];
-        acc.x += v.x;
-        acc.y += v.y;
+        const float2 t = a.ynow[((size_t)sp * a.n_out + o) * N + k];
+        acc.x += t.x;
+        acc.y += t.y;
       }
-      bufB[k] = acc;
+      v[m] = acc;
+      sA[phys(k)] = acc;
     }
   }
   __syncthreads();
   if (active) {
-    for (int k = t; k < n; k += T) bufA[k] = c2r_bin(bufB, n, k, a.tw);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int k = j + m * T8;
+      if (k == 0) {
+        v[m] = make_float2(0.5f * (v[m].x + v[m].y), 0.5f * (v[m].x - v[m].y));
+      } else {
+        v[m] = c2r_bin(v[m], sA[phys(N - k)], tw[k]);
+      }
+    }
   }
-  __syncthreads();
-  const float2* z = stockham_passes<true>(bufA, bufB, n, t, T, a.tw);
+
+  fft_passes<LOG2N, true>(v, sA, sB, 1, j, tw);  // first exchange goes to sB: sA may still be read above
+
   if (active) {
-    // overlap-save: output samples of the open block live at window positions [B+fill, B+fill+take)
+    // overlap-save: the open block's output samples live at window positions [N+fill, N+fill+take);
+    // element q = j + m*T8 carries window samples 2q (re) and 2q+1 (im)
     const int s = o / a.c_out, c = o - s * a.c_out;
     float* y = a.y + (int64_t)s * a.ys + (int64_t)c * a.yc;
-    for (int i = t; i < a.take; i += T) {
-      const int idx = n + a.fill + i;
-      const float2 zz = z[idx >> 1];
-      y[(int64_t)(a.y_off + i) * a.yi] = (idx & 1) ? zz.y : zz.x;
+    const int lo = N + a.fill, hi = lo + a.take;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int i0 = 2 * (j + m * T8);
+      if (i0 >= lo && i0 < hi) y[(int64_t)(a.y_off + i0 - lo) * a.yi] = v[m].x;
+      if (i0 + 1 >= lo && i0 + 1 < hi) y[(int64_t)(a.y_off + i0 + 1 - lo) * a.yi] = v[m].y;
     }
   }
 }
 
-void launch_c2r_emit(const C2RArgs& a, cudaStream_t st) {
-  const int T = threads_per_fft(a.B);
-  const int fpb = kFftThreads / T;
-  const int grid = (a.n_out + fpb - 1) / fpb;
-  const int smem = fft_smem_bytes(a.B);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(k_c2r_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k_c2r_emit<<<grid, kFftThreads, smem, st>>>(a);
+// ---- launchers ---------------------------------------------------------------------------------
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
 }
+
+int fft_smem_bytes(int B) {
+  switch (ilog2(B)) {
+#define PGX_CASE(L) case L: return FftCfg<L>::SMEM_BYTES;
+    PGX_CASE(4) PGX_CASE(5) PGX_CASE(6) PGX_CASE(7) PGX_CASE(8) PGX_CASE(9) PGX_CASE(10) PGX_CASE(11) PGX_CASE(12) PGX_CASE(13)
+#undef PGX_CASE
+    default: return 0;
+  }
+}
+
+template <int LOG2N, int MODE>
+static void launch_r2c_t(const R2CArgs& a, const FilterPrepArgs& fp, int64_t total, cudaStream_t st) {
+  using C = FftCfg<LOG2N>;
+  static bool attr_done = false;
+  if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
+    cudaFuncSetAttribute(k_r2c<LOG2N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    attr_done = true;
+  }
+  const int grid = (int)((total + C::FPB - 1) / C::FPB);
+  k_r2c<LOG2N, MODE><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a, fp);
+}
+
+template <int LOG2N>
+static void launch_c2r_t(const C2RArgs& a, cudaStream_t st) {
+  using C = FftCfg<LOG2N>;
+  static bool attr_done = false;
+  if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
+    cudaFuncSetAttribute(k_c2r<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    attr_done = true;
+  }
+  const int grid = (a.n_out + C::FPB - 1) / C::FPB;
+  k_c2r<LOG2N><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a);
+}
+
+#define PGX_DISPATCH(LOG, CALL)                                                                              \
+  switch (LOG) {                                                                                             \
+    case 4: { constexpr int L_ = 4; CALL; } break;                                                           \
+    case 5: { constexpr int L_ = 5; CALL; } break;                                                           \
+    case 6: { constexpr int L_ = 6; CALL; } break;                                                           \
+    case 7: { constexpr int L_ = 7; CALL; } break;                                                           \
+    case 8: { constexpr int L_ = 8; CALL; } break;                                                           \
+    case 9: { constexpr int L_ = 9; CALL; } break;                                                           \
+    case 10: { constexpr int L_ = 10; CALL; } break;                                                         \
+    case 11: { constexpr int L_ = 11; CALL; } break;                                                         \
+    case 12: { constexpr int L_ = 12; CALL; } break;                                                         \
+    case 13: { constexpr int L_ = 13; CALL; } break;                                                         \
+    default: break;                                                                                          \
+  }
+
+void launch_r2c_ingest(const R2CArgs& a, cudaStream_t st) {
+  FilterPrepArgs fp{};
+  PGX_DISPATCH(ilog2(a.B), (launch_r2c_t<L_, 0>(a, fp, a.n_fft, st)));
+}
+
+void launch_filter_prep(const FilterPrepArgs& fp, cudaStream_t st) {
+  R2CArgs a{};
+  PGX_DISPATCH(ilog2(fp.B), (launch_r2c_t<L_, 1>(a, fp, (int64_t)fp.n_rows * fp.P, st)));
+}
+
+void launch_c2r_emit(const C2RArgs& a, cudaStream_t st) { PGX_DISPATCH(ilog2(a.B), (launch_c2r_t<L_>(a, st))); }
 
 }  // namespace pgx

@@ -161,3 +161,62 @@ class ModelBank:
                 self.half ^= 1
                 self.fill = 0
         return y
+
+
+# ---------------------------------------------------------------------------
+# v2 transform (csrc/fft.cuh, register-resident radix-8 passes): thread j of T8 = n/8 holds the 8
+# elements at positions j + m*T8 before the first and after the last pass.
+def _bfly(v, R, inverse):
+    s = 1j if inverse else -1j
+    if R == 2:
+        return [v[0] + v[1], v[0] - v[1]]
+    if R == 4:
+        c0, c1, c2, c3 = v[0] + v[2], v[0] - v[2], v[1] + v[3], (v[1] - v[3]) * s
+        return [c0 + c2, c1 + c3, c0 - c2, c1 - c3]
+    w = np.complex64(np.exp(s * np.pi / 4))  # w8 (forward: e^{-i pi/4})
+    a = [v[0] + v[4], v[1] + v[5], v[2] + v[6], v[3] + v[7]]
+    b = [v[0] - v[4], (v[1] - v[5]) * w, (v[2] - v[6]) * s, (v[3] - v[7]) * (w * s)]
+    e, o = _bfly(a, 4, inverse), _bfly(b, 4, inverse)
+    return [e[0], o[0], e[1], o[1], e[2], o[2], e[3], o[3]]
+
+
+def stockham8(z: np.ndarray, twM: np.ndarray, inverse: bool) -> np.ndarray:
+    """n-point complex FFT (n = 2^b >= 8): radix-8 passes, then one radix-4 / radix-2 pass if b % 3 != 0.
+    Twiddles: w1, w2, w4 from the table, the other powers by multiplication (as the kernel does)."""
+    n = z.shape[0]
+    lg = n.bit_length() - 1
+    radices = [8] * (lg // 3) + ([1 << (lg % 3)] if lg % 3 else [])
+    a = z.astype(np.complex64).copy()
+    b = np.empty_like(a)
+    T8 = n // 8
+    Ns = 1
+    for R in radices:
+        nb = n // R                      # butterflies in this pass
+        for j in range(T8):
+            for u in range(8 // R):
+                jj = j + u * T8
+                k = jj % Ns
+                v = [a[jj + r * nb] for r in range(R)]
+                if Ns > 1:
+                    m = 2 * k * (n // (Ns * R))
+                    w1 = twM[m]
+                    w2 = twM[2 * m] if R > 2 else None
+                    w4 = twM[4 * m] if R > 4 else None
+                    if inverse:
+                        w1 = np.conj(w1)
+                        w2 = np.conj(w2) if w2 is not None else None
+                        w4 = np.conj(w4) if w4 is not None else None
+                    ws = [None, w1]
+                    if R > 2:
+                        ws += [w2, np.complex64(w1 * w2)]
+                    if R > 4:
+                        ws += [w4, np.complex64(w4 * w1), np.complex64(w4 * w2), np.complex64(w4 * np.complex64(w1 * w2))]
+                    for r in range(1, R):
+                        v[r] = np.complex64(v[r] * ws[r])
+                o = _bfly(v, R, inverse)
+                j0 = (jj - k) * R + k
+                for r in range(R):
+                    b[j0 + r * Ns] = np.complex64(o[r])
+        a, b = b, a
+        Ns *= R
+    return a
