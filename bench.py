@@ -323,7 +323,7 @@ def run_gpu(args):
         if traj_dev is not None:
             bank.use_filter_map_device(traj_dev.data_ptr() + (i % 64) * N * 4)
         bank.process_device(x_dev.data_ptr() + (i % N_INPUT_BLOCKS) * blk_bytes, y_dev.data_ptr(), pull,
-                            mix=mix, cuda_stream=sh)
+                            mix=mix, cuda_stream=sh, input_resident=True)
         if do_reduce:
             with torch.cuda.stream(stream):
                 dist.reduce(y_dev, dst=0, op=dist.ReduceOp.SUM)

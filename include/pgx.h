@@ -148,10 +148,13 @@ PGX_API int pgx_bank_process(pgx_bank* bank, const float* x, pgx_layout x_layout
 PGX_API int pgx_bank_process_mix(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y_mix,
                          pgx_layout y_layout, int32_t n);
 
-/* Device-resident variants: x / y are device pointers; work is enqueued on
- * cuda_stream (NULL = the bank's stream) and NOT synchronised. */
+/* Device-resident variant: x / y are device pointers; work is enqueued and NOT synchronised; y is
+ * complete when cuda_stream (NULL = the bank's stream) drains.  flags: PGX_PULL_*. */
+#define PGX_PULL_MIX 1u            /* fused MixPE sum over streams, as pgx_bank_process_mix */
+#define PGX_PULL_INPUT_RESIDENT 2u /* x is already complete in memory (not produced by work still queued on
+                                      cuda_stream): the ingest of this pull may overlap earlier pulls' output stage */
 PGX_API int pgx_bank_process_device(pgx_bank* bank, const float* x_dev, pgx_layout x_layout, float* y_dev,
-                            pgx_layout y_layout, int32_t n, int32_t mix, void* cuda_stream);
+                            pgx_layout y_layout, int32_t n, int32_t flags, void* cuda_stream);
 PGX_API int pgx_bank_synchronize(pgx_bank* bank);
 
 /* ---- measurement: per-kernel device time, CUDA events on the launching stream ---- */

@@ -191,11 +191,15 @@ class ConvolveBank:
 
     # -- device-resident pulls (pointers from torch / cuda-python; not synchronised) ------------
     def process_device(self, x_ptr: int, y_ptr: int, n: int, *, mix: bool = False, cuda_stream: int = 0,
-                       x_layout: Layout | None = None, y_layout: Layout | None = None) -> None:
+                       input_resident: bool = False, x_layout: Layout | None = None,
+                       y_layout: Layout | None = None) -> None:
+        """Enqueue one pull on device buffers (planar by default). ``input_resident``: x is already complete
+        in memory, so its ingest may overlap the output stage of pulls queued earlier."""
         xl = x_layout or Layout(self.c_in * n, n, 1)
         yl = y_layout or Layout(0 if mix else self.c_out * n, n, 1)
+        flags = (1 if mix else 0) | (2 if input_resident else 0)
         check(lib().pgx_bank_process_device(self._h, C.c_void_p(x_ptr), xl, C.c_void_p(y_ptr), yl, int(n),
-                                            1 if mix else 0, C.c_void_p(cuda_stream)))
+                                            flags, C.c_void_p(cuda_stream)))
 
     def synchronize(self) -> None:
         check(lib().pgx_bank_synchronize(self._h))

@@ -47,9 +47,12 @@ struct FftCfg {
   static constexpr int NP8 = LOG2N / 3;              // radix-8 passes
   static constexpr int RLAST = 1 << (LOG2N % 3);     // 1 = none, else a final radix-2 / radix-4 pass
   static constexpr int PADN = N + N / 16;            // padded buffer length (elements)
-  static constexpr int CTA = T8 < 256 ? 256 : T8;    // threads per CTA
+  // Small CTAs on purpose: a 64-thread CTA needs ~3K registers, so the latency-critical FFT kernels fit into
+  // what the resident accumulate CTAs leave free on an SM instead of displacing one of them.
+  static constexpr int CTA = T8 < 64 ? 64 : T8;      // threads per CTA
   static constexpr int FPB = CTA / T8;               // transforms per CTA
-  static constexpr bool SMEM_TW = N <= 1024;         // stage the 2N-entry twiddle table in shared memory
+  static constexpr bool SMEM_TW = FPB >= 4;          // stage the 2N-entry twiddle table in shared memory when
+                                                     // several transforms share it; else read it through L1
   static constexpr int SMEM_BYTES = (SMEM_TW ? 2 * N : 0) * 8 + FPB * 2 * PADN * 8;
 };
 

@@ -110,12 +110,12 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
     float2 *row0, *row1 = nullptr;
     float scale = 1.f;
     if (MODE == 0) {
-      row0 = a.fdl + ((size_t)f * a.P + a.slot) * N;
+      row0 = a.fdl + ((size_t)f * a.R + a.slot) * N;
     } else {
-      // reversed + doubled layout: partition p at rows P-1-p and 2P-1-p (see k_mac.cu); 1/N of the inverse
+      // reversed + doubled layout: partition p at rows R-1-p and 2R-1-p (see k_mac.cu); 1/N of the inverse
       // transform is folded in here
-      row0 = fp.Hd + ((size_t)frow * 2 * fp.P + (fp.P - 1 - fpart)) * N;
-      row1 = row0 + (size_t)fp.P * N;
+      row0 = fp.Hd + ((size_t)frow * 2 * fp.R + (fp.R - 1 - fpart)) * N;
+      row1 = row0 + (size_t)fp.R * N;
       scale = 1.0f / (float)N;
     }
 #pragma unroll
@@ -155,11 +155,11 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
   for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
   if (active) {
     const float2 *xrow = nullptr, *hrow = nullptr;
-    if (a.fdl) {  // conv mode: present term = delay-line slot `head` x filter partition 0 (row P-1 of Hd)
+    if (a.fdl) {  // conv mode: present term = delay-line slot `head` x filter partition 0 (row R-1 of Hd)
       const int s = o / a.c_out, c = o - s * a.c_out;
       const int gx = (a.c_x == 1) ? 0 : c, fc = (a.c_f == 1) ? 0 : c;
-      xrow = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + a.head) * N;
-      hrow = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + (a.P - 1)) * N;
+      xrow = a.fdl + ((size_t)(s * a.c_x + gx) * a.R + a.head) * N;
+      hrow = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.R + (a.R - 1)) * N;
     }
 #pragma unroll
     for (int m = 0; m < 8; ++m) {

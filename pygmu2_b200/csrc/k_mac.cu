@@ -3,8 +3,8 @@
 //   Y[o][k] = sum over terms r of  X[xrow(o,r)][k] * H[hrow(o,r)][k]
 //
 // conv mode (mix=0): o = (stream s, out channel c), terms j = 0..P-1 are the delay-line slots of
-//   (s, g(c)); slot j pairs with filter row q0 + j of the reversed+doubled spectrum set, q0 = P-1-head,
-//   i.e. partition p = (head - j) mod P.  This is the uniformly partitioned form of the reference's
+//   (s, g(c)); slot j pairs with filter row q0 + j of the reversed+doubled spectrum set, q0 = R-1-head,
+//   i.e. partition p = (head - j) mod R (R = ring rows).  This is the uniformly partitioned form of the reference's
 //   single X*H product (convolve_pe.py:314-317).
 // mix mode (mix=1): o = c and the terms run over (s, j): the MixPE sum over streams (mix_pe.py:92-94)
 //   and the per-source HRTF multiply (spatial_pe.py:503-504) are the same accumulation.
@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(kMacThreads) k_fdl_mac(const MacArgs a) {
   const int fc = (a.c_f == 1) ? 0 : c;
   const bool bin0 = (kv == 0);  // packed bin 0 = two independent real bins (DC, Nyquist)
   const size_t rs = (size_t)a.W4;
-  const size_t stream_stride = (size_t)a.c_x * a.P * rs;  // delay-line rows of one stream
-  const float4* hbase = a.Hd + ((size_t)(a.fmap[s0] * a.c_f + fc) * 2 * a.P + a.q0) * rs + kv;
-  const float4* xbase = a.fdl + ((size_t)(s0 * a.c_x + gx) * a.P) * rs + kv;
+  const size_t stream_stride = (size_t)a.c_x * a.R * rs;  // delay-line rows of one stream
+  const float4* hbase = a.Hd + ((size_t)(a.fmap[s0] * a.c_f + fc) * 2 * a.R + a.q0) * rs + kv;
+  const float4* xbase = a.fdl + ((size_t)(s0 * a.c_x + gx) * a.R) * rs + kv;
 
   float4 acc[ST];
   float2 acc0[ST];
@@ -95,11 +95,13 @@ __global__ void __launch_bounds__(kMacThreads) k_fdl_mac(const MacArgs a) {
         const float4 *xp, *hp;
         if (MIX) {
           const int s = rr / a.Pt, jj = rr - s * a.Pt;
-          const int j = (a.jfix >= 0) ? a.jfix : jj + (jj >= a.skip ? 1 : 0);
-          xp = a.fdl + ((size_t)(s * a.c_x + gx) * a.P + j) * rs + kv;
-          hp = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.P + a.q0 + j) * rs + kv;
+          int j = a.off + jj;
+          j = (a.jfix >= 0) ? a.jfix : j + (j >= a.skip ? a.nskip : 0);
+          xp = a.fdl + ((size_t)(s * a.c_x + gx) * a.R + j) * rs + kv;
+          hp = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.R + a.q0 + j) * rs + kv;
         } else {
-          const int j = (a.jfix >= 0) ? a.jfix : rr + (rr >= a.skip ? 1 : 0);
+          int j = a.off + rr;
+          j = (a.jfix >= 0) ? a.jfix : j + (j >= a.skip ? a.nskip : 0);
           xp = xbase + (size_t)j * rs;
           hp = hbase + (size_t)j * rs;
         }
@@ -206,6 +208,50 @@ void launch_fdl_mac(const MacArgs& a, cudaStream_t st) {
     k_fdl_mac<false, 4, 4><<<grid, kMacThreads, 0, st>>>(a);
   else
     k_fdl_mac<false, 1, 8><<<grid, kMacThreads, 0, st>>>(a);
+}
+
+// Second stage of the split accumulation: out[e] = sum_sp in[sp][e], e over n_out*W4 float4 columns.
+// 32 columns x 8 split-groups per CTA; each group walks its splits with 4 loads in flight, then the
+// groups are folded through shared memory in a fixed order (deterministic result).
+__global__ void __launch_bounds__(256) k_reduce_partials(const float4* __restrict__ in, float4* __restrict__ out,
+                                                         const int n_split, const int64_t n_cols) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t col = (int64_t)blockIdx.x * 32 + lane;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < n_cols) {
+    int sp = grp;
+    for (; sp + 24 < n_split; sp += 32) {
+      const float4 a = __ldg(in + (int64_t)sp * n_cols + col);
+      const float4 b = __ldg(in + (int64_t)(sp + 8) * n_cols + col);
+      const float4 c = __ldg(in + (int64_t)(sp + 16) * n_cols + col);
+      const float4 d = __ldg(in + (int64_t)(sp + 24) * n_cols + col);
+      acc.x += (a.x + b.x) + (c.x + d.x);
+      acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z);
+      acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; sp < n_split; sp += 8) {
+      const float4 a = __ldg(in + (int64_t)sp * n_cols + col);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  red[grp][lane] = acc;
+  __syncthreads();
+  if (grp == 0 && col < n_cols) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) {
+      const float4 v = red[g][lane];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[col] = acc;
+  }
+}
+
+void launch_reduce_partials(const float4* in, float4* out, int n_split, int n_out, int W4, cudaStream_t st) {
+  const int64_t n_cols = (int64_t)n_out * W4;
+  const int grid = (int)((n_cols + 31) / 32);
+  k_reduce_partials<<<grid, 256, 0, st>>>(in, out, n_split, n_cols);
 }
 
 // K5 -- MixPE: out = ((in0 + in1) + in2) + ... per element, float32, input order (bit-exact with

@@ -11,21 +11,22 @@ struct R2CArgs {
   int64_t xs, xc, xi;
   int32_t x_off;
   float* hist;           // [n_fft][2][B] time-domain halves (previous block / open block)
-  float2* fdl;           // [n_fft][P][B] packed input spectra (frequency-domain delay line)
+  float2* fdl;           // [n_fft][R][B] packed input spectra (frequency-domain delay line, R ring rows)
   const float2* tw;      // [2B] exp(-2*pi*i*k/2B)
   int32_t n_fft;         // N * c_x transforms
-  int32_t c_in, c_x, B, P;
+  int32_t c_in, c_x, B, R;
   int32_t slot, half, fill, take;
   int32_t mixdown;
 };
 void launch_r2c_ingest(const R2CArgs& a, cudaStream_t st);
 
-// Filter preparation: partition p of filter row f -> spectrum rows (P-1-p) and (2P-1-p), scaled 1/B.
+// Filter preparation: partition p < P of filter row f -> spectrum rows (R-1-p) and (2R-1-p), scaled 1/B.
+// (R = ring rows >= P; rows of partitions P..R-1 stay zero.)
 struct FilterPrepArgs {
   const float* h;        // device [n_rows][L]
-  float2* Hd;            // [n_rows][2P][B]
+  float2* Hd;            // [n_rows][2R][B]
   const float2* tw;
-  int32_t n_rows, L, B, P;
+  int32_t n_rows, L, B, P, R;
 };
 void launch_filter_prep(const FilterPrepArgs& a, cudaStream_t st);
 
@@ -35,18 +36,21 @@ struct MacArgs {
   const float4* Hd;
   float4* yspec;         // [n_split][n_out][W4]
   const int32_t* fmap;   // [N] filter of stream
-  int32_t N, c_x, c_out, c_f, P, W4, q0;
+  int32_t N, c_x, c_out, c_f, R, W4, q0;  // R = ring rows per (stream, channel); q0 = R-1-head
   int32_t n_out, n_terms, terms_per_split, n_split;
   int32_t n_otiles, st;  // out tiles in the flat grid; streams per CTA sharing the filter rows (1 or 4)
   int32_t mix;           // 0: out o=(s,c), terms j<P.  1: out o=c, terms (s,j) (fused MixPE / HRTF stereo mix)
-  // which delay-line slots are terms: Pt slots per stream; slot = jfix if jfix >= 0 (only that slot),
-  // else jj + (jj >= skip) for jj in [0, Pt) (skip = the open slot `head` for the background pass, or a
-  // value >= P for "all slots").  n_terms = Pt (conv) or N*Pt (mix).
-  int32_t Pt, skip, jfix;
+  // which ring slots are terms: Pt slots per stream; slot = jfix if jfix >= 0 (only that slot), else
+  // j = off + jj, plus nskip when j >= skip, for jj in [0, Pt): the background pass leaves out the open
+  // slot `head` and the spare slot head+1 (being written by the next block's K1).
+  // n_terms = Pt (conv) or N*Pt (mix).
+  int32_t Pt, off, skip, nskip, jfix;
 };
 struct MacPlan {
   int32_t st, n_otiles, n_split, terms_per_split, grid, occupancy;
 };
+// Fold split partial sums: out[o][k] = sum_sp in[sp][o][k] (rows of W4 float4), deterministic order.
+void launch_reduce_partials(const float4* in, float4* out, int n_split, int n_out, int W4, cudaStream_t st);
 MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count);
 void launch_fdl_mac(const MacArgs& a, cudaStream_t st);
 
@@ -60,7 +64,7 @@ struct C2RArgs {
   const float2* fdl;     // NULL when ynow carries the present term
   const float2* Hd;
   const int32_t* fmap;
-  int32_t c_x, c_f, P, head;
+  int32_t c_x, c_f, R, head;
   float* y;              // element (s, c, i) at y[s*ys + c*yc + (y_off+i)*yi]; o = s*c_out + c
   int64_t ys, yc, yi;
   int32_t y_off;

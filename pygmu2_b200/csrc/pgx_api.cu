@@ -1,27 +1,35 @@
 // pgx_api.cu -- host engine + C ABI of libpgx.so (see include/pgx.h).
 //
 // A bank owns, on one GPU, for N lock-stepped audio streams:
-//   hist  [N*c_x][2][B]      float   previous block / open block (time domain)
-//   fdl   [N*c_x][P][B]      float2  frequency-domain delay line: packed spectra of the last P windows
-//   Hd    [F*c_f][2P][B]     float2  filter partition spectra, reversed + doubled, scaled 1/B
-//   yspec [n_split][n_out][B] float2 split partial sums of the multiply-accumulate
+//   hist  [N*c_x][2][B]       float   previous block / open block (time domain)
+//   fdl   [N*c_x][R][B]       float2  frequency-domain delay line: packed spectra of the last windows,
+//                                     a ring of R = P+1 rows (R = 1 when P = 1): P live rows + one spare
+//   Hd    [F*c_f][2R][B]      float2  filter partition spectra, reversed + doubled, scaled 1/B
+//   ypast [2][<=8][n_out][B]  float2  sums over the past partitions of the open block (by block parity)
+//   ypart [n_split][n_out][B] float2  split partials of the background pass in flight
+//   ynow  [n_split][c_out][B] float2  present-slot partials (mix mode)
 // and advances them one "block step" at a time.  A pull of n samples is cut at block boundaries; a
 // partially filled block is transformed with zeros in the not-yet-known positions (causality makes the
 // emitted samples exact) and re-transformed when more samples arrive, so any (start, duration) pull
 // pattern is zero-latency like the reference (convolve_pe.py:250-342), while the block grid stays
 // aligned for the partitioned filter.
 //
-// Schedule of one block step (two CUDA streams):
-//   critical stream : K1 ingest + R2C of the open block  ->  [mix mode: K3 over the open slot of every
-//                     stream]  ->  K2: past partial sums + present term, C2R, emit
-//   background      : K3 over the P-1 *past* partitions of the open block.  It depends only on rows
-//                     committed before the block opened, so it is launched as soon as the previous
-//                     block's K1 has run, overlaps K1/K2, and is reused by every partial pull of the block.
+// Schedule of block step i (block t), three CUDA streams joined by events:
+//   ingest stream     : K1(i)  ingest + R2C of the open block -> ring row slot(t)
+//   background stream : K3 over the P-1 *past* partitions of block t+1, launched as soon as the step that
+//                       completes block t has its K1; it needs only committed rows, overlaps everything
+//                       else and is reused by every partial pull of block t+1
+//   critical stream   : [mix mode: K3 over the open slot of every stream] -> K2(i): past sums + present
+//                       term, C2R, emit.  This is the caller's stream: y is complete when it drains.
+// The spare ring row lets K1 of block t+1 run while the background pass of block t is still reading, so
+// in a back-to-back queue of pulls the step time is the accumulate kernel alone.  Hazards and the event
+// that orders each one are listed at run_step().
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -68,33 +76,50 @@ bool layout_dense(const pgx_layout& l, int64_t S, int64_t C, int64_t n) {
   return span == S * C * n;
 }
 
+// K2 folds up to this many split partials itself; beyond that a fold kernel runs right after the
+// background pass, off the critical path.
+constexpr int kFoldAbove = 8;
+constexpr int kRing = 4;  // event ring depth (steps / blocks in flight)
+
 }  // namespace
 
 struct pgx_bank {
   pgx_bank_config cfg{};
-  int c_x = 1, P = 1, B = 0;
-  cudaStream_t stream = nullptr;  // default critical stream
-  cudaStream_t bg = nullptr;      // background stream for the past-partition pass
-  cudaEvent_t ev_fork = nullptr, ev_past = nullptr;
-  bool ev_past_recorded = false;
+  int c_x = 1, P = 1, R = 1, B = 0;
+  cudaStream_t stream = nullptr;   // default critical stream
+  cudaStream_t s_in = nullptr;     // ingest stream (K1)
+  cudaStream_t s_bg = nullptr;     // background stream (past-partition pass)
+  cudaEvent_t ev_call = nullptr;
+  cudaEvent_t ev_k1[kRing] = {}, ev_k2[kRing] = {}, ev_mac[kRing] = {};
   float* hist = nullptr;
   float2* fdl = nullptr;
   float2* Hd = nullptr;
-  float2* ypast[2] = {nullptr, nullptr};  // past-partition partial sums, double buffered by block parity
-  float2* ynow = nullptr;                 // present-slot partial sums (mix mode)
+  float2* ypast[2] = {nullptr, nullptr};
+  float2* ypart = nullptr;
+  float2* ynow = nullptr;
   float2* tw = nullptr;
-  int32_t* fmap = nullptr;
-  int32_t* fmap_pinned = nullptr;
+  int32_t* fmap = nullptr;         // map in use (own buffer or the caller's device array)
+  int32_t* fmap_own = nullptr;
+  static constexpr int kMapSlots = 8;
+  int32_t* fmap_pinned = nullptr;  // kMapSlots x [N] pinned staging ring
+  cudaEvent_t fmap_ev[kMapSlots] = {};
+  int fmap_slot = 0;
   float* x_stage = nullptr;
   float* y_stage = nullptr;
-  size_t hist_bytes = 0, fdl_bytes = 0, Hd_bytes = 0, yspec_bytes = 0, xs_bytes = 0, ys_bytes = 0;
+  size_t hist_bytes = 0, fdl_bytes = 0, Hd_bytes = 0, ypart_bytes = 0, ysum_bytes = 0, ynow_bytes = 0, xs_bytes = 0,
+         ys_bytes = 0;
+  // ring / schedule state
   int head = 0, fill = 0, half = 0;
-  int par = 0;               // which ypast buffer belongs to the open block
-  bool past_valid = false;   // ypast[par] holds the past sum of the open block ...
-  int past_mode = -1;        // ... for this mode (0 conv, 1 mix)
+  int64_t step = 0;                // steps issued since the last full reset
+  int64_t block = 0;               // index of the open block since the last full reset
+  int64_t past_block = -1;         // block whose past sum was last issued ...
+  int past_mode = -1;              // ... for this mode (0 conv, 1 mix)
+  int64_t last_k2_of_par[2] = {-1, -1};  // last step whose K2 read ypast[par]
   pgx::MacPlan plan_conv{}, plan_mix{}, plan_now{};
   int sm_count = 148;
+  bool serial = false;
   int64_t launches = 0, steps = 0;
+  // per-kernel CUDA-event timing
   bool profiling = false;
   struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3, 2 = K2
   std::vector<ProfSpan> prof_spans;
@@ -108,24 +133,29 @@ namespace {
 void free_bank(pgx_bank* b) {
   if (!b) return;
   cudaSetDevice(b->cfg.device);
-  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (cudaStream_t s : {b->stream, b->s_in, b->s_bg})
+    if (s) cudaStreamSynchronize(s);
   cudaFree(b->hist);
   cudaFree(b->fdl);
   cudaFree(b->Hd);
   cudaFree(b->ypast[0]);
   cudaFree(b->ypast[1]);
+  cudaFree(b->ypart);
   cudaFree(b->ynow);
   cudaFree(b->tw);
-  cudaFree(b->fmap);
+  cudaFree(b->fmap_own);
   cudaFree(b->x_stage);
   cudaFree(b->y_stage);
-  for (cudaEvent_t e : b->prof_pool) cudaEventDestroy(e);
-  if (b->bg) cudaStreamSynchronize(b->bg);
-  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
-  if (b->ev_past) cudaEventDestroy(b->ev_past);
-  if (b->bg) cudaStreamDestroy(b->bg);
   if (b->fmap_pinned) cudaFreeHost(b->fmap_pinned);
-  if (b->stream) cudaStreamDestroy(b->stream);
+  for (cudaEvent_t e : b->prof_pool) cudaEventDestroy(e);
+  for (int i = 0; i < kRing; ++i)
+    for (cudaEvent_t e : {b->ev_k1[i], b->ev_k2[i], b->ev_mac[i]})
+      if (e) cudaEventDestroy(e);
+  for (int i = 0; i < pgx_bank::kMapSlots; ++i)
+    if (b->fmap_ev[i]) cudaEventDestroy(b->fmap_ev[i]);
+  if (b->ev_call) cudaEventDestroy(b->ev_call);
+  for (cudaStream_t s : {b->stream, b->s_in, b->s_bg})
+    if (s) cudaStreamDestroy(s);
   delete b;
 }
 
@@ -158,127 +188,188 @@ struct ProfScope {  // records a CUDA-event pair around one launch when profilin
   }
 };
 
-void fill_mac_common(pgx_bank* b, pgx::MacArgs& m, bool mix) {
+void fill_mac_common(pgx_bank* b, pgx::MacArgs& m, bool mix, int head) {
   const pgx_bank_config& c = b->cfg;
   m.fdl = reinterpret_cast<const float4*>(b->fdl);
   m.Hd = reinterpret_cast<const float4*>(b->Hd);
   m.fmap = b->fmap;
-  m.N = c.n_streams; m.c_x = b->c_x; m.c_out = c.c_out; m.c_f = c.filter_channels; m.P = b->P; m.W4 = b->B / 2;
-  m.q0 = b->P - 1 - b->head;
+  m.N = c.n_streams; m.c_x = b->c_x; m.c_out = c.c_out; m.c_f = c.filter_channels; m.R = b->R; m.W4 = b->B / 2;
+  m.q0 = b->R - 1 - head;
   m.mix = mix ? 1 : 0;
   m.n_out = mix ? c.c_out : c.n_streams * c.c_out;
 }
 
-// Background pass: sum over the P-1 committed partitions of the open block into ypast[par].
-// Forked from `after` (an event on the critical stream after which every committed row is written).
-void launch_past(pgx_bank* b, bool mix, cudaStream_t crit) {
-  cudaEventRecord(b->ev_fork, crit);
-  cudaStreamWaitEvent(b->bg, b->ev_fork, 0);
+// Background pass for block `blk` whose ring slot is `head`: sum over its P-1 past partitions, i.e. every
+// ring row except slot head (the open block) and slot head+1 (the spare row, free for the next block's K1).
+// Ordered after `after` (an event on the ingest stream by which every committed row is written) and after
+// the last K2 that read the ypast buffer it overwrites.
+void issue_past(pgx_bank* b, bool mix, int64_t blk, int head, cudaEvent_t after) {
+  const int par = (int)(blk & 1);
+  cudaStreamWaitEvent(b->s_bg, after, 0);
+  if (b->last_k2_of_par[par] >= 0) cudaStreamWaitEvent(b->s_bg, b->ev_k2[b->last_k2_of_par[par] % kRing], 0);
   pgx::MacArgs m{};
-  fill_mac_common(b, m, mix);
+  fill_mac_common(b, m, mix, head);
   const pgx::MacPlan& pl = mix ? b->plan_mix : b->plan_conv;
-  m.yspec = reinterpret_cast<float4*>(b->ypast[b->par]);
-  m.Pt = b->P - 1; m.skip = b->head; m.jfix = -1;
-  m.n_terms = mix ? b->cfg.n_streams * (b->P - 1) : (b->P - 1);
+  const bool fold = pl.n_split > kFoldAbove;
+  m.yspec = reinterpret_cast<float4*>(fold ? b->ypart : b->ypast[par]);
+  m.Pt = b->R - 2;  // = P - 1
+  m.jfix = -1;
+  if (head + 1 < b->R) { m.off = 0; m.skip = head; m.nskip = 2; }
+  else                 { m.off = 1; m.skip = b->R; m.nskip = 0; }  // open slot R-1, spare slot 0
+  m.n_terms = mix ? b->cfg.n_streams * m.Pt : m.Pt;
   m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
   {
-    ProfScope ps(b, b->bg, 1);
-    pgx::launch_fdl_mac(m, b->bg);
+    ProfScope ps(b, b->s_bg, 1);
+    pgx::launch_fdl_mac(m, b->s_bg);
+    b->launches += 1;
+    if (fold) {
+      pgx::launch_reduce_partials(reinterpret_cast<const float4*>(b->ypart), reinterpret_cast<float4*>(b->ypast[par]),
+                                  pl.n_split, m.n_out, b->B / 2, b->s_bg);
+      b->launches += 1;
+    }
   }
-  cudaEventRecord(b->ev_past, b->bg);
-  b->ev_past_recorded = true;
-  b->launches += 1;
-  b->past_valid = true;
+  cudaEventRecord(b->ev_mac[blk % kRing], b->s_bg);
+  b->past_block = blk;
   b->past_mode = mix ? 1 : 0;
 }
 
-// One pull on device buffers, enqueued on st (no synchronisation).
-int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int n,
-             bool mix, cudaStream_t st) {
+// One block step.  Buffers, accessors and the ordering of every cross-stream hazard:
+//   K1(i)   [ingest]     R x, hist[prev];  W hist[cur], fdl[slot(t)]
+//   PAST(t) [background] R fdl[all but slot(t), slot(t+1)], Hd, fmap;  W ypart, ypast[t&1]
+//   NOW(i)  [critical]   R fdl[slot(t)], Hd, fmap;  W ynow                      (mix mode only)
+//   K2(i)   [critical]   R ypast[t&1], ynow, fdl[slot(t)], Hd, fmap;  W y
+//   RAW  PAST(t+1) <- K1 of the step completing block t ............ wait ev_k1       (issue_past `after`)
+//   RAW  K2(i), NOW(i) <- K1(i) ................................... critical waits ev_k1[i]
+//   RAW  K2(i) <- PAST(t) ......................................... critical waits ev_mac[t]
+//   WAR  K1(i) rewrites slot(t) / hist[cur] of an open block that K2(i-1), NOW(i-1) read (also every step
+//        when R = 1: a single row) ................................ ingest waits ev_k2[i-1]
+//   WAR  K1 of a new block t overwrites slot(t) = block t-R: read by PAST(t-2) (oldest term) and, as
+//        present term, by K2/NOW of block t-R ..................... ingest waits ev_mac[t-2] and ev_k2[i-2]
+//   WAR  PAST(t+1) overwrites ypast[(t+1)&1] read by K2 of block t-1 . background waits that K2's event
+//   same-stream order covers hist halves (K1 only), ypart (background only), ynow (critical only).
+int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int pos,
+             int take, bool mix, cudaStream_t crit) {
+  struct StreamSwap {  // PGX_DEBUG_SERIAL=1: run all three roles on the critical stream
+    pgx_bank* b; cudaStream_t in, bg;
+    StreamSwap(pgx_bank* b_, cudaStream_t crit_) : b(b_), in(b_->s_in), bg(b_->s_bg) {
+      if (b->serial) b->s_in = b->s_bg = crit_;
+    }
+    ~StreamSwap() { b->s_in = in; b->s_bg = bg; }
+  } swap_guard(b, crit);
   const pgx_bank_config& c = b->cfg;
-  const int B = b->B, P = b->P;
+  const int B = b->B, P = b->P, R = b->R;
+  const int64_t i = b->step, t = b->block;
+  const bool completes = (b->fill + take == B);
+
+  // ---- ingest stream: K1
+  if (b->fill > 0 || R == 1) {  // same ring row (and open half) as the previous step
+    if (i >= 1) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 1) % kRing], 0);
+  } else {
+    if (i >= 2) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 2) % kRing], 0);
+    if (t >= 2) cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);  // every block had its past pass issued
+  }
+  pgx::R2CArgs r{};
+  r.x = x_dev; r.xs = xl.stream; r.xc = xl.chan; r.xi = xl.samp; r.x_off = pos;
+  r.hist = b->hist; r.fdl = b->fdl; r.tw = b->tw;
+  r.n_fft = c.n_streams * b->c_x; r.c_in = c.c_in; r.c_x = b->c_x; r.B = B; r.R = R;
+  r.slot = b->head; r.half = b->half; r.fill = b->fill; r.take = take;
+  r.mixdown = (c.flags & PGX_FLAG_MIXDOWN_INPUT) ? 1 : 0;
+  {
+    ProfScope ps(b, b->s_in, 0);
+    pgx::launch_r2c_ingest(r, b->s_in);
+  }
+  cudaEventRecord(b->ev_k1[i % kRing], b->s_in);
+  b->launches += 1;
+
+  // ---- background stream: past sum of the open block, if it is not in flight / valid already
+  int n_split_past = 0;
+  const int par = (int)(t & 1);
+  if (P > 1) {
+    if (b->past_block != t || b->past_mode != (mix ? 1 : 0)) issue_past(b, mix, t, b->head, b->ev_k1[i % kRing]);
+    cudaStreamWaitEvent(crit, b->ev_mac[t % kRing], 0);
+    const int ns = (mix ? b->plan_mix : b->plan_conv).n_split;
+    n_split_past = ns > kFoldAbove ? 1 : ns;
+  }
+
+  // ---- critical stream: [NOW] + K2
+  cudaStreamWaitEvent(crit, b->ev_k1[i % kRing], 0);
+  pgx::C2RArgs k{};
+  k.yspec = b->ypast[par]; k.n_split = n_split_past;
+  k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
+  if (mix) {  // present term of every stream: K3 restricted to the open slot
+    pgx::MacArgs m{};
+    fill_mac_common(b, m, true, b->head);
+    m.yspec = reinterpret_cast<float4*>(b->ynow);
+    m.Pt = 1; m.off = 0; m.skip = R; m.nskip = 0; m.jfix = b->head;
+    m.n_terms = c.n_streams;
+    m.n_split = b->plan_now.n_split; m.terms_per_split = b->plan_now.terms_per_split;
+    m.n_otiles = b->plan_now.n_otiles; m.st = b->plan_now.st;
+    {
+      ProfScope ps(b, crit, 1);
+      pgx::launch_fdl_mac(m, crit);
+    }
+    b->launches += 1;
+    k.ynow = b->ynow; k.n_split_now = m.n_split;
+    k.fdl = nullptr;
+  } else {
+    k.ynow = nullptr; k.n_split_now = 0;
+    k.fdl = b->fdl;
+  }
+  k.Hd = b->Hd; k.fmap = b->fmap; k.c_x = b->c_x; k.c_f = c.filter_channels; k.R = R; k.head = b->head;
+  k.y = y_dev; k.ys = mix ? 0 : yl.stream; k.yc = yl.chan; k.yi = yl.samp; k.y_off = pos;
+  k.c_out = c.c_out; k.B = B; k.fill = b->fill; k.take = take; k.tw = b->tw;
+
+  // the block commits with this step: its row is final once K1 has run, so the next block's past pass
+  // can start now, overlapping this step's K2 and the next step's K1
+  if (completes && P > 1) issue_past(b, mix, t + 1, (b->head + 1) % R, b->ev_k1[i % kRing]);
+
+  {
+    ProfScope ps(b, crit, 2);
+    pgx::launch_c2r_emit(k, crit);
+  }
+  cudaEventRecord(b->ev_k2[i % kRing], crit);
+  b->last_k2_of_par[par] = i;
+  b->launches += 1;
+  b->steps += 1;
+  if (b->profiling) b->prof_steps += 1;
+  b->step += 1;
+  b->fill += take;
+  if (completes) {  // block complete: commit the row, advance the ring
+    b->head = (b->head + 1) % R;
+    b->half ^= 1;
+    b->fill = 0;
+    b->block += 1;
+  }
+  return PGX_OK;
+}
+
+// One pull on device buffers, enqueued on crit (no synchronisation).
+int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int n,
+             bool mix, bool input_resident, cudaStream_t crit) {
+  if (!input_resident) {
+    // x is produced by work queued earlier on the caller's stream: the ingest stream must see it
+    cudaEventRecord(b->ev_call, crit);
+    cudaStreamWaitEvent(b->s_in, b->ev_call, 0);
+  }
   int pos = 0;
   while (pos < n) {
-    const int take = (B - b->fill < n - pos) ? (B - b->fill) : (n - pos);
-
-    pgx::R2CArgs r{};
-    r.x = x_dev; r.xs = xl.stream; r.xc = xl.chan; r.xi = xl.samp; r.x_off = pos;
-    r.hist = b->hist; r.fdl = b->fdl; r.tw = b->tw;
-    r.n_fft = c.n_streams * b->c_x; r.c_in = c.c_in; r.c_x = b->c_x; r.B = B; r.P = P;
-    r.slot = b->head; r.half = b->half; r.fill = b->fill; r.take = take;
-    r.mixdown = (c.flags & PGX_FLAG_MIXDOWN_INPUT) ? 1 : 0;
-    {
-      ProfScope ps(b, st, 0);
-      pgx::launch_r2c_ingest(r, st);
-    }
-    b->launches += 1;
-
-    const bool completes = (b->fill + take == B);
-    int n_split_past = 0;
-    if (P > 1) {
-      if (!b->past_valid || b->past_mode != (mix ? 1 : 0)) launch_past(b, mix, st);
-      cudaStreamWaitEvent(st, b->ev_past, 0);
-      n_split_past = (mix ? b->plan_mix : b->plan_conv).n_split;
-    }
-
-    pgx::C2RArgs k{};
-    k.yspec = b->ypast[b->par]; k.n_split = n_split_past;
-    k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
-    if (mix) {  // present term of every stream: K3 restricted to the open slot
-      pgx::MacArgs m{};
-      fill_mac_common(b, m, true);
-      m.yspec = reinterpret_cast<float4*>(b->ynow);
-      m.Pt = 1; m.skip = P; m.jfix = b->head;
-      m.n_terms = c.n_streams;
-      m.n_split = b->plan_now.n_split; m.terms_per_split = b->plan_now.terms_per_split;
-      m.n_otiles = b->plan_now.n_otiles; m.st = b->plan_now.st;
-      {
-        ProfScope ps(b, st, 1);
-        pgx::launch_fdl_mac(m, st);
-      }
-      b->launches += 1;
-      k.ynow = b->ynow; k.n_split_now = m.n_split;
-      k.fdl = nullptr;
-    } else {
-      k.ynow = nullptr; k.n_split_now = 0;
-      k.fdl = b->fdl;
-    }
-    k.Hd = b->Hd; k.fmap = b->fmap; k.c_x = b->c_x; k.c_f = c.filter_channels; k.P = P; k.head = b->head;
-    k.y = y_dev; k.ys = mix ? 0 : yl.stream; k.yc = yl.chan; k.yi = yl.samp; k.y_off = pos;
-    k.c_out = c.c_out; k.B = B; k.fill = b->fill; k.take = take; k.tw = b->tw;
-    if (completes && P > 1) {
-      // the block commits with this step: its row is final once K1 has run, so the next block's past
-      // pass can start now and overlap this step's K2 (and the next step's K1)
-      b->head = (b->head + 1) % P;
-      b->par ^= 1;
-      launch_past(b, mix, st);
-      b->head = (b->head + P - 1) % P;
-      b->par ^= 1;
-    }
-    {
-      ProfScope ps(b, st, 2);
-      pgx::launch_c2r_emit(k, st);
-    }
-    b->launches += 1;
-    b->steps += 1;
-    if (b->profiling) b->prof_steps += 1;
-    b->fill += take;
+    const int take = (b->B - b->fill < n - pos) ? (b->B - b->fill) : (n - pos);
+    const int rc = run_step(b, x_dev, xl, y_dev, yl, pos, take, mix, crit);
+    if (rc != PGX_OK) return rc;
     pos += take;
-    if (completes) {  // block complete: commit the row, advance the ring
-      b->head = (b->head + 1) % P;
-      b->half ^= 1;
-      b->fill = 0;
-      if (P > 1) b->par ^= 1;  // past sum of the new open block was launched above
-    }
   }
   PGX_CUDA(cudaGetLastError());
   return PGX_OK;
 }
 
-// state changes outside run_pull invalidate the cached past sum and must not race the background pass
-void quiesce_background(pgx_bank* b) {
-  if (b->ev_past_recorded) cudaStreamWaitEvent(b->stream, b->ev_past, 0);
-  b->past_valid = false;
+// State changes outside run_pull (reset, filter reload / re-selection) are rare and synchronous: drain the
+// bank's streams (a caller-owned critical stream is the caller's to drain) and drop the cached past sum.
+void quiesce(pgx_bank* b) {
+  cudaStreamSynchronize(b->s_in);
+  cudaStreamSynchronize(b->s_bg);
+  cudaStreamSynchronize(b->stream);
+  b->past_block = -1;
+  b->past_mode = -1;
 }
 
 int check_pull_args(pgx_bank* b, const void* x, const void* y, int n) {
@@ -286,6 +377,27 @@ int check_pull_args(pgx_bank* b, const void* x, const void* y, int n) {
   if (!x || !y) return fail(PGX_ERR_INVALID, "x / y must not be NULL");
   if (n < 1 || n > b->cfg.max_pull)
     return fail(PGX_ERR_INVALID, "pull of %d samples outside [1, max_pull=%d]", n, b->cfg.max_pull);
+  return PGX_OK;
+}
+
+int prep_filters(pgx_bank* b, const float* h_host, int first_row, int n_rows) {
+  const pgx_bank_config& c = b->cfg;
+  float* h_dev = nullptr;
+  const size_t hb = (size_t)n_rows * c.filter_len * sizeof(float);
+  PGX_CUDA(cudaMalloc(&h_dev, hb));
+  cudaError_t e = cudaMemcpyAsync(h_dev, h_host, hb, cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) {
+    pgx::FilterPrepArgs fp{};
+    fp.h = h_dev;
+    fp.Hd = b->Hd + (size_t)first_row * 2 * b->R * b->B;
+    fp.tw = b->tw; fp.n_rows = n_rows; fp.L = c.filter_len; fp.B = b->B; fp.P = b->P; fp.R = b->R;
+    pgx::launch_filter_prep(fp, b->stream);
+    b->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  cudaFree(h_dev);
+  if (e != cudaSuccess) return fail(PGX_ERR_CUDA, "filter preparation: %s", cudaGetErrorString(e));
   return PGX_OK;
 }
 
@@ -364,13 +476,15 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
   b->c_x = c_x;
   b->B = c.block;
   b->P = (c.filter_len + c.block - 1) / c.block;
-  const int B = b->B, P = b->P;
+  b->R = b->P > 1 ? b->P + 1 : 1;
+  const int B = b->B, P = b->P, R = b->R;
   const size_t n_fft = (size_t)c.n_streams * c_x;
   const size_t h_rows = (size_t)c.n_filters * c.filter_channels;
+  const size_t n_out_max = (size_t)c.n_streams * c.c_out;
 
   b->hist_bytes = n_fft * 2 * B * sizeof(float);
-  b->fdl_bytes = n_fft * P * B * sizeof(float2);
-  b->Hd_bytes = h_rows * 2 * P * B * sizeof(float2);
+  b->fdl_bytes = n_fft * R * B * sizeof(float2);
+  b->Hd_bytes = h_rows * 2 * R * B * sizeof(float2);
   {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess && prop.multiProcessorCount > 0)
@@ -384,9 +498,10 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     y_mix = (size_t)b->plan_mix.n_split * c.c_out;
   }
   b->plan_now = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams, true, c.n_filters == 1, b->sm_count);
-  b->yspec_bytes = (y_conv > y_mix ? y_conv : y_mix) * B * sizeof(float2);
-  if (b->yspec_bytes == 0) b->yspec_bytes = sizeof(float2);
-  const size_t ynow_bytes = (size_t)b->plan_now.n_split * c.c_out * B * sizeof(float2);
+  b->ypart_bytes = (y_conv > y_mix ? y_conv : y_mix) * B * sizeof(float2);
+  if (b->ypart_bytes == 0) b->ypart_bytes = sizeof(float2);
+  b->ysum_bytes = n_out_max * B * sizeof(float2) * kFoldAbove;
+  b->ynow_bytes = (size_t)b->plan_now.n_split * c.c_out * B * sizeof(float2);
   b->xs_bytes = (size_t)c.n_streams * c.c_in * c.max_pull * sizeof(float);
   b->ys_bytes = (size_t)c.n_streams * c.c_out * c.max_pull * sizeof(float);
 
@@ -396,28 +511,41 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
       rc = fail(e == cudaErrorMemoryAllocation ? PGX_ERR_NOMEM : PGX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   };
   {
-    int lo = 0, hi = 0;  // the critical path (K1/K2) outranks the background pass when both want an SM
+    int lo = 0, hi = 0;  // the latency-critical kernels (K1, K2) outrank the background pass for SM slots
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     guard(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, hi), "cudaStreamCreate");
-    guard(cudaStreamCreateWithPriority(&b->bg, cudaStreamNonBlocking, lo), "cudaStreamCreate(bg)");
+    guard(cudaStreamCreateWithPriority(&b->s_in, cudaStreamNonBlocking, hi), "cudaStreamCreate(in)");
+    guard(cudaStreamCreateWithPriority(&b->s_bg, cudaStreamNonBlocking, lo), "cudaStreamCreate(bg)");
+    if (const char* e = getenv("PGX_DEBUG_SERIAL")) {  // debugging aid: no overlap, one stream for everything
+      if (e[0] == '1') b->serial = true;
+    }
   }
-  guard(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
-  guard(cudaEventCreateWithFlags(&b->ev_past, cudaEventDisableTiming), "cudaEventCreate");
+  guard(cudaEventCreateWithFlags(&b->ev_call, cudaEventDisableTiming), "cudaEventCreate");
+  for (int i = 0; i < kRing; ++i) {
+    guard(cudaEventCreateWithFlags(&b->ev_k1[i], cudaEventDisableTiming), "cudaEventCreate");
+    guard(cudaEventCreateWithFlags(&b->ev_k2[i], cudaEventDisableTiming), "cudaEventCreate");
+    guard(cudaEventCreateWithFlags(&b->ev_mac[i], cudaEventDisableTiming), "cudaEventCreate");
+  }
+  for (int i = 0; i < pgx_bank::kMapSlots; ++i)
+    guard(cudaEventCreateWithFlags(&b->fmap_ev[i], cudaEventDisableTiming), "cudaEventCreate(fmap)");
   guard(cudaMalloc(&b->hist, b->hist_bytes), "cudaMalloc(hist)");
   guard(cudaMalloc(&b->fdl, b->fdl_bytes), "cudaMalloc(fdl)");
   guard(cudaMalloc(&b->Hd, b->Hd_bytes), "cudaMalloc(Hd)");
-  guard(cudaMalloc(&b->ypast[0], b->yspec_bytes), "cudaMalloc(ypast0)");
-  guard(cudaMalloc(&b->ypast[1], b->yspec_bytes), "cudaMalloc(ypast1)");
-  guard(cudaMalloc(&b->ynow, ynow_bytes), "cudaMalloc(ynow)");
+  guard(cudaMalloc(&b->ypast[0], b->ysum_bytes), "cudaMalloc(ypast0)");
+  guard(cudaMalloc(&b->ypast[1], b->ysum_bytes), "cudaMalloc(ypast1)");
+  guard(cudaMalloc(&b->ypart, b->ypart_bytes), "cudaMalloc(ypart)");
+  guard(cudaMalloc(&b->ynow, b->ynow_bytes), "cudaMalloc(ynow)");
   guard(cudaMalloc(&b->tw, (size_t)2 * B * sizeof(float2)), "cudaMalloc(tw)");
-  guard(cudaMalloc(&b->fmap, (size_t)c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
+  guard(cudaMalloc(&b->fmap_own, (size_t)c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
   guard(cudaMalloc(&b->x_stage, b->xs_bytes), "cudaMalloc(x_stage)");
   guard(cudaMalloc(&b->y_stage, b->ys_bytes), "cudaMalloc(y_stage)");
-  guard(cudaHostAlloc(&b->fmap_pinned, (size_t)c.n_streams * sizeof(int32_t), cudaHostAllocDefault), "cudaHostAlloc");
+  guard(cudaHostAlloc(&b->fmap_pinned, (size_t)pgx_bank::kMapSlots * c.n_streams * sizeof(int32_t), cudaHostAllocDefault),
+        "cudaHostAlloc");
   if (rc != PGX_OK) {
     free_bank(b);
     return rc;
   }
+  b->fmap = b->fmap_own;
 
   // twiddles in double, stored float: tw[k] = exp(-2*pi*i*k/2B)
   {
@@ -428,27 +556,13 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     guard(cudaStreamSynchronize(b->stream), "sync tw");
   }
   for (int s = 0; s < c.n_streams; ++s) b->fmap_pinned[s] = filter_of_stream ? filter_of_stream[s] : (s % c.n_filters);
-  guard(cudaMemcpyAsync(b->fmap, b->fmap_pinned, (size_t)c.n_streams * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream),
+  guard(cudaMemcpyAsync(b->fmap_own, b->fmap_pinned, (size_t)c.n_streams * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream),
         "H2D fmap");
-
-  // filter spectra (replaces the one-time np.fft.rfft(h, n=nfft), convolve_pe.py:236-239)
-  {
-    float* h_dev = nullptr;
-    const size_t hb = h_rows * (size_t)c.filter_len * sizeof(float);
-    guard(cudaMalloc(&h_dev, hb), "cudaMalloc(h)");
-    if (rc == PGX_OK) {
-      guard(cudaMemcpyAsync(h_dev, h, hb, cudaMemcpyHostToDevice, b->stream), "H2D h");
-      pgx::FilterPrepArgs fp{};
-      fp.h = h_dev; fp.Hd = b->Hd; fp.tw = b->tw; fp.n_rows = (int)h_rows; fp.L = c.filter_len; fp.B = B; fp.P = P;
-      pgx::launch_filter_prep(fp, b->stream);
-      b->launches += 1;
-      guard(cudaGetLastError(), "k_filter_prep launch");
-      guard(cudaStreamSynchronize(b->stream), "k_filter_prep");
-    }
-    cudaFree(h_dev);
-  }
+  guard(cudaMemsetAsync(b->Hd, 0, b->Hd_bytes, b->stream), "memset Hd");
   guard(cudaMemsetAsync(b->hist, 0, b->hist_bytes, b->stream), "memset hist");
   guard(cudaMemsetAsync(b->fdl, 0, b->fdl_bytes, b->stream), "memset fdl");
+  // filter spectra (replaces the one-time np.fft.rfft(h, n=nfft), convolve_pe.py:236-239)
+  if (rc == PGX_OK) rc = prep_filters(b, h, 0, (int)h_rows);
   guard(cudaStreamSynchronize(b->stream), "sync init");
   if (rc != PGX_OK) {
     free_bank(b);
@@ -470,7 +584,8 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->filter_len = c.filter_len; info->filter_channels = c.filter_channels; info->n_filters = c.n_filters;
   info->block = b->B; info->partitions = b->P; info->max_pull = c.max_pull; info->device = c.device;
   info->head = b->head; info->fill = b->fill;
-  info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + 2 * b->yspec_bytes + b->xs_bytes + b->ys_bytes);
+  info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + b->ypart_bytes + 2 * b->ysum_bytes +
+                                b->ynow_bytes + b->xs_bytes + b->ys_bytes);
   info->kernel_launches = b->launches;
   info->block_steps = b->steps;
   info->mac_grid = b->plan_conv.grid; info->mac_split = b->plan_conv.n_split;
@@ -481,22 +596,25 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
 int pgx_bank_reset(pgx_bank* b, const int32_t* stream_ids, int32_t k) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
-  quiesce_background(b);
+  quiesce(b);
   if (k <= 0 || !stream_ids) {
     PGX_CUDA(cudaMemsetAsync(b->hist, 0, b->hist_bytes, b->stream));
     PGX_CUDA(cudaMemsetAsync(b->fdl, 0, b->fdl_bytes, b->stream));
     b->head = b->fill = b->half = 0;
-    b->par = 0;
+    b->step = b->block = 0;
+    b->last_k2_of_par[0] = b->last_k2_of_par[1] = -1;
+    PGX_CUDA(cudaStreamSynchronize(b->stream));
     return PGX_OK;
   }
   const size_t hs = (size_t)b->c_x * 2 * b->B * sizeof(float);
-  const size_t fs = (size_t)b->c_x * b->P * b->B * sizeof(float2);
+  const size_t fs = (size_t)b->c_x * b->R * b->B * sizeof(float2);
   for (int i = 0; i < k; ++i) {
     const int s = stream_ids[i];
     if (s < 0 || s >= b->cfg.n_streams) return fail(PGX_ERR_INVALID, "stream id %d outside [0,%d)", s, b->cfg.n_streams);
     PGX_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(b->hist) + s * hs, 0, hs, b->stream));
     PGX_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(b->fdl) + s * fs, 0, fs, b->stream));
   }
+  PGX_CUDA(cudaStreamSynchronize(b->stream));
   return PGX_OK;
 }
 
@@ -506,37 +624,34 @@ int pgx_bank_load_filter(pgx_bank* b, int32_t filter_index, const float* h) {
   if (filter_index < 0 || filter_index >= c.n_filters)
     return fail(PGX_ERR_INVALID, "filter_index %d outside [0,%d)", filter_index, c.n_filters);
   PGX_CUDA(cudaSetDevice(c.device));
-  quiesce_background(b);
-  float* h_dev = nullptr;
-  const size_t hb = (size_t)c.filter_channels * c.filter_len * sizeof(float);
-  PGX_CUDA(cudaMalloc(&h_dev, hb));
-  cudaError_t e = cudaMemcpyAsync(h_dev, h, hb, cudaMemcpyHostToDevice, b->stream);
-  if (e == cudaSuccess) {
-    pgx::FilterPrepArgs fp{};
-    fp.h = h_dev;
-    fp.Hd = b->Hd + (size_t)filter_index * c.filter_channels * 2 * b->P * b->B;
-    fp.tw = b->tw; fp.n_rows = c.filter_channels; fp.L = c.filter_len; fp.B = b->B; fp.P = b->P;
-    pgx::launch_filter_prep(fp, b->stream);
-    b->launches += 1;
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
-  cudaFree(h_dev);
-  if (e != cudaSuccess) return fail(PGX_ERR_CUDA, "pgx_bank_load_filter: %s", cudaGetErrorString(e));
-  return PGX_OK;
+  quiesce(b);
+  return prep_filters(b, h, filter_index * c.filter_channels, c.filter_channels);
 }
 
 int pgx_bank_set_filter_map(pgx_bank* b, const int32_t* filter_of_stream) {
   if (!b || !filter_of_stream) return fail(PGX_ERR_INVALID, "NULL argument");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
-  for (int s = 0; s < b->cfg.n_streams; ++s)
+  const int N = b->cfg.n_streams;
+  for (int s = 0; s < N; ++s)
     if (filter_of_stream[s] < 0 || filter_of_stream[s] >= b->cfg.n_filters)
       return fail(PGX_ERR_INVALID, "filter_of_stream[%d]=%d outside [0,%d)", s, filter_of_stream[s], b->cfg.n_filters);
-  quiesce_background(b);
-  PGX_CUDA(cudaStreamSynchronize(b->stream));  // the pinned staging copy may still be in flight
-  memcpy(b->fmap_pinned, filter_of_stream, (size_t)b->cfg.n_streams * sizeof(int32_t));
-  PGX_CUDA(cudaMemcpyAsync(b->fmap, b->fmap_pinned, (size_t)b->cfg.n_streams * sizeof(int32_t), cudaMemcpyHostToDevice,
-                           b->stream));
+  quiesce(b);
+  // pinned staging ring: a slot is reused only after the copy that last read it has completed
+  const int slot = b->fmap_slot;
+  b->fmap_slot = (slot + 1) % pgx_bank::kMapSlots;
+  PGX_CUDA(cudaEventSynchronize(b->fmap_ev[slot]));
+  int32_t* stage = b->fmap_pinned + (size_t)slot * N;
+  memcpy(stage, filter_of_stream, (size_t)N * sizeof(int32_t));
+  PGX_CUDA(cudaMemcpyAsync(b->fmap_own, stage, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+  PGX_CUDA(cudaEventRecord(b->fmap_ev[slot], b->stream));
+  b->fmap = b->fmap_own;
+  return PGX_OK;
+}
+
+int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
+  if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  b->fmap = fmap_dev ? const_cast<int32_t*>(fmap_dev) : b->fmap_own;
+  b->past_block = -1;  // a cached past sum was computed with the previous map
   return PGX_OK;
 }
 
@@ -553,7 +668,7 @@ static int process_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pg
   const size_t xb = (size_t)c.n_streams * c.c_in * n * sizeof(float);
   const size_t yb = (size_t)(mix ? 1 : c.n_streams) * c.c_out * n * sizeof(float);
   PGX_CUDA(cudaMemcpyAsync(b->x_stage, x, xb, cudaMemcpyHostToDevice, b->stream));
-  rc = run_pull(b, b->x_stage, xl, b->y_stage, yd, n, mix, b->stream);
+  rc = run_pull(b, b->x_stage, xl, b->y_stage, yd, n, mix, false, b->stream);
   if (rc != PGX_OK) return rc;
   PGX_CUDA(cudaMemcpyAsync(y, b->y_stage, yb, cudaMemcpyDeviceToHost, b->stream));
   PGX_CUDA(cudaStreamSynchronize(b->stream));
@@ -569,7 +684,8 @@ int pgx_bank_process_mix(pgx_bank* b, const float* x, pgx_layout xl, float* y, p
 }
 
 int pgx_bank_process_device(pgx_bank* b, const float* x_dev, pgx_layout xl, float* y_dev, pgx_layout yl, int32_t n,
-                            int32_t mix, void* cuda_stream) {
+                            int32_t flags, void* cuda_stream) {
+  const bool mix = (flags & PGX_PULL_MIX) != 0;
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   if (!x_dev || !y_dev) return fail(PGX_ERR_INVALID, "x / y must not be NULL");
   if (n < 1) return fail(PGX_ERR_INVALID, "pull of %d samples", n);
@@ -577,14 +693,15 @@ int pgx_bank_process_device(pgx_bank* b, const float* x_dev, pgx_layout xl, floa
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->stream;
   pgx_layout yd = yl;
   if (mix) yd.stream = 0;
-  return run_pull(b, x_dev, xl, y_dev, yd, n, mix != 0, st);
+  return run_pull(b, x_dev, xl, y_dev, yd, n, mix, (flags & PGX_PULL_INPUT_RESIDENT) != 0, st);
 }
 
 int pgx_bank_synchronize(pgx_bank* b) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   PGX_CUDA(cudaStreamSynchronize(b->stream));
-  PGX_CUDA(cudaStreamSynchronize(b->bg));
+  PGX_CUDA(cudaStreamSynchronize(b->s_in));
+  PGX_CUDA(cudaStreamSynchronize(b->s_bg));
   return PGX_OK;
 }
 
