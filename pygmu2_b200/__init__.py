@@ -13,20 +13,21 @@ from .core import (ErrorMode, ExtendMode, Extent, ProcessingElement, Snippet, So
                    diagnostics_report, enable_diagnostics, get_error_mode, get_sample_rate,
                    handle_error, set_error_mode, set_sample_rate)
 from .sources import ArrayPE, CachePE, ConstantPE, CropPE, DelayPE, GainPE, SinePE
-from .renderer import BankRenderer, NullRenderer, Renderer
+from .renderer import AudioRenderer, BankRenderer, NullRenderer, Renderer
 from .bank import ConvolveBank, choose_block
 from .hrtf_bank import HrtfMixBank
 from .convolve_pe import ConvolvePE
 from .spatial_pe import (SpatialAdapter, SpatialConstantPower, SpatialHRTF, SpatialLinear,
                          SpatialMethod, SpatialPE)
 from .mix_pe import MixPE, device_mix_sum
+from .reverb_pe import ReverbPE
 
 __all__ = [
     "ErrorMode", "ExtendMode", "Extent", "ProcessingElement", "Snippet", "SourcePE",
     "set_sample_rate", "get_sample_rate", "set_error_mode", "get_error_mode", "handle_error",
     "enable_diagnostics", "diagnostics_report",
     "ArrayPE", "CachePE", "ConstantPE", "CropPE", "DelayPE", "GainPE", "SinePE",
-    "Renderer", "NullRenderer", "BankRenderer",
+    "Renderer", "NullRenderer", "AudioRenderer", "BankRenderer", "ReverbPE",
     "ConvolveBank", "HrtfMixBank", "choose_block",
     "ConvolvePE", "SpatialPE", "SpatialMethod", "SpatialAdapter", "SpatialLinear",
     "SpatialConstantPower", "SpatialHRTF", "MixPE", "device_mix_sum",

@@ -117,6 +117,75 @@ class NullRenderer(Renderer):
         pass
 
 
+class AudioRenderer(Renderer):
+    """Blocking playback pull loop (reference audio_renderer.py:91-116,118-181).
+
+    The device PEs are pulled exactly as the reference pulls them -- ``render`` writes one Snippet,
+    ``play_extent`` walks the source extent in chunks of ``blocksize * 16`` -- and each float32
+    ``(frames, channels)`` array is handed to an output stream with ``start() / write(data) / stop() /
+    close()``.  By default that stream is ``sounddevice.OutputStream`` (PortAudio), as in the reference;
+    ``stream_factory(samplerate, channels, blocksize)`` substitutes any sink (a file writer, a test
+    double).  PortAudio itself is host I/O and out of scope: without sounddevice and without a factory,
+    output raises.
+    """
+
+    def __init__(self, sample_rate: int = 44100, device=None, blocksize: int = 1024, latency="low",
+                 stream_factory=None):
+        super().__init__(sample_rate=sample_rate)
+        self._device, self._blocksize, self._latency = device, int(blocksize), latency
+        self._factory = stream_factory
+        self._blocking_stream = None
+
+    device = property(lambda self: self._device)
+    blocksize = property(lambda self: self._blocksize)
+
+    def _open(self, channels: int):
+        if self._factory is not None:
+            return self._factory(self._sample_rate, channels, self._blocksize)
+        try:
+            import sounddevice as sd
+        except Exception as exc:  # pragma: no cover - depends on the host
+            raise RuntimeError("AudioRenderer needs the sounddevice package (PortAudio) or a stream_factory") from exc
+        return sd.OutputStream(samplerate=self._sample_rate, channels=channels, dtype="float32",
+                               device=self._device, blocksize=self._blocksize, latency=self._latency)
+
+    def _output(self, snippet: Snippet) -> None:
+        if self._blocking_stream is None:  # one long-lived stream, opened on the first write
+            self._blocking_stream = self._open(snippet.channels)
+            self._blocking_stream.start()
+        self._blocking_stream.write(snippet.data)
+
+    def play_range(self, start: int, duration: int) -> None:
+        self.render(start, duration)
+
+    def play_extent(self, chunk_size: int | None = None) -> None:
+        if self._source is None:
+            handle_error("No source set. Call set_source() first.", fatal=True)
+        ext = self._source.extent()
+        if ext.start is None or ext.end is None:
+            handle_error("Cannot play_extent() on infinite source. "
+                         "Use CropPE to limit the extent, or use play_range().", fatal=True)
+        chunk = int(chunk_size) if chunk_size else self._blocksize * 16
+        stream = self._open(self._channel_count or 1)
+        stream.start()
+        try:
+            pos = ext.start
+            while pos < ext.end:
+                n = min(chunk, ext.end - pos)
+                stream.write(self._source.render(pos, n).data)
+                pos += n
+        finally:
+            stream.stop()
+            stream.close()
+
+    def stop(self) -> None:
+        if self._blocking_stream is not None:
+            self._blocking_stream.stop()
+            self._blocking_stream.close()
+            self._blocking_stream = None
+        super().stop()
+
+
 class BankRenderer:
     """Batched block-pull loop over a device bank.
 

@@ -361,3 +361,140 @@ def test_full_size_c5_impulse_response():
     y = _pull_pe(pe, (64,) * 40)[:, 0]   # 40 low-latency pulls through P = 6891 partitions
     assert rel_err(y, ir[:y.shape[0]]) <= TOL
     del L
+
+
+# ---------------------------------------------------------------------------
+# callers of the path: ReverbPE, AudioRenderer pull loop, BankRenderer
+class _CountingPE(pg.ProcessingElement):
+    def __init__(self, source):
+        self._source, self.render_calls = source, 0
+
+    def inputs(self):
+        return [self._source]
+
+    def channel_count(self):
+        return self._source.channel_count()
+
+    def _compute_extent(self):
+        return self._source.extent()
+
+    def _render(self, start, duration):
+        self.render_calls += 1
+        return self._source.render(start, duration)
+
+
+def test_reverb_uses_single_source_pull():
+    # reference tests/test_convolve_pe.py:210-221
+    pg.set_sample_rate(10_000)
+    src = _CountingPE(pg.ArrayPE([1.0, 2.0, 3.0, 4.0]))
+    pe = pg.ReverbPE(src, pg.ArrayPE([1.0]), mix=0.5, normalize_ir=False)
+    pg.NullRenderer(sample_rate=10_000).set_source(pe)
+    _ = pe.render(0, 4)
+    assert src.render_calls == 1
+
+
+def test_reverb_wet_dry_matches_oracle():
+    rng = np.random.default_rng(31)
+    x = rng.uniform(-1, 1, (3000, 2)).astype(np.float32)
+    ir = (rng.standard_normal(2500) * np.exp(-np.arange(2500) / 400.0)).astype(np.float32)
+    pe = pg.ReverbPE(pg.ArrayPE(x), pg.ArrayPE(ir), mix=0.3)
+    y = _pull_pe(pe, (512,) * 5 + (440,))
+    wet = orc.OracleConvolve(ir, 2).render(x)
+    e = orc.ir_energy_norm(ir)
+    ref = orc.oracle_mix([x * np.float32(0.7), wet * np.float32(0.3 / e)])
+    assert pe.ir_energy == pytest.approx(e)
+    assert rel_err(y, ref) <= TOL
+
+
+class _Sink:
+    def __init__(self, sr, ch, bs):
+        self.meta, self.blocks, self.state = (sr, ch, bs), [], []
+
+    def start(self):
+        self.state.append("start")
+
+    def write(self, data):
+        assert data.dtype == np.float32 and data.ndim == 2
+        self.blocks.append(data.copy())
+
+    def stop(self):
+        self.state.append("stop")
+
+    def close(self):
+        self.state.append("close")
+
+
+def test_audio_renderer_play_extent_pulls_in_chunks():
+    rng = np.random.default_rng(32)
+    x = rng.uniform(-1, 1, 5000).astype(np.float32)
+    h = (rng.standard_normal(300) / 17).astype(np.float32)
+    sinks = []
+
+    def factory(sr, ch, bs):
+        sinks.append(_Sink(sr, ch, bs))
+        return sinks[-1]
+
+    r = pg.AudioRenderer(sample_rate=44_100, blocksize=64, stream_factory=factory)
+    r.set_source(pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h)))
+    r.start()
+    r.play_extent()                       # chunks of blocksize*16 = 1024 over extent [0, 5299)
+    r.stop()
+    got = np.concatenate(sinks[0].blocks)[:, 0]
+    assert [b.shape[0] for b in sinks[0].blocks] == [1024] * 5 + [179]
+    assert sinks[0].state == ["start", "stop", "close"] and sinks[0].meta == (44_100, 1, 64)
+    ref = orc.OracleConvolve(h, 1).render(np.concatenate([x, np.zeros(299, np.float32)]))[:, 0]
+    assert rel_err(got, ref) <= TOL
+
+
+def test_bank_renderer_lockstep_pull():
+    rng = np.random.default_rng(33)
+    N, L = 5, 1200
+    xs = [rng.uniform(-1, 1, 2048).astype(np.float32) for _ in range(N)]
+    hs = (rng.standard_normal((N, L)) / 30).astype(np.float32)
+    bank = pg.ConvolveBank(hs, N, 1, pull_hint=256)
+    bank.attach_sources([pg.ArrayPE(x) for x in xs])
+    outs = []
+    with pg.BankRenderer(bank, sink=outs.append) as r:
+        r.start()
+        for p in range(0, 2048, 256):
+            r.render(p, 256)
+    y = np.concatenate(outs, axis=2)
+    for s in range(N):
+        ref = orc.OracleConvolve(hs[s], 1).render(xs[s])[:, 0]
+        assert rel_err(y[s, 0], ref) <= TOL
+
+
+# ---------------------------------------------------------------------------
+# device-resident queue: pulls enqueued back to back with no host synchronisation, ingest of pull i+1
+# allowed to overtake the output stage of pull i (PGX_PULL_INPUT_RESIDENT) -- exercises every
+# cross-stream hazard of the three-stream schedule
+@pytest.mark.parametrize("mix", [False, True])
+@pytest.mark.parametrize("L,B", [(3000, 256), (700, 64), (100, 128)])
+def test_device_queue_back_to_back(mix, L, B):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(77 + L)
+    N, C = 3, 2
+    h = (rng.standard_normal((N, L, C)) / np.sqrt(L)).astype(np.float32)
+    pulls = [B] * 9 + [1, B - 1, 17, B, 2 * B + 5, B // 2, B // 2, B] + [B] * 9
+    total = sum(pulls)
+    x = rng.uniform(-1, 1, (N, C, total)).astype(np.float32)
+    bank = pg.ConvolveBank(h, N, C, block=B, max_pull=4 * B)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    xs, ys, pos = [], [], 0
+    for d in pulls:                      # every pull has its own resident input / output buffer
+        xs.append(torch.from_numpy(np.ascontiguousarray(x[:, :, pos:pos + d])).to(dev))
+        ys.append(torch.empty((C, d) if mix else (N, C, d), dtype=torch.float32, device=dev))
+        pos += d
+    torch.cuda.synchronize(dev)
+    for rep in range(3):                 # repeat the whole queue: different interleavings, same answer
+        bank.reset()
+        for xt, yt, d in zip(xs, ys, pulls):
+            bank.process_device(xt.data_ptr(), yt.data_ptr(), d, mix=mix, cuda_stream=st.cuda_stream,
+                                input_resident=True)
+        st.synchronize()
+        y = np.concatenate([t.cpu().numpy() for t in ys], axis=-1)
+        per = np.stack([orc.OracleConvolve(h[s], C).render(x[s].T).T for s in range(N)])
+        ref = per.astype(np.float64).sum(axis=0) if mix else per
+        assert rel_err(y, ref) <= TOL, f"rep {rep}"
+    bank.synchronize()
