@@ -14,6 +14,9 @@
 // streams share one filter (ST > 1) a CTA covers ST streams so each filter row is fetched once per
 // ST delay-line rows.  The work list (out tile x bin tile x term split) is a flat 1-D grid whose
 // size the host picks as a near-integer number of full waves (see mac_plan()).
+#include <cstdlib>
+#include <cstring>
+
 #include "kernels.h"
 
 namespace pgx {
@@ -161,14 +164,25 @@ static int mac_occupancy() {
   return nb > 0 ? nb : 1;
 }
 
-// Pick the stream tile and the term split so the flat grid is a near-integer number of full waves.
+// Which accumulate kernel: PGX_MAC=ldg|tma overrides the default.
+static bool want_tma(int W4) {
+  const char* e = getenv("PGX_MAC");
+  if (e && !strcmp(e, "ldg")) return false;
+  if (e && !strcmp(e, "tma")) return tma_supported(W4);
+  return false;  // default (measured A/B)
+}
+
+// Pick the kernel variant, the stream tile and the term split so that the work list is a near-integer
+// number of full waves over the SMs.
 MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count) {
   MacPlan p{};
-  const int lanes = W4 < kMacThreads ? W4 : kMacThreads;
-  const int groups = kMacThreads / lanes, ktiles = W4 / lanes;
   p.st = (!mix && shared_filter && N >= 4) ? 4 : 1;
+  p.variant = want_tma(W4) ? 1 : 0;
+  const int lanes = p.variant ? 256 : (W4 < kMacThreads ? W4 : kMacThreads);
+  const int groups = p.variant ? 1 : kMacThreads / lanes, ktiles = W4 / lanes;
   int occ;
-  if (mix) occ = mac_occupancy<true, 1, 8>();
+  if (p.variant) occ = tma_occupancy_of(mix, p.st);
+  else if (mix) occ = mac_occupancy<true, 1, 8>();
   else if (p.st == 4) occ = mac_occupancy<false, 4, 4>();
   else occ = mac_occupancy<false, 1, 8>();
   p.n_otiles = mix ? c_out : ((N + p.st - 1) / p.st) * c_out;
@@ -178,14 +192,15 @@ MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_fi
   int max_split = n_terms / min_terms;
   if (max_split < 1) max_split = 1;
   if (max_split > 1024) max_split = 1024;
-  // cost model: waves x (terms per CTA + fixed per-CTA overhead expressed in row-terms)
+  // cost model: waves x (terms per CTA + fixed per-item overhead expressed in row-terms)
+  const int overhead = p.variant ? 2 : 6 * groups;
   double best = 1e300;
   int best_s = 1;
   for (int s = 1; s <= max_split; ++s) {
     const long items = base * s;
     const long waves = (items + resident - 1) / resident;
     const int tps = (n_terms + s - 1) / s;
-    const double cost = (double)waves * (double)(tps + 6 * groups);
+    const double cost = (double)waves * (double)(tps + overhead);
     if (cost < best * 0.995) {
       best = cost;
       best_s = s;
@@ -196,10 +211,15 @@ MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_fi
   p.n_split = (n_terms + p.terms_per_split - 1) / p.terms_per_split;
   p.grid = (int)(base * p.n_split);
   p.occupancy = occ;
+  p.persistent_ctas = (int)resident;
   return p;
 }
 
 void launch_fdl_mac(const MacArgs& a, cudaStream_t st) {
+  if (a.variant == 1) {
+    launch_fdl_mac_tma(a, a.persistent_ctas, st);
+    return;
+  }
   const int lanes = a.W4 < kMacThreads ? a.W4 : kMacThreads;
   const int grid = a.n_otiles * (a.W4 / lanes) * a.n_split;
   if (a.mix)

@@ -45,10 +45,16 @@ struct MacArgs {
   // slot `head` and the spare slot head+1 (being written by the next block's K1).
   // n_terms = Pt (conv) or N*Pt (mix).
   int32_t Pt, off, skip, nskip, jfix;
+  int32_t variant;       // 0 = LDG kernel (k_mac.cu), 1 = bulk-async staged kernel (k_mac_tma.cu)
+  int32_t persistent_ctas;
 };
 struct MacPlan {
-  int32_t st, n_otiles, n_split, terms_per_split, grid, occupancy;
+  int32_t st, n_otiles, n_split, terms_per_split, grid, occupancy, variant, persistent_ctas;
 };
+// bulk-async (TMA) staged variant, k_mac_tma.cu
+bool tma_supported(int W4);
+int tma_occupancy_of(bool mix, int st);
+void launch_fdl_mac_tma(const MacArgs& a, int persistent_ctas, cudaStream_t st);
 // Fold split partial sums: out[o][k] = sum_sp in[sp][o][k] (rows of W4 float4), deterministic order.
 void launch_reduce_partials(const float4* in, float4* out, int n_split, int n_out, int W4, cudaStream_t st);
 MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count);

@@ -218,6 +218,7 @@ void issue_past(pgx_bank* b, bool mix, int64_t blk, int head, cudaEvent_t after)
   else                 { m.off = 1; m.skip = b->R; m.nskip = 0; }  // open slot R-1, spare slot 0
   m.n_terms = mix ? b->cfg.n_streams * m.Pt : m.Pt;
   m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
+  m.variant = pl.variant; m.persistent_ctas = pl.persistent_ctas;
   {
     ProfScope ps(b, b->s_bg, 1);
     pgx::launch_fdl_mac(m, b->s_bg);
@@ -304,6 +305,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     m.n_terms = c.n_streams;
     m.n_split = b->plan_now.n_split; m.terms_per_split = b->plan_now.terms_per_split;
     m.n_otiles = b->plan_now.n_otiles; m.st = b->plan_now.st;
+    m.variant = b->plan_now.variant; m.persistent_ctas = b->plan_now.persistent_ctas;
     {
       ProfScope ps(b, crit, 1);
       pgx::launch_fdl_mac(m, crit);
