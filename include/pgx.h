@@ -148,11 +148,25 @@ PGX_API int pgx_bank_process(pgx_bank* bank, const float* x, pgx_layout x_layout
 PGX_API int pgx_bank_process_mix(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y_mix,
                          pgx_layout y_layout, int32_t n);
 
-/* Device-resident variant: x / y are device pointers; work is enqueued and NOT synchronised; y is
- * complete when cuda_stream (NULL = the bank's stream) drains.  flags: PGX_PULL_*. */
+/* flags of a pull */
 #define PGX_PULL_MIX 1u            /* fused MixPE sum over streams, as pgx_bank_process_mix */
 #define PGX_PULL_INPUT_RESIDENT 2u /* x is already complete in memory (not produced by work still queued on
                                       cuda_stream): the ingest of this pull may overlap earlier pulls' output stage */
+
+/*
+ * Pipelined host-buffer pulls (the batched renderer loop, renderer.py:297-327, with more than one pull in
+ * flight): submit stages x (H2D on a copy stream), enqueues the pull and the D2H of y, and returns a ticket
+ * without waiting; pgx_bank_wait(ticket) returns when that pull's y is complete in host memory.  Pulls
+ * execute in submission order.  x and y must stay valid (and should be pinned, pgx_host_alloc) until the
+ * wait returns; at most 3 pulls are in flight - a further submit first waits for the oldest.
+ * flags: PGX_PULL_MIX.  pgx_bank_process[_mix] = submit + wait.
+ */
+PGX_API int pgx_bank_submit(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y, pgx_layout y_layout,
+                    int32_t n, int32_t flags, int64_t* ticket);
+PGX_API int pgx_bank_wait(pgx_bank* bank, int64_t ticket);
+
+/* Device-resident variant: x / y are device pointers; work is enqueued and NOT synchronised; y is
+ * complete when cuda_stream (NULL = the bank's stream) drains.  flags: PGX_PULL_*. */
 PGX_API int pgx_bank_process_device(pgx_bank* bank, const float* x_dev, pgx_layout x_layout, float* y_dev,
                             pgx_layout y_layout, int32_t n, int32_t flags, void* cuda_stream);
 PGX_API int pgx_bank_synchronize(pgx_bank* bank);

@@ -59,6 +59,9 @@ PROTOTYPES = {
     "pgx_bank_use_filter_map_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgx_bank_process": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32]),
     "pgx_bank_process_mix": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32]),
+    "pgx_bank_submit": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32, C.c_int32,
+                                  C.POINTER(C.c_int64)]),
+    "pgx_bank_wait": (C.c_int, [C.c_void_p, C.c_int64]),
     "pgx_bank_process_device": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32,
                                           C.c_int32, C.c_void_p]),
     "pgx_bank_synchronize": (C.c_int, [C.c_void_p]),

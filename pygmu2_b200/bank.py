@@ -189,6 +189,32 @@ class ConvolveBank:
                                          _lib.f32_ptr(yc), Layout(0, 1, self.c_out), d))
         return y
 
+    # -- pipelined host-buffer pulls (several in flight; copies overlap the kernels) ------------
+    def submit(self, x: np.ndarray, out: np.ndarray, *, mix: bool = False) -> int:
+        """Enqueue one pull: x (N, C_in, n) -> out (N, C_out, n), or (C_out, n) when ``mix``.  Returns a
+        ticket for ``wait``.  x and out must be C-contiguous float32 (pinned for real overlap: ``PinnedArray``)
+        and must not be touched until the wait returns; at most 3 pulls are in flight."""
+        if x.dtype != np.float32 or not x.flags.c_contiguous or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("submit needs C-contiguous float32 arrays")
+        if x.ndim != 3 or x.shape[0] != self.n_streams or x.shape[1] != self.c_in:
+            raise ValueError(f"x must be ({self.n_streams}, {self.c_in}, n), got {x.shape}")
+        n = x.shape[2]
+        want = (self.c_out, n) if mix else (self.n_streams, self.c_out, n)
+        if out.shape != want:
+            raise ValueError(f"out must be {want}, got {out.shape}")
+        tk = C.c_int64(-1)
+        check(lib().pgx_bank_submit(self._h, _lib.f32_ptr(x), Layout(self.c_in * n, n, 1), _lib.f32_ptr(out),
+                                    Layout(0 if mix else self.c_out * n, n, 1), n, 1 if mix else 0, C.byref(tk)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[tk.value] = (x, out)  # keep the buffers alive until waited
+        return int(tk.value)
+
+    def wait(self, ticket: int) -> None:
+        check(lib().pgx_bank_wait(self._h, int(ticket)))
+        infl = getattr(self, "_inflight", {})
+        for t in [t for t in infl if t <= ticket]:
+            del infl[t]
+
     # -- device-resident pulls (pointers from torch / cuda-python; not synchronised) ------------
     def process_device(self, x_ptr: int, y_ptr: int, n: int, *, mix: bool = False, cuda_stream: int = 0,
                        input_resident: bool = False, x_layout: Layout | None = None,

@@ -99,13 +99,26 @@ struct pgx_bank {
   float2* ynow = nullptr;
   float2* tw = nullptr;
   int32_t* fmap = nullptr;         // map in use (own buffer or the caller's device array)
-  int32_t* fmap_own = nullptr;
+  // the bank's own maps: a ring of kMapSlots device rows + pinned staging rows, so that re-selecting the
+  // filters between pulls (a moving HRTF source) neither drains the queue nor races with pulls in flight
   static constexpr int kMapSlots = 8;
-  int32_t* fmap_pinned = nullptr;  // kMapSlots x [N] pinned staging ring
-  cudaEvent_t fmap_ev[kMapSlots] = {};
-  int fmap_slot = 0;
-  float* x_stage = nullptr;
-  float* y_stage = nullptr;
+  int32_t* fmap_own = nullptr;     // kMapSlots x [N] device
+  int32_t* fmap_pinned = nullptr;  // kMapSlots x [N] pinned staging
+  cudaEvent_t fmap_ev[kMapSlots] = {};        // H2D of the row done (copy-in stream)
+  cudaEvent_t fmap_ret_crit[kMapSlots] = {};  // row retired: every reader was enqueued before these
+  cudaEvent_t fmap_ret_bg[kMapSlots] = {};
+  int fmap_cur = 0;
+  int64_t fmap_sets = 0;
+  bool fmap_pending = false;       // the next pull must order itself after fmap_ev[fmap_cur]
+  cudaStream_t last_crit = nullptr;
+  // host-buffer pulls: a ring of staging slots so that the H2D of pull i+1 and the D2H of pull i-1 overlap
+  // the kernels of pull i (copy engines on their own streams)
+  static constexpr int kSlots = 3;
+  float* x_stage[kSlots] = {};
+  float* y_stage[kSlots] = {};
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_y[kSlots] = {}, ev_done[kSlots] = {};
+  int64_t next_ticket = 0;
   size_t hist_bytes = 0, fdl_bytes = 0, Hd_bytes = 0, ypart_bytes = 0, ysum_bytes = 0, ynow_bytes = 0, xs_bytes = 0,
          ys_bytes = 0;
   // ring / schedule state
@@ -133,7 +146,7 @@ namespace {
 void free_bank(pgx_bank* b) {
   if (!b) return;
   cudaSetDevice(b->cfg.device);
-  for (cudaStream_t s : {b->stream, b->s_in, b->s_bg})
+  for (cudaStream_t s : {b->s_h2d, b->stream, b->s_in, b->s_bg, b->s_d2h})
     if (s) cudaStreamSynchronize(s);
   cudaFree(b->hist);
   cudaFree(b->fdl);
@@ -144,17 +157,22 @@ void free_bank(pgx_bank* b) {
   cudaFree(b->ynow);
   cudaFree(b->tw);
   cudaFree(b->fmap_own);
-  cudaFree(b->x_stage);
-  cudaFree(b->y_stage);
+  for (int i = 0; i < pgx_bank::kSlots; ++i) {
+    cudaFree(b->x_stage[i]);
+    cudaFree(b->y_stage[i]);
+    for (cudaEvent_t e : {b->ev_h2d[i], b->ev_y[i], b->ev_done[i]})
+      if (e) cudaEventDestroy(e);
+  }
   if (b->fmap_pinned) cudaFreeHost(b->fmap_pinned);
   for (cudaEvent_t e : b->prof_pool) cudaEventDestroy(e);
   for (int i = 0; i < kRing; ++i)
     for (cudaEvent_t e : {b->ev_k1[i], b->ev_k2[i], b->ev_mac[i]})
       if (e) cudaEventDestroy(e);
   for (int i = 0; i < pgx_bank::kMapSlots; ++i)
-    if (b->fmap_ev[i]) cudaEventDestroy(b->fmap_ev[i]);
+    for (cudaEvent_t e : {b->fmap_ev[i], b->fmap_ret_crit[i], b->fmap_ret_bg[i]})
+      if (e) cudaEventDestroy(e);
   if (b->ev_call) cudaEventDestroy(b->ev_call);
-  for (cudaStream_t s : {b->stream, b->s_in, b->s_bg})
+  for (cudaStream_t s : {b->stream, b->s_in, b->s_bg, b->s_h2d, b->s_d2h})
     if (s) cudaStreamDestroy(s);
   delete b;
 }
@@ -353,6 +371,12 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     cudaEventRecord(b->ev_call, crit);
     cudaStreamWaitEvent(b->s_in, b->ev_call, 0);
   }
+  b->last_crit = crit;
+  if (b->fmap_pending) {  // a re-selected filter map is still being copied in: its readers wait for it
+    cudaStreamWaitEvent(crit, b->fmap_ev[b->fmap_cur], 0);
+    cudaStreamWaitEvent(b->s_bg, b->fmap_ev[b->fmap_cur], 0);
+    b->fmap_pending = false;
+  }
   int pos = 0;
   while (pos < n) {
     const int take = (b->B - b->fill < n - pos) ? (b->B - b->fill) : (n - pos);
@@ -360,6 +384,7 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     if (rc != PGX_OK) return rc;
     pos += take;
   }
+  if (crit != b->stream) cudaEventRecord(b->fmap_ret_crit[b->fmap_cur], crit);
   PGX_CUDA(cudaGetLastError());
   return PGX_OK;
 }
@@ -367,9 +392,11 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
 // State changes outside run_pull (reset, filter reload / re-selection) are rare and synchronous: drain the
 // bank's streams (a caller-owned critical stream is the caller's to drain) and drop the cached past sum.
 void quiesce(pgx_bank* b) {
+  cudaStreamSynchronize(b->s_h2d);
   cudaStreamSynchronize(b->s_in);
   cudaStreamSynchronize(b->s_bg);
   cudaStreamSynchronize(b->stream);
+  cudaStreamSynchronize(b->s_d2h);
   b->past_block = -1;
   b->past_mode = -1;
 }
@@ -518,6 +545,8 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     guard(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, hi), "cudaStreamCreate");
     guard(cudaStreamCreateWithPriority(&b->s_in, cudaStreamNonBlocking, hi), "cudaStreamCreate(in)");
     guard(cudaStreamCreateWithPriority(&b->s_bg, cudaStreamNonBlocking, lo), "cudaStreamCreate(bg)");
+    guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
+    guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");
     if (const char* e = getenv("PGX_DEBUG_SERIAL")) {  // debugging aid: no overlap, one stream for everything
       if (e[0] == '1') b->serial = true;
     }
@@ -529,7 +558,11 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     guard(cudaEventCreateWithFlags(&b->ev_mac[i], cudaEventDisableTiming), "cudaEventCreate");
   }
   for (int i = 0; i < pgx_bank::kMapSlots; ++i)
+  {
     guard(cudaEventCreateWithFlags(&b->fmap_ev[i], cudaEventDisableTiming), "cudaEventCreate(fmap)");
+    guard(cudaEventCreateWithFlags(&b->fmap_ret_crit[i], cudaEventDisableTiming), "cudaEventCreate(fmap)");
+    guard(cudaEventCreateWithFlags(&b->fmap_ret_bg[i], cudaEventDisableTiming), "cudaEventCreate(fmap)");
+  }
   guard(cudaMalloc(&b->hist, b->hist_bytes), "cudaMalloc(hist)");
   guard(cudaMalloc(&b->fdl, b->fdl_bytes), "cudaMalloc(fdl)");
   guard(cudaMalloc(&b->Hd, b->Hd_bytes), "cudaMalloc(Hd)");
@@ -538,9 +571,14 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
   guard(cudaMalloc(&b->ypart, b->ypart_bytes), "cudaMalloc(ypart)");
   guard(cudaMalloc(&b->ynow, b->ynow_bytes), "cudaMalloc(ynow)");
   guard(cudaMalloc(&b->tw, (size_t)2 * B * sizeof(float2)), "cudaMalloc(tw)");
-  guard(cudaMalloc(&b->fmap_own, (size_t)c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
-  guard(cudaMalloc(&b->x_stage, b->xs_bytes), "cudaMalloc(x_stage)");
-  guard(cudaMalloc(&b->y_stage, b->ys_bytes), "cudaMalloc(y_stage)");
+  guard(cudaMalloc(&b->fmap_own, (size_t)pgx_bank::kMapSlots * c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
+  for (int i = 0; i < pgx_bank::kSlots; ++i) {
+    guard(cudaMalloc(&b->x_stage[i], b->xs_bytes), "cudaMalloc(x_stage)");
+    guard(cudaMalloc(&b->y_stage[i], b->ys_bytes), "cudaMalloc(y_stage)");
+    guard(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming), "cudaEventCreate");
+    guard(cudaEventCreateWithFlags(&b->ev_y[i], cudaEventDisableTiming), "cudaEventCreate");
+    guard(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming), "cudaEventCreate");
+  }
   guard(cudaHostAlloc(&b->fmap_pinned, (size_t)pgx_bank::kMapSlots * c.n_streams * sizeof(int32_t), cudaHostAllocDefault),
         "cudaHostAlloc");
   if (rc != PGX_OK) {
@@ -587,7 +625,7 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->block = b->B; info->partitions = b->P; info->max_pull = c.max_pull; info->device = c.device;
   info->head = b->head; info->fill = b->fill;
   info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + b->ypart_bytes + 2 * b->ysum_bytes +
-                                b->ynow_bytes + b->xs_bytes + b->ys_bytes);
+                                b->ynow_bytes + pgx_bank::kSlots * (b->xs_bytes + b->ys_bytes));
   info->kernel_launches = b->launches;
   info->block_steps = b->steps;
   info->mac_grid = b->plan_conv.grid; info->mac_split = b->plan_conv.n_split;
@@ -637,27 +675,40 @@ int pgx_bank_set_filter_map(pgx_bank* b, const int32_t* filter_of_stream) {
   for (int s = 0; s < N; ++s)
     if (filter_of_stream[s] < 0 || filter_of_stream[s] >= b->cfg.n_filters)
       return fail(PGX_ERR_INVALID, "filter_of_stream[%d]=%d outside [0,%d)", s, filter_of_stream[s], b->cfg.n_filters);
-  quiesce(b);
-  // pinned staging ring: a slot is reused only after the copy that last read it has completed
-  const int slot = b->fmap_slot;
-  b->fmap_slot = (slot + 1) % pgx_bank::kMapSlots;
-  PGX_CUDA(cudaEventSynchronize(b->fmap_ev[slot]));
-  int32_t* stage = b->fmap_pinned + (size_t)slot * N;
+  // retire the row in use: everything that reads it has been enqueued on these two streams by now
+  const int cur = b->fmap_cur, nxt = (cur + 1) % pgx_bank::kMapSlots;
+  // (a caller-owned critical stream may be gone by now: run_pull recorded the event on it after each pull)
+  if (!b->last_crit || b->last_crit == b->stream) PGX_CUDA(cudaEventRecord(b->fmap_ret_crit[cur], b->stream));
+  PGX_CUDA(cudaEventRecord(b->fmap_ret_bg[cur], b->s_bg));
+  if (b->fmap_sets + 1 >= pgx_bank::kMapSlots) {  // row nxt was used before: its readers and its copy are done?
+    PGX_CUDA(cudaEventSynchronize(b->fmap_ret_crit[nxt]));
+    PGX_CUDA(cudaEventSynchronize(b->fmap_ret_bg[nxt]));
+    PGX_CUDA(cudaEventSynchronize(b->fmap_ev[nxt]));
+  }
+  int32_t* stage = b->fmap_pinned + (size_t)nxt * N;
   memcpy(stage, filter_of_stream, (size_t)N * sizeof(int32_t));
-  PGX_CUDA(cudaMemcpyAsync(b->fmap_own, stage, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
-  PGX_CUDA(cudaEventRecord(b->fmap_ev[slot], b->stream));
-  b->fmap = b->fmap_own;
+  PGX_CUDA(cudaMemcpyAsync(b->fmap_own + (size_t)nxt * N, stage, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice,
+                           b->s_h2d));
+  PGX_CUDA(cudaEventRecord(b->fmap_ev[nxt], b->s_h2d));
+  b->fmap_cur = nxt;
+  b->fmap_sets += 1;
+  b->fmap = b->fmap_own + (size_t)nxt * N;
+  b->fmap_pending = true;
+  b->past_block = -1;  // a cached past sum was computed with the previous map
   return PGX_OK;
 }
 
 int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
-  b->fmap = fmap_dev ? const_cast<int32_t*>(fmap_dev) : b->fmap_own;
+  b->fmap = fmap_dev ? const_cast<int32_t*>(fmap_dev) : b->fmap_own + (size_t)b->fmap_cur * b->cfg.n_streams;
   b->past_block = -1;  // a cached past sum was computed with the previous map
   return PGX_OK;
 }
 
-static int process_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, bool mix) {
+// Host-buffer pull, asynchronous: stage x into the next slot (H2D on the copy-in stream), enqueue the block
+// steps, copy y back on the copy-out stream.  Returns a ticket; y is complete after submit_wait(ticket).
+static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, bool mix,
+                       int64_t* ticket) {
   int rc = check_pull_args(b, x, y, n);
   if (rc != PGX_OK) return rc;
   const pgx_bank_config& c = b->cfg;
@@ -669,13 +720,47 @@ static int process_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pg
   PGX_CUDA(cudaSetDevice(c.device));
   const size_t xb = (size_t)c.n_streams * c.c_in * n * sizeof(float);
   const size_t yb = (size_t)(mix ? 1 : c.n_streams) * c.c_out * n * sizeof(float);
-  PGX_CUDA(cudaMemcpyAsync(b->x_stage, x, xb, cudaMemcpyHostToDevice, b->stream));
-  rc = run_pull(b, b->x_stage, xl, b->y_stage, yd, n, mix, false, b->stream);
+  const int64_t tk = b->next_ticket;
+  const int slot = (int)(tk % pgx_bank::kSlots);
+  // the slot's previous pull is over once its D2H has completed (its K1s read x_stage before that)
+  if (tk >= pgx_bank::kSlots) PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
+  PGX_CUDA(cudaMemcpyAsync(b->x_stage[slot], x, xb, cudaMemcpyHostToDevice, b->s_h2d));
+  PGX_CUDA(cudaEventRecord(b->ev_h2d[slot], b->s_h2d));
+  PGX_CUDA(cudaStreamWaitEvent(b->s_in, b->ev_h2d[slot], 0));
+  PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
+  rc = run_pull(b, b->x_stage[slot], xl, b->y_stage[slot], yd, n, mix, true, b->stream);
   if (rc != PGX_OK) return rc;
-  PGX_CUDA(cudaMemcpyAsync(y, b->y_stage, yb, cudaMemcpyDeviceToHost, b->stream));
-  PGX_CUDA(cudaStreamSynchronize(b->stream));
+  PGX_CUDA(cudaEventRecord(b->ev_y[slot], b->stream));
+  PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_y[slot], 0));
+  PGX_CUDA(cudaMemcpyAsync(y, b->y_stage[slot], yb, cudaMemcpyDeviceToHost, b->s_d2h));
+  PGX_CUDA(cudaEventRecord(b->ev_done[slot], b->s_d2h));
+  b->next_ticket = tk + 1;
+  if (ticket) *ticket = tk;
   return PGX_OK;
 }
+
+static int submit_wait(pgx_bank* b, int64_t ticket) {
+  if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  if (ticket < 0 || ticket >= b->next_ticket) return fail(PGX_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
+  if (ticket + pgx_bank::kSlots < b->next_ticket) return PGX_OK;  // its slot was recycled: long complete
+  PGX_CUDA(cudaSetDevice(b->cfg.device));
+  PGX_CUDA(cudaEventSynchronize(b->ev_done[ticket % pgx_bank::kSlots]));
+  return PGX_OK;
+}
+
+static int process_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, bool mix) {
+  int64_t tk = 0;
+  const int rc = submit_host(b, x, xl, y, yl, n, mix, &tk);
+  return rc != PGX_OK ? rc : submit_wait(b, tk);
+}
+
+int pgx_bank_submit(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, int32_t flags,
+                    int64_t* ticket) {
+  if (!ticket) return fail(PGX_ERR_INVALID, "ticket is NULL");
+  return submit_host(b, x, xl, y, yl, n, (flags & PGX_PULL_MIX) != 0, ticket);
+}
+
+int pgx_bank_wait(pgx_bank* b, int64_t ticket) { return submit_wait(b, ticket); }
 
 int pgx_bank_process(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n) {
   return process_host(b, x, xl, y, yl, n, false);
@@ -701,9 +786,11 @@ int pgx_bank_process_device(pgx_bank* b, const float* x_dev, pgx_layout xl, floa
 int pgx_bank_synchronize(pgx_bank* b) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
+  PGX_CUDA(cudaStreamSynchronize(b->s_h2d));
   PGX_CUDA(cudaStreamSynchronize(b->stream));
   PGX_CUDA(cudaStreamSynchronize(b->s_in));
   PGX_CUDA(cudaStreamSynchronize(b->s_bg));
+  PGX_CUDA(cudaStreamSynchronize(b->s_d2h));
   return PGX_OK;
 }
 
