@@ -173,8 +173,12 @@ PGX_API int pgx_bank_synchronize(pgx_bank* bank);
 
 /* ---- measurement: per-kernel device time, CUDA events on the launching stream ---- */
 typedef struct pgx_profile {
-  double ms_r2c, ms_mac, ms_c2r; /* summed durations of K1 / K3 / K2 launches */
+  double ms_r2c, ms_mac, ms_c2r; /* summed durations of K1 / K3 (past-partition pass) / K2 launches */
   int64_t steps;                 /* block steps covered */
+  double ms_fold, ms_now;        /* fold of split partials; K3 over the present slot (mix mode) */
+  int64_t n_mac;                 /* K3 past-pass launches timed */
+  double ms_mac_union;           /* time during which at least one of them was running (launches of consecutive
+                                    blocks overlap on two streams) */
 } pgx_profile;
 /* begin: every following block step records events around each of its three kernels.
  * end: synchronise, sum the durations into *out, stop recording. */

@@ -37,7 +37,9 @@ class BankInfo(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms_r2c", C.c_double), ("ms_mac", C.c_double), ("ms_c2r", C.c_double), ("steps", C.c_int64)]
+    _fields_ = [("ms_r2c", C.c_double), ("ms_mac", C.c_double), ("ms_c2r", C.c_double), ("steps", C.c_int64),
+                ("ms_fold", C.c_double), ("ms_now", C.c_double), ("n_mac", C.c_int64),
+                ("ms_mac_union", C.c_double)]
 
 
 _f32p = C.POINTER(C.c_float)

@@ -151,8 +151,11 @@ __global__ void __launch_bounds__(kMacThreads) k_fdl_mac(const MacArgs a) {
       }
     }
     if (g == 0 && t < nst) {
-      const int o = MIX ? c : (s0 + t) * a.c_out + c;
-      a.yspec[((size_t)sp * a.n_out + o) * rs + kv] = acc[t];
+      size_t prow;  // partial row: [split][out] -- or, per-stream mix (mix == 2), [stream][split][channel]
+      if (MIX) prow = (size_t)sp * a.n_out + c;
+      else if (a.mix == 2) prow = ((size_t)(s0 + t) * a.n_split + sp) * a.c_out + c;
+      else prow = (size_t)sp * a.n_out + (s0 + t) * a.c_out + c;
+      a.yspec[prow * rs + kv] = acc[t];
     }
   }
 }
@@ -172,26 +175,35 @@ static bool want_tma(int W4) {
   return false;  // default (measured A/B)
 }
 
-// Pick the kernel variant, the stream tile and the term split so that the work list is a near-integer
-// number of full waves over the SMs.
+// Pick the kernel variant, the work layout, the stream tile and the term split so that the work list is a
+// near-integer number of full waves over the SMs.
+//   mix = false          : one out row per (stream, channel), terms = the stream's Pt partitions
+//   mix, Pt >= 32        : "per-stream" mix (layout 2): the same items as conv mode -- the filter row base is
+//                          resolved once per CTA, no per-row stream lookup -- writing N*n_split partial rows per
+//                          channel that the fold kernel sums (the MixPE sum over streams, mix_pe.py:92-94)
+//   mix, short Pt        : "flattened" mix (layout 1): terms run over (stream, partition) pairs
 MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count) {
   MacPlan p{};
+  const int Pt = mix ? (n_terms / (N > 0 ? N : 1)) : n_terms;
+  p.layout = !mix ? 0 : (Pt >= 32 ? 2 : 1);
+  const bool flat = p.layout == 1;
+  if (p.layout == 2) n_terms = Pt;
   p.st = (!mix && shared_filter && N >= 4) ? 4 : 1;
-  p.variant = want_tma(W4) ? 1 : 0;
+  p.variant = want_tma(W4) && p.layout != 2 ? 1 : 0;
   const int lanes = p.variant ? 256 : (W4 < kMacThreads ? W4 : kMacThreads);
   const int groups = p.variant ? 1 : kMacThreads / lanes, ktiles = W4 / lanes;
   int occ;
-  if (p.variant) occ = tma_occupancy_of(mix, p.st);
-  else if (mix) occ = mac_occupancy<true, 1, 8>();
+  if (p.variant) occ = tma_occupancy_of(flat, p.st);
+  else if (flat) occ = mac_occupancy<true, 1, 8>();
   else if (p.st == 4) occ = mac_occupancy<false, 4, 4>();
   else occ = mac_occupancy<false, 1, 8>();
-  p.n_otiles = mix ? c_out : ((N + p.st - 1) / p.st) * c_out;
+  p.n_otiles = flat ? c_out : ((N + p.st - 1) / p.st) * c_out;
   const long resident = (long)sm_count * occ;
   const long base = (long)p.n_otiles * ktiles;
   const int min_terms = 16 * groups;  // at least two unrolled batches per group and split
   int max_split = n_terms / min_terms;
   if (max_split < 1) max_split = 1;
-  if (max_split > 1024) max_split = 1024;
+  if (max_split > 4096) max_split = 4096;
   // cost model: waves x (terms per CTA + fixed per-item overhead expressed in row-terms)
   const int overhead = p.variant ? 2 : 6 * groups;
   double best = 1e300;
@@ -209,6 +221,7 @@ MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_fi
   p.n_split = best_s;
   p.terms_per_split = (n_terms + best_s - 1) / best_s;
   p.n_split = (n_terms + p.terms_per_split - 1) / p.terms_per_split;
+  p.n_partials = p.layout == 2 ? N * p.n_split : p.n_split;
   p.grid = (int)(base * p.n_split);
   p.occupancy = occ;
   p.persistent_ctas = (int)resident;
@@ -222,7 +235,7 @@ void launch_fdl_mac(const MacArgs& a, cudaStream_t st) {
   }
   const int lanes = a.W4 < kMacThreads ? a.W4 : kMacThreads;
   const int grid = a.n_otiles * (a.W4 / lanes) * a.n_split;
-  if (a.mix)
+  if (a.mix == 1)
     k_fdl_mac<true, 1, 8><<<grid, kMacThreads, 0, st>>>(a);
   else if (a.st == 4)
     k_fdl_mac<false, 4, 4><<<grid, kMacThreads, 0, st>>>(a);

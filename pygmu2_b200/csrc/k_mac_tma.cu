@@ -264,7 +264,7 @@ int tma_occupancy_of(bool mix, int st) {
 void launch_fdl_mac_tma(const MacArgs& a, int persistent_ctas, cudaStream_t st) {
   const int n_items = a.n_otiles * (a.W4 / kSegF4) * a.n_split;
   const int grid = n_items < persistent_ctas ? n_items : persistent_ctas;
-  if (a.mix)
+  if (a.mix == 1)
     k_fdl_mac_tma<TMA_MIX><<<grid, kTmaThreads, tma_smem_bytes<TMA_MIX>(), st>>>(a, n_items);
   else if (a.st == 4)
     k_fdl_mac_tma<TMA_SHARED><<<grid, kTmaThreads, tma_smem_bytes<TMA_SHARED>(), st>>>(a, n_items);

@@ -39,7 +39,8 @@ struct MacArgs {
   int32_t N, c_x, c_out, c_f, R, W4, q0;  // R = ring rows per (stream, channel); q0 = R-1-head
   int32_t n_out, n_terms, terms_per_split, n_split;
   int32_t n_otiles, st;  // out tiles in the flat grid; streams per CTA sharing the filter rows (1 or 4)
-  int32_t mix;           // 0: out o=(s,c), terms j<P.  1: out o=c, terms (s,j) (fused MixPE / HRTF stereo mix)
+  int32_t mix;           // 0: out o=(s,c), terms j<P.  1: out o=c, terms (s,j) (fused MixPE / HRTF stereo mix).
+                         // 2: items as 0, partial rows [stream][split][channel] folded over streams afterwards
   // which ring slots are terms: Pt slots per stream; slot = jfix if jfix >= 0 (only that slot), else
   // j = off + jj, plus nskip when j >= skip, for jj in [0, Pt): the background pass leaves out the open
   // slot `head` and the spare slot head+1 (being written by the next block's K1).
@@ -50,6 +51,8 @@ struct MacArgs {
 };
 struct MacPlan {
   int32_t st, n_otiles, n_split, terms_per_split, grid, occupancy, variant, persistent_ctas;
+  int32_t layout;      // MacArgs.mix value: 0 conv, 1 flattened mix, 2 per-stream mix
+  int32_t n_partials;  // partial rows per out row that the consumer has to sum
 };
 // bulk-async (TMA) staged variant, k_mac_tma.cu
 bool tma_supported(int W4);

@@ -32,7 +32,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pgx.h"
@@ -88,14 +90,18 @@ struct pgx_bank {
   int c_x = 1, P = 1, R = 1, B = 0;
   cudaStream_t stream = nullptr;   // default critical stream
   cudaStream_t s_in = nullptr;     // ingest stream (K1)
-  cudaStream_t s_bg = nullptr;     // background stream (past-partition pass)
+  cudaStream_t s_bg = nullptr;     // background stream (past-partition pass) of even blocks ...
+  cudaStream_t s_bg2 = nullptr;    // ... and of odd blocks: the passes of consecutive blocks share nothing they
+                                   // write, so the tail wave of one overlaps the first wave of the next
+  cudaEvent_t ev_bgjoin = nullptr;
+  bool two_bg = true;
   cudaEvent_t ev_call = nullptr;
   cudaEvent_t ev_k1[kRing] = {}, ev_k2[kRing] = {}, ev_mac[kRing] = {};
   float* hist = nullptr;
   float2* fdl = nullptr;
   float2* Hd = nullptr;
   float2* ypast[2] = {nullptr, nullptr};
-  float2* ypart = nullptr;
+  float2* ypart[2] = {nullptr, nullptr};  // by block parity, like ypast
   float2* ynow = nullptr;
   float2* tw = nullptr;
   int32_t* fmap = nullptr;         // map in use (own buffer or the caller's device array)
@@ -134,7 +140,7 @@ struct pgx_bank {
   int64_t launches = 0, steps = 0;
   // per-kernel CUDA-event timing
   bool profiling = false;
-  struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3, 2 = K2
+  struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3 (past pass), 2 = K2, 3 = fold, 4 = K3 (present slot, mix)
   std::vector<ProfSpan> prof_spans;
   std::vector<cudaEvent_t> prof_pool;
   size_t prof_pool_used = 0;
@@ -146,14 +152,15 @@ namespace {
 void free_bank(pgx_bank* b) {
   if (!b) return;
   cudaSetDevice(b->cfg.device);
-  for (cudaStream_t s : {b->s_h2d, b->stream, b->s_in, b->s_bg, b->s_d2h})
+  for (cudaStream_t s : {b->s_h2d, b->stream, b->s_in, b->s_bg, b->s_bg2, b->s_d2h})
     if (s) cudaStreamSynchronize(s);
   cudaFree(b->hist);
   cudaFree(b->fdl);
   cudaFree(b->Hd);
   cudaFree(b->ypast[0]);
   cudaFree(b->ypast[1]);
-  cudaFree(b->ypart);
+  cudaFree(b->ypart[0]);
+  cudaFree(b->ypart[1]);
   cudaFree(b->ynow);
   cudaFree(b->tw);
   cudaFree(b->fmap_own);
@@ -172,7 +179,8 @@ void free_bank(pgx_bank* b) {
     for (cudaEvent_t e : {b->fmap_ev[i], b->fmap_ret_crit[i], b->fmap_ret_bg[i]})
       if (e) cudaEventDestroy(e);
   if (b->ev_call) cudaEventDestroy(b->ev_call);
-  for (cudaStream_t s : {b->stream, b->s_in, b->s_bg, b->s_h2d, b->s_d2h})
+  if (b->ev_bgjoin) cudaEventDestroy(b->ev_bgjoin);
+  for (cudaStream_t s : {b->stream, b->s_in, b->s_bg, b->s_bg2, b->s_h2d, b->s_d2h})
     if (s) cudaStreamDestroy(s);
   delete b;
 }
@@ -213,7 +221,7 @@ void fill_mac_common(pgx_bank* b, pgx::MacArgs& m, bool mix, int head) {
   m.fmap = b->fmap;
   m.N = c.n_streams; m.c_x = b->c_x; m.c_out = c.c_out; m.c_f = c.filter_channels; m.R = b->R; m.W4 = b->B / 2;
   m.q0 = b->R - 1 - head;
-  m.mix = mix ? 1 : 0;
+  m.mix = mix ? 1 : 0;  // the caller overrides this with its plan's layout
   m.n_out = mix ? c.c_out : c.n_streams * c.c_out;
 }
 
@@ -223,31 +231,34 @@ void fill_mac_common(pgx_bank* b, pgx::MacArgs& m, bool mix, int head) {
 // the last K2 that read the ypast buffer it overwrites.
 void issue_past(pgx_bank* b, bool mix, int64_t blk, int head, cudaEvent_t after) {
   const int par = (int)(blk & 1);
-  cudaStreamWaitEvent(b->s_bg, after, 0);
-  if (b->last_k2_of_par[par] >= 0) cudaStreamWaitEvent(b->s_bg, b->ev_k2[b->last_k2_of_par[par] % kRing], 0);
+  cudaStream_t sbg = (par && b->two_bg) ? b->s_bg2 : b->s_bg;
+  cudaStreamWaitEvent(sbg, after, 0);
+  if (b->last_k2_of_par[par] >= 0) cudaStreamWaitEvent(sbg, b->ev_k2[b->last_k2_of_par[par] % kRing], 0);
   pgx::MacArgs m{};
   fill_mac_common(b, m, mix, head);
   const pgx::MacPlan& pl = mix ? b->plan_mix : b->plan_conv;
-  const bool fold = pl.n_split > kFoldAbove;
-  m.yspec = reinterpret_cast<float4*>(fold ? b->ypart : b->ypast[par]);
+  const bool fold = pl.n_partials > kFoldAbove;
+  m.mix = pl.layout;
+  m.yspec = reinterpret_cast<float4*>(fold ? b->ypart[par] : b->ypast[par]);
   m.Pt = b->R - 2;  // = P - 1
   m.jfix = -1;
   if (head + 1 < b->R) { m.off = 0; m.skip = head; m.nskip = 2; }
   else                 { m.off = 1; m.skip = b->R; m.nskip = 0; }  // open slot R-1, spare slot 0
-  m.n_terms = mix ? b->cfg.n_streams * m.Pt : m.Pt;
+  m.n_terms = pl.layout == 1 ? b->cfg.n_streams * m.Pt : m.Pt;
   m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
   m.variant = pl.variant; m.persistent_ctas = pl.persistent_ctas;
   {
-    ProfScope ps(b, b->s_bg, 1);
-    pgx::launch_fdl_mac(m, b->s_bg);
+    ProfScope ps(b, sbg, 1);
+    pgx::launch_fdl_mac(m, sbg);
     b->launches += 1;
-    if (fold) {
-      pgx::launch_reduce_partials(reinterpret_cast<const float4*>(b->ypart), reinterpret_cast<float4*>(b->ypast[par]),
-                                  pl.n_split, m.n_out, b->B / 2, b->s_bg);
-      b->launches += 1;
-    }
   }
-  cudaEventRecord(b->ev_mac[blk % kRing], b->s_bg);
+  if (fold) {
+    ProfScope ps(b, sbg, 3);
+    pgx::launch_reduce_partials(reinterpret_cast<const float4*>(b->ypart[par]),
+                                reinterpret_cast<float4*>(b->ypast[par]), pl.n_partials, m.n_out, b->B / 2, sbg);
+    b->launches += 1;
+  }
+  cudaEventRecord(b->ev_mac[blk % kRing], sbg);
   b->past_block = blk;
   b->past_mode = mix ? 1 : 0;
 }
@@ -270,10 +281,11 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
              int take, bool mix, cudaStream_t crit) {
   struct StreamSwap {  // PGX_DEBUG_SERIAL=1: run all three roles on the critical stream
     pgx_bank* b; cudaStream_t in, bg;
-    StreamSwap(pgx_bank* b_, cudaStream_t crit_) : b(b_), in(b_->s_in), bg(b_->s_bg) {
-      if (b->serial) b->s_in = b->s_bg = crit_;
+    cudaStream_t bg2;
+    StreamSwap(pgx_bank* b_, cudaStream_t crit_) : b(b_), in(b_->s_in), bg(b_->s_bg), bg2(b_->s_bg2) {
+      if (b->serial) b->s_in = b->s_bg = b->s_bg2 = crit_;
     }
-    ~StreamSwap() { b->s_in = in; b->s_bg = bg; }
+    ~StreamSwap() { b->s_in = in; b->s_bg = bg; b->s_bg2 = bg2; }
   } swap_guard(b, crit);
   const pgx_bank_config& c = b->cfg;
   const int B = b->B, P = b->P, R = b->R;
@@ -306,7 +318,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   if (P > 1) {
     if (b->past_block != t || b->past_mode != (mix ? 1 : 0)) issue_past(b, mix, t, b->head, b->ev_k1[i % kRing]);
     cudaStreamWaitEvent(crit, b->ev_mac[t % kRing], 0);
-    const int ns = (mix ? b->plan_mix : b->plan_conv).n_split;
+    const int ns = (mix ? b->plan_mix : b->plan_conv).n_partials;
     n_split_past = ns > kFoldAbove ? 1 : ns;
   }
 
@@ -318,6 +330,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   if (mix) {  // present term of every stream: K3 restricted to the open slot
     pgx::MacArgs m{};
     fill_mac_common(b, m, true, b->head);
+    m.mix = b->plan_now.layout;  // always the flattened layout: one term per stream
     m.yspec = reinterpret_cast<float4*>(b->ynow);
     m.Pt = 1; m.off = 0; m.skip = R; m.nskip = 0; m.jfix = b->head;
     m.n_terms = c.n_streams;
@@ -325,7 +338,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     m.n_otiles = b->plan_now.n_otiles; m.st = b->plan_now.st;
     m.variant = b->plan_now.variant; m.persistent_ctas = b->plan_now.persistent_ctas;
     {
-      ProfScope ps(b, crit, 1);
+      ProfScope ps(b, crit, 4);
       pgx::launch_fdl_mac(m, crit);
     }
     b->launches += 1;
@@ -375,6 +388,7 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   if (b->fmap_pending) {  // a re-selected filter map is still being copied in: its readers wait for it
     cudaStreamWaitEvent(crit, b->fmap_ev[b->fmap_cur], 0);
     cudaStreamWaitEvent(b->s_bg, b->fmap_ev[b->fmap_cur], 0);
+    cudaStreamWaitEvent(b->s_bg2, b->fmap_ev[b->fmap_cur], 0);
     b->fmap_pending = false;
   }
   int pos = 0;
@@ -395,6 +409,7 @@ void quiesce(pgx_bank* b) {
   cudaStreamSynchronize(b->s_h2d);
   cudaStreamSynchronize(b->s_in);
   cudaStreamSynchronize(b->s_bg);
+  cudaStreamSynchronize(b->s_bg2);
   cudaStreamSynchronize(b->stream);
   cudaStreamSynchronize(b->s_d2h);
   b->past_block = -1;
@@ -523,8 +538,8 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
   if (P > 1) {  // background pass over the P-1 committed partitions
     b->plan_conv = pgx::mac_plan(c.n_streams, c.c_out, B / 2, P - 1, false, c.n_filters == 1, b->sm_count);
     b->plan_mix = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams * (P - 1), true, c.n_filters == 1, b->sm_count);
-    y_conv = (size_t)b->plan_conv.n_split * c.n_streams * c.c_out;
-    y_mix = (size_t)b->plan_mix.n_split * c.c_out;
+    y_conv = (size_t)b->plan_conv.n_partials * c.n_streams * c.c_out;
+    y_mix = (size_t)b->plan_mix.n_partials * c.c_out;
   }
   b->plan_now = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams, true, c.n_filters == 1, b->sm_count);
   b->ypart_bytes = (y_conv > y_mix ? y_conv : y_mix) * B * sizeof(float2);
@@ -545,6 +560,9 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     guard(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, hi), "cudaStreamCreate");
     guard(cudaStreamCreateWithPriority(&b->s_in, cudaStreamNonBlocking, hi), "cudaStreamCreate(in)");
     guard(cudaStreamCreateWithPriority(&b->s_bg, cudaStreamNonBlocking, lo), "cudaStreamCreate(bg)");
+    guard(cudaStreamCreateWithPriority(&b->s_bg2, cudaStreamNonBlocking, lo), "cudaStreamCreate(bg2)");
+    guard(cudaEventCreateWithFlags(&b->ev_bgjoin, cudaEventDisableTiming), "cudaEventCreate");
+    if (const char* e = getenv("PGX_BG_STREAMS")) b->two_bg = (e[0] != '1');
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");
     if (const char* e = getenv("PGX_DEBUG_SERIAL")) {  // debugging aid: no overlap, one stream for everything
@@ -568,7 +586,8 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
   guard(cudaMalloc(&b->Hd, b->Hd_bytes), "cudaMalloc(Hd)");
   guard(cudaMalloc(&b->ypast[0], b->ysum_bytes), "cudaMalloc(ypast0)");
   guard(cudaMalloc(&b->ypast[1], b->ysum_bytes), "cudaMalloc(ypast1)");
-  guard(cudaMalloc(&b->ypart, b->ypart_bytes), "cudaMalloc(ypart)");
+  guard(cudaMalloc(&b->ypart[0], b->ypart_bytes), "cudaMalloc(ypart)");
+  guard(cudaMalloc(&b->ypart[1], b->ypart_bytes), "cudaMalloc(ypart)");
   guard(cudaMalloc(&b->ynow, b->ynow_bytes), "cudaMalloc(ynow)");
   guard(cudaMalloc(&b->tw, (size_t)2 * B * sizeof(float2)), "cudaMalloc(tw)");
   guard(cudaMalloc(&b->fmap_own, (size_t)pgx_bank::kMapSlots * c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
@@ -624,7 +643,7 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->filter_len = c.filter_len; info->filter_channels = c.filter_channels; info->n_filters = c.n_filters;
   info->block = b->B; info->partitions = b->P; info->max_pull = c.max_pull; info->device = c.device;
   info->head = b->head; info->fill = b->fill;
-  info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + b->ypart_bytes + 2 * b->ysum_bytes +
+  info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + 2 * b->ypart_bytes + 2 * b->ysum_bytes +
                                 b->ynow_bytes + pgx_bank::kSlots * (b->xs_bytes + b->ys_bytes));
   info->kernel_launches = b->launches;
   info->block_steps = b->steps;
@@ -679,6 +698,8 @@ int pgx_bank_set_filter_map(pgx_bank* b, const int32_t* filter_of_stream) {
   const int cur = b->fmap_cur, nxt = (cur + 1) % pgx_bank::kMapSlots;
   // (a caller-owned critical stream may be gone by now: run_pull recorded the event on it after each pull)
   if (!b->last_crit || b->last_crit == b->stream) PGX_CUDA(cudaEventRecord(b->fmap_ret_crit[cur], b->stream));
+  PGX_CUDA(cudaEventRecord(b->ev_bgjoin, b->s_bg2));
+  PGX_CUDA(cudaStreamWaitEvent(b->s_bg, b->ev_bgjoin, 0));
   PGX_CUDA(cudaEventRecord(b->fmap_ret_bg[cur], b->s_bg));
   if (b->fmap_sets + 1 >= pgx_bank::kMapSlots) {  // row nxt was used before: its readers and its copy are done?
     PGX_CUDA(cudaEventSynchronize(b->fmap_ret_crit[nxt]));
@@ -790,6 +811,7 @@ int pgx_bank_synchronize(pgx_bank* b) {
   PGX_CUDA(cudaStreamSynchronize(b->stream));
   PGX_CUDA(cudaStreamSynchronize(b->s_in));
   PGX_CUDA(cudaStreamSynchronize(b->s_bg));
+  PGX_CUDA(cudaStreamSynchronize(b->s_bg2));
   PGX_CUDA(cudaStreamSynchronize(b->s_d2h));
   return PGX_OK;
 }
@@ -807,16 +829,42 @@ int pgx_bank_profile_end(pgx_bank* b, pgx_profile* out) {
   if (!b || !out) return fail(PGX_ERR_INVALID, "NULL argument");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   b->profiling = false;
-  out->ms_r2c = out->ms_mac = out->ms_c2r = 0.0;
+  out->ms_r2c = out->ms_mac = out->ms_c2r = out->ms_fold = out->ms_now = 0.0;
+  out->n_mac = 0;
+  out->ms_mac_union = 0.0;
   out->steps = b->prof_steps;
   PGX_CUDA(cudaDeviceSynchronize());
+  std::vector<std::pair<float, float>> mac_iv;  // K3 past-pass launches as [start, end) from the first event
+  cudaEvent_t base = b->prof_spans.empty() ? nullptr : b->prof_spans.front().a;
   for (const pgx_bank::ProfSpan& sp : b->prof_spans) {
     float ms = 0.f;
     PGX_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
     if (sp.kind == 0) out->ms_r2c += ms;
-    else if (sp.kind == 1) out->ms_mac += ms;
-    else out->ms_c2r += ms;
+    else if (sp.kind == 1) {
+      out->ms_mac += ms;
+      out->n_mac += 1;
+      float t0 = 0.f;
+      if (sp.a != base) PGX_CUDA(cudaEventElapsedTime(&t0, base, sp.a));
+      mac_iv.emplace_back(t0, t0 + ms);
+    }
+    else if (sp.kind == 2) out->ms_c2r += ms;
+    else if (sp.kind == 3) out->ms_fold += ms;
+    else out->ms_now += ms;
   }
+  // launches of consecutive blocks overlap on the two background streams: the kernel's busy time is the
+  // union of their intervals
+  std::sort(mac_iv.begin(), mac_iv.end());
+  float cur0 = 0.f, cur1 = -1.f;
+  for (const auto& iv : mac_iv) {
+    if (cur1 < cur0 || iv.first > cur1) {
+      if (cur1 > cur0) out->ms_mac_union += cur1 - cur0;
+      cur0 = iv.first;
+      cur1 = iv.second;
+    } else if (iv.second > cur1) {
+      cur1 = iv.second;
+    }
+  }
+  if (cur1 > cur0) out->ms_mac_union += cur1 - cur0;
   b->prof_spans.clear();
   b->prof_pool_used = 0;
   return PGX_OK;
