@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
   }
 }
 
-template <int LOG2N>
+// PART: split partials are summed in (P > 1 or mix mode); the P = 1 conv instantiation carries no such registers
+template <int LOG2N, bool PART>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
   using C = FftCfg<LOG2N>;
   constexpr int N = C::N, T8 = C::T8;
@@ -164,24 +165,45 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       const int k = j + m * T8;
-      float2 acc = make_float2(0.f, 0.f);
       if (xrow) {
         const float2 x = xrow[k], h = __ldg(hrow + k);
-        acc = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);
+        v[m] = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);
       }
-      for (int sp = 0; sp < a.n_split; ++sp) {
-        const float2 t = a.yspec[((size_t)sp * a.n_out + o) * N + k];
-        acc.x += t.x;
-        acc.y += t.y;
-      }
-      for (int sp = 0; sp < a.n_split_now; ++sp) {
-        const float2 t = a.ynow[((size_t)sp * a.n_out + o) * N + k];
-        acc.x += t.x;
-        acc.y += t.y;
-      }
-      v[m] = acc;
-      sA[phys(k)] = acc;
     }
+    // split partials: 4 splits x 8 bins = 32 independent loads in flight per thread (fixed summation order)
+    auto add_partials = [&](const float2* __restrict__ part, const int n) {
+      const float2* p0 = part + (size_t)o * N + j;
+      const size_t ss = (size_t)a.n_out * N;
+      int sp = 0;
+      for (; sp + 4 <= n; sp += 4) {
+        float2 t[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int m = 0; m < 8; ++m) t[u][m] = p0[(size_t)(sp + u) * ss + m * T8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            v[m].x += t[u][m].x;
+            v[m].y += t[u][m].y;
+          }
+      }
+      for (; sp < n; ++sp) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float2 t = p0[(size_t)sp * ss + m * T8];
+          v[m].x += t.x;
+          v[m].y += t.y;
+        }
+      }
+    };
+    if (PART) {
+      add_partials(a.yspec, a.n_split);
+      add_partials(a.ynow, a.n_split_now);
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
   }
   __syncthreads();
   if (active) {
@@ -241,16 +263,16 @@ static void launch_r2c_t(const R2CArgs& a, const FilterPrepArgs& fp, int64_t tot
   k_r2c<LOG2N, MODE><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a, fp);
 }
 
-template <int LOG2N>
+template <int LOG2N, bool PART>
 static void launch_c2r_t(const C2RArgs& a, cudaStream_t st) {
   using C = FftCfg<LOG2N>;
   static bool attr_done = false;
   if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
-    cudaFuncSetAttribute(k_c2r<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(k_c2r<LOG2N, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     attr_done = true;
   }
   const int grid = (a.n_out + C::FPB - 1) / C::FPB;
-  k_c2r<LOG2N><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a);
+  k_c2r<LOG2N, PART><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a);
 }
 
 #define PGX_DISPATCH(LOG, CALL)                                                                              \
@@ -278,6 +300,12 @@ void launch_filter_prep(const FilterPrepArgs& fp, cudaStream_t st) {
   PGX_DISPATCH(ilog2(fp.B), (launch_r2c_t<L_, 1>(a, fp, (int64_t)fp.n_rows * fp.P, st)));
 }
 
-void launch_c2r_emit(const C2RArgs& a, cudaStream_t st) { PGX_DISPATCH(ilog2(a.B), (launch_c2r_t<L_>(a, st))); }
+void launch_c2r_emit(const C2RArgs& a, cudaStream_t st) {
+  if (a.n_split > 0 || a.n_split_now > 0) {
+    PGX_DISPATCH(ilog2(a.B), (launch_c2r_t<L_, true>(a, st)));
+  } else {
+    PGX_DISPATCH(ilog2(a.B), (launch_c2r_t<L_, false>(a, st)));
+  }
+}
 
 }  // namespace pgx
