@@ -148,10 +148,22 @@ PGX_API int pgx_bank_process(pgx_bank* bank, const float* x, pgx_layout x_layout
 PGX_API int pgx_bank_process_mix(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y_mix,
                          pgx_layout y_layout, int32_t n);
 
+/*
+ * Fused output stage for the following pulls: y = dry * x + wet * (x * h), each product and the sum rounded to
+ * float32.  Replaces the GainPE(dry) + GainPE(wet) -> MixPE tail of ReverbPE (reverb_pe.py:82-95,
+ * gain_pe.py:123-125, mix_pe.py:92-94) - bit-identical to those three float32 steps given the same
+ * convolution output.  dry != 0 needs c_in == c_out without mix-down; in a fused-mix pull only wet applies.
+ * Default wet = 1, dry = 0.
+ */
+PGX_API int pgx_bank_set_output_gains(pgx_bank* bank, float wet, float dry);
+
 /* flags of a pull */
 #define PGX_PULL_MIX 1u            /* fused MixPE sum over streams, as pgx_bank_process_mix */
 #define PGX_PULL_INPUT_RESIDENT 2u /* x is already complete in memory (not produced by work still queued on
                                       cuda_stream): the ingest of this pull may overlap earlier pulls' output stage */
+#define PGX_PULL_X_DEVICE 4u       /* pgx_bank_submit only: x is a DEVICE pointer whose producer was enqueued on the
+                                      bank's own stream (pgx_bank_stream) - e.g. pgx_osc_render_device - so there is
+                                      no H2D copy; y is still delivered to host memory */
 
 /*
  * Pipelined host-buffer pulls (the batched renderer loop, renderer.py:297-327, with more than one pull in
@@ -164,6 +176,8 @@ PGX_API int pgx_bank_process_mix(pgx_bank* bank, const float* x, pgx_layout x_la
 PGX_API int pgx_bank_submit(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y, pgx_layout y_layout,
                     int32_t n, int32_t flags, int64_t* ticket);
 PGX_API int pgx_bank_wait(pgx_bank* bank, int64_t ticket);
+/* The bank's own (critical) CUDA stream as a cudaStream_t: producers of device-resident input enqueue on it. */
+PGX_API void* pgx_bank_stream(pgx_bank* bank);
 
 /* Device-resident variant: x / y are device pointers; work is enqueued and NOT synchronised; y is
  * complete when cuda_stream (NULL = the bank's stream) drains.  flags: PGX_PULL_*. */
@@ -184,6 +198,36 @@ typedef struct pgx_profile {
  * end: synchronise, sum the durations into *out, stop recording. */
 PGX_API int pgx_bank_profile_begin(pgx_bank* bank);
 PGX_API int pgx_bank_profile_end(pgx_bank* bank, pgx_profile* out);
+
+/* ---- device-resident sources: the inputs of the path rendered in HBM -------------
+ * SINE: n_voices constant-parameter SinePE streams (sine_pe.py:135-175): float64 phase from the sample
+ *       index, float32 out.  freq / gain (= amplitude) / phase (radians) are [n_voices]; unison is ignored.
+ * BLIT: n_voices voices of `unison` band-limited sawtooth oscillators each: BlitSawPE (unison = 1,
+ *       blit_saw_pe.py:152-264) and SuperSawPE (super_saw_pe.py:282-305).  freq / gain (oscillator amplitude) /
+ *       phase (initial phase in [0,1)) are [n_voices*unison], m_fixed [n_voices*unison] harmonics (0 = auto)
+ *       or NULL, amp [n_voices] voice amplitude.  Stateful: a pull whose start is not the previous pull's end
+ *       re-initialises phase and integrator (blit_saw_pe.py:183-186).
+ * Output is planar [n_voices][channels][n] (channels are copies, as np.tile in the reference) or, with
+ * PGX_PULL_MIX, the MixPE sum over voices [channels][n] in float32 input order (mix_pe.py:92-94, bit-exact).
+ */
+#define PGX_OSC_SINE 0
+#define PGX_OSC_BLIT 1
+typedef struct pgx_osc pgx_osc;
+typedef struct pgx_osc_config {
+  int32_t device, kind, n_voices, unison, channels, sample_rate, max_pull, reserved;
+  double leak; /* BLIT leaky-integrator coefficient (blit_saw_pe.py:75, default 0.999) */
+} pgx_osc_config;
+PGX_API int pgx_osc_create(pgx_osc** out, const pgx_osc_config* cfg, const double* freq, const double* gain,
+                   const double* phase, const int32_t* m_fixed, const double* amp);
+PGX_API int pgx_osc_destroy(pgx_osc* osc);
+PGX_API int pgx_osc_reset(pgx_osc* osc); /* on_start / on_stop: the next pull starts from the initial state */
+/* Enqueue one pull on cuda_stream (NULL = the handle's own); *out_dev points at the handle's output buffer,
+ * valid until the next render on this handle.  Not synchronised. */
+PGX_API int pgx_osc_render_device(pgx_osc* osc, int64_t start, int32_t n, int32_t flags, void* cuda_stream,
+                          const float** out_dev);
+/* Same pull delivered to host memory (D2H inside, returns when y is complete). */
+PGX_API int pgx_osc_render(pgx_osc* osc, int64_t start, int32_t n, int32_t flags, float* y);
+PGX_API int pgx_osc_launches(pgx_osc* osc, int64_t* launches);
 
 /* ---- MixPE: replaces the float32 left-to-right sum of mix_pe.py:92-94 ------ */
 /*

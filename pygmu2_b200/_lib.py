@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpgx.so")
 
 PGX_OK, PGX_ERR_INVALID, PGX_ERR_CUDA, PGX_ERR_NO_DEVICE, PGX_ERR_NOMEM = 0, -1, -2, -3, -4
 PGX_FLAG_MIXDOWN_INPUT = 1
+PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE = 1, 2, 4
+PGX_OSC_SINE, PGX_OSC_BLIT = 0, 1
 ABI_VERSION = 1
 
 
@@ -34,6 +36,11 @@ class BankInfo(C.Structure):
                                           "fill")] + \
                [(n, C.c_int64) for n in ("state_bytes", "kernel_launches", "block_steps")] + \
                [(n, C.c_int32) for n in ("mac_grid", "mac_split", "mac_stream_tile", "mac_occupancy")]
+
+
+class OscConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("device", "kind", "n_voices", "unison", "channels", "sample_rate",
+                                          "max_pull", "reserved")] + [("leak", C.c_double)]
 
 
 class Profile(C.Structure):
@@ -58,12 +65,22 @@ PROTOTYPES = {
     "pgx_bank_reset": (C.c_int, [C.c_void_p, _i32p, C.c_int32]),
     "pgx_bank_load_filter": (C.c_int, [C.c_void_p, C.c_int32, _f32p]),
     "pgx_bank_set_filter_map": (C.c_int, [C.c_void_p, _i32p]),
+    "pgx_bank_set_output_gains": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "pgx_bank_use_filter_map_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgx_bank_process": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32]),
     "pgx_bank_process_mix": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32]),
     "pgx_bank_submit": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32, C.c_int32,
                                   C.POINTER(C.c_int64)]),
     "pgx_bank_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "pgx_bank_stream": (C.c_void_p, [C.c_void_p]),
+    "pgx_osc_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(OscConfig), C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "pgx_osc_destroy": (C.c_int, [C.c_void_p]),
+    "pgx_osc_reset": (C.c_int, [C.c_void_p]),
+    "pgx_osc_render_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.POINTER(C.c_void_p)]),
+    "pgx_osc_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "pgx_osc_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "pgx_bank_process_device": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32,
                                           C.c_int32, C.c_void_p]),
     "pgx_bank_synchronize": (C.c_int, [C.c_void_p]),

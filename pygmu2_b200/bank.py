@@ -129,6 +129,11 @@ class ConvolveBank:
             raise ValueError("filter_of_stream must have one entry per stream")
         check(lib().pgx_bank_set_filter_map(self._h, fmap.ctypes.data_as(C.POINTER(C.c_int32))))
 
+    def set_output_gains(self, wet: float = 1.0, dry: float = 0.0) -> None:
+        """Fused output stage of the following pulls: y = dry * x + wet * (x * h) in float32 (ReverbPE's
+        GainPE/GainPE/MixPE tail, reverb_pe.py:82-95)."""
+        check(lib().pgx_bank_set_output_gains(self._h, float(np.float32(wet)), float(np.float32(dry))))
+
     def use_filter_map_device(self, ptr: int | None) -> None:
         """Point the bank at an int32 [n_streams] map already resident on the device (None: its own)."""
         check(lib().pgx_bank_use_filter_map_device(self._h, C.c_void_p(ptr) if ptr else None))
@@ -215,6 +220,36 @@ class ConvolveBank:
         for t in [t for t in infl if t <= ticket]:
             del infl[t]
 
+    # -- device-resident INPUT (a DeviceBlock from osc_pe / VoiceBank), host output ------------------
+    @property
+    def stream_ptr(self) -> int:
+        """The bank's critical CUDA stream (cudaStream_t as int): producers of device input enqueue on it."""
+        return int(lib().pgx_bank_stream(self._h) or 0)
+
+    def process_device_block(self, blk, *, mix: bool = False, interleaved: bool = False) -> np.ndarray:
+        """One pull whose input is already in HBM (produced on ``stream_ptr``): no H2D copy.  Returns host
+        (N, C_out, n), the fused mix (C_out, n), or -- single stream, ``interleaved`` -- Snippet layout (n, C_out)."""
+        n = int(blk.duration)
+        if blk.n_streams != self.n_streams or blk.channels != self.c_in:
+            raise ValueError(f"device block is {blk.n_streams} streams x {blk.channels} channels, "
+                             f"bank expects {self.n_streams} x {self.c_in}")
+        if n > self.max_pull:
+            raise ValueError(f"device block of {n} samples exceeds max_pull={self.max_pull}")
+        if interleaved:
+            if self.n_streams != 1 or mix:
+                raise ValueError("interleaved output is for single-stream banks")
+            y, yl = np.empty((n, self.c_out), dtype=np.float32), Layout(0, 1, self.c_out)
+        elif mix:
+            y, yl = np.empty((self.c_out, n), dtype=np.float32), Layout(0, n, 1)
+        else:
+            y, yl = np.empty((self.n_streams, self.c_out, n), dtype=np.float32), Layout(self.c_out * n, n, 1)
+        tk = C.c_int64(-1)
+        flags = (_lib.PGX_PULL_MIX if mix else 0) | _lib.PGX_PULL_X_DEVICE
+        check(lib().pgx_bank_submit(self._h, C.c_void_p(blk.ptr), blk.layout, _lib.f32_ptr(y), yl, n, flags,
+                                    C.byref(tk)))
+        check(lib().pgx_bank_wait(self._h, tk.value))
+        return y
+
     # -- device-resident pulls (pointers from torch / cuda-python; not synchronised) ------------
     def process_device(self, x_ptr: int, y_ptr: int, n: int, *, mix: bool = False, cuda_stream: int = 0,
                        input_resident: bool = False, x_layout: Layout | None = None,
@@ -250,12 +285,30 @@ class ConvolveBank:
         self._pos = None
         self.mix_output = False
 
+    def attach_device_source(self, source) -> None:
+        """One device-resident producer for all N streams (``VoiceBank`` or anything with
+        ``device_block(start, duration, cuda_stream=...)`` yielding N x C_in planar samples): the lockstep
+        pull then has no host input at all."""
+        self.sources = source
+        self._pos = None
+        self.mix_output = False
+        self._device_source = True
+
     def render(self, start: int, duration: int) -> np.ndarray:
         """One lockstep pull of every attached source: (N, C_out, n), or (C_out, n) when mix_output."""
         if self.sources is None:
             raise RuntimeError("no sources attached")
         if self._pos is None or start != self._pos:
             self.reset()  # non-contiguous pull: history := 0 (convolve_pe.py:255-256)
+        if getattr(self, "_device_source", False):
+            outs, pos = [], 0
+            while pos < duration:
+                d = min(self.max_pull, getattr(self.sources, "max_pull", self.max_pull), duration - pos)
+                blk = self.sources.device_block(start + pos, d, cuda_stream=self.stream_ptr)
+                outs.append(self.process_device_block(blk, mix=self.mix_output))
+                pos += d
+            self._pos = start + duration
+            return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=-1)
         x = np.empty((self.n_streams, self.c_in, duration), dtype=np.float32)
         for s, pe in enumerate(self.sources):
             x[s] = pe.render(start, duration).data.T

@@ -40,6 +40,7 @@ class ConvolvePE(ProcessingElement):
         self._fir_len = None
         self._bank = None
         self._last_render_end = None
+        self._out_gains = None  # (wet, dry) set by ReverbPE: fused GainPE/GainPE/MixPE tail
 
     src = property(lambda self: self._src)
     fir = property(lambda self: self._fir)
@@ -124,12 +125,20 @@ class ConvolvePE(ProcessingElement):
         block = self._block_size or choose_block(filt_len, pull_hint)
         # channel-rule violations raise ValueError inside ConvolveBank (convolve_pe.py:219-223)
         self._bank = ConvolveBank(h, 1, int(src_ch), block=block, device=self._device, single_filter_dims=True)
+        if self._out_gains is not None:
+            self._bank.set_output_gains(*self._out_gains)
         self._fir_len = filt_len
 
     def _render(self, start: int, duration: int) -> Snippet:
         self._ensure_filter_prepared(duration)
         if self._last_render_end is None or start != self._last_render_end:
             self._bank.reset()  # non-contiguous pull: prior samples are zeros (convolve_pe.py:255-256)
+        dev = getattr(self._src, "device_block", None)
+        if dev is not None:  # device-resident source: its samples never visit the host
+            y = self._render_from_device(dev, start, duration)
+            if y is not None:
+                self._last_render_end = start + duration
+                return Snippet(start, y)
         x = self._src.render(start, duration).data
         if x.ndim != 2:
             raise ValueError(f"ConvolvePE src returned invalid shape {getattr(x, 'shape', None)}")
@@ -138,6 +147,22 @@ class ConvolvePE(ProcessingElement):
         y = self._bank.process_interleaved(x)
         self._last_render_end = start + duration
         return Snippet(start, y)
+
+    def _render_from_device(self, dev, start: int, duration: int):
+        bank = self._bank
+        outs, pos = [], 0
+        while pos < duration:
+            d = min(bank.max_pull, duration - pos)
+            blk = dev(start + pos, d, cuda_stream=bank.stream_ptr)
+            if blk is None:
+                if pos:
+                    raise RuntimeError("device source stopped producing blocks in the middle of a pull")
+                return None  # the source declined (e.g. pull larger than its buffer): host path
+            if blk.n_streams != 1 or blk.channels != bank.c_in:
+                raise ValueError(f"ConvolvePE src returned {blk.channels} channels, prepared for {bank.c_in}")
+            outs.append(bank.process_device_block(blk, interleaved=True))
+            pos += d
+        return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)
 
     @property
     def bank(self):

@@ -225,12 +225,25 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
     // element q = j + m*T8 carries window samples 2q (re) and 2q+1 (im)
     const int s = o / a.c_out, c = o - s * a.c_out;
     float* y = a.y + (int64_t)s * a.ys + (int64_t)c * a.yc;
+    const float* xd = a.xdry ? a.xdry + (int64_t)s * a.xs + (int64_t)c * a.xc : nullptr;
+    const bool gains = (a.wet != 1.0f) || xd;
     const int lo = N + a.fill, hi = lo + a.take;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       const int i0 = 2 * (j + m * T8);
-      if (i0 >= lo && i0 < hi) y[(int64_t)(a.y_off + i0 - lo) * a.yi] = v[m].x;
-      if (i0 + 1 >= lo && i0 + 1 < hi) y[(int64_t)(a.y_off + i0 + 1 - lo) * a.yi] = v[m].y;
+      const float e[2] = {v[m].x, v[m].y};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = i0 + h;
+        if (i >= lo && i < hi) {
+          float val = e[h];
+          if (gains) {
+            val = __fmul_rn(val, a.wet);
+            if (xd) val = __fadd_rn(__fmul_rn(xd[(int64_t)(a.x_off + i - lo) * a.xi], a.dry), val);
+          }
+          y[(int64_t)(a.y_off + i - lo) * a.yi] = val;
+        }
+      }
     }
   }
 }

@@ -1,0 +1,156 @@
+// k_osc.cu -- device-resident sources for the convolution path.
+//
+//   k_sine_bank : N constant-parameter SinePE streams        (reference sine_pe.py:135-175)
+//   k_blit_bank : V voices x U band-limited sawtooth oscillators, i.e. BlitSawPE (U = 1) and SuperSawPE
+//                 (reference blit_saw_pe.py:152-264, super_saw_pe.py:282-305)
+//
+// All arithmetic is float64 like the reference (float64 phase, float64 Dirichlet kernel, float64 leaky
+// integrator whose gain 1/(1-leak) = 1000 would amplify float32 noise), rounded to float32 exactly where the
+// reference rounds (every oscillator's Snippet, then the voice sum).  There is no HBM traffic to speak of:
+// the kernels are FP64-transcendental bound and tiny next to the convolution they feed; what they buy is
+// that the inputs of the convolution never exist on the host.
+//
+// The BLIT recurrence  saw[k] = x[k] + leak * saw[k-1]  (scipy.signal.lfilter in the reference) is a linear
+// scan: a warp owns one oscillator and walks the pull in tiles of 128 samples; each lane integrates 4
+// consecutive samples, the 32 lane carries are combined with a weighted warp-shuffle scan, and the carry
+// into the tile is the integrator state.
+#include "kernels.h"
+
+namespace pgx {
+
+__global__ void __launch_bounds__(256) k_sine_bank(const SineArgs a) {
+  const int64_t total = (int64_t)a.n_streams * a.n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e / a.n), i = (int)(e - (int64_t)s * a.n);
+    const double f = a.params[3 * s], amp = a.params[3 * s + 1], ph = a.params[3 * s + 2];
+    const double time = (double)(a.start + i) / (double)a.sample_rate;    // sine_pe.py:173-174
+    const double phase = ph + ((2.0 * 3.141592653589793) * f) * time;     // :175 (left-to-right product)
+    const float v = (float)(amp * sin(phase));                            // :146,157
+    for (int c = 0; c < a.channels; ++c) a.out[(int64_t)s * a.os + (int64_t)c * a.oc + (int64_t)i * a.oi] = v;
+  }
+}
+
+void launch_sine_bank(const SineArgs& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.n_streams * a.n;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  k_sine_bank<<<(int)blocks, 256, 0, st>>>(a);
+}
+
+static constexpr int kOscT = 4;              // consecutive samples per lane
+static constexpr int kOscTile = 32 * kOscT;  // samples per warp tile
+
+__device__ __forceinline__ double shfl_up_d(double v, int d) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, d);
+  hi = __shfl_up_sync(0xffffffffu, hi, d);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+// One CTA per voice, one warp per oscillator of the voice (U <= 32 warps).
+__global__ void __launch_bounds__(1024) k_blit_bank(const BlitArgs a) {
+  extern __shared__ float tile_sm[];  // [U][kOscTile] float32 oscillator outputs of the current tile
+  const int v = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int U = a.unison;
+  const int o = v * U + w;
+  const double sr = (double)a.sample_rate;
+  const double f = a.freq[o], gain = a.gain[o];
+  const double fm = fmax(f, 1.0);
+  const double inc = f / sr;          // blit_saw_pe.py:189
+  const double P = sr / fm;           // :198
+  const double invP = 1.0 / P;        // :218
+  double M;                           // :167-177
+  if (a.m_fixed && a.m_fixed[o] > 0) {
+    M = (double)a.m_fixed[o];
+  } else {
+    int m = (int)floor(sr / (2.0 * fm));
+    m = m - (1 - m % 2);
+    if (m < 1) m = 1;
+    M = (double)m;
+  }
+  const double leak = a.leak;
+  double lk[kOscT + 1];  // leak^q
+  lk[0] = 1.0;
+#pragma unroll
+  for (int q = 1; q <= kOscT; ++q) lk[q] = lk[q - 1] * leak;
+  const double lane_pow = pow(leak, (double)(kOscT * lane));  // weight of the tile's carry-in at this lane
+  double ph0 = a.st_phase[o], y0 = a.st_int[o];               // state at the start of the pull
+  double ph_last = ph0;
+
+  for (int t0 = 0; t0 < a.n; t0 += kOscTile) {
+    const int n_here = min(kOscTile, a.n - t0);
+    const int klast = t0 + n_here - 1;
+    // ---- this lane's 4 samples: BLIT minus DC, integrated from zero
+    double loc[kOscT];
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kOscT; ++q) {
+      const int k = t0 + lane * kOscT + q;
+      double x = 0.0;
+      if (k < a.n) {
+        double ph = ph0 + (double)(k + 1) * inc;   // :192 (cumsum of a constant increment)
+        ph -= floor(ph);                           // :195 np.mod(phase, 1.0)
+        if (k == a.n - 1) ph_last = ph;
+        const double theta = 3.141592653589793 * ph;
+        const double sd = sin(theta);
+        const double blit = (fabs(sd) < 1e-9) ? (M / P) : (sin(M * theta) / (P * sd));  // :203-214
+        x = blit - invP;
+      }
+      s = x + leak * s;
+      loc[q] = s;
+    }
+    // ---- weighted inclusive scan of the lane carries: B[l] = sum_{j<=l} leak^(4(l-j)) s_j
+    double B = s, pw = lk[kOscT];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double up = shfl_up_d(B, d);
+      if (lane >= d) B = fma(pw, up, B);
+      pw *= pw;
+    }
+    double carry = shfl_up_d(B, 1);
+    if (lane == 0) carry = 0.0;
+    carry = fma(lane_pow, y0, carry);  // integrator value just before this lane's first sample
+    float* row = tile_sm + w * kOscTile + lane * kOscT;
+    double ylast = 0.0;
+#pragma unroll
+    for (int q = 0; q < kOscT; ++q) {
+      const double y = fma(lk[q + 1], carry, loc[q]);
+      if (t0 + lane * kOscT + q == klast) ylast = y;
+      row[q] = (float)(y * 2.0 * gain);  // :256-262 each oscillator's Snippet is float32
+    }
+    // new integrator state: the last valid sample of the tile
+    y0 = shfl_d(ylast, (n_here - 1) / kOscT);
+    __syncthreads();
+    // ---- voice output: float64 sum of the float32 oscillator outputs, x amplitude (super_saw_pe.py:292-303)
+    for (int i = threadIdx.x; i < n_here; i += blockDim.x) {
+      double acc = 0.0;
+      for (int u = 0; u < U; ++u) acc += (double)tile_sm[u * kOscTile + i];
+      const float val = (float)(acc * a.amp[v]);
+      for (int c = 0; c < a.channels; ++c)  // np.tile over channels (super_saw_pe.py:304-305)
+        a.out[(int64_t)v * a.os + (int64_t)c * a.oc + (int64_t)(t0 + i) * a.oi] = val;
+    }
+    __syncthreads();
+  }
+  // ---- carry the state to the next pull (:249-250)
+  const int last_lane = ((a.n - 1) % kOscTile) / kOscT;
+  ph_last = shfl_d(ph_last, last_lane);
+  if (lane == 0) {
+    a.st_phase[o] = ph_last;
+    a.st_int[o] = y0;
+  }
+}
+
+void launch_blit_bank(const BlitArgs& a, cudaStream_t st) {
+  const int threads = a.unison * 32;
+  const size_t smem = (size_t)a.unison * kOscTile * sizeof(float);
+  k_blit_bank<<<a.n_voices, threads, smem, st>>>(a);
+}
+
+}  // namespace pgx

@@ -79,11 +79,43 @@ struct C2RArgs {
   int32_t y_off;
   int32_t c_out, B, fill, take;
   const float2* tw;
+  // fused wet/dry output stage (ReverbPE: GainPE(dry) + GainPE(wet) -> MixPE, reverb_pe.py:82-95):
+  // y = dry * x + wet * conv, each product and the sum rounded to float32 like the reference's three PEs.
+  // xdry = the pull's input samples (same addressing as R2CArgs.x), NULL when dry == 0.
+  const float* xdry;
+  int64_t xs, xc, xi;
+  int32_t x_off;
+  float wet, dry;
 };
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st);
 
 // K5: MixPE left-to-right float32 sum of n_inputs dense arrays.
 void launch_mix_sum(const float* in, int32_t n_inputs, int64_t n_elems, float* out, cudaStream_t st);
+
+// Device-resident sources (k_osc.cu).  Output element (voice/stream s, channel c, sample i) at
+// out[s*os + c*oc + i*oi].
+struct SineArgs {
+  const double* params;  // [n_streams][3] = frequency, amplitude, phase offset
+  float* out;
+  int64_t os, oc, oi;
+  int64_t start;         // sample index of the first sample
+  int32_t n_streams, channels, n, sample_rate;
+};
+void launch_sine_bank(const SineArgs& a, cudaStream_t st);
+
+struct BlitArgs {
+  const double* freq;      // [V*U] oscillator frequency (Hz)
+  const double* gain;      // [V*U] oscillator amplitude
+  const int32_t* m_fixed;  // [V*U] harmonics (0 = auto: largest odd M below Nyquist), or NULL
+  const double* amp;       // [V] voice amplitude
+  double* st_phase;        // [V*U] state: phase in [0,1) at the end of the previous pull
+  double* st_int;          // [V*U] state: leaky-integrator output at the end of the previous pull
+  float* out;
+  int64_t os, oc, oi;
+  double leak;
+  int32_t n_voices, unison, channels, n, sample_rate;
+};
+void launch_blit_bank(const BlitArgs& a, cudaStream_t st);
 
 int fft_smem_bytes(int B);
 

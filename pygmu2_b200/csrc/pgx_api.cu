@@ -37,14 +37,14 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/pgx.h"
+#include "host_util.h"
 #include "kernels.h"
 
 namespace {
-
 thread_local std::string g_err;
+}
 
-int fail(int code, const char* fmt, ...) {
+int pgx_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -53,14 +53,9 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+#define fail pgx_fail
 
-#define PGX_CUDA(expr)                                                                          \
-  do {                                                                                          \
-    cudaError_t e__ = (expr);                                                                   \
-    if (e__ != cudaSuccess)                                                                     \
-      return fail(e__ == cudaErrorMemoryAllocation ? PGX_ERR_NOMEM : PGX_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
-                  cudaGetErrorString(e__), __FILE__, __LINE__);                                 \
-  } while (0)
+namespace {
 
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -136,6 +131,7 @@ struct pgx_bank {
   int64_t last_k2_of_par[2] = {-1, -1};  // last step whose K2 read ypast[par]
   pgx::MacPlan plan_conv{}, plan_mix{}, plan_now{};
   int sm_count = 148;
+  float wet = 1.0f, dry = 0.0f;    // fused output stage: y = dry * x + wet * conv
   bool serial = false;
   int64_t launches = 0, steps = 0;
   // per-kernel CUDA-event timing
@@ -351,6 +347,9 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   k.Hd = b->Hd; k.fmap = b->fmap; k.c_x = b->c_x; k.c_f = c.filter_channels; k.R = R; k.head = b->head;
   k.y = y_dev; k.ys = mix ? 0 : yl.stream; k.yc = yl.chan; k.yi = yl.samp; k.y_off = pos;
   k.c_out = c.c_out; k.B = B; k.fill = b->fill; k.take = take; k.tw = b->tw;
+  k.wet = b->wet; k.dry = b->dry;
+  k.xdry = (!mix && b->dry != 0.0f) ? x_dev : nullptr;
+  k.xs = xl.stream; k.xc = xl.chan; k.xi = xl.samp; k.x_off = pos;
 
   // the block commits with this step: its row is final once K1 has run, so the next block's past pass
   // can start now, overlapping this step's K2 and the next step's K1
@@ -719,6 +718,16 @@ int pgx_bank_set_filter_map(pgx_bank* b, const int32_t* filter_of_stream) {
   return PGX_OK;
 }
 
+int pgx_bank_set_output_gains(pgx_bank* b, float wet, float dry) {
+  if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  if (dry != 0.0f && ((b->cfg.flags & PGX_FLAG_MIXDOWN_INPUT) || b->cfg.c_in != b->cfg.c_out))
+    return fail(PGX_ERR_INVALID, "a dry path needs as many source channels (%d) as output channels (%d) and no mix-down",
+                b->cfg.c_in, b->cfg.c_out);
+  b->wet = wet;  // host-side state read at enqueue time: applies to the pulls submitted from now on
+  b->dry = dry;
+  return PGX_OK;
+}
+
 int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   b->fmap = fmap_dev ? const_cast<int32_t*>(fmap_dev) : b->fmap_own + (size_t)b->fmap_cur * b->cfg.n_streams;
@@ -729,7 +738,7 @@ int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
 // Host-buffer pull, asynchronous: stage x into the next slot (H2D on the copy-in stream), enqueue the block
 // steps, copy y back on the copy-out stream.  Returns a ticket; y is complete after submit_wait(ticket).
 static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, bool mix,
-                       int64_t* ticket) {
+                       int64_t* ticket, bool x_device = false) {
   int rc = check_pull_args(b, x, y, n);
   if (rc != PGX_OK) return rc;
   const pgx_bank_config& c = b->cfg;
@@ -745,11 +754,15 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   const int slot = (int)(tk % pgx_bank::kSlots);
   // the slot's previous pull is over once its D2H has completed (its K1s read x_stage before that)
   if (tk >= pgx_bank::kSlots) PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
-  PGX_CUDA(cudaMemcpyAsync(b->x_stage[slot], x, xb, cudaMemcpyHostToDevice, b->s_h2d));
-  PGX_CUDA(cudaEventRecord(b->ev_h2d[slot], b->s_h2d));
-  PGX_CUDA(cudaStreamWaitEvent(b->s_in, b->ev_h2d[slot], 0));
-  PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
-  rc = run_pull(b, b->x_stage[slot], xl, b->y_stage[slot], yd, n, mix, true, b->stream);
+  if (x_device) {  // produced by work already queued on the bank's stream: run_pull orders the ingest after it
+    rc = run_pull(b, x, xl, b->y_stage[slot], yd, n, mix, false, b->stream);
+  } else {
+    PGX_CUDA(cudaMemcpyAsync(b->x_stage[slot], x, xb, cudaMemcpyHostToDevice, b->s_h2d));
+    PGX_CUDA(cudaEventRecord(b->ev_h2d[slot], b->s_h2d));
+    PGX_CUDA(cudaStreamWaitEvent(b->s_in, b->ev_h2d[slot], 0));
+    PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
+    rc = run_pull(b, b->x_stage[slot], xl, b->y_stage[slot], yd, n, mix, true, b->stream);
+  }
   if (rc != PGX_OK) return rc;
   PGX_CUDA(cudaEventRecord(b->ev_y[slot], b->stream));
   PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_y[slot], 0));
@@ -778,8 +791,10 @@ static int process_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pg
 int pgx_bank_submit(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, int32_t flags,
                     int64_t* ticket) {
   if (!ticket) return fail(PGX_ERR_INVALID, "ticket is NULL");
-  return submit_host(b, x, xl, y, yl, n, (flags & PGX_PULL_MIX) != 0, ticket);
+  return submit_host(b, x, xl, y, yl, n, (flags & PGX_PULL_MIX) != 0, ticket, (flags & PGX_PULL_X_DEVICE) != 0);
 }
+
+void* pgx_bank_stream(pgx_bank* b) { return b ? static_cast<void*>(b->stream) : nullptr; }
 
 int pgx_bank_wait(pgx_bank* b, int64_t ticket) { return submit_wait(b, ticket); }
 

@@ -24,6 +24,7 @@ from .bank import ConvolveBank, choose_block
 from .convolve_pe import ConvolvePE
 from .core import Extent, ProcessingElement, Snippet
 from .hrtf_bank import HrtfMixBank
+from .osc_pe import BlitSawPE, SinePE, SuperSawPE, VoiceBank
 from .spatial_pe import SpatialHRTF, SpatialPE
 
 
@@ -74,6 +75,11 @@ class MixPE(ProcessingElement):
                 if len(chans) == 1 and None not in chans:
                     return HrtfMixBank([p.source for p in ins], [p.method for p in ins],
                                        pull_hint=duration, device=self._device)
+            if len({type(p) for p in ins}) == 1 and type(ins[0]) in (SuperSawPE, BlitSawPE, SinePE):
+                try:
+                    return _VoiceMix(VoiceBank(ins, device=self._device))
+                except ValueError:
+                    return False  # voices of different shapes: general path
         except _NotFusable:
             return False
         return False
@@ -115,6 +121,14 @@ class MixPE(ProcessingElement):
             return Snippet(start, rendered[0].copy())
         return Snippet(start, device_mix_sum(rendered, self._device))
 
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0):
+        """The mix left in HBM (only when the inputs are oscillator voices fused into one VoiceBank)."""
+        if self._fused is None:
+            self._fused = self._try_adopt(duration)
+        if isinstance(self._fused, _VoiceMix):
+            return self._fused.device_block(start, duration, cuda_stream)
+        return None
+
     def _reset_state(self) -> None:
         self._fused_pos = None
         if self._fused not in (None, False):
@@ -147,3 +161,19 @@ class MixPE(ProcessingElement):
 
 class _NotFusable(Exception):
     pass
+
+
+class _VoiceMix:
+    """MixPE over oscillator voices: one VoiceBank launch plus the bit-exact float32 voice sum (K5)."""
+
+    def __init__(self, vb: VoiceBank):
+        self.vb = vb
+
+    def render(self, start: int, duration: int) -> np.ndarray:
+        return self.vb.render(start, duration, mix=True)
+
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0):
+        return self.vb.device_block(start, duration, mix=True, cuda_stream=cuda_stream)
+
+    def reset(self) -> None:
+        self.vb.reset()

@@ -5,8 +5,7 @@ feed ConvolvePE / SpatialPE / MixPE.  They are *not* accelerated (SURVEY.md §2b
 out of scope) and exist so graphs can be built on a machine without pygmu2.
 
 ArrayPE   array_pe.py:17-133     ConstantPE constant_pe.py:15-72
-SinePE    sine_pe.py:119-175 (constant parameters only)
-GainPE    gain_pe.py:92-127 (constant gain only)   DelayPE delay_pe.py:153-160 (integer delay)
+GainPE    gain_pe.py:60-155                        DelayPE delay_pe.py:153-160 (integer delay)
 CropPE    crop_pe.py:18-96       CachePE    cache_pe.py:17-84
 """
 from __future__ import annotations
@@ -71,28 +70,6 @@ class ConstantPE(SourcePE):
         return f"ConstantPE(value={self._value}, channels={self._channels})"
 
 
-class SinePE(SourcePE):
-    """Constant-parameter sine: float64 phase straight from the sample index, float32 out."""
-
-    def __init__(self, frequency: float = 440.0, amplitude: float = 1.0, phase: float = 0.0, channels: int = 1):
-        self._frequency, self._amplitude = float(frequency), float(amplitude)
-        self._phase, self._channels = float(phase), int(channels)
-
-    def channel_count(self) -> int:
-        return self._channels
-
-    def _render(self, start: int, duration: int) -> Snippet:
-        t = np.arange(start, start + duration, dtype=np.float64) / self.sample_rate
-        ph = self._phase + 2.0 * np.pi * self._frequency * t
-        s = (self._amplitude * np.sin(ph)).reshape(-1, 1)
-        if self._channels > 1:
-            s = np.tile(s, (1, self._channels))
-        return Snippet(start, s.astype(np.float32))
-
-    def __repr__(self):
-        return f"SinePE(frequency={self._frequency}, amplitude={self._amplitude})"
-
-
 class _Unary(ProcessingElement):
     def __init__(self, source: ProcessingElement):
         self._source = source
@@ -113,16 +90,30 @@ class _Unary(ProcessingElement):
 
 
 class GainPE(_Unary):
-    def __init__(self, source: ProcessingElement, gain: float = 1.0):
-        if isinstance(gain, ProcessingElement):
-            raise NotImplementedError("pygmu2_b200.GainPE supports constant gain only (out of scope: gain_pe.py:104-121)")
+    """gain_pe.py:60-155: constant gain (float32 multiply) or a PE of per-sample gains."""
+
+    def __init__(self, source: ProcessingElement, gain=1.0):
         super().__init__(source)
         self._gain = gain
+        self._gain_is_pe = isinstance(gain, ProcessingElement)
 
     gain = property(lambda self: self._gain)
 
+    def inputs(self) -> list:
+        return [self._source, self._gain] if self._gain_is_pe else [self._source]
+
+    def _compute_extent(self) -> Extent:
+        e = self._source.extent()
+        return e.intersection(self._gain.extent()) if self._gain_is_pe else e
+
     def _render(self, start: int, duration: int) -> Snippet:
-        return Snippet(start, self._source.render(start, duration).data * np.float32(self._gain))
+        x = self._source.render(start, duration).data
+        if not self._gain_is_pe:
+            return Snippet(start, x * np.float32(self._gain))
+        g = self._gain.render(start, duration).data.astype(np.float32, copy=False)
+        if g.shape[1] == 1 and x.shape[1] > 1:
+            g = np.tile(g, (1, x.shape[1]))
+        return Snippet(start, x * g)
 
 
 class DelayPE(_Unary):

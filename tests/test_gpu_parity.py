@@ -577,3 +577,49 @@ def test_submit_pipeline_with_filter_map_reselected_every_pull():
     for a in xin + yout:
         a.free()
     bank.close()
+
+
+# ---------------------------------------------------------------------------
+# ReverbPE: fused wet/dry epilogue (pgx_bank_set_output_gains) vs the reference's composite graph
+def test_reverb_fused_is_bit_identical_to_composite_graph():
+    rng = np.random.default_rng(41)
+    x = rng.uniform(-1, 1, (4000, 2)).astype(np.float32)
+    ir = (rng.standard_normal((1800, 2)) * np.exp(-np.arange(1800)[:, None] / 300.0)).astype(np.float32)
+    pulls = (512, 17, 512, 1000, 959, 1000)
+    fused = pg.ReverbPE(pg.ArrayPE(x), pg.ArrayPE(ir), mix=0.35)
+    assert fused._fused
+    e = fused.ir_energy
+    src = pg.CachePE(pg.ArrayPE(x))
+    comp = pg.MixPE(pg.GainPE(src, gain=1.0 - 0.35),
+                    pg.GainPE(pg.ConvolvePE(src, pg.ArrayPE(ir)), gain=0.35 / e), fuse=False)
+    np.testing.assert_array_equal(_pull_pe(fused, pulls), _pull_pe(comp, pulls))
+
+
+def test_reverb_pe_valued_mix_matches_oracle():
+    rng = np.random.default_rng(42)
+    n = 3000
+    x = rng.uniform(-1, 1, (n, 1)).astype(np.float32)
+    ir = (rng.standard_normal(700) / 20).astype(np.float32)
+    mixv = np.linspace(0.0, 1.0, n + 699, dtype=np.float32)
+    pe = pg.ReverbPE(pg.ArrayPE(x), pg.ArrayPE(ir), mix=pg.ArrayPE(mixv))
+    assert not pe._fused
+    y = _pull_pe(pe, (512,) * 5 + (440,))
+    wet = orc.OracleConvolve(ir, 1).render(x)
+    e = np.float32(1.0 / orc.ir_energy_norm(ir))
+    m = mixv[:n, None]
+    dry_g = np.float32(1.0) + m * np.float32(-1.0)
+    ref = x * dry_g + wet * (m * e)
+    assert rel_err(y, ref) <= TOL
+
+
+def test_output_gains_contract():
+    bank = pg.ConvolveBank(np.ones((1, 8), np.float32), 2, 1, block=16)
+    bank.set_output_gains(0.5, 0.25)
+    x = np.random.default_rng(5).uniform(-1, 1, (2, 1, 40)).astype(np.float32)
+    y = bank.process(x)
+    wet = np.stack([np.convolve(x[s, 0].astype(np.float64), np.ones(8))[:40] for s in range(2)])[:, None, :]
+    assert rel_err(y, 0.25 * x + 0.5 * wet) <= TOL
+    fan = pg.ConvolveBank(np.ones((1, 8, 2), np.float32), 1, 1, block=16)   # mono source, stereo filter
+    with pytest.raises(ValueError):
+        fan.set_output_gains(1.0, 0.5)
+    fan.set_output_gains(0.5, 0.0)

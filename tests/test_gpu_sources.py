@@ -1,0 +1,148 @@
+"""
+Device-resident sources through the C ABI (pgx_osc_*): SinePE, BlitSawPE, SuperSawPE
+against golden outputs of the REAL reference (tests/golden/src_oscillators.npz) and the oracle restatement,
+and the device-to-device hand-over into ConvolvePE / MixPE / ConvolveBank.  Needs a B200: ``-m gpu``.
+
+Tolerance: the kernels use float64 like the reference and round to float32 at the same places; what differs is
+the libm (CUDA sin vs glibc) and the order of the phase / integrator sums, so outputs agree to ~1 float32 ulp.
+The bar stays the path's: max-abs error <= 1e-5 of full scale.
+"""
+import numpy as np
+import pytest
+
+import pygmu2_b200 as pg
+import pygmu2_oracle as orc
+import pygmu2_oracle_sources as osrc
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+SR = 44_100
+MIX = {0: "center_heavy", 1: "linear", 2: "equal"}
+
+
+def _pull(pe, pulls, start=0):
+    out, pos = [], start
+    for d in pulls:
+        out.append(pe.render(pos, int(d)).data.copy())
+        pos += int(d)
+    return np.concatenate(out, axis=0)
+
+
+def test_sine_matches_reference_goldens():
+    g = golden("src_oscillators.npz")
+    pulls = g["pulls"]
+    (f0, a0, p0), (f1, a1, p1), (f2, a2, p2) = g["sine_params"]
+    y = _pull(pg.SinePE(frequency=f0), pulls)
+    assert y.shape == g["sine_440"].shape and rel_err(y, g["sine_440"]) <= 2e-7
+    yb = _pull(pg.SinePE(frequency=f1, amplitude=a1, phase=p1, channels=2), pulls, start=4_000_000)
+    assert yb.shape == g["sine_b"].shape and rel_err(yb, g["sine_b"]) <= 2e-7
+    yc = _pull(pg.SinePE(frequency=f2, amplitude=a2, phase=p2), pulls, start=-300)
+    assert rel_err(yc, g["sine_c"]) <= 2e-7
+
+
+def test_blit_saw_matches_reference_goldens_including_restart():
+    g = golden("src_oscillators.npz")
+    pulls = g["pulls"]
+    for i, (f, a, p, m, lk) in enumerate(g["blit_cases"]):
+        pe = pg.BlitSawPE(frequency=f, amplitude=a, initial_phase=p, m=None if m < 0 else int(m), leak=lk)
+        y = np.concatenate([_pull(pe, pulls), _pull(pe, [64, 64], start=10_000)])
+        ref = g[f"blit_{i}"]
+        assert y.shape == ref.shape
+        # full scale of a BlitSaw is its amplitude (case 5, 10 kHz: M = 1, the output is pure rounding noise ~1e-15)
+        err = float(np.max(np.abs(y.astype(np.float64) - ref)) / max(float(np.max(np.abs(ref))), a))
+        assert err <= TOL, f"case {i}: {err:.3e}"
+
+
+def test_supersaw_matches_reference_goldens():
+    g = golden("src_oscillators.npz")
+    pulls = g["pulls"]
+    for i, (f, a, v, d, mm, rp, sd) in enumerate(g["ssaw_cases"]):
+        pe = pg.SuperSawPE(frequency=f, amplitude=a, voices=int(v), detune_cents=d, mix_mode=MIX[int(mm)],
+                           randomize_phase=bool(rp), seed=int(sd))
+        y = _pull(pe, pulls)
+        assert rel_err(y, g[f"ssaw_{i}"]) <= TOL, f"case {i}: {rel_err(y, g[f'ssaw_{i}']):.3e}"
+
+
+def test_supersaw_long_pull_and_start_stop_reset():
+    """4096-sample pulls (32 warp tiles per launch) and the on_start reset, against the oracle."""
+    pe = pg.SuperSawPE(frequency=523.25, amplitude=0.8, voices=9, detune_cents=25.0, seed=11, channels=2)
+    o = osrc.OracleSuperSaw(523.25, 0.8, 9, 25.0, seed=11, sample_rate=SR)
+    with pg.NullRenderer(sample_rate=SR) as r:
+        r.set_source(pe)
+        r.start()
+        y = _pull(pe, [4096, 4096, 1000])
+        ref = np.concatenate([o.render(0, 4096), o.render(4096, 4096), o.render(8192, 1000)])
+        assert y.shape == (9192, 2)
+        assert rel_err(y[:, 0], ref) <= TOL and np.array_equal(y[:, 0], y[:, 1])
+        r.stop()
+        r.start()                                   # restart: phases and integrators back to their initial values
+        o.reset()
+        assert rel_err(_pull(pe, [300])[:, 0], o.render(0, 300)) <= TOL
+
+
+def test_voice_mix_fused_matches_reference_golden():
+    """C5 front end in miniature: MixPE of 16 SuperSaw voices = one VoiceBank launch + the float32 voice sum."""
+    g = golden("src_oscillators.npz")
+    voices = [pg.SuperSawPE(frequency=110.0 * 2 ** (i / 12.0), amplitude=1.0 / 16, seed=i) for i in range(16)]
+    mix = pg.MixPE(*voices)
+    y = _pull(mix, [64] * 12)
+    assert rel_err(y, g["c5_voicemix16"]) <= TOL
+    from pygmu2_b200.mix_pe import _VoiceMix
+    assert isinstance(mix._fused, _VoiceMix) and mix._fused.vb.bank.launches == 2 * 12
+
+
+def test_modulated_parameters_are_rejected_loudly():
+    with pytest.raises(NotImplementedError):
+        pg.SinePE(frequency=pg.ConstantPE(440.0))
+    with pytest.raises(NotImplementedError):
+        pg.SuperSawPE(frequency=pg.ConstantPE(440.0))
+
+
+def test_c1_sine_source_stays_on_device_through_convolve():
+    """SinePE -> ConvolvePE with the samples handed over in HBM (no H2D): same answer as the host hand-over."""
+    rng = np.random.default_rng(3)
+    h = (rng.standard_normal(700) / 20).astype(np.float32)
+    pe = pg.ConvolvePE(pg.SinePE(frequency=440.0), pg.ArrayPE(h))
+    pulls = [512, 17, 512, 1000, 259]
+    y = _pull(pe, pulls)
+    x = osrc.sine(440.0, 1.0, 0.0, SR, 0, sum(pulls))
+    ref = orc.OracleConvolve(h, 1).render(x[:, None])
+    assert rel_err(y, ref) <= TOL
+    host = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h))
+    assert rel_err(y, _pull(host, pulls)) <= 1e-6
+
+
+def test_c5_pipeline_voices_to_long_ir_all_on_device():
+    """MixPE(64 SuperSaw voices) -> ConvolvePE(2000-tap IR) at 64-sample pulls: voices, voice sum and the
+    convolution input never leave the device; checked against oracle voices -> float32 mix -> oracle convolve."""
+    V, n_pulls = 64, 40
+    rng = np.random.default_rng(8)
+    ir = (rng.standard_normal(2000) * np.exp(-np.arange(2000) / 333.0) / 10).astype(np.float32)
+    voices = [pg.SuperSawPE(frequency=55.0 * 2 ** (i / 24.0), amplitude=1.0 / 32, seed=i) for i in range(V)]
+    pe = pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(ir), block_size=64)
+    y = _pull(pe, [64] * n_pulls)
+    ov = [osrc.OracleSuperSaw(55.0 * 2 ** (i / 24.0), 1.0 / 32, seed=i, sample_rate=SR) for i in range(V)]
+    xs = []
+    for p in range(n_pulls):
+        acc = ov[0].render(p * 64, 64).copy()
+        for o in ov[1:]:
+            acc += o.render(p * 64, 64)
+        xs.append(acc)
+    ref = orc.OracleConvolve(ir, 1).render(np.concatenate(xs)[:, None])
+    assert rel_err(y, ref) <= TOL
+
+
+def test_bank_with_device_voice_source_lockstep():
+    """N independent SinePE streams -> N distinct FIRs: one VoiceBank feeds the ConvolveBank in HBM."""
+    N, L = 6, 300
+    rng = np.random.default_rng(12)
+    hs = (rng.standard_normal((N, L)) / 15).astype(np.float32)
+    sines = [pg.SinePE(frequency=200.0 * (i + 1), amplitude=0.5, phase=0.1 * i) for i in range(N)]
+    bank = pg.ConvolveBank(hs, N, 1, pull_hint=256)
+    bank.attach_device_source(pg.VoiceBank(sines))
+    ys = [bank.render(p, 256) for p in range(0, 1024, 256)]
+    y = np.concatenate(ys, axis=2)
+    for s in range(N):
+        x = osrc.sine(200.0 * (s + 1), 0.5, 0.1 * s, SR, 0, 1024)
+        assert rel_err(y[s, 0], orc.OracleConvolve(hs[s], 1).render(x[:, None])[:, 0]) <= TOL

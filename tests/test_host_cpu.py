@@ -19,7 +19,7 @@ from conftest import ROOT, golden
 # ---- C ABI -------------------------------------------------------------------------------------
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "pgx.h")).read()
-    declared = set(re.findall(r"PGX_API\s+(?:const\s+char\*|int)\s+(pgx_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"PGX_API\s+(?:const\s+char\*|void\*|int)\s+(pgx_\w+)\s*\(", hdr))
     assert declared, "no prototypes parsed from pgx.h"
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     h = _lib.lib()
@@ -34,6 +34,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Layout) == 24
     assert C.sizeof(_lib.BankConfig) == 40
     assert C.sizeof(_lib.Profile) == 64
+    assert C.sizeof(_lib.OscConfig) == 40
 
 
 def test_no_silent_cpu_path():

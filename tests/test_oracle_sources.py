@@ -1,0 +1,62 @@
+"""
+The source-PE oracle (oracle/pygmu2_oracle_sources.py) against golden outputs of the REAL reference
+(tests/golden/src_oscillators.npz, made by oracle/gen_golden_sources.py).  CPU only.
+Sine / BlitSaw / SuperSaw restatements use the same numpy / scipy calls as the reference, so the
+float32 outputs must be bit-identical.
+"""
+import numpy as np
+
+import pygmu2_oracle_sources as osrc
+from conftest import golden
+
+SR = 44_100
+MIX = {0: "center_heavy", 1: "linear", 2: "equal"}
+
+
+def _pull(render, pulls, start=0):
+    out, pos = [], start
+    for d in pulls:
+        out.append(render(pos, int(d)))
+        pos += int(d)
+    return np.concatenate(out)
+
+
+def test_sine_bit_exact():
+    g = golden("src_oscillators.npz")
+    pulls = g["pulls"]
+    (f0, a0, p0), (f1, a1, p1), (f2, a2, p2) = g["sine_params"]
+    np.testing.assert_array_equal(_pull(lambda s, d: osrc.sine(f0, a0, p0, SR, s, d), pulls), g["sine_440"][:, 0])
+    yb = _pull(lambda s, d: osrc.sine(f1, a1, p1, SR, s, d), pulls, start=4_000_000)
+    np.testing.assert_array_equal(yb, g["sine_b"][:, 0])
+    np.testing.assert_array_equal(yb, g["sine_b"][:, 1])
+    np.testing.assert_array_equal(_pull(lambda s, d: osrc.sine(f2, a2, p2, SR, s, d), pulls, start=-300), g["sine_c"][:, 0])
+
+
+def test_blit_saw_bit_exact_including_restart():
+    g = golden("src_oscillators.npz")
+    pulls = g["pulls"]
+    for i, (f, a, p, m, lk) in enumerate(g["blit_cases"]):
+        o = osrc.OracleBlitSaw(f, a, p, None if m < 0 else int(m), lk, SR)
+        y = np.concatenate([_pull(o.render, pulls), _pull(o.render, [64, 64], start=10_000)])
+        np.testing.assert_array_equal(y, g[f"blit_{i}"][:, 0], err_msg=f"case {i}")
+
+
+def test_supersaw_bit_exact():
+    g = golden("src_oscillators.npz")
+    pulls = g["pulls"]
+    for i, (f, a, v, d, mm, rp, sd) in enumerate(g["ssaw_cases"]):
+        o = osrc.OracleSuperSaw(f, a, int(v), d, MIX[int(mm)], bool(rp), int(sd), SR)
+        np.testing.assert_array_equal(_pull(o.render, pulls), g[f"ssaw_{i}"][:, 0], err_msg=f"case {i}")
+
+
+def test_c5_voice_mix_bit_exact():
+    g = golden("src_oscillators.npz")
+    voices = [osrc.OracleSuperSaw(110.0 * 2 ** (i / 12.0), 1.0 / 16, seed=i, sample_rate=SR) for i in range(16)]
+    out, pos = [], 0
+    for _ in range(12):
+        acc = voices[0].render(pos, 64).copy()
+        for v in voices[1:]:
+            acc += v.render(pos, 64)            # MixPE: float32 left-to-right (mix_pe.py:92-94)
+        out.append(acc)
+        pos += 64
+    np.testing.assert_array_equal(np.concatenate(out), g["c5_voicemix16"][:, 0])
