@@ -138,6 +138,37 @@ def cpu_baseline_single(seconds_budget: float = 12.0):
                       f"overlap-save, nfft=262144), {t:.1f} s on 1 host core; filter prep excluded"}
 
 
+def cpu_baseline_c5v(n_voices: int, seconds_budget: float = 12.0):
+    """C5 with its front end on ONE host core, bounded sample: the oracle port of SuperSawPE (7 BlitSaw
+    oscillators, float64, scipy lfilter) for a few voices x pulls, plus the oracle ConvolvePE pull
+    (one 524288-point float64 rfft/irfft pair per 64-sample pull); voice time is scaled to n_voices."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pygmu2_oracle_sources as osrc  # timed CPU baseline only
+    orc = _oracle()
+    sv, pulls = 8, 16
+    voices = [osrc.OracleSuperSaw(55.0 * 2.0 ** (i / 128.0), 1.0 / 32.0, seed=i, sample_rate=wl.SR_441) for i in range(sv)]
+    for v in voices:
+        v.render(0, 64)
+    t0 = time.perf_counter()
+    for p in range(1, pulls + 1):
+        for v in voices:
+            v.render(p * 64, 64)
+    t_voice = (time.perf_counter() - t0) / (sv * pulls)           # seconds per voice per 64-sample pull
+    conv = orc.OracleConvolve(wl.c5_ir(), 1)
+    x = np.random.default_rng(0).uniform(-1, 1, (64, 1)).astype(np.float32)
+    conv.render(x)
+    cp = int(max(3, min(40, (seconds_budget - 2.0) / 0.08)))
+    t0 = time.perf_counter()
+    for _ in range(cp):
+        conv.render(x)
+    t_conv = (time.perf_counter() - t0) / cp
+    per_pull = t_voice * n_voices + t_conv
+    return {"value": (64 / wl.SR_441) / per_pull, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{sv} SuperSaw voices x {pulls} pulls of 64 ({t_voice * 1e6:.0f} us per voice-pull, scaled to "
+                      f"{n_voices} voices) + {cp} ConvolvePE pulls with the 441000-tap IR ({t_conv * 1e3:.1f} ms each, "
+                      "nfft=524288), 1 host core, oracle port of the reference"}
+
+
 _REF = {}
 
 
@@ -229,8 +260,12 @@ def make_workload(args, rank, local):
             bank = pg.ConvolveBank(irs, N, CH, block=B, max_pull=PULL, device=local)
         else:
             bank = pg.ConvolveBank(wl.c2_ir(), N, CH, block=B, max_pull=PULL, device=local, single_filter_dims=True)
+        cfg = _config(args)
+        if args.reverb:  # ReverbPE's wet/dry tail fused into the inverse-FFT kernel (reverb_pe.py:82-95)
+            bank.set_output_gains(0.3, 0.7)
+            cfg["output_stage"] = "fused ReverbPE wet/dry: y = 0.7*x + 0.3*conv (pgx_bank_set_output_gains)"
         return dict(bank=bank, N=N, c_in=CH, c_out=CH, L=L, B=B, pull=PULL, sr=SR, distinct=distinct, mix=False,
-                    config=_config(args), fill_steps=bank.partitions)
+                    config=cfg, fill_steps=bank.partitions)
     if w == "c1":   # 4096 mono streams x distinct 4096-tap FIRs, B = 4096 (P = 1): FFT-stage bound
         N = args.streams or 4096
         rng = np.random.default_rng(1234 + rank)
@@ -273,6 +308,21 @@ def make_workload(args, rank, local):
                       f"delay line streamed per step: {N * bank.partitions * 64 * 8 / 1e6:.0f} MB vs 126 MB L2")}
         return dict(bank=bank, N=N, c_in=1, c_out=1, L=wl.C5_L, B=64, pull=64, sr=wl.SR_441, distinct=False, mix=False,
                     config=cfg, fill_steps=min(bank.partitions, 400))
+    if w == "c5v":  # C5 with its front end: 1024 SuperSawPE voices -> MixPE -> 10 s IR at 64-sample pulls, all in HBM
+        V = args.streams or wl.C5_VOICES
+        pg.set_sample_rate(wl.SR_441)
+        voices = [pg.SuperSawPE(frequency=55.0 * 2.0 ** (i / 128.0), amplitude=1.0 / 32.0, seed=i) for i in range(V)]
+        mixpe = pg.MixPE(*voices)
+        pe = pg.ConvolvePE(mixpe, pg.ArrayPE(wl.c5_ir()), block_size=64)
+        pe.render(0, 64)                       # builds the VoiceBank (V x 7 oscillators) and the 6891-partition bank
+        bank, vb = pe.bank, mixpe._fused.vb
+        cfg = {"workload": f"C5 with its front end on the device: {V} SuperSawPE voices (7 BLIT oscillators each, "
+                           "float64) -> MixPE (float32 voice sum) -> ConvolvePE with a 10 s IR (441000 taps) @44.1 kHz, "
+                           "64-sample pulls; voice generation INCLUDED in every step",
+               "voices": V, "oscillators": V * 7, "block": 64, "partitions": bank.partitions, "pull": 64,
+               "sample_rate": wl.SR_441, "l2": "state 7 MB: L2-resident, latency-bound"}
+        return dict(bank=bank, N=1, c_in=1, c_out=1, L=wl.C5_L, B=64, pull=64, sr=wl.SR_441, distinct=False, mix=False,
+                    config=cfg, fill_steps=400, voicebank=vb, pe=pe)
     raise SystemExit(f"unknown workload {w}")
 
 
@@ -309,17 +359,28 @@ def run_gpu(args):
     if args.workload in ("c3", "c4"):
         x_host /= np.float32(N)
     x_dev = torch.from_numpy(x_host).to(dev)
+    if spec.get("voicebank") is not None:
+        spec["pe"].render(64, 64 * 8)  # leave the build pull behind; positions below continue from a round number
+
     y_dev = torch.empty((n_out_ch, pull), dtype=torch.float32, device=dev)
     stream = torch.cuda.Stream(device=dev, priority=-1)  # the critical (output) stream outranks the background pass
     sh = stream.cuda_stream
-    blk_bytes = N * c_in * pull * 4
+    blk_bytes = 0 if spec.get("voicebank") is not None else N * c_in * pull * 4
     out_bytes = n_out_ch * pull * 4
     traj = traj_dev = None
     if spec.get("moving"):  # per-pull filter choice of every source, resident as one int32 row per pull
         traj = np.random.default_rng(6).integers(0, spec["n_filters"], (64, N)).astype(np.int32)
         traj_dev = torch.from_numpy(traj).to(dev)
 
+    vb = spec.get("voicebank")
+    vpos = [64 * 9]  # running sample position of the voice front end (contiguous pulls; 0..64 was the build pull)
+
     def step(i):
+        if vb is not None:  # voices + voice sum rendered into HBM on the same stream, then the convolution pull
+            blk = vb.device_block(vpos[0], pull, mix=True, cuda_stream=sh)
+            vpos[0] += pull
+            bank.process_device(blk.ptr, y_dev.data_ptr(), pull, cuda_stream=sh, input_resident=False)
+            return
         if traj_dev is not None:
             bank.use_filter_map_device(traj_dev.data_ptr() + (i % 64) * N * 4)
         bank.process_device(x_dev.data_ptr() + (i % N_INPUT_BLOCKS) * blk_bytes, y_dev.data_ptr(), pull,
@@ -342,7 +403,7 @@ def run_gpu(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = bank.info().kernel_launches
+    l0 = bank.info().kernel_launches + (vb.bank.launches if vb is not None else 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -354,7 +415,7 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1)
     info = bank.info()
-    launches = int(info.kernel_launches - l0)
+    launches = int(info.kernel_launches + (vb.bank.launches if vb is not None else 0) - l0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -383,6 +444,10 @@ def run_gpu(args):
 
     def e2e_step(i):
         """One pull through the public host API.  Pipelined: submit pull i, then wait for pull i-(DEPTH-1)."""
+        if vb is not None:  # the PE graph itself: ConvolvePE(MixPE(voices), ir).render -> host Snippet
+            yp.array[0, 0, :] = spec["pe"].render(vpos[0], pull).data[:, 0]
+            vpos[0] += pull
+            return None
         if traj is not None:
             bank.set_filter_map(traj[i % 64])
         if pipelined:
@@ -449,7 +514,8 @@ def run_gpu(args):
             "config": spec["config"],
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": blk_bytes, "d2h_bytes_per_step": out_bytes,
-                    "steps": ke, "api": ("ConvolveBank.submit/wait (pgx_bank_submit / pgx_bank_wait): pinned host buffers, "
+                    "steps": ke, "api": ("ConvolvePE(MixPE(SuperSawPE...), ir).render(start, 64) -> host Snippet (device-resident sources)"
+                            if vb is not None else "ConvolveBank.submit/wait (pgx_bank_submit / pgx_bank_wait): pinned host buffers, "
                             f"{E2E_DEPTH} pulls in flight, every pull's H2D and D2H inside the timed region"
                             if pipelined else "ConvolveBank.process_mix (pgx_bank_process_mix) + NCCL reduce, synchronous"),
                     "checksum_mean_abs_y": checksum},
@@ -475,6 +541,8 @@ def run_gpu(args):
         }
         if not args.no_cpu and world == 1 and args.workload == "c2":
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_seconds)
+        elif not args.no_cpu and world == 1 and args.workload == "c5v":
+            line["cpu_baseline"] = cpu_baseline_c5v(spec["config"]["voices"], args.cpu_seconds)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -496,8 +564,9 @@ def main():
     ap.add_argument("--variant", default="shared", choices=["shared", "distinct"],
                     help="one IR shared by all streams (the named reverb) or one IR per stream")
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's named size)")
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5v"],
                     help="c2 = BASELINE.json configs[1] (headline); the others are the remaining configs, for profiling")
+    ap.add_argument("--reverb", action="store_true", help="c2: add ReverbPE's fused wet/dry output stage")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

@@ -300,7 +300,55 @@ __global__ void __launch_bounds__(256) k_mix_sum(const float* __restrict__ in, c
   }
 }
 
+// Same sum when there are many inputs and few elements (a 1024-voice bank at 64-sample pulls): one thread per
+// element would walk 1024 dependent global loads.  Here a CTA owns 32 elements; warps 1..31 stage chunks of
+// input rows in shared memory (every load of a chunk in flight at once, double-buffered) while warp 0 adds
+// the previous chunk's rows in input order -- the float32 result is the same left-to-right sum, bit for bit.
+static constexpr int kTallRows = 192;
+__global__ void __launch_bounds__(1024) k_mix_sum_tall(const float* __restrict__ in, const int n_inputs,
+                                                       const int64_t n_elems, float* __restrict__ out) {
+  __shared__ float rows[2][kTallRows][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = e < n_elems;
+  const int n_chunks = (n_inputs + kTallRows - 1) / kTallRows;
+  auto stage = [&](int c) {
+    const int r0 = c * kTallRows, nr = min(kTallRows, n_inputs - r0);
+    for (int r = warp - 1; r < nr; r += 31) rows[c & 1][r][lane] = live ? in[(int64_t)(r0 + r) * n_elems + e] : 0.f;
+  };
+  if (warp > 0) stage(0);
+  __syncthreads();
+  float acc = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    if (warp > 0) {
+      if (c + 1 < n_chunks) stage(c + 1);
+    } else {
+      const int nr = min(kTallRows, n_inputs - c * kTallRows);
+      const float(*buf)[32] = rows[c & 1];
+      int r = 0;
+      if (c == 0) {  // the sum starts from the first input itself (first.data.copy(), mix_pe.py:92)
+        acc = buf[0][lane];
+        r = 1;
+      }
+      for (; r + 8 <= nr; r += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = buf[r + u][lane];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, t[u]);
+      }
+      for (; r < nr; ++r) acc = __fadd_rn(acc, buf[r][lane]);
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && live) out[e] = acc;
+}
+
 void launch_mix_sum(const float* in, int32_t n_inputs, int64_t n_elems, float* out, cudaStream_t st) {
+  if (n_inputs >= 32 && n_elems <= 8192) {
+    k_mix_sum_tall<<<(int)((n_elems + 31) / 32), 1024, 0, st>>>(in, n_inputs, n_elems, out);
+    return;
+  }
   int64_t blocks = (n_elems + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;

@@ -38,8 +38,6 @@ void launch_sine_bank(const SineArgs& a, cudaStream_t st) {
   k_sine_bank<<<(int)blocks, 256, 0, st>>>(a);
 }
 
-static constexpr int kOscT = 4;              // consecutive samples per lane
-static constexpr int kOscTile = 32 * kOscT;  // samples per warp tile
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) {
   int lo = __double2loint(v), hi = __double2hiint(v);
@@ -54,8 +52,12 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
-// One CTA per voice, one warp per oscillator of the voice (U <= 32 warps).
+// One CTA per voice, one warp per oscillator of the voice (U <= 32 warps).  kOscT = consecutive samples per
+// lane (a warp tile is 32*kOscT samples): 1 or 2 for the short pulls of a low-latency voice bank so that all
+// lanes work, 4 for long pulls.
+template <int kOscT>
 __global__ void __launch_bounds__(1024) k_blit_bank(const BlitArgs a) {
+  constexpr int kOscTile = 32 * kOscT;
   extern __shared__ float tile_sm[];  // [U][kOscTile] float32 oscillator outputs of the current tile
   const int v = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int U = a.unison;
@@ -149,8 +151,9 @@ __global__ void __launch_bounds__(1024) k_blit_bank(const BlitArgs a) {
 
 void launch_blit_bank(const BlitArgs& a, cudaStream_t st) {
   const int threads = a.unison * 32;
-  const size_t smem = (size_t)a.unison * kOscTile * sizeof(float);
-  k_blit_bank<<<a.n_voices, threads, smem, st>>>(a);
+  if (a.n <= 32) k_blit_bank<1><<<a.n_voices, threads, (size_t)a.unison * 32 * sizeof(float), st>>>(a);
+  else if (a.n <= 64) k_blit_bank<2><<<a.n_voices, threads, (size_t)a.unison * 64 * sizeof(float), st>>>(a);
+  else k_blit_bank<4><<<a.n_voices, threads, (size_t)a.unison * 128 * sizeof(float), st>>>(a);
 }
 
 }  // namespace pgx
