@@ -499,9 +499,9 @@ def run_gpu(args):
     ksum = prof.ms_r2c + prof.ms_mac + prof.ms_c2r + prof.ms_fold + prof.ms_now
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "mac_traffic.json")
-    if args.workload == "c2" and os.path.exists(tr_path):
+    if args.workload in ("c2", "c4") and os.path.exists(tr_path) and not args.streams:
         try:
-            traffic = json.load(open(tr_path)).get(args.variant)
+            traffic = json.load(open(tr_path)).get(args.variant if args.workload == "c2" else args.workload)
         except Exception:
             traffic = None
 
