@@ -14,7 +14,7 @@ from .core import (ErrorMode, ExtendMode, Extent, ProcessingElement, Snippet, So
                    handle_error, set_error_mode, set_sample_rate)
 from .sources import ArrayPE, CachePE, ConstantPE, CropPE, DelayPE, GainPE
 from .osc_pe import BlitSawPE, DeviceBlock, OscBank, SinePE, SuperSawPE, VoiceBank
-from .renderer import AudioRenderer, BankRenderer, NullRenderer, Renderer
+from .renderer import AudioRenderer, BankRenderer, CallbackStop, NullRenderer, Renderer
 from .bank import ConvolveBank, choose_block
 from .hrtf_bank import HrtfMixBank
 from .convolve_pe import ConvolvePE
@@ -29,7 +29,7 @@ __all__ = [
     "enable_diagnostics", "diagnostics_report",
     "ArrayPE", "CachePE", "ConstantPE", "CropPE", "DelayPE", "GainPE", "SinePE", "BlitSawPE", "SuperSawPE",
     "OscBank", "VoiceBank", "DeviceBlock",
-    "Renderer", "NullRenderer", "AudioRenderer", "BankRenderer", "ReverbPE",
+    "Renderer", "NullRenderer", "AudioRenderer", "BankRenderer", "CallbackStop", "ReverbPE",
     "ConvolveBank", "HrtfMixBank", "choose_block",
     "ConvolvePE", "SpatialPE", "SpatialMethod", "SpatialAdapter", "SpatialLinear",
     "SpatialConstantPower", "SpatialHRTF", "MixPE", "device_mix_sum",

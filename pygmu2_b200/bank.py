@@ -276,12 +276,16 @@ class ConvolveBank:
         return out
 
     # -- batched renderer support ------------------------------------------------
-    def attach_sources(self, sources) -> None:
-        """N host PEs feeding the N streams; enables ``render`` for BankRenderer."""
+    def attach_sources(self, sources, delays=None, gains=None) -> None:
+        """N host PEs feeding the N streams; enables ``render`` for BankRenderer.  ``delays`` (integer samples:
+        the source is pulled that much earlier, delay_pe.py:153-160) and ``gains`` (float32, applied to the
+        source samples, gain_pe.py:123-125) fold per-stream DelayPE / GainPE wrappers into the pull."""
         sources = list(sources)
         if len(sources) != self.n_streams:
             raise ValueError("need one source PE per stream")
         self.sources = sources
+        self._src_delays = [0] * len(sources) if delays is None else [int(d) for d in delays]
+        self._src_gains = [None] * len(sources) if gains is None else [None if g is None else np.float32(g) for g in gains]
         self._pos = None
         self.mix_output = False
 
@@ -311,6 +315,9 @@ class ConvolveBank:
             return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=-1)
         x = np.empty((self.n_streams, self.c_in, duration), dtype=np.float32)
         for s, pe in enumerate(self.sources):
-            x[s] = pe.render(start, duration).data.T
+            data = pe.render(start - self._src_delays[s], duration).data
+            if self._src_gains[s] is not None:
+                data = data * self._src_gains[s]
+            x[s] = data.T
         self._pos = start + duration
         return self.process_mix(x) if self.mix_output else self.process(x)

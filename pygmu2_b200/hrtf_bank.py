@@ -8,6 +8,12 @@ of mix_pe.py:92-94).  The whole HRTF table lives on the device as partition spec
 azimuth, spatial_pe.py:486-489); a pull re-selects each source's pair from the current
 ``azimuth`` / ``elevation`` attributes (:446-449), then one fused call does
 FFT(source) -> multiply by (H_L, H_R) and accumulate over sources -> one inverse FFT per ear.
+
+Folded in (the graph shape of examples/27_spatial.py:223-234): a per-source integer
+``DelayPE`` (the source is simply pulled ``delay`` samples earlier, delay_pe.py:153-160), a per-source constant
+``GainPE`` (applied to the source samples; convolution is linear), and sources panned by ``SpatialLinear`` /
+``SpatialConstantPower`` with a constant azimuth: a pan law is a 1-tap stereo filter, so it rides in the same
+filter table and the same accumulation.
 """
 from __future__ import annotations
 
@@ -15,14 +21,27 @@ import numpy as np
 
 from . import kemar
 from .bank import ConvolveBank, choose_block
-from .core import handle_error
+from .core import Extent, handle_error
+
+
+def _is_pan(m) -> bool:
+    from .spatial_pe import _Pan
+    return isinstance(m, _Pan)
+
+
+def _shifted(e: Extent, d: int) -> Extent:
+    """Extent of DelayPE(src, d) (delay_pe.py:118-128)."""
+    return Extent(None if e.start is None else e.start + d, None if e.end is None else e.end + d)
 
 
 class HrtfMixBank:
     def __init__(self, sources, methods, *, table: np.ndarray | None = None, table_sample_rate: int | None = None,
-                 pull_hint: int | None = 512, block: int | None = None, device: int = 0):
+                 pull_hint: int | None = 512, block: int | None = None, device: int = 0, delays=None, gains=None):
         self.sources = list(sources)
         self.methods = list(methods)
+        n = len(self.sources)
+        self.delays = [0] * n if delays is None else [int(d) for d in delays]
+        self.gains = [None] * n if gains is None else [None if g is None else np.float32(g) for g in gains]
         if len(self.sources) != len(self.methods) or not self.sources:
             raise ValueError("need one SpatialHRTF-like method (azimuth, elevation) per source")
         if table is None:
@@ -33,24 +52,47 @@ class HrtfMixBank:
         self.n_entries = table.shape[0]
         self.table_sample_rate = table_sample_rate
         chans = {p.channel_count() for p in self.sources}
-        if len(chans) != 1 or None in chans:
-            raise ValueError("all sources must declare the same channel count")
-        self.c_in = int(chans.pop())
-        both = np.concatenate([table, table[:, :, ::-1]], axis=0)  # [e] as measured, [E + e] ears swapped
+        if None in chans:
+            raise ValueError("all sources must declare their channel count")
+        # one channel count: the device averages the channels (spatial_pe.py:483); mixed counts: the host does
+        self.host_mixdown = len(chans) != 1
+        self.c_in = 1 if self.host_mixdown else int(chans.pop())
+        self.pan_index = {i: k for k, i in enumerate(i for i, m in enumerate(self.methods) if _is_pan(m))}
+        self._pan_loaded = {}
+        # [e] as measured, [E + e] ears swapped, [2E] silence: the filter of a source MixPE does not render
+        both = np.concatenate([table, table[:, :, ::-1], np.zeros_like(table[:1]),
+                               np.zeros((len(self.pan_index),) + table.shape[1:], np.float32)], axis=0)
         B = block or choose_block(table.shape[1], pull_hint)
         self.bank = ConvolveBank(both, len(self.sources), self.c_in, block=B, device=device,
                                  mixdown_input=True, filter_of_stream=self._select())
+        self._refresh_pans()
         self._selected = self._select()
         self._pos = None
         self._warned = False
+        self._was_active = np.ones(len(self.sources), dtype=bool)
 
     def _select(self) -> np.ndarray:
         idx = np.empty(len(self.methods), dtype=np.int32)
         for i, m in enumerate(self.methods):
+            if i in self.pan_index:
+                idx[i] = 2 * self.n_entries + 1 + self.pan_index[i]
+                continue
             e = kemar.nearest_index(m.azimuth, m.elevation) if self.n_entries == len(kemar.KEMAR_HRTF_ENTRIES) \
                 else int(getattr(m, "entry", 0))
             idx[i] = e + (self.n_entries if m.azimuth < 0 else 0)
         return idx
+
+    def _refresh_pans(self) -> None:
+        """(Re)load the 1-tap filter of every panned source whose azimuth changed (public attribute, like HRTF's)."""
+        for i, k in self.pan_index.items():
+            m = self.methods[i]
+            gl, gr = m._gains(m._azimuths(0, 1))          # float32, exactly the gains of spatial_pe.py:179-214,250-286
+            key = (float(gl[0]), float(gr[0]))
+            if self._pan_loaded.get(i) != key:
+                h = np.zeros((self.bank.filter_len, 2), dtype=np.float32)
+                h[0] = key
+                self.bank.load_filter(2 * self.n_entries + 1 + k, h)
+                self._pan_loaded[i] = key
 
     def reset(self) -> None:
         self.bank.reset()
@@ -59,21 +101,41 @@ class HrtfMixBank:
     def render(self, start: int, duration: int) -> np.ndarray:
         """One lockstep pull of every source -> (2, duration) float32 stereo mix."""
         sr = self.sources[0].sample_rate
-        if self.table_sample_rate is not None and sr != self.table_sample_rate and not self._warned:
+        has_hrtf = len(self.pan_index) < len(self.methods)
+        if has_hrtf and self.table_sample_rate is not None and sr != self.table_sample_rate and not self._warned:
             handle_error(
                 f"SpatialHRTF: IR sample rate is {self.table_sample_rate} Hz but source is {sr} Hz. "
                 "Proceeding without resampling.",
                 fatal=False,
             )
             self._warned = True
+        # MixPE renders only the inputs whose extent meets the request (mix_pe.py:81-85; a SpatialPE's extent is
+        # its source's, spatial_pe.py:640-642).  A skipped source contributes nothing - the silent filter - and
+        # its next render starts a new run (spatial_pe.py:461-463): its history is cleared when it comes back.
+        req = Extent(start, start + duration)
+        active = np.array([_shifted(pe.extent(), d).intersects(req) for pe, d in zip(self.sources, self.delays)],
+                          dtype=bool)
+        self._refresh_pans()
         sel = self._select()
+        sel[~active] = 2 * self.n_entries
+        if self._pos is None or start != self._pos:
+            self.bank.reset()
+        else:
+            back = np.flatnonzero(active & ~self._was_active)
+            if back.size:
+                self.bank.reset(back)
         if not np.array_equal(sel, self._selected):
             self.bank.set_filter_map(sel)
             self._selected = sel
-        if self._pos is None or start != self._pos:
-            self.bank.reset()
-        x = np.empty((len(self.sources), self.c_in, duration), dtype=np.float32)
+        x = np.zeros((len(self.sources), self.c_in, duration), dtype=np.float32)
         for s, pe in enumerate(self.sources):
-            x[s] = pe.render(start, duration).data.T
+            if active[s]:
+                data = pe.render(start - self.delays[s], duration).data
+                if self.host_mixdown:
+                    data = np.mean(data, axis=1, keepdims=True).astype(np.float32)   # spatial_pe.py:483
+                if self.gains[s] is not None:
+                    data = data * self.gains[s]                                    # gain_pe.py:123-125, float32
+                x[s] = data.T
         self._pos = start + duration
+        self._was_active = active
         return self.bank.process_mix(x)

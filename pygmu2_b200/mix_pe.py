@@ -25,7 +25,8 @@ from .convolve_pe import ConvolvePE
 from .core import Extent, ProcessingElement, Snippet
 from .hrtf_bank import HrtfMixBank
 from .osc_pe import BlitSawPE, SinePE, SuperSawPE, VoiceBank
-from .spatial_pe import SpatialHRTF, SpatialPE
+from .sources import DelayPE, GainPE
+from .spatial_pe import SpatialConstantPower, SpatialHRTF, SpatialLinear, SpatialPE
 
 
 def device_mix_sum(arrays, device: int = 0) -> np.ndarray:
@@ -68,13 +69,13 @@ class MixPE(ProcessingElement):
             return False
         ins = self._inputs
         try:
-            if all(type(p) is ConvolvePE and p.bank is None for p in ins):
-                return self._adopt_convolves(duration)
-            if all(type(p) is SpatialPE and type(p.method) is SpatialHRTF and p.method._bank is None for p in ins):
-                chans = {p.source.channel_count() for p in ins}
-                if len(chans) == 1 and None not in chans:
-                    return HrtfMixBank([p.source for p in ins], [p.method for p in ins],
-                                       pull_hint=duration, device=self._device)
+            cores, delays, gains = zip(*[_unwrap(p) for p in ins])
+            if all(type(p) is ConvolvePE and p.bank is None for p in cores):
+                return self._adopt_convolves(duration, cores, delays, gains)
+            if all(type(p) is SpatialPE and _foldable_method(p.method) for p in cores):
+                if None not in {p.source.channel_count() for p in cores}:
+                    return HrtfMixBank([p.source for p in cores], [p.method for p in cores], pull_hint=duration,
+                                       device=self._device, delays=delays, gains=gains)
             if len({type(p) for p in ins}) == 1 and type(ins[0]) in (SuperSawPE, BlitSawPE, SinePE):
                 try:
                     return _VoiceMix(VoiceBank(ins, device=self._device))
@@ -84,8 +85,7 @@ class MixPE(ProcessingElement):
             return False
         return False
 
-    def _adopt_convolves(self, duration: int):
-        ins = self._inputs
+    def _adopt_convolves(self, duration: int, ins, delays, gains):
         taps, src_ch = [], set()
         for p in ins:
             ext = p.extent()  # validates the filter contract (raises ValueError like the reference)
@@ -102,7 +102,7 @@ class MixPE(ProcessingElement):
             raise _NotFusable
         bank = ConvolveBank(np.stack(taps), len(ins), int(src_ch.pop()),
                             block=choose_block(taps[0].shape[0], duration), device=self._device)
-        bank.attach_sources([p.src for p in ins])
+        bank.attach_sources([p.src for p in ins], delays=delays, gains=gains)
         bank.mix_output = True
         return bank
 
@@ -161,6 +161,30 @@ class MixPE(ProcessingElement):
 
 class _NotFusable(Exception):
     pass
+
+
+def _unwrap(pe):
+    """Peel integer DelayPE and constant GainPE wrappers off a MixPE input:
+    -> (core PE, total delay in samples, combined float32 gain or None)."""
+    delay, gain = 0, None
+    while True:
+        if type(pe) is DelayPE:
+            delay += pe.delay
+            pe = pe.source
+        elif type(pe) is GainPE and not isinstance(pe.gain, ProcessingElement):
+            g = np.float32(pe.gain)
+            gain = g if gain is None else np.float32(gain * g)
+            pe = pe.source
+        else:
+            return pe, delay, gain
+
+
+def _foldable_method(m) -> bool:
+    if type(m) is SpatialHRTF:
+        return m._bank is None
+    if type(m) in (SpatialLinear, SpatialConstantPower):
+        return not isinstance(m.azimuth, ProcessingElement)
+    return False
 
 
 class _VoiceMix:

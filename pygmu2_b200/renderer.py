@@ -117,6 +117,11 @@ class NullRenderer(Renderer):
         pass
 
 
+class CallbackStop(Exception):
+    """Raised by the streaming callback when the requested range has been played (``sounddevice.CallbackStop``
+    when PortAudio is the sink; this class for any other ``stream_factory``)."""
+
+
 class AudioRenderer(Renderer):
     """Blocking playback pull loop (reference audio_renderer.py:91-116,118-181).
 
@@ -135,19 +140,34 @@ class AudioRenderer(Renderer):
         self._device, self._blocksize, self._latency = device, int(blocksize), latency
         self._factory = stream_factory
         self._blocking_stream = None
+        self._stream = None            # callback-mode stream (stream_start / stream_stop)
+        self._stream_position = 0
+        self._stream_end = None
 
     device = property(lambda self: self._device)
     blocksize = property(lambda self: self._blocksize)
 
-    def _open(self, channels: int):
+    def _open(self, channels: int, callback=None):
         if self._factory is not None:
-            return self._factory(self._sample_rate, channels, self._blocksize)
+            if callback is None:
+                return self._factory(self._sample_rate, channels, self._blocksize)
+            return self._factory(self._sample_rate, channels, self._blocksize, callback=callback)
         try:
             import sounddevice as sd
         except Exception as exc:  # pragma: no cover - depends on the host
             raise RuntimeError("AudioRenderer needs the sounddevice package (PortAudio) or a stream_factory") from exc
+        kw = {"callback": callback} if callback is not None else {}
         return sd.OutputStream(samplerate=self._sample_rate, channels=channels, dtype="float32",
-                               device=self._device, blocksize=self._blocksize, latency=self._latency)
+                               device=self._device, blocksize=self._blocksize, latency=self._latency, **kw)
+
+    def _callback_stop(self):
+        if self._factory is None:
+            try:
+                import sounddevice as sd
+                return sd.CallbackStop
+            except Exception:  # pragma: no cover
+                pass
+        return CallbackStop
 
     def _output(self, snippet: Snippet) -> None:
         if self._blocking_stream is None:  # one long-lived stream, opened on the first write
@@ -178,7 +198,45 @@ class AudioRenderer(Renderer):
             stream.stop()
             stream.close()
 
+    # -- audio_renderer.py:183-262: non-blocking playback, the source is pulled on the sink's callback thread
+    def stream_start(self, start: int = 0, end: int | None = None) -> None:
+        if not self._started:
+            handle_error("Not started. Call start() first.", fatal=True)
+        if self._stream is not None:
+            handle_error("Already streaming. Call stream_stop() first.", fatal=True)
+        if self._source is None:
+            handle_error("No source set.", fatal=True)
+        self._stream_position, self._stream_end = int(start), end
+        stop_exc = self._callback_stop()
+
+        def callback(outdata, frames, time_info, status):
+            if status:
+                log.warning(f"Stream status: {status}")
+            if self._stream_end is not None:
+                remaining = self._stream_end - self._stream_position
+                if remaining <= 0:
+                    outdata.fill(0)
+                    raise stop_exc()
+                frames = min(frames, remaining)
+            snippet = self._source.render(self._stream_position, frames)   # device PEs: any thread may pull
+            if snippet.duration < len(outdata):
+                outdata[:snippet.duration] = snippet.data
+                outdata[snippet.duration:] = 0
+            else:
+                outdata[:] = snippet.data[:len(outdata)]
+            self._stream_position += frames
+
+        self._stream = self._open(self._channel_count or 1, callback=callback)
+        self._stream.start()
+
+    def stream_stop(self) -> None:
+        if self._stream is not None:
+            self._stream.stop()
+            self._stream.close()
+            self._stream = None
+
     def stop(self) -> None:
+        self.stream_stop()
         if self._blocking_stream is not None:
             self._blocking_stream.stop()
             self._blocking_stream.close()

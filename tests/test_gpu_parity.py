@@ -623,3 +623,118 @@ def test_output_gains_contract():
     with pytest.raises(ValueError):
         fan.set_output_gains(1.0, 0.5)
     fan.set_output_gains(0.5, 0.0)
+
+
+# ---------------------------------------------------------------------------
+# AudioRenderer.stream_start (audio_renderer.py:183-248): the sink's own thread pulls the device PE
+class _CallbackSink:
+    """Stand-in for sounddevice.OutputStream(callback=...): a thread that asks for `frames` samples at a time."""
+
+    def __init__(self, sr, ch, bs, callback=None):
+        import threading
+        self.ch, self.bs, self.cb = ch, bs, callback
+        self.blocks, self.done = [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.done.is_set():
+            out = np.full((self.bs, self.ch), np.nan, dtype=np.float32)
+            try:
+                self.cb(out, self.bs, None, None)
+            except pg.CallbackStop:
+                self.done.set()
+                break
+            self.blocks.append(out)
+
+    def start(self):
+        self.thread.start()
+
+    def stop(self):
+        self.done.set()
+        self.thread.join(timeout=10)
+
+    def close(self):
+        pass
+
+
+def test_audio_renderer_stream_start_pulls_from_the_callback_thread():
+    rng = np.random.default_rng(51)
+    x = rng.uniform(-1, 1, 3000).astype(np.float32)
+    h = (rng.standard_normal(400) / 10).astype(np.float32)
+    pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h))
+    sinks = []
+
+    def factory(sr, ch, bs, callback=None):
+        sinks.append(_CallbackSink(sr, ch, bs, callback))
+        return sinks[-1]
+
+    r = pg.AudioRenderer(sample_rate=44_100, blocksize=256, stream_factory=factory)
+    r.set_source(pe)
+    r.start()
+    r.stream_start(0, 3399)                 # extent end: 3000 + 400 - 1
+    assert sinks[0].done.wait(timeout=30)
+    r.stream_stop()
+    r.stop()
+    got = np.concatenate(sinks[0].blocks)[:, 0]
+    assert got.shape[0] == 14 * 256          # 13 full blocks + a zero-padded one of 71 samples
+    ref = orc.OracleConvolve(h, 1).render(np.concatenate([x, np.zeros(399, np.float32)]))[:, 0]
+    assert rel_err(got[:3399], ref) <= TOL and not np.any(got[3399:])
+
+
+# ---------------------------------------------------------------------------
+# SURVEY.md §8f rank 3: DelayPE / GainPE / pan laws folded into the fused mix, and MixPE's extent gating of
+# SpatialPE inputs -- against the REAL reference's output for the same graph (oracle/gen_golden_mixfold.py)
+def _mixfold_graph(fuse=True):
+    lengths, chans = [3000, 4000, 2000, 5000, 700, 1500], [1, 2, 1, 1, 1, 1]
+    s = []
+    for i, (n, c) in enumerate(zip(lengths, chans)):
+        x = np.random.default_rng(700 + i).uniform(-1, 1, (n, c)).astype(np.float32) / 4
+        s.append(pg.ArrayPE(x if c > 1 else x[:, 0]))
+    return pg.MixPE(
+        pg.DelayPE(pg.SpatialPE(s[0], method=pg.SpatialHRTF(30.0, 0.0)), 300),
+        pg.GainPE(pg.SpatialPE(s[1], method=pg.SpatialHRTF(-100.0, 20.0)), 0.5),
+        pg.DelayPE(pg.GainPE(pg.SpatialPE(s[2], method=pg.SpatialLinear(-45.0)), 0.8), 1000),
+        pg.SpatialPE(s[3], method=pg.SpatialConstantPower(60.0)),
+        pg.SpatialPE(s[4], method=pg.SpatialHRTF(170.0, -10.0)),
+        pg.DelayPE(pg.SpatialPE(s[5], method=pg.SpatialHRTF(0.0, 90.0)), 2500),
+        fuse=fuse)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_golden_mix_fold_delay_gain_pan_and_extent_gating(fuse):
+    g = golden("mix_fold.npz")
+    mix = _mixfold_graph(fuse)
+    ext = mix.extent()
+    assert [ext.start, ext.end] == list(g["extent"])
+    y = _pull_pe(mix, g["pulls"])
+    assert y.shape == g["y"].shape
+    assert rel_err(y, g["y"]) <= TOL
+    if fuse:
+        from pygmu2_b200.hrtf_bank import HrtfMixBank
+        assert isinstance(mix._fused, HrtfMixBank) and len(mix._fused.pan_index) == 2
+        # source 4 ends at 700: the reference's MixPE stops rendering it, cutting its HRTF tail (pull 2 onwards)
+        assert not mix._fused._was_active[4]
+
+
+def test_mix_of_delayed_scaled_convolves_folds_into_one_bank():
+    rng = np.random.default_rng(61)
+    N, L = 4, 900
+    xs = [rng.uniform(-1, 1, 2000 + 100 * i).astype(np.float32) for i in range(N)]
+    hs = (rng.standard_normal((N, L)) / 30).astype(np.float32)
+    delays, gains = [0, 128, 777, 1500], [None, 0.5, 2.0, 0.25]
+
+    def chain(i):
+        pe = pg.ConvolvePE(pg.ArrayPE(xs[i]), pg.ArrayPE(hs[i]))
+        if gains[i] is not None:
+            pe = pg.GainPE(pe, gains[i])
+        return pg.DelayPE(pe, delays[i]) if delays[i] else pe
+
+    mix = pg.MixPE(*[chain(i) for i in range(N)])
+    y = _pull_pe(mix, [256] * 20)[:, 0]
+    assert isinstance(mix._fused, pg.ConvolveBank)
+    ref = np.zeros(256 * 20)
+    for i in range(N):
+        full = np.convolve(xs[i].astype(np.float64), hs[i].astype(np.float64)) * (gains[i] or 1.0)
+        n = min(full.shape[0], ref.shape[0] - delays[i])
+        ref[delays[i]:delays[i] + n] += full[:n]
+    assert rel_err(y, ref) <= TOL
