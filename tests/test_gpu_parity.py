@@ -738,3 +738,90 @@ def test_mix_of_delayed_scaled_convolves_folds_into_one_bank():
         n = min(full.shape[0], ref.shape[0] - delays[i])
         ref[delays[i]:delays[i] + n] += full[:n]
     assert rel_err(y, ref) <= TOL
+
+
+# ---------------------------------------------------------------------------
+# more size-independent properties at BASELINE.json's full sizes
+def test_full_size_c4_512_streams_fused_mix_impulse_sum_and_oracle_sample():
+    """C4 per-GPU shard at the named size (512 mono streams x 88200-tap distinct IRs, B=512, P=173, fused mix):
+    an impulse into every stream makes the mix the SUM of all 512 IRs; an impulse into one stream isolates its IR;
+    and the mix is linear in the inputs."""
+    pg.set_sample_rate(wl.SR_441)
+    N, L = 512, wl.C4_L
+    irs = np.stack([wl.c4_ir(s) for s in range(N)])
+    bank = pg.ConvolveBank(irs, N, 1, block=512, max_pull=4096)
+    n = 4096 * 2
+    x = np.zeros((N, 1, n), np.float32)
+    x[:, 0, 0] = 1.0
+    y_all = bank.process_mix(x)[0]
+    ref = irs[:, :n].astype(np.float64).sum(axis=0)
+    assert rel_err(y_all, ref) <= TOL
+    bank.reset()
+    x[:] = 0.0
+    x[137, 0, 5] = 0.5                                   # one stream, delayed and scaled
+    y_one = bank.process_mix(x)[0]
+    ref1 = np.zeros(n)
+    ref1[5:] = 0.5 * irs[137, :n - 5]
+    assert rel_err(y_one, ref1) <= TOL
+    bank.reset()
+    rng = np.random.default_rng(44)
+    xa = (rng.uniform(-1, 1, (N, 1, 1024)) / N).astype(np.float32)
+    ya = bank.process_mix(xa)[0]
+    bank.reset()
+    yb = bank.process_mix(2.0 * xa)[0]
+    assert rel_err(yb, 2.0 * ya.astype(np.float64)) <= 1e-6
+    sample = [3, 200, 511]                                # oracle on a sample of streams: the rest silent
+    bank.reset()
+    xs = np.zeros((N, 1, 1024), np.float32)
+    xs[sample] = xa[sample] * N
+    ysamp = bank.process_mix(xs)[0]
+    refs = sum(orc.OracleConvolve(irs[s], 1).render(xs[s].T)[:, 0].astype(np.float64) for s in sample)
+    assert rel_err(ysamp, refs) <= TOL
+    bank.close()
+
+
+def test_full_size_c3_256_moving_sources_512_taps_vs_direct_convolution():
+    """C3 at the named shape (256 sources x 512-tap synthetic HRTF pairs, filter re-selected every 512-pull,
+    fused stereo mix): every pull against the float64 direct form of the reference's contract (Appendix A:
+    the CURRENT pull's IR applied to the carried history)."""
+    pg.set_sample_rate(wl.SR_441)
+    N, taps, pulls = 256, 512, 6
+    table = wl.c3_synthetic_hrtf_table(taps)
+    both = np.concatenate([table, table[:, :, ::-1]], axis=0)
+    rng = np.random.default_rng(6)
+    traj = rng.integers(0, both.shape[0], (pulls, N)).astype(np.int32)
+    x = np.stack([wl.c3_source(pulls * 512, s) for s in range(N)])[:, None, :]
+    bank = pg.ConvolveBank(both, N, 1, block=512, max_pull=512, mixdown_input=True, filter_of_stream=traj[0])
+    for p in range(pulls):
+        bank.set_filter_map(traj[p])
+        y = bank.process_mix(np.ascontiguousarray(x[:, :, p * 512:(p + 1) * 512]))
+        ref = np.zeros((2, 512))
+        lo = max(0, p * 512 - (taps - 1))
+        for s in range(N):
+            seg = x[s, 0, lo:(p + 1) * 512].astype(np.float64)
+            for c in range(2):
+                ref[c] += np.convolve(seg, both[traj[p, s], :, c].astype(np.float64))[seg.shape[0] - 512:seg.shape[0]]
+        assert rel_err(y, ref) <= TOL, f"pull {p}"
+    bank.close()
+
+
+def test_full_size_c1_many_streams_distinct_fir4096_block4096():
+    """C1's throughput shape (B = 4096, P = 1, distinct 4096-tap FIRs): 64 streams, impulse -> own FIR, plus the
+    reference's sine input against the oracle for a sample of streams."""
+    pg.set_sample_rate(wl.SR_441)
+    N = 64
+    firs = np.stack([wl.c1_fir(s) for s in range(N)])
+    bank = pg.ConvolveBank(firs, N, 1, block=4096, max_pull=4096)
+    x = np.zeros((N, 1, 8192), np.float32)
+    x[:, 0, 0] = 1.0
+    y = np.concatenate([bank.process(np.ascontiguousarray(x[:, :, :4096])),
+                        bank.process(np.ascontiguousarray(x[:, :, 4096:]))], axis=2)
+    assert rel_err(y[:, 0, :4096], firs) <= TOL and np.max(np.abs(y[:, 0, 4096:])) <= TOL
+    bank.reset()
+    xs = np.stack([wl.c1_sine(8192, s, N) for s in range(N)])[:, None, :]
+    ys = np.concatenate([bank.process(np.ascontiguousarray(xs[:, :, :4096])),
+                         bank.process(np.ascontiguousarray(xs[:, :, 4096:]))], axis=2)
+    for s in (0, 31, 63):
+        ref = orc.OracleConvolve(firs[s], 1).render(xs[s].T)[:, 0]
+        assert rel_err(ys[s, 0], ref) <= TOL
+    bank.close()
