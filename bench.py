@@ -433,13 +433,14 @@ def run_gpu(args):
 
     # e2e: public host API, pinned host buffers, H2D + step + D2H every step
     from pygmu2_b200._lib import PinnedArray
-    xp = PinnedArray((N_INPUT_BLOCKS, N, c_in, pull))
-    yp = PinnedArray((c_out, pull) if mix else (N, c_out, pull))
-    xp.array[...] = x_host
+    io_dt = np.int16 if args.pcm16 else np.float32   # --pcm16: WAV staging, int16 over PCIe, converted in HBM
+    xp = PinnedArray((N_INPUT_BLOCKS, N, c_in, pull), io_dt)
+    yp = PinnedArray((c_out, pull) if mix else (N, c_out, pull), io_dt)
+    xp.array[...] = np.clip(np.rint(x_host * 32768.0), -32768, 32767).astype(np.int16) if args.pcm16 else x_host
     ke = min(K, 400)
 
     E2E_DEPTH = 3  # pulls in flight: H2D of pull i+1 and D2H of pull i-1 overlap the kernels of pull i
-    yps = [yp] + [PinnedArray(yp.shape) for _ in range(E2E_DEPTH - 1)]
+    yps = [yp] + [PinnedArray(yp.shape, io_dt) for _ in range(E2E_DEPTH - 1)]
     pipelined = not do_reduce
 
     def e2e_step(i):
@@ -481,7 +482,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     dt_e2e = float(te.item())
-    checksum = float(np.abs(yp.array).mean())
+    checksum = float(np.abs(yp.array.astype(np.float32)).mean()) / (32768.0 if args.pcm16 else 1.0)
 
     # audio-seconds x channels per step: every rank's streams for independent outputs, ONE mix when mixed
     units = (c_out if (mix and (do_reduce or world == 1)) else world * n_out_ch) * pull / sr
@@ -513,7 +514,8 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": spec["config"],
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": blk_bytes, "d2h_bytes_per_step": out_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": blk_bytes // (2 if args.pcm16 else 1),
+                    "d2h_bytes_per_step": out_bytes // (2 if args.pcm16 else 1),
                     "steps": ke, "api": ("ConvolvePE(MixPE(SuperSawPE...), ir).render(start, 64) -> host Snippet (device-resident sources)"
                             if vb is not None else "ConvolveBank.submit/wait (pgx_bank_submit / pgx_bank_wait): pinned host buffers, "
                             f"{E2E_DEPTH} pulls in flight, every pull's H2D and D2H inside the timed region"
@@ -567,6 +569,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5v"],
                     help="c2 = BASELINE.json configs[1] (headline); the others are the remaining configs, for profiling")
     ap.add_argument("--reverb", action="store_true", help="c2: add ReverbPE's fused wet/dry output stage")
+    ap.add_argument("--pcm16", action="store_true",
+                    help="e2e leg with int16 PCM host buffers converted on the device (WAV staging, half the PCIe bytes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

@@ -164,6 +164,12 @@ PGX_API int pgx_bank_set_output_gains(pgx_bank* bank, float wet, float dry);
 #define PGX_PULL_X_DEVICE 4u       /* pgx_bank_submit only: x is a DEVICE pointer whose producer was enqueued on the
                                       bank's own stream (pgx_bank_stream) - e.g. pgx_osc_render_device - so there is
                                       no H2D copy; y is still delivered to host memory */
+#define PGX_PULL_X_PCM16 8u        /* pgx_bank_submit only: host x holds int16 PCM samples (same layout, in int16
+                                      elements); float32 = int16/32768 on the device - what soundfile.read(dtype=
+                                      "float32") gives WavReaderPE (wav_reader_pe.py:127-132) - half the H2D bytes */
+#define PGX_PULL_Y_PCM16 16u       /* pgx_bank_submit only: y is delivered as int16 PCM, clip(lrintf(y*32768)) on the
+                                      device - libsndfile's float -> PCM_16 rule with clipping on, as python-soundfile
+                                      writes for WavWriterPE (wav_writer_pe.py:153) - half the D2H bytes */
 
 /*
  * Pipelined host-buffer pulls (the batched renderer loop, renderer.py:297-327, with more than one pull in
@@ -171,7 +177,8 @@ PGX_API int pgx_bank_set_output_gains(pgx_bank* bank, float wet, float dry);
  * without waiting; pgx_bank_wait(ticket) returns when that pull's y is complete in host memory.  Pulls
  * execute in submission order.  x and y must stay valid (and should be pinned, pgx_host_alloc) until the
  * wait returns; at most 3 pulls are in flight - a further submit first waits for the oldest.
- * flags: PGX_PULL_MIX.  pgx_bank_process[_mix] = submit + wait.
+ * flags: PGX_PULL_MIX, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16.  pgx_bank_process[_mix] =
+ * submit + wait.
  */
 PGX_API int pgx_bank_submit(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y, pgx_layout y_layout,
                     int32_t n, int32_t flags, int64_t* ticket);

@@ -22,6 +22,7 @@ from .spatial_pe import (SpatialAdapter, SpatialConstantPower, SpatialHRTF, Spat
                          SpatialMethod, SpatialPE)
 from .mix_pe import MixPE, device_mix_sum
 from .reverb_pe import ReverbPE
+from .wav_pe import WavReaderPE, WavWriterPE, render_to_file
 
 __all__ = [
     "ErrorMode", "ExtendMode", "Extent", "ProcessingElement", "Snippet", "SourcePE",
@@ -33,5 +34,6 @@ __all__ = [
     "ConvolveBank", "HrtfMixBank", "choose_block",
     "ConvolvePE", "SpatialPE", "SpatialMethod", "SpatialAdapter", "SpatialLinear",
     "SpatialConstantPower", "SpatialHRTF", "MixPE", "device_mix_sum",
+    "WavReaderPE", "WavWriterPE", "render_to_file",
 ]
 __version__ = "0.1.0"

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpgx.so")
 
 PGX_OK, PGX_ERR_INVALID, PGX_ERR_CUDA, PGX_ERR_NO_DEVICE, PGX_ERR_NOMEM = 0, -1, -2, -3, -4
 PGX_FLAG_MIXDOWN_INPUT = 1
-PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE = 1, 2, 4
+PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16 = 1, 2, 4, 8, 16
 PGX_OSC_SINE, PGX_OSC_BLIT = 0, 1
 ABI_VERSION = 1
 
@@ -140,15 +140,16 @@ def f32_ptr(a: np.ndarray):
 
 
 class PinnedArray:
-    """A float32 numpy view over cudaHostAlloc'ed memory (pinned, for async H2D/D2H)."""
+    """A numpy view (float32, or int16 for PCM staging) over cudaHostAlloc'ed memory (pinned, for async H2D/D2H)."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, dtype=np.float32):
         self.shape = tuple(int(s) for s in shape)
+        dt = np.dtype(dtype)
         n = int(np.prod(self.shape)) if self.shape else 1
         self._ptr = C.c_void_p()
-        check(lib().pgx_host_alloc(C.byref(self._ptr), max(n, 1) * 4))
-        buf = (C.c_float * max(n, 1)).from_address(self._ptr.value)
-        self.array = np.frombuffer(buf, dtype=np.float32, count=n).reshape(self.shape)
+        check(lib().pgx_host_alloc(C.byref(self._ptr), max(n, 1) * dt.itemsize))
+        buf = (C.c_char * (max(n, 1) * dt.itemsize)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=n).reshape(self.shape)
 
     def free(self) -> None:
         if self._ptr is not None and self._ptr.value:

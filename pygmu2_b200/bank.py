@@ -181,17 +181,27 @@ class ConvolveBank:
                 y[:, pos:pos + d] = yc
         return y
 
-    def process_interleaved(self, x: np.ndarray) -> np.ndarray:
-        """Single-stream Snippet layout: x (n, C_in) -> y (n, C_out). Used by the PE shims."""
+    def process_interleaved(self, x: np.ndarray, pcm16_out: bool = False) -> np.ndarray:
+        """Single-stream Snippet layout: x (n, C_in) -> y (n, C_out). Used by the PE shims.  An int16 ``x`` is
+        raw PCM_16 converted on the device (int16/32768); ``pcm16_out`` delivers y as int16 PCM converted on the
+        device (clip(rint(y*32768))) -- WAV staging, SURVEY.md §8f rank 4."""
         if self.n_streams != 1:
             raise ValueError("process_interleaved is for single-stream banks")
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        pcm_in = x.dtype == np.int16
+        x = np.ascontiguousarray(x, dtype=np.int16 if pcm_in else np.float32)
         n = x.shape[0]
-        y = np.empty((n, self.c_out), dtype=np.float32)
+        y = np.empty((n, self.c_out), dtype=np.int16 if pcm16_out else np.float32)
+        flags = (_lib.PGX_PULL_X_PCM16 if pcm_in else 0) | (_lib.PGX_PULL_Y_PCM16 if pcm16_out else 0)
         for pos, d in self._chunks(n):
             xc, yc = x[pos:pos + d], y[pos:pos + d]  # row slices of C-contiguous arrays stay dense
-            check(lib().pgx_bank_process(self._h, _lib.f32_ptr(xc), Layout(0, 1, self.c_in),
-                                         _lib.f32_ptr(yc), Layout(0, 1, self.c_out), d))
+            if flags == 0:
+                check(lib().pgx_bank_process(self._h, _lib.f32_ptr(xc), Layout(0, 1, self.c_in),
+                                             _lib.f32_ptr(yc), Layout(0, 1, self.c_out), d))
+            else:
+                tk = C.c_int64(-1)
+                check(lib().pgx_bank_submit(self._h, _lib.f32_ptr(xc), Layout(0, 1, self.c_in), _lib.f32_ptr(yc),
+                                            Layout(0, 1, self.c_out), d, flags, C.byref(tk)))
+                check(lib().pgx_bank_wait(self._h, tk.value))
         return y
 
     # -- pipelined host-buffer pulls (several in flight; copies overlap the kernels) ------------
@@ -199,8 +209,9 @@ class ConvolveBank:
         """Enqueue one pull: x (N, C_in, n) -> out (N, C_out, n), or (C_out, n) when ``mix``.  Returns a
         ticket for ``wait``.  x and out must be C-contiguous float32 (pinned for real overlap: ``PinnedArray``)
         and must not be touched until the wait returns; at most 3 pulls are in flight."""
-        if x.dtype != np.float32 or not x.flags.c_contiguous or out.dtype != np.float32 or not out.flags.c_contiguous:
-            raise ValueError("submit needs C-contiguous float32 arrays")
+        if x.dtype not in (np.float32, np.int16) or out.dtype not in (np.float32, np.int16) \
+                or not x.flags.c_contiguous or not out.flags.c_contiguous:
+            raise ValueError("submit needs C-contiguous float32 (or int16 PCM) arrays")
         if x.ndim != 3 or x.shape[0] != self.n_streams or x.shape[1] != self.c_in:
             raise ValueError(f"x must be ({self.n_streams}, {self.c_in}, n), got {x.shape}")
         n = x.shape[2]
@@ -209,7 +220,9 @@ class ConvolveBank:
             raise ValueError(f"out must be {want}, got {out.shape}")
         tk = C.c_int64(-1)
         check(lib().pgx_bank_submit(self._h, _lib.f32_ptr(x), Layout(self.c_in * n, n, 1), _lib.f32_ptr(out),
-                                    Layout(0 if mix else self.c_out * n, n, 1), n, 1 if mix else 0, C.byref(tk)))
+                                    Layout(0 if mix else self.c_out * n, n, 1), n,
+                                    (1 if mix else 0) | (_lib.PGX_PULL_X_PCM16 if x.dtype == np.int16 else 0)
+                                    | (_lib.PGX_PULL_Y_PCM16 if out.dtype == np.int16 else 0), C.byref(tk)))
         self._inflight = getattr(self, "_inflight", {})
         self._inflight[tk.value] = (x, out)  # keep the buffers alive until waited
         return int(tk.value)

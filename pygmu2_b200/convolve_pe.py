@@ -129,24 +129,34 @@ class ConvolvePE(ProcessingElement):
             self._bank.set_output_gains(*self._out_gains)
         self._fir_len = filt_len
 
-    def _render(self, start: int, duration: int) -> Snippet:
+    def render_pcm16_out(self, start: int, duration: int) -> np.ndarray:
+        """One pull delivered as (duration, channels) int16 PCM, converted on the device (WAV staging; what
+        WavWriterPE would write for this pull).  Same state and contiguity rules as ``render``."""
+        if duration < 0:
+            raise ValueError(f"duration must be non-negative, got {duration}")
+        if duration == 0:
+            return np.zeros((0, self.channel_count() or 1), dtype=np.int16)
+        return self._render(start, duration, pcm16_out=True)
+
+    def _render(self, start: int, duration: int, pcm16_out: bool = False):
         self._ensure_filter_prepared(duration)
         if self._last_render_end is None or start != self._last_render_end:
             self._bank.reset()  # non-contiguous pull: prior samples are zeros (convolve_pe.py:255-256)
-        dev = getattr(self._src, "device_block", None)
+        dev = None if pcm16_out else getattr(self._src, "device_block", None)
         if dev is not None:  # device-resident source: its samples never visit the host
             y = self._render_from_device(dev, start, duration)
             if y is not None:
                 self._last_render_end = start + duration
                 return Snippet(start, y)
-        x = self._src.render(start, duration).data
+        raw = getattr(self._src, "render_pcm16", None)   # WavReaderPE: raw int16 frames, converted in HBM
+        x = raw(start, duration) if raw is not None else self._src.render(start, duration).data
         if x.ndim != 2:
             raise ValueError(f"ConvolvePE src returned invalid shape {getattr(x, 'shape', None)}")
         if x.shape[1] != self._bank.c_in:
             raise ValueError(f"ConvolvePE src returned {x.shape[1]} channels, prepared for {self._bank.c_in}")
-        y = self._bank.process_interleaved(x)
+        y = self._bank.process_interleaved(x, pcm16_out=pcm16_out)
         self._last_render_end = start + duration
-        return Snippet(start, y)
+        return y if pcm16_out else Snippet(start, y)
 
     def _render_from_device(self, dev, start: int, duration: int):
         bank = self._bank

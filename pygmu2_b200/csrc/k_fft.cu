@@ -249,6 +249,16 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
 }
 
 // ---- launchers ---------------------------------------------------------------------------------
+// cudaFuncSetAttribute is per device: remember it per (kernel instantiation, device), not once per process
+static bool need_smem_attr(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 static int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -267,11 +277,9 @@ int fft_smem_bytes(int B) {
 template <int LOG2N, int MODE>
 static void launch_r2c_t(const R2CArgs& a, const FilterPrepArgs& fp, int64_t total, cudaStream_t st) {
   using C = FftCfg<LOG2N>;
-  static bool attr_done = false;
-  if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
+  static bool attr_done[64] = {};
+  if (C::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
     cudaFuncSetAttribute(k_r2c<LOG2N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    attr_done = true;
-  }
   const int grid = (int)((total + C::FPB - 1) / C::FPB);
   k_r2c<LOG2N, MODE><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a, fp);
 }
@@ -279,11 +287,9 @@ static void launch_r2c_t(const R2CArgs& a, const FilterPrepArgs& fp, int64_t tot
 template <int LOG2N, bool PART>
 static void launch_c2r_t(const C2RArgs& a, cudaStream_t st) {
   using C = FftCfg<LOG2N>;
-  static bool attr_done = false;
-  if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
+  static bool attr_done[64] = {};
+  if (C::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
     cudaFuncSetAttribute(k_c2r<LOG2N, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    attr_done = true;
-  }
   const int grid = (a.n_out + C::FPB - 1) / C::FPB;
   k_c2r<LOG2N, PART><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a);
 }

@@ -156,4 +156,41 @@ void launch_blit_bank(const BlitArgs& a, cudaStream_t st) {
   else k_blit_bank<4><<<a.n_voices, threads, (size_t)a.unison * 128 * sizeof(float), st>>>(a);
 }
 
+// ---- PCM16 <-> float32 staging for WAV I/O -----------------------------------------
+// in : float32 = int16 / 32768, what soundfile.read(dtype="float32") returns for a PCM_16 file
+//      (wav_reader_pe.py:127-132; libsndfile pcm.c s2f_array, normfact 1/0x8000)
+// out: int16 = clip(lrintf(x * 32768)) with round-half-even, libsndfile's float -> PCM_16 conversion when
+//      clipping is on, which python-soundfile always enables (wav_writer_pe.py:153; libsndfile pcm.c
+//      f2s_clip_array).  soundfile / libsndfile are not in this image: parity for this pair is anchored on
+//      the formulas and round-trip properties, not on golden files.
+__global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t* __restrict__ in, float* __restrict__ out,
+                                                      const int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = (float)in[e] * (1.0f / 32768.0f);
+}
+
+__global__ void __launch_bounds__(256) k_f32_to_pcm16(const float* __restrict__ in, int16_t* __restrict__ out,
+                                                      const int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const float scaled = in[e] * 32768.0f;
+    int v;
+    if (scaled >= 32767.0f) v = 32767;
+    else if (scaled <= -32768.0f) v = -32768;
+    else v = __float2int_rn(scaled);
+    out[e] = (int16_t)v;
+  }
+}
+
+static int pcm_grid(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)(b < 1 ? 1 : b);
+}
+void launch_pcm16_to_f32(const int16_t* in, float* out, int64_t n, cudaStream_t st) {
+  k_pcm16_to_f32<<<pcm_grid(n), 256, 0, st>>>(in, out, n);
+}
+void launch_f32_to_pcm16(const float* in, int16_t* out, int64_t n, cudaStream_t st) {
+  k_f32_to_pcm16<<<pcm_grid(n), 256, 0, st>>>(in, out, n);
+}
+
 }  // namespace pgx

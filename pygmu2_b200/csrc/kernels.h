@@ -117,6 +117,10 @@ struct BlitArgs {
 };
 void launch_blit_bank(const BlitArgs& a, cudaStream_t st);
 
+// PCM16 <-> float32 staging (k_osc.cu): dense arrays of n elements
+void launch_pcm16_to_f32(const int16_t* in, float* out, int64_t n, cudaStream_t st);
+void launch_f32_to_pcm16(const float* in, int16_t* out, int64_t n, cudaStream_t st);
+
 int fft_smem_bytes(int B);
 
 }  // namespace pgx

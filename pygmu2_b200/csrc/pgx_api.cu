@@ -117,6 +117,8 @@ struct pgx_bank {
   static constexpr int kSlots = 3;
   float* x_stage[kSlots] = {};
   float* y_stage[kSlots] = {};
+  int16_t* xpcm_stage[kSlots] = {};  // PCM16 staging, allocated on first use
+  int16_t* ypcm_stage[kSlots] = {};
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[kSlots] = {}, ev_y[kSlots] = {}, ev_done[kSlots] = {};
   int64_t next_ticket = 0;
@@ -163,6 +165,8 @@ void free_bank(pgx_bank* b) {
   for (int i = 0; i < pgx_bank::kSlots; ++i) {
     cudaFree(b->x_stage[i]);
     cudaFree(b->y_stage[i]);
+    cudaFree(b->xpcm_stage[i]);
+    cudaFree(b->ypcm_stage[i]);
     for (cudaEvent_t e : {b->ev_h2d[i], b->ev_y[i], b->ev_done[i]})
       if (e) cudaEventDestroy(e);
   }
@@ -738,7 +742,7 @@ int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
 // Host-buffer pull, asynchronous: stage x into the next slot (H2D on the copy-in stream), enqueue the block
 // steps, copy y back on the copy-out stream.  Returns a ticket; y is complete after submit_wait(ticket).
 static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, bool mix,
-                       int64_t* ticket, bool x_device = false) {
+                       int64_t* ticket, bool x_device = false, bool x_pcm = false, bool y_pcm = false) {
   int rc = check_pull_args(b, x, y, n);
   if (rc != PGX_OK) return rc;
   const pgx_bank_config& c = b->cfg;
@@ -754,9 +758,16 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   const int slot = (int)(tk % pgx_bank::kSlots);
   // the slot's previous pull is over once its D2H has completed (its K1s read x_stage before that)
   if (tk >= pgx_bank::kSlots) PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
+  if (x_pcm && !b->xpcm_stage[slot]) PGX_CUDA(cudaMalloc(&b->xpcm_stage[slot], b->xs_bytes / 2));
+  if (y_pcm && !b->ypcm_stage[slot]) PGX_CUDA(cudaMalloc(&b->ypcm_stage[slot], b->ys_bytes / 2));
   if (x_device) {  // produced by work already queued on the bank's stream: run_pull orders the ingest after it
     rc = run_pull(b, x, xl, b->y_stage[slot], yd, n, mix, false, b->stream);
   } else {
+    if (x_pcm) {   // half the H2D bytes; int16 / 32768 on the device, on the copy-in stream
+      PGX_CUDA(cudaMemcpyAsync(b->xpcm_stage[slot], x, xb / 2, cudaMemcpyHostToDevice, b->s_h2d));
+      pgx::launch_pcm16_to_f32(b->xpcm_stage[slot], b->x_stage[slot], (int64_t)(xb / sizeof(float)), b->s_h2d);
+      b->launches += 1;
+    } else
     PGX_CUDA(cudaMemcpyAsync(b->x_stage[slot], x, xb, cudaMemcpyHostToDevice, b->s_h2d));
     PGX_CUDA(cudaEventRecord(b->ev_h2d[slot], b->s_h2d));
     PGX_CUDA(cudaStreamWaitEvent(b->s_in, b->ev_h2d[slot], 0));
@@ -764,8 +775,14 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
     rc = run_pull(b, b->x_stage[slot], xl, b->y_stage[slot], yd, n, mix, true, b->stream);
   }
   if (rc != PGX_OK) return rc;
+  if (y_pcm) {     // clip(lrint(y * 32768)) on the device, half the D2H bytes
+    pgx::launch_f32_to_pcm16(b->y_stage[slot], b->ypcm_stage[slot], (int64_t)(yb / sizeof(float)), b->stream);
+    b->launches += 1;
+  }
   PGX_CUDA(cudaEventRecord(b->ev_y[slot], b->stream));
   PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_y[slot], 0));
+  if (y_pcm) PGX_CUDA(cudaMemcpyAsync(y, b->ypcm_stage[slot], yb / 2, cudaMemcpyDeviceToHost, b->s_d2h));
+  else
   PGX_CUDA(cudaMemcpyAsync(y, b->y_stage[slot], yb, cudaMemcpyDeviceToHost, b->s_d2h));
   PGX_CUDA(cudaEventRecord(b->ev_done[slot], b->s_d2h));
   b->next_ticket = tk + 1;
@@ -791,7 +808,10 @@ static int process_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pg
 int pgx_bank_submit(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, int32_t flags,
                     int64_t* ticket) {
   if (!ticket) return fail(PGX_ERR_INVALID, "ticket is NULL");
-  return submit_host(b, x, xl, y, yl, n, (flags & PGX_PULL_MIX) != 0, ticket, (flags & PGX_PULL_X_DEVICE) != 0);
+  if ((flags & PGX_PULL_X_DEVICE) && (flags & PGX_PULL_X_PCM16))
+    return fail(PGX_ERR_INVALID, "PGX_PULL_X_DEVICE and PGX_PULL_X_PCM16 exclude each other");
+  return submit_host(b, x, xl, y, yl, n, (flags & PGX_PULL_MIX) != 0, ticket, (flags & PGX_PULL_X_DEVICE) != 0,
+                     (flags & PGX_PULL_X_PCM16) != 0, (flags & PGX_PULL_Y_PCM16) != 0);
 }
 
 void* pgx_bank_stream(pgx_bank* b) { return b ? static_cast<void*>(b->stream) : nullptr; }

@@ -19,6 +19,11 @@ from .mix_pe import MixPE
 from .sources import CachePE, ConstantPE, GainPE
 
 
+def f32_to_pcm16_host(x):
+    from .wav_pe import f32_to_pcm16
+    return f32_to_pcm16(x)
+
+
 class ReverbPE(ProcessingElement):
     def __init__(self, source: ProcessingElement, ir: ProcessingElement, mix: float = 0.5, *,
                  normalize_ir: bool = True, fft_size: int | None = None):
@@ -72,6 +77,12 @@ class ReverbPE(ProcessingElement):
         if self._fused:
             return self._wet_stream.render(start, duration)
         return self._out.render(start, duration)
+
+    def render_pcm16_out(self, start: int, duration: int):
+        """int16 PCM straight off the device (fused form only); None tells the writer to use ``render``."""
+        if not self._fused:
+            return f32_to_pcm16_host(self.render(start, duration).data)
+        return self._wet_stream.render_pcm16_out(start, duration)
 
     def __repr__(self):
         return (f"ReverbPE(source={self._source.__class__.__name__}, ir={self._ir.__class__.__name__}, "

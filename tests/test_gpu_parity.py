@@ -825,3 +825,47 @@ def test_full_size_c1_many_streams_distinct_fir4096_block4096():
         ref = orc.OracleConvolve(firs[s], 1).render(xs[s].T)[:, 0]
         assert rel_err(ys[s, 0], ref) <= TOL
     bank.close()
+
+
+# ---------------------------------------------------------------------------
+# WAV staging -- PCM16 converted on the device on the way in and on the way out
+def test_wav_reader_feeds_convolve_with_raw_pcm16_frames(tmp_path):
+    import wave
+    rng = np.random.default_rng(71)
+    pcm = rng.integers(-32768, 32768, (5000, 2), dtype=np.int64).astype(np.int16)
+    path = str(tmp_path / "in.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(44_100)
+        w.writeframes(pcm.astype("<i2").tobytes())
+    ir = (rng.standard_normal((600, 2)) / 25).astype(np.float32)
+    pulls = [512, 100, 2000, 512, 2475]
+    y = _pull_pe(pg.ConvolvePE(pg.WavReaderPE(path), pg.ArrayPE(ir)), pulls)        # int16 H2D, /32768 in HBM
+    x = pcm.astype(np.float32) / np.float32(32768.0)
+    y_host = _pull_pe(pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(ir)), pulls)          # float32 H2D
+    np.testing.assert_array_equal(y, y_host)                                        # the device conversion is exact
+    xz = np.concatenate([x, np.zeros((599, 2), np.float32)])
+    assert rel_err(y, orc.OracleConvolve(ir, 2).render(xz)) <= TOL
+
+
+def test_render_to_file_takes_pcm16_off_the_device(tmp_path):
+    import wave
+    from pygmu2_b200.wav_pe import f32_to_pcm16
+    rng = np.random.default_rng(72)
+    x = rng.uniform(-1, 1, (9000, 2)).astype(np.float32)
+    ir = (rng.standard_normal(500) / 6).astype(np.float32)                          # loud enough to clip sometimes
+    path = str(tmp_path / "out.wav")
+    pg.render_to_file(pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(ir)), path, chunk=4096)
+    with wave.open(path, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (2, 2, 44_100, 9499)
+        got = np.frombuffer(w.readframes(9499), dtype="<i2").reshape(-1, 2)
+    y = _pull_pe(pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(ir)), [4096, 4096, 1307])
+    want = f32_to_pcm16(y)                                                           # host formula on the float32 output
+    assert np.any(np.abs(want) == 32767) or np.any(want == -32768)                   # the clip branch is exercised
+    np.testing.assert_array_equal(got, want)
+    # fused ReverbPE -> file, same route
+    path2 = str(tmp_path / "rev.wav")
+    pg.render_to_file(pg.ReverbPE(pg.ArrayPE(x), pg.ArrayPE(ir), mix=0.4), path2, chunk=5000)
+    yr = _pull_pe(pg.ReverbPE(pg.ArrayPE(x), pg.ArrayPE(ir), mix=0.4), [5000, 4499])
+    with wave.open(path2, "rb") as w:
+        got2 = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").reshape(-1, 2)
+    np.testing.assert_array_equal(got2, f32_to_pcm16(yr))

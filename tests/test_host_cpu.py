@@ -318,3 +318,32 @@ def test_sharded_mix_gloo_world2():
                   axis=0, dtype=np.float64)
     assert ret["span0"] == (0, 3)
     assert np.max(np.abs(ret["y"][0] - full)) <= 1e-5 * np.max(np.abs(full))
+
+
+# ---- WAV staging: host formulas and file round trip ------------------------
+def test_pcm16_conversion_rules_and_wav_round_trip(tmp_path):
+    from pygmu2_b200.wav_pe import f32_to_pcm16, pcm16_to_f32
+    x = np.array([0.0, 1.0, -1.0, 2.0, -2.0, 0.5 / 32768, 1.5 / 32768, 2.5 / 32768, -0.5 / 32768, -1.5 / 32768,
+                  32766.6 / 32768, 32767.0 / 32768, -32767.5 / 32768], dtype=np.float32)
+    want = np.array([0, 32767, -32768, 32767, -32768, 0, 2, 2, 0, -2, 32767, 32767, -32768], dtype=np.int16)
+    np.testing.assert_array_equal(f32_to_pcm16(x), want)          # clip + round-half-even (libsndfile f2s_clip_array)
+    p = np.arange(-32768, 32768, 7, dtype=np.int16)
+    np.testing.assert_array_equal(f32_to_pcm16(pcm16_to_f32(p)), p)   # int16 -> float32 -> int16 is the identity
+    pg.set_sample_rate(22_050)
+    rng = np.random.default_rng(2)
+    data = rng.uniform(-1.2, 1.2, (1000, 2)).astype(np.float32)       # includes samples that clip
+    path = str(tmp_path / "rt.wav")
+    w = pg.WavWriterPE(pg.ArrayPE(data), path)
+    r = pg.NullRenderer(sample_rate=22_050)
+    r.set_source(w)
+    with r:
+        r.start()
+        r.render(0, 600)
+        r.render(600, 400)
+    assert w.frames_written == 1000
+    rd = pg.WavReaderPE(path)
+    assert rd.extent() == pg.Extent(0, 1000) and rd.channel_count() == 2 and rd.sample_rate == 22_050
+    got = rd.render(-10, 1020).data
+    assert not got[:10].any() and not got[1010:].any()
+    np.testing.assert_array_equal(got[10:1010], pcm16_to_f32(f32_to_pcm16(data)))
+    np.testing.assert_array_equal(rd.render_pcm16(0, 1000), f32_to_pcm16(data))
