@@ -497,7 +497,7 @@ def run_gpu(args):
     nprof = max(prof.steps, 1)
     mac_ms = prof.ms_mac_union / max(prof.n_mac, 1)      # busy time per launch (union of overlapping launches)
     mac_ms_each = prof.ms_mac / max(prof.n_mac, 1)       # mean start-to-end of one launch
-    ksum = prof.ms_r2c + prof.ms_mac + prof.ms_c2r + prof.ms_fold + prof.ms_now
+    ksum = prof.ms_r2c + prof.ms_mac + prof.ms_c2r + prof.ms_fold + prof.ms_now + prof.ms_conv1
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "mac_traffic.json")
     if args.workload in ("c2", "c4") and os.path.exists(tr_path) and not args.streams:
@@ -539,7 +539,8 @@ def run_gpu(args):
                                   "frac": step_bytes / (ms_max / K * 1e-3) / 1e9 / peak,
                                   "kernel_ms": {"k_r2c_ingest": prof.ms_r2c / nprof, "k_fdl_mac": mac_ms,
                                                 "k_c2r_emit": prof.ms_c2r / nprof, "k_reduce_partials": prof.ms_fold / nprof,
-                                                "k_fdl_mac_present_slot": prof.ms_now / nprof, "sum": ksum / nprof}}},
+                                                "k_fdl_mac_present_slot": prof.ms_now / nprof,
+                                                "k_conv1_fused": prof.ms_conv1 / nprof, "sum": ksum / nprof}}},
         }
         if not args.no_cpu and world == 1 and args.workload == "c2":
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_seconds)

@@ -200,6 +200,7 @@ typedef struct pgx_profile {
   int64_t n_mac;                 /* K3 past-pass launches timed */
   double ms_mac_union;           /* time during which at least one of them was running (launches of consecutive
                                     blocks overlap on two streams) */
+  double ms_conv1;               /* fused K1+K2 launches of single-partition (P = 1) conv pulls */
 } pgx_profile;
 /* begin: every following block step records events around each of its three kernels.
  * end: synchronise, sum the durations into *out, stop recording. */

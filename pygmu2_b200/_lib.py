@@ -46,7 +46,7 @@ class OscConfig(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("ms_r2c", C.c_double), ("ms_mac", C.c_double), ("ms_c2r", C.c_double), ("steps", C.c_int64),
                 ("ms_fold", C.c_double), ("ms_now", C.c_double), ("n_mac", C.c_int64),
-                ("ms_mac_union", C.c_double)]
+                ("ms_mac_union", C.c_double), ("ms_conv1", C.c_double)]
 
 
 _f32p = C.POINTER(C.c_float)

@@ -29,9 +29,10 @@ template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 d) {
   return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
 }
-template <bool INV>
+// GLOBAL_TW: the table is read from global memory through the read-only path; otherwise it was staged in shared
+template <bool INV, bool GLOBAL_TW>
 __device__ __forceinline__ float2 tw_get(const float2* tw, int idx) {
-  float2 w = tw[idx];
+  float2 w = GLOBAL_TW ? __ldg(tw + idx) : tw[idx];
   if (INV) w.y = -w.y;
   return w;
 }
@@ -97,17 +98,23 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
                                            const float2* tw) {
   using C = FftCfg<LOG2N>;
   constexpr int N = C::N, T8 = C::T8;
+  constexpr bool GTW = !C::SMEM_TW;
   float2* cur = nullptr;
   int Ns = 1;
+  float2 w1 = make_float2(1.f, 0.f), w2 = w1, w4 = w1;  // twiddles of the coming pass, fetched one barrier early
 #pragma unroll
   for (int p = 0; p < C::NP8; ++p) {
     const int k = j & (Ns - 1);
     if (p > 0) {
       __syncthreads();
+      if (!GTW) {  // table staged in shared memory by the caller: readable only after the first barrier
+        const int m = 2 * k * (N / (8 * Ns));
+        w1 = tw_get<INV, GTW>(tw, m);
+        w2 = tw_get<INV, GTW>(tw, 2 * m);
+        w4 = tw_get<INV, GTW>(tw, 4 * m);
+      }
 #pragma unroll
       for (int r = 0; r < 8; ++r) v[r] = cur[phys(j + r * T8)];
-      const int m = 2 * k * (N / (8 * Ns));
-      const float2 w1 = tw_get<INV>(tw, m), w2 = tw_get<INV>(tw, 2 * m), w4 = tw_get<INV>(tw, 4 * m);
       const float2 w3 = cmul(w1, w2);
       v[1] = cmul(v[1], w1);
       v[2] = cmul(v[2], w2);
@@ -116,6 +123,13 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
       v[5] = cmul(v[5], cmul(w4, w1));
       v[6] = cmul(v[6], cmul(w4, w2));
       v[7] = cmul(v[7], cmul(w4, w3));
+    }
+    if (GTW && p + 1 < C::NP8) {  // issue the next pass's twiddle loads now: their latency hides behind this pass
+      const int Nn = Ns * 8;
+      const int m = 2 * (j & (Nn - 1)) * (N / (8 * Nn));
+      w1 = tw_get<INV, GTW>(tw, m);
+      w2 = tw_get<INV, GTW>(tw, 2 * m);
+      w4 = tw_get<INV, GTW>(tw, 4 * m);
     }
     bfly8<INV>(v);
     if (p < C::NP8 - 1 || C::RLAST > 1) {
@@ -128,28 +142,38 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
     Ns *= 8;
   }
   if (C::RLAST == 4) {
-    __syncthreads();
     constexpr int NB = N / 4;  // butterflies in this pass; Ns == NB, so k == jj
+    float2 a1[2], a2[2];
+    if (!GTW) __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {  // global table: twiddles are requested before the barrier
+      const int m = 2 * (j + u * T8);  // 2*k*(N/(4*Ns)) with Ns = N/4
+      a1[u] = tw_get<INV, GTW>(tw, m);
+      a2[u] = tw_get<INV, GTW>(tw, 2 * m);
+    }
+    if (GTW) __syncthreads();
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int jj = j + u * T8;
       float2 t0 = cur[phys(jj)], t1 = cur[phys(jj + NB)], t2 = cur[phys(jj + 2 * NB)], t3 = cur[phys(jj + 3 * NB)];
-      const int m = 2 * jj;  // 2*k*(N/(4*Ns)) with Ns = N/4
-      const float2 w1 = tw_get<INV>(tw, m), w2 = tw_get<INV>(tw, 2 * m);
-      t1 = cmul(t1, w1);
-      t2 = cmul(t2, w2);
-      t3 = cmul(t3, cmul(w1, w2));
+      t1 = cmul(t1, a1[u]);
+      t2 = cmul(t2, a2[u]);
+      t3 = cmul(t3, cmul(a1[u], a2[u]));
       bfly4<INV>(t0, t1, t2, t3);
       v[u] = t0; v[u + 2] = t1; v[u + 4] = t2; v[u + 6] = t3;  // position jj + r*NB = j + (u + 2r)*T8
     }
   } else if (C::RLAST == 2) {
-    __syncthreads();
     constexpr int NB = N / 2;
+    float2 a1[4];
+    if (!GTW) __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a1[u] = tw_get<INV, GTW>(tw, 2 * (j + u * T8));
+    if (GTW) __syncthreads();
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int jj = j + u * T8;
       float2 t0 = cur[phys(jj)], t1 = cur[phys(jj + NB)];
-      t1 = cmul(t1, tw_get<INV>(tw, 2 * jj));
+      t1 = cmul(t1, a1[u]);
       bfly2<INV>(t0, t1);
       v[u] = t0; v[u + 4] = t1;  // position jj + r*NB = j + (u + 4r)*T8
     }

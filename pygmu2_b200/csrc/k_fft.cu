@@ -24,6 +24,61 @@ __device__ __forceinline__ const float2* stage_twiddles(float2* smem, const floa
   }
 }
 
+// K1's input stage: window w = [prev block (N) | open block cur[0:fill+take) | zeros], element q = (w[2q], w[2q+1]);
+// the new samples are also stored into the open half of hist.  f = stream * c_x + channel.
+template <int LOG2N>
+__device__ __forceinline__ void ingest_window(const R2CArgs& a, const int64_t f, const int j, float2 (&v)[8]) {
+  using C = FftCfg<LOG2N>;
+  constexpr int N = C::N, T8 = C::T8;
+  // window w = [prev block (N) | open block cur[0:m_new) | zeros]; element q is (w[2q], w[2q+1])
+  const int s = (int)f / a.c_x, cx = (int)f - s * a.c_x;
+  float* cur = a.hist + ((size_t)f * 2 + a.half) * N;
+  const float* prev = a.hist + ((size_t)f * 2 + (a.half ^ 1)) * N;
+  const int m_new = a.fill + a.take;
+  const float* xs = a.x + (int64_t)s * a.xs + (a.mixdown ? 0 : (int64_t)cx * a.xc);
+  if (a.fast) {
+    // a whole block of contiguous, 8-byte aligned samples: elements 0..N/2-1 (m < 4) are the previous block,
+    // N/2..N-1 (m >= 4) the new one -- vector loads, and the new block goes to hist as vector stores
+    const float* xn = xs + a.x_off;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[m] = *reinterpret_cast<const float2*>(prev + 2 * (j + m * T8));
+#pragma unroll
+    for (int m = 4; m < 8; ++m) v[m] = __ldg(reinterpret_cast<const float2*>(xn + 2 * (j + m * T8) - N));
+#pragma unroll
+    for (int m = 4; m < 8; ++m) *reinterpret_cast<float2*>(cur + 2 * (j + m * T8) - N) = v[m];
+  } else
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int i0 = 2 * (j + m * T8);
+    if (i0 < N) {
+      v[m] = *reinterpret_cast<const float2*>(prev + i0);
+    } else {
+      const int c0 = i0 - N;
+      float e[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + h;
+        float val = 0.f;
+        if (c < a.fill) {
+          val = cur[c];                               // already ingested by an earlier partial pull
+        } else if (c < m_new) {
+          const int64_t off = (int64_t)(a.x_off + c - a.fill) * a.xi;
+          if (a.mixdown) {
+            float acc = 0.f;
+            for (int ch = 0; ch < a.c_in; ++ch) acc += xs[off + (int64_t)ch * a.xc];
+            val = acc / (float)a.c_in;
+          } else {
+            val = xs[off];
+          }
+          cur[c] = val;                               // each sample has exactly one owner thread
+        }
+        e[h] = val;
+      }
+      v[m] = make_float2(e[0], e[1]);
+    }
+  }
+}
+
 // MODE 0: stream ingest -> one delay-line row.  MODE 1: filter partition -> two (reversed, doubled) rows.
 template <int LOG2N, int MODE>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, const FilterPrepArgs fp) {
@@ -45,44 +100,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
   int frow = 0, fpart = 0;
   if (active) {
     if (MODE == 0) {
-      // window w = [prev block (N) | open block cur[0:m_new) | zeros]; element q is (w[2q], w[2q+1])
-      const int s = (int)f / a.c_x, cx = (int)f - s * a.c_x;
-      float* cur = a.hist + ((size_t)f * 2 + a.half) * N;
-      const float* prev = a.hist + ((size_t)f * 2 + (a.half ^ 1)) * N;
-      const int m_new = a.fill + a.take;
-      const float* xs = a.x + (int64_t)s * a.xs + (a.mixdown ? 0 : (int64_t)cx * a.xc);
-      const float inv_c = 1.0f / (float)a.c_in;
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int i0 = 2 * (j + m * T8);
-        if (i0 < N) {
-          v[m] = *reinterpret_cast<const float2*>(prev + i0);
-        } else {
-          const int c0 = i0 - N;
-          float e[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = c0 + h;
-            float val = 0.f;
-            if (c < a.fill) {
-              val = cur[c];                               // already ingested by an earlier partial pull
-            } else if (c < m_new) {
-              const int64_t off = (int64_t)(a.x_off + c - a.fill) * a.xi;
-              if (a.mixdown) {
-                float acc = 0.f;
-                for (int ch = 0; ch < a.c_in; ++ch) acc += xs[off + (int64_t)ch * a.xc];
-                val = acc / (float)a.c_in;
-              } else {
-                val = xs[off];
-              }
-              cur[c] = val;                               // each sample has exactly one owner thread
-            }
-            e[h] = val;
-          }
-          v[m] = make_float2(e[0], e[1]);
-        }
-      }
-      (void)inv_c;
+      ingest_window<LOG2N>(a, f, j, v);
     } else {
       frow = (int)(f / fp.P);
       fpart = (int)(f - (int64_t)frow * fp.P);
@@ -105,6 +123,9 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
   __syncthreads();
 #pragma unroll
   for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+  float2 tws[8];  // requested before the barrier
+#pragma unroll
+  for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
   __syncthreads();
   if (active) {
     float2 *row0, *row1 = nullptr;
@@ -125,7 +146,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
       if (k == 0) {
         o = make_float2(v[m].x + v[m].y, v[m].x - v[m].y);
       } else {
-        o = r2c_bin(v[m], sA[phys(N - k)], tw[k]);
+        o = r2c_bin(v[m], sA[phys(N - k)], tws[m]);
       }
       if (MODE == 1) {
         o.x *= scale;
@@ -137,9 +158,58 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
   }
 }
 
+// K2's output stage.  o = stream * c_out + channel.
+template <int LOG2N>
+__device__ __forceinline__ void emit_block(const C2RArgs& a, const int o, const int j, const float2 (&v)[8]) {
+  using C = FftCfg<LOG2N>;
+  constexpr int N = C::N, T8 = C::T8;
+  // overlap-save: the open block's output samples live at window positions [N+fill, N+fill+take);
+  // element q = j + m*T8 carries window samples 2q (re) and 2q+1 (im)
+  const int s = o / a.c_out, c = o - s * a.c_out;
+  float* y = a.y + (int64_t)s * a.ys + (int64_t)c * a.yc;
+  const float* xd = a.xdry ? a.xdry + (int64_t)s * a.xs + (int64_t)c * a.xc : nullptr;
+  const bool gains = (a.wet != 1.0f) || xd;
+  const int lo = N + a.fill, hi = lo + a.take;
+  if (a.fast) {  // a whole block into contiguous, 8-byte aligned output: elements N/2.. (m >= 4), vector stores
+    float* yo = y + a.y_off;
+#pragma unroll
+    for (int m = 4; m < 8; ++m) {
+      const int i = 2 * (j + m * T8) - N;
+      float2 val = v[m];
+      if (gains) {
+        val.x = __fmul_rn(val.x, a.wet);
+        val.y = __fmul_rn(val.y, a.wet);
+        if (xd) {
+          const float2 d = __ldg(reinterpret_cast<const float2*>(xd + a.x_off + i));
+          val.x = __fadd_rn(__fmul_rn(d.x, a.dry), val.x);
+          val.y = __fadd_rn(__fmul_rn(d.y, a.dry), val.y);
+        }
+      }
+      *reinterpret_cast<float2*>(yo + i) = val;
+    }
+  } else
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int i0 = 2 * (j + m * T8);
+    const float e[2] = {v[m].x, v[m].y};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = i0 + h;
+      if (i >= lo && i < hi) {
+        float val = e[h];
+        if (gains) {
+          val = __fmul_rn(val, a.wet);
+          if (xd) val = __fadd_rn(__fmul_rn(xd[(int64_t)(a.x_off + i - lo) * a.xi], a.dry), val);
+        }
+        y[(int64_t)(a.y_off + i - lo) * a.yi] = val;
+      }
+    }
+  }
+  }
+
 // PART: split partials are summed in (P > 1 or mix mode); the P = 1 conv instantiation carries no such registers
 template <int LOG2N, bool PART>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
+__global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 ? 3 : 1) k_c2r(const C2RArgs a) {
   using C = FftCfg<LOG2N>;
   constexpr int N = C::N, T8 = C::T8;
   extern __shared__ float2 sm[];
@@ -162,13 +232,16 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
       xrow = a.fdl + ((size_t)(s * a.c_x + gx) * a.R + a.head) * N;
       hrow = a.Hd + ((size_t)(__ldg(a.fmap + s) * a.c_f + fc) * 2 * a.R + (a.R - 1)) * N;
     }
+    if (xrow) {  // all 16 loads in flight before the first product
+      float2 xx[8], hh[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int k = j + m * T8;
-      if (xrow) {
-        const float2 x = xrow[k], h = __ldg(hrow + k);
-        v[m] = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);
+      for (int m = 0; m < 8; ++m) {
+        xx[m] = __ldcg(xrow + j + m * T8);   // written by K1 moments ago: L2
+        hh[m] = __ldg(hrow + j + m * T8);
       }
+#pragma unroll
+      for (int m = 0; m < 8; ++m) v[m] = cmul(xx[m], hh[m]);
+      if (j == 0) v[0] = make_float2(xx[0].x * hh[0].x, xx[0].y * hh[0].y);  // packed bin 0: two real bins
     }
     // split partials: 4 splits x 8 bins = 32 independent loads in flight per thread (fixed summation order)
     auto add_partials = [&](const float2* __restrict__ part, const int n) {
@@ -205,7 +278,16 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
   }
+  float2 tws[8];
+  if (!C::SMEM_TW) {  // global table: requested before the barrier
+#pragma unroll
+    for (int m = 0; m < 8; ++m) tws[m] = __ldg(tw + j + m * T8);
+  }
   __syncthreads();
+  if (C::SMEM_TW) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
+  }
   if (active) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -213,7 +295,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
       if (k == 0) {
         v[m] = make_float2(0.5f * (v[m].x + v[m].y), 0.5f * (v[m].x - v[m].y));
       } else {
-        v[m] = c2r_bin(v[m], sA[phys(N - k)], tw[k]);
+        v[m] = c2r_bin(v[m], sA[phys(N - k)], tws[m]);
       }
     }
   }
@@ -221,30 +303,79 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_c2r(const C2RArgs a) {
   fft_passes<LOG2N, true>(v, sA, sB, 1, j, tw);  // first exchange goes to sB: sA may still be read above
 
   if (active) {
-    // overlap-save: the open block's output samples live at window positions [N+fill, N+fill+take);
-    // element q = j + m*T8 carries window samples 2q (re) and 2q+1 (im)
-    const int s = o / a.c_out, c = o - s * a.c_out;
-    float* y = a.y + (int64_t)s * a.ys + (int64_t)c * a.yc;
-    const float* xd = a.xdry ? a.xdry + (int64_t)s * a.xs + (int64_t)c * a.xc : nullptr;
-    const bool gains = (a.wet != 1.0f) || xd;
-    const int lo = N + a.fill, hi = lo + a.take;
+    emit_block<LOG2N>(a, o, j, v);
+  }
+}
+
+// K1 + K2 fused for single-partition banks (P = 1, conv mode): ingest -> forward FFT -> split -> X * H ->
+// merge -> inverse FFT -> emit, one kernel, one transform group per (stream, source channel).  The spectrum
+// never goes to the delay line (nothing ever reads it back when P = 1): per stream-step the traffic is
+// 2B*4 (window) + B*4 (hist) + B*8 (H) + B*4 (y) instead of that plus a B*8 row written and read again.
+// FAN: a mono source fanned out to c_out filter channels (convolve_pe.py:300-310): one forward transform,
+// c_out inverse transforms.
+template <int LOG2N, bool FAN>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 ? 2 : 1)
+    k_conv1(const R2CArgs a, const C2RArgs k) {
+  using C = FftCfg<LOG2N>;
+  constexpr int N = C::N, T8 = C::T8;
+  extern __shared__ float2 sm[];
+  const float2* tw = stage_twiddles<LOG2N>(sm, a.tw);
+  float2* bufs = sm + (C::SMEM_TW ? 2 * N : 0);
+  const int g = threadIdx.x / T8, j = threadIdx.x - g * T8;
+  float2* sA = bufs + (size_t)g * 2 * C::PADN;
+  float2* sB = sA + C::PADN;
+  const int64_t f = (int64_t)blockIdx.x * C::FPB + g;
+  const bool active = f < (int64_t)a.n_fft;
+
+  float2 v[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int i0 = 2 * (j + m * T8);
-      const float e[2] = {v[m].x, v[m].y};
+  for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
+  if (active) ingest_window<LOG2N>(a, f, j, v);
+  fft_passes<LOG2N, false>(v, sA, sB, 0, j, tw);
+
+  // split: packed half spectrum X[k], k = j + m*T8, from Z[k] and Z[N-k]
+  __syncthreads();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = i0 + h;
-        if (i >= lo && i < hi) {
-          float val = e[h];
-          if (gains) {
-            val = __fmul_rn(val, a.wet);
-            if (xd) val = __fadd_rn(__fmul_rn(xd[(int64_t)(a.x_off + i - lo) * a.xi], a.dry), val);
-          }
-          y[(int64_t)(a.y_off + i - lo) * a.yi] = val;
-        }
+  for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+  float2 tws[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
+  __syncthreads();
+  float2 X[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int kk = j + m * T8;
+    X[m] = (kk == 0) ? make_float2(v[m].x + v[m].y, v[m].x - v[m].y) : r2c_bin(v[m], sA[phys(N - kk)], tws[m]);
+  }
+
+  const int s = active ? (int)(f / a.c_x) : 0, cx = active ? (int)(f - (int64_t)s * a.c_x) : 0;
+  const int n_c = FAN ? k.c_out : 1;
+  for (int ci = 0; ci < n_c; ++ci) {
+    const int c = FAN ? ci : cx;
+    const int fc = (k.c_f == 1) ? 0 : c;
+    __syncthreads();  // every read of sA / sB above (or by the previous channel's inverse passes) is done
+    if (active) {
+      const float2* hrow = k.Hd + ((size_t)(__ldg(k.fmap + s) * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N;
+      float2 hh[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) hh[m] = __ldg(hrow + j + m * T8);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) v[m] = cmul(X[m], hh[m]);
+      if (j == 0) v[0] = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
+#pragma unroll
+      for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int kk = j + m * T8;
+        v[m] = (kk == 0) ? make_float2(0.5f * (v[m].x + v[m].y), 0.5f * (v[m].x - v[m].y))
+                         : c2r_bin(v[m], sA[phys(N - kk)], tws[m]);
       }
     }
+    fft_passes<LOG2N, true>(v, sA, sB, 1, j, tw);  // first exchange goes to sB: sA may still be read above
+    if (active) emit_block<LOG2N>(k, s * k.c_out + c, j, v);
   }
 }
 
@@ -294,6 +425,16 @@ static void launch_c2r_t(const C2RArgs& a, cudaStream_t st) {
   k_c2r<LOG2N, PART><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a);
 }
 
+template <int LOG2N, bool FAN>
+static void launch_conv1_t(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
+  using C = FftCfg<LOG2N>;
+  static bool attr_done[64] = {};
+  if (C::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
+    cudaFuncSetAttribute(k_conv1<LOG2N, FAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  const int grid = (a.n_fft + C::FPB - 1) / C::FPB;
+  k_conv1<LOG2N, FAN><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a, k);
+}
+
 #define PGX_DISPATCH(LOG, CALL)                                                                              \
   switch (LOG) {                                                                                             \
     case 4: { constexpr int L_ = 4; CALL; } break;                                                           \
@@ -317,6 +458,14 @@ void launch_r2c_ingest(const R2CArgs& a, cudaStream_t st) {
 void launch_filter_prep(const FilterPrepArgs& fp, cudaStream_t st) {
   R2CArgs a{};
   PGX_DISPATCH(ilog2(fp.B), (launch_r2c_t<L_, 1>(a, fp, (int64_t)fp.n_rows * fp.P, st)));
+}
+
+void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
+  if (a.c_x == 1 && k.c_out > 1) {
+    PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, true>(a, k, st)));
+  } else {
+    PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, false>(a, k, st)));
+  }
 }
 
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st) {

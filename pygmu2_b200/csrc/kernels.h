@@ -17,6 +17,7 @@ struct R2CArgs {
   int32_t c_in, c_x, B, R;
   int32_t slot, half, fill, take;
   int32_t mixdown;
+  int32_t fast;          // whole block (fill 0, take B) of contiguous, 8-byte aligned samples, no mix-down
 };
 void launch_r2c_ingest(const R2CArgs& a, cudaStream_t st);
 
@@ -86,8 +87,11 @@ struct C2RArgs {
   int64_t xs, xc, xi;
   int32_t x_off;
   float wet, dry;
+  int32_t fast;          // whole block into contiguous, 8-byte aligned y (and xdry): vector stores
 };
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st);
+// K1 + K2 in one kernel for single-partition conv banks (P = 1): the spectrum never visits the delay line.
+void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st);
 
 // K5: MixPE left-to-right float32 sum of n_inputs dense arrays.
 void launch_mix_sum(const float* in, int32_t n_inputs, int64_t n_elems, float* out, cudaStream_t st);

@@ -135,10 +135,11 @@ struct pgx_bank {
   int sm_count = 148;
   float wet = 1.0f, dry = 0.0f;    // fused output stage: y = dry * x + wet * conv
   bool serial = false;
+  bool use_conv1 = true;           // P = 1 conv pulls: K1 and K2 fused into one kernel (PGX_CONV1=0 disables)
   int64_t launches = 0, steps = 0;
   // per-kernel CUDA-event timing
   bool profiling = false;
-  struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3 (past pass), 2 = K2, 3 = fold, 4 = K3 (present slot, mix)
+  struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3 (past pass), 2 = K2, 3 = fold, 4 = K3 (present slot, mix), 5 = fused K1+K2 (P = 1)
   std::vector<ProfSpan> prof_spans;
   std::vector<cudaEvent_t> prof_pool;
   size_t prof_pool_used = 0;
@@ -292,25 +293,37 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   const int64_t i = b->step, t = b->block;
   const bool completes = (b->fill + take == B);
 
-  // ---- ingest stream: K1
-  if (b->fill > 0 || R == 1) {  // same ring row (and open half) as the previous step
-    if (i >= 1) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 1) % kRing], 0);
-  } else {
-    if (i >= 2) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 2) % kRing], 0);
-    if (t >= 2) cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);  // every block had its past pass issued
-  }
+  const bool fused1 = (R == 1 && !mix && b->use_conv1);
   pgx::R2CArgs r{};
   r.x = x_dev; r.xs = xl.stream; r.xc = xl.chan; r.xi = xl.samp; r.x_off = pos;
   r.hist = b->hist; r.fdl = b->fdl; r.tw = b->tw;
   r.n_fft = c.n_streams * b->c_x; r.c_in = c.c_in; r.c_x = b->c_x; r.B = B; r.R = R;
   r.slot = b->head; r.half = b->half; r.fill = b->fill; r.take = take;
   r.mixdown = (c.flags & PGX_FLAG_MIXDOWN_INPUT) ? 1 : 0;
-  {
-    ProfScope ps(b, b->s_in, 0);
-    pgx::launch_r2c_ingest(r, b->s_in);
+  const bool whole = (b->fill == 0 && take == B);
+  auto vec_ok = [&](const void* p, const pgx_layout& l) {  // float2 access at p[s*stream + c*chan + pos + even]
+    return l.samp == 1 && (l.stream % 2) == 0 && (l.chan % 2) == 0 && (pos % 2) == 0 &&
+           (reinterpret_cast<uintptr_t>(p) % 8) == 0;
+  };
+  r.fast = (whole && !r.mixdown && vec_ok(x_dev, xl)) ? 1 : 0;
+
+  // ---- ingest stream: K1 (single-partition conv pulls run K1 and K2 as one kernel on the critical stream)
+  if (!fused1) {
+    if (b->fill > 0 || R == 1) {  // same ring row (and open half) as the previous step
+      if (i >= 1) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 1) % kRing], 0);
+    } else {
+      if (i >= 2) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 2) % kRing], 0);
+      if (t >= 2) cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);  // every block had its past pass issued
+    }
+    {
+      ProfScope ps(b, b->s_in, 0);
+      pgx::launch_r2c_ingest(r, b->s_in);
+    }
+    cudaEventRecord(b->ev_k1[i % kRing], b->s_in);
+    b->launches += 1;
+  } else if (i >= 1) {
+    cudaStreamWaitEvent(crit, b->ev_k2[(i - 1) % kRing], 0);  // hist of the previous step (no-op on one stream)
   }
-  cudaEventRecord(b->ev_k1[i % kRing], b->s_in);
-  b->launches += 1;
 
   // ---- background stream: past sum of the open block, if it is not in flight / valid already
   int n_split_past = 0;
@@ -323,7 +336,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   }
 
   // ---- critical stream: [NOW] + K2
-  cudaStreamWaitEvent(crit, b->ev_k1[i % kRing], 0);
+  if (!fused1) cudaStreamWaitEvent(crit, b->ev_k1[i % kRing], 0);
   pgx::C2RArgs k{};
   k.yspec = b->ypast[par]; k.n_split = n_split_past;
   k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
@@ -354,15 +367,22 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   k.wet = b->wet; k.dry = b->dry;
   k.xdry = (!mix && b->dry != 0.0f) ? x_dev : nullptr;
   k.xs = xl.stream; k.xc = xl.chan; k.xi = xl.samp; k.x_off = pos;
+  {
+    pgx_layout ye = yl;
+    if (mix) ye.stream = 0;
+    k.fast = (whole && vec_ok(y_dev, ye) && (!k.xdry || vec_ok(x_dev, xl))) ? 1 : 0;
+  }
 
   // the block commits with this step: its row is final once K1 has run, so the next block's past pass
   // can start now, overlapping this step's K2 and the next step's K1
   if (completes && P > 1) issue_past(b, mix, t + 1, (b->head + 1) % R, b->ev_k1[i % kRing]);
 
   {
-    ProfScope ps(b, crit, 2);
-    pgx::launch_c2r_emit(k, crit);
+    ProfScope ps(b, crit, fused1 ? 5 : 2);
+    if (fused1) pgx::launch_conv1(r, k, crit);
+    else pgx::launch_c2r_emit(k, crit);
   }
+  if (fused1) cudaEventRecord(b->ev_k1[i % kRing], crit);
   cudaEventRecord(b->ev_k2[i % kRing], crit);
   b->last_k2_of_par[par] = i;
   b->launches += 1;
@@ -566,6 +586,7 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     guard(cudaStreamCreateWithPriority(&b->s_bg2, cudaStreamNonBlocking, lo), "cudaStreamCreate(bg2)");
     guard(cudaEventCreateWithFlags(&b->ev_bgjoin, cudaEventDisableTiming), "cudaEventCreate");
     if (const char* e = getenv("PGX_BG_STREAMS")) b->two_bg = (e[0] != '1');
+    if (const char* e = getenv("PGX_CONV1")) b->use_conv1 = (e[0] != '0');
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");
     if (const char* e = getenv("PGX_DEBUG_SERIAL")) {  // debugging aid: no overlap, one stream for everything
@@ -867,6 +888,7 @@ int pgx_bank_profile_end(pgx_bank* b, pgx_profile* out) {
   out->ms_r2c = out->ms_mac = out->ms_c2r = out->ms_fold = out->ms_now = 0.0;
   out->n_mac = 0;
   out->ms_mac_union = 0.0;
+  out->ms_conv1 = 0.0;
   out->steps = b->prof_steps;
   PGX_CUDA(cudaDeviceSynchronize());
   std::vector<std::pair<float, float>> mac_iv;  // K3 past-pass launches as [start, end) from the first event
@@ -884,6 +906,7 @@ int pgx_bank_profile_end(pgx_bank* b, pgx_profile* out) {
     }
     else if (sp.kind == 2) out->ms_c2r += ms;
     else if (sp.kind == 3) out->ms_fold += ms;
+    else if (sp.kind == 5) out->ms_conv1 += ms;
     else out->ms_now += ms;
   }
   // launches of consecutive blocks overlap on the two background streams: the kernel's busy time is the

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Layout) == 24
     assert C.sizeof(_lib.BankConfig) == 40
-    assert C.sizeof(_lib.Profile) == 64
+    assert C.sizeof(_lib.Profile) == 72
     assert C.sizeof(_lib.OscConfig) == 40
 
 
