@@ -337,6 +337,8 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        from pygmu2_b200.dist import bind_host_to_gpu
+        numa_bound = bind_host_to_gpu(local)   # host staging buffers next to this rank's GPU
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:

@@ -347,3 +347,35 @@ def test_pcm16_conversion_rules_and_wav_round_trip(tmp_path):
     assert not got[:10].any() and not got[1010:].any()
     np.testing.assert_array_equal(got[10:1010], pcm16_to_f32(f32_to_pcm16(data)))
     np.testing.assert_array_equal(rd.render_pcm16(0, 1000), f32_to_pcm16(data))
+
+
+# ---- device-source PEs: host-side parameter logic against the oracle restatement (no GPU needed) -------
+def test_supersaw_host_parameters_match_reference_rules():
+    import pygmu2_oracle_sources as osrc
+    g = golden("src_oscillators.npz")
+    mixname = {0: "center_heavy", 1: "linear", 2: "equal"}
+    for f, a, v, d, mm, rp, sd in g["ssaw_cases"]:
+        pe = pg.SuperSawPE(frequency=f, amplitude=a, voices=int(v), detune_cents=d, mix_mode=mixname[int(mm)],
+                           randomize_phase=bool(rp), seed=int(sd))
+        fr, ga, ph = osrc.supersaw_params(f, int(v), d, mixname[int(mm)], bool(rp), int(sd))
+        np.testing.assert_array_equal(np.array(pe._osc_freq), fr)
+        np.testing.assert_array_equal(np.array(pe._osc_gain), ga)
+        np.testing.assert_array_equal(np.array(pe._osc_phase), ph)
+        assert pe.channel_count() == 1 and not pe.is_pure() and pe.extent() == pg.Extent(None, None)
+    with pytest.raises(ValueError):
+        pg.SuperSawPE(440.0, mix_mode="nope")
+    assert pg.SinePE().is_pure() and pg.SinePE(channels=2).channel_count() == 2
+    assert pg.BlitSawPE(100.0, initial_phase=1.25).initial_phase == 0.25 and pg.BlitSawPE(100.0).m is None
+
+
+def test_mix_unwrap_folds_delay_and_gain_wrappers():
+    from pygmu2_b200.mix_pe import _unwrap, _foldable_method
+    core = pg.SpatialPE(pg.ArrayPE(np.zeros(8, np.float32)), method=pg.SpatialHRTF(10.0))
+    pe = pg.DelayPE(pg.GainPE(pg.DelayPE(pg.GainPE(core, 0.5), 100), 0.25), 7)
+    c, d, gn = _unwrap(pe)
+    assert c is core and d == 107 and gn == np.float32(0.125)
+    assert _unwrap(core) == (core, 0, None)
+    dyn = pg.GainPE(core, gain=pg.ConstantPE(0.5))                    # a PE-valued gain is not folded
+    assert _unwrap(dyn)[0] is dyn
+    assert _foldable_method(pg.SpatialLinear(30.0)) and _foldable_method(pg.SpatialConstantPower(-30.0))
+    assert not _foldable_method(pg.SpatialLinear(pg.ConstantPE(0.0))) and not _foldable_method(pg.SpatialAdapter(2))
