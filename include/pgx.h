@@ -92,6 +92,13 @@ PGX_API int pgx_device_count(int* count);
 PGX_API int pgx_host_alloc(void** ptr, int64_t bytes);
 PGX_API int pgx_host_free(void* ptr);
 
+/* device memory for inputs that stay resident (ArrayPE sources uploaded once; see PGX_PULL_X_DEVICE).
+ * Synchronous, like cudaMalloc / cudaMemcpy / cudaMemset. */
+PGX_API int pgx_device_alloc(int32_t device, int64_t bytes, void** ptr);
+PGX_API int pgx_device_free(int32_t device, void* ptr);
+PGX_API int pgx_device_upload(int32_t device, void* dst_dev, const void* src_host, int64_t bytes);
+PGX_API int pgx_device_zero(int32_t device, void* dst_dev, int64_t bytes);
+
 /* ---- bank: replaces ConvolvePE state + _render (convolve_pe.py:185-342) and
  *      SpatialHRTF.render (spatial_pe.py:465-518) for N streams at once ------ */
 

@@ -59,6 +59,10 @@ PROTOTYPES = {
     "pgx_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pgx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "pgx_host_free": (C.c_int, [C.c_void_p]),
+    "pgx_device_alloc": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    "pgx_device_free": (C.c_int, [C.c_int32, C.c_void_p]),
+    "pgx_device_upload": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
+    "pgx_device_zero": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64]),
     "pgx_bank_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(BankConfig), _f32p, _i32p]),
     "pgx_bank_destroy": (C.c_int, [C.c_void_p]),
     "pgx_bank_get_info": (C.c_int, [C.c_void_p, C.POINTER(BankInfo)]),

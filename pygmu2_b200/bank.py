@@ -299,6 +299,11 @@ class ConvolveBank:
         self.sources = sources
         self._src_delays = [0] * len(sources) if delays is None else [int(d) for d in delays]
         self._src_gains = [None] * len(sources) if gains is None else [None if g is None else np.float32(g) for g in gains]
+        self._resident = None
+        from .resident import ResidentSources  # plain in-memory sources are uploaded once and stay in HBM
+        if ResidentSources.eligible(sources, self._src_delays, self.c_in, False):
+            self._resident = ResidentSources(sources, self._src_delays, self._src_gains, self.c_in, False,
+                                             device=self.device)
         self._pos = None
         self.mix_output = False
 
@@ -310,6 +315,7 @@ class ConvolveBank:
         self._pos = None
         self.mix_output = False
         self._device_source = True
+        self._resident = None
 
     def render(self, start: int, duration: int) -> np.ndarray:
         """One lockstep pull of every attached source: (N, C_out, n), or (C_out, n) when mix_output."""
@@ -317,6 +323,14 @@ class ConvolveBank:
             raise RuntimeError("no sources attached")
         if self._pos is None or start != self._pos:
             self.reset()  # non-contiguous pull: history := 0 (convolve_pe.py:255-256)
+        if getattr(self, "_resident", None) is not None and not getattr(self, "_device_source", False):
+            outs, pos = [], 0
+            while pos < duration:
+                d = min(self.max_pull, self._resident.max_pull, duration - pos)
+                outs.append(self.process_device_block(self._resident.device_block(start + pos, d), mix=self.mix_output))
+                pos += d
+            self._pos = start + duration
+            return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=-1)
         if getattr(self, "_device_source", False):
             outs, pos = [], 0
             while pos < duration:

@@ -499,6 +499,34 @@ int pgx_host_free(void* ptr) {
   return PGX_OK;
 }
 
+int pgx_device_alloc(int32_t device, int64_t bytes, void** ptr) {
+  if (!ptr || bytes <= 0) return fail(PGX_ERR_INVALID, "pgx_device_alloc: bad arguments");
+  PGX_CUDA(cudaSetDevice(device));
+  PGX_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  return PGX_OK;
+}
+
+int pgx_device_free(int32_t device, void* ptr) {
+  if (!ptr) return PGX_OK;
+  PGX_CUDA(cudaSetDevice(device));
+  PGX_CUDA(cudaFree(ptr));
+  return PGX_OK;
+}
+
+int pgx_device_upload(int32_t device, void* dst_dev, const void* src_host, int64_t bytes) {
+  if (!dst_dev || (!src_host && bytes > 0) || bytes < 0) return fail(PGX_ERR_INVALID, "pgx_device_upload: bad arguments");
+  PGX_CUDA(cudaSetDevice(device));
+  if (src_host) PGX_CUDA(cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+  return PGX_OK;
+}
+
+int pgx_device_zero(int32_t device, void* dst_dev, int64_t bytes) {
+  if (!dst_dev || bytes < 0) return fail(PGX_ERR_INVALID, "pgx_device_zero: bad arguments");
+  PGX_CUDA(cudaSetDevice(device));
+  PGX_CUDA(cudaMemset(dst_dev, 0, (size_t)bytes));
+  return PGX_OK;
+}
+
 int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, const int32_t* filter_of_stream) {
   if (!out || !cfg || !h) return fail(PGX_ERR_INVALID, "pgx_bank_create: NULL argument");
   *out = nullptr;
@@ -767,7 +795,9 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   int rc = check_pull_args(b, x, y, n);
   if (rc != PGX_OK) return rc;
   const pgx_bank_config& c = b->cfg;
-  if (!layout_dense(xl, c.n_streams, c.c_in, n)) return fail(PGX_ERR_INVALID, "x layout does not tile a dense block");
+  // host x is staged with one copy, so it has to be one dense block; device-resident x is read in place
+  if (!x_device && !layout_dense(xl, c.n_streams, c.c_in, n))
+    return fail(PGX_ERR_INVALID, "x layout does not tile a dense block");
   pgx_layout yd = yl;
   if (mix) yd.stream = 0;
   if (!layout_dense(yd, mix ? 1 : c.n_streams, c.c_out, n))

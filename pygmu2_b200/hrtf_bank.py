@@ -22,6 +22,7 @@ import numpy as np
 from . import kemar
 from .bank import ConvolveBank, choose_block
 from .core import Extent, handle_error
+from .resident import ResidentSources
 
 
 def _is_pan(m) -> bool:
@@ -70,16 +71,35 @@ class HrtfMixBank:
         self._pos = None
         self._warned = False
         self._was_active = np.ones(len(self.sources), dtype=bool)
+        # extents are static: [lo, hi) of every (delayed) source as arrays, for the per-pull gating
+        ext = [_shifted(pe.extent(), d) for pe, d in zip(self.sources, self.delays)]
+        self._ext_lo = np.array([-np.inf if e.start is None else e.start for e in ext])
+        self._ext_hi = np.array([np.inf if e.end is None else e.end for e in ext])
+        self._ext_empty = np.array([e.is_empty() for e in ext], dtype=bool)
+        # plain in-memory sources are uploaded once and stay in HBM (no per-pull host samples)
+        self._resident = None
+        if ResidentSources.eligible(self.sources, self.delays, self.c_in, self.host_mixdown):
+            self._resident = ResidentSources(self.sources, self.delays, self.gains, self.c_in, self.host_mixdown,
+                                             device=device)
 
     def _select(self) -> np.ndarray:
-        idx = np.empty(len(self.methods), dtype=np.int32)
-        for i, m in enumerate(self.methods):
-            if i in self.pan_index:
-                idx[i] = 2 * self.n_entries + 1 + self.pan_index[i]
-                continue
-            e = kemar.nearest_index(m.azimuth, m.elevation) if self.n_entries == len(kemar.KEMAR_HRTF_ENTRIES) \
-                else int(getattr(m, "entry", 0))
-            idx[i] = e + (self.n_entries if m.azimuth < 0 else 0)
+        """Filter-table row of every source for the CURRENT azimuth / elevation attributes (re-resolved on every
+        pull like spatial_pe.py:446-449), vectorised over the sources."""
+        n = len(self.methods)
+        az = np.fromiter((float(m.azimuth) for m in self.methods), dtype=np.float64, count=n)
+        if self.n_entries == len(kemar.KEMAR_HRTF_ENTRIES):
+            el = np.fromiter((float(getattr(m, "elevation", 0.0)) for m in self.methods), dtype=np.float64, count=n)
+            last = getattr(self, "_dir_cache", None)   # directions unchanged since the last pull: same rows
+            if last is not None and np.array_equal(last[0], az) and np.array_equal(last[1], el):
+                e = last[2]
+            else:
+                e = kemar.nearest_indices(az, el)
+                self._dir_cache = (az, el, e)
+        else:
+            e = np.fromiter((int(getattr(m, "entry", 0)) for m in self.methods), dtype=np.int64, count=n)
+        idx = (e + np.where(az < 0, self.n_entries, 0)).astype(np.int32)
+        for i, k in self.pan_index.items():
+            idx[i] = 2 * self.n_entries + 1 + k
         return idx
 
     def _refresh_pans(self) -> None:
@@ -112,9 +132,7 @@ class HrtfMixBank:
         # MixPE renders only the inputs whose extent meets the request (mix_pe.py:81-85; a SpatialPE's extent is
         # its source's, spatial_pe.py:640-642).  A skipped source contributes nothing - the silent filter - and
         # its next render starts a new run (spatial_pe.py:461-463): its history is cleared when it comes back.
-        req = Extent(start, start + duration)
-        active = np.array([_shifted(pe.extent(), d).intersects(req) for pe, d in zip(self.sources, self.delays)],
-                          dtype=bool)
+        active = ~self._ext_empty & (self._ext_lo < start + duration) & (self._ext_hi > start)   # Extent.intersects
         self._refresh_pans()
         sel = self._select()
         sel[~active] = 2 * self.n_entries
@@ -127,6 +145,15 @@ class HrtfMixBank:
         if not np.array_equal(sel, self._selected):
             self.bank.set_filter_map(sel)
             self._selected = sel
+        self._was_active = active
+        if self._resident is not None:  # sources live in HBM: a pull is a pointer into the resident buffer
+            self._pos = start + duration
+            outs, pos = [], 0
+            while pos < duration:
+                d = min(self.bank.max_pull, self._resident.max_pull, duration - pos)
+                outs.append(self.bank.process_device_block(self._resident.device_block(start + pos, d), mix=True))
+                pos += d
+            return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=-1)
         x = np.zeros((len(self.sources), self.c_in, duration), dtype=np.float32)
         for s, pe in enumerate(self.sources):
             if active[s]:

@@ -47,6 +47,14 @@ def nearest_index(azimuth: float, elevation: float) -> int:
     return int(np.argmin(d))  # argmin returns the first minimum, like python's min()
 
 
+def nearest_indices(azimuth: np.ndarray, elevation: np.ndarray) -> np.ndarray:
+    """``nearest_index`` for arrays of directions at once (same arithmetic, same first-minimum rule)."""
+    az = np.minimum(180.0, np.abs(np.asarray(azimuth, dtype=np.float64)))[:, None]
+    el = np.asarray(elevation, dtype=np.float64)[:, None]
+    d = (_ELEV[None, :] - el) ** 2 + (_AZ[None, :] - az) ** 2
+    return np.argmin(d, axis=1)
+
+
 _table_cache = {}
 
 
