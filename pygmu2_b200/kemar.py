@@ -47,12 +47,43 @@ def nearest_index(azimuth: float, elevation: float) -> int:
     return int(np.argmin(d))  # argmin returns the first minimum, like python's min()
 
 
+def _rings():
+    """The table is 14 elevation rings in ascending order, azimuths ascending within a ring."""
+    rings, i = [], 0
+    while i < len(KEMAR_HRTF_ENTRIES):
+        j = i
+        while j < len(KEMAR_HRTF_ENTRIES) and KEMAR_HRTF_ENTRIES[j][0] == KEMAR_HRTF_ENTRIES[i][0]:
+            j += 1
+        rings.append((float(KEMAR_HRTF_ENTRIES[i][0]), _AZ[i:j].copy(), i))
+        i = j
+    return rings
+
+
+_RINGS = _rings()
+_R_ELEV = np.array([r[0] for r in _RINGS])[:, None]                          # (14, 1)
+_R_LEN = np.array([r[1].shape[0] for r in _RINGS])[:, None, None]            # (14, 1, 1)
+_R_FIRST = np.array([r[2] for r in _RINGS])[:, None]                         # (14, 1)
+_R_STEP = np.array([360.0 / _AZ_COUNTS[int(r[0])] for r in _RINGS])[:, None]  # (14, 1) nominal azimuth spacing
+_R_AZ = np.stack([np.pad(r[1], (0, 37 - r[1].shape[0]), mode="edge") for r in _RINGS])   # (14, 37)
+_R_ROW = np.arange(len(_RINGS))[:, None, None]
+
+
 def nearest_indices(azimuth: np.ndarray, elevation: np.ndarray) -> np.ndarray:
-    """``nearest_index`` for arrays of directions at once (same arithmetic, same first-minimum rule)."""
-    az = np.minimum(180.0, np.abs(np.asarray(azimuth, dtype=np.float64)))[:, None]
-    el = np.asarray(elevation, dtype=np.float64)[:, None]
-    d = (_ELEV[None, :] - el) ** 2 + (_AZ[None, :] - az) ** 2
-    return np.argmin(d, axis=1)
+    """``nearest_index`` for arrays of directions at once: same float64 arithmetic, same first-minimum rule.
+    On each of the 14 elevation rings only the entries around az/step can be nearest (ring azimuths are
+    round(i*step)), so 4 candidates per ring are examined instead of the whole ring: 56 distances per query
+    instead of 368, all rings in one vectorised pass."""
+    az = np.minimum(180.0, np.abs(np.asarray(azimuth, dtype=np.float64)))[None, :]   # (1, Q)
+    el = np.asarray(elevation, dtype=np.float64)[None, :]
+    base = np.floor(az / _R_STEP).astype(np.int64)[:, :, None]                       # (14, Q, 1)
+    cand = np.clip(base + np.arange(-1, 3)[None, None, :], 0, _R_LEN - 1)            # (14, Q, 4) ascending indices
+    d = ((_R_ELEV - el) ** 2)[:, :, None] + (_R_AZ[_R_ROW, cand] - az[:, :, None]) ** 2
+    k = np.argmin(d, axis=2)                                                         # first minimum: lowest index
+    q = np.arange(az.shape[1])[None, :]
+    ring_best_d = d[_R_ROW[:, :, 0], q, k]                                           # (14, Q)
+    ring_best_i = _R_FIRST + cand[_R_ROW[:, :, 0], q, k]
+    ring = np.argmin(ring_best_d, axis=0)                                            # lowest ring on ties
+    return ring_best_i[ring, q[0]]
 
 
 _table_cache = {}

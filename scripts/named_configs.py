@@ -17,7 +17,7 @@ import pygmu2_b200 as pg  # noqa: E402
 from pygmu2_b200 import workloads as wl  # noqa: E402
 
 
-def run(name, pe, sr, pull, seconds, channels):
+def run(name, pe, sr, pull, seconds, channels, before_pull=None):
     n_pulls = int(seconds * sr / pull)
     with pg.NullRenderer(sample_rate=sr) as r:
         r.set_source(pe)
@@ -26,6 +26,8 @@ def run(name, pe, sr, pull, seconds, channels):
             r.render(p * pull, pull)
         t0 = time.perf_counter()
         for p in range(4, 4 + n_pulls):
+            if before_pull is not None:
+                before_pull(p)
             r.render(p * pull, pull)
         dt = time.perf_counter() - t0
     audio = n_pulls * pull / sr
@@ -53,7 +55,17 @@ def main():
     n3 = int((S + 1) * wl.SR_441)
     srcs = [pg.SpatialPE(pg.ArrayPE(wl.c3_source(n3, i)), method=pg.SpatialHRTF(wl.c3_azimuth(i, 0, 2), el[i]))
             for i in range(wl.C3_SOURCES)]
-    run("C3 256 HRTF sources -> MixPE", pg.MixPE(*srcs), wl.SR_441, 512, S, 2)
+    run("C3 256 HRTF sources -> MixPE (static)", pg.MixPE(*srcs), wl.SR_441, 512, S, 2)
+    srcs = [pg.SpatialPE(pg.ArrayPE(wl.c3_source(n3, i)), method=pg.SpatialHRTF(wl.c3_azimuth(i, 0, 2), el[i]))
+            for i in range(wl.C3_SOURCES)]
+    n_total = int(S * wl.SR_441 / 512) + 4
+    az_tab = np.array([[wl.c3_azimuth(i, p, n_total) for i in range(wl.C3_SOURCES)] for p in range(n_total + 1)])
+
+    def move(p):                                # the user's own per-pull code: every source gets a new azimuth
+        for i, sp in enumerate(srcs):
+            sp.method.azimuth = az_tab[p, i]
+
+    run("C3 256 MOVING HRTF sources -> MixPE", pg.MixPE(*srcs), wl.SR_441, 512, S, 2, before_pull=move)
     # C5: 1024 SuperSawPE voices -> MixPE -> 10 s IR at 64-sample pulls
     voices = [pg.SuperSawPE(frequency=55.0 * 2.0 ** (i / 128.0), amplitude=1.0 / 32.0, seed=i) for i in range(wl.C5_VOICES)]
     run("C5 1024 SuperSaw -> MixPE -> 441000-tap IR", pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(wl.c5_ir()), block_size=64),

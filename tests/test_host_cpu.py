@@ -379,3 +379,16 @@ def test_mix_unwrap_folds_delay_and_gain_wrappers():
     assert _unwrap(dyn)[0] is dyn
     assert _foldable_method(pg.SpatialLinear(30.0)) and _foldable_method(pg.SpatialConstantPower(-30.0))
     assert not _foldable_method(pg.SpatialLinear(pg.ConstantPE(0.0))) and not _foldable_method(pg.SpatialAdapter(2))
+
+
+def test_vectorised_hrtf_lookup_equals_the_reference_rule():
+    """kemar.nearest_indices (4 candidates per elevation ring) must pick exactly the entry of the full
+    first-minimum scan (spatial_pe.py:395-426), ties, clamping and out-of-range elevations included."""
+    g = golden("hrtf_lookup.npz")
+    np.testing.assert_array_equal(kemar.nearest_indices(g["az"], g["el"]), g["idx"])
+    rng = np.random.default_rng(9)
+    az = np.concatenate([rng.uniform(-250, 250, 5000), np.arange(-180, 181, 0.5), np.repeat(np.arange(0, 181, 2.5), 2)])
+    el = np.concatenate([rng.uniform(-90, 130, 5000), np.tile([0.0, 5.0, -45.0, 85.0, 95.0], 145)[:721],
+                         np.tile([15.0, 45.0], 73)])
+    full = np.array([kemar.nearest_index(a, e) for a, e in zip(az, el)])
+    np.testing.assert_array_equal(kemar.nearest_indices(az, el), full)
