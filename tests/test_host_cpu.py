@@ -390,5 +390,7 @@ def test_vectorised_hrtf_lookup_equals_the_reference_rule():
     az = np.concatenate([rng.uniform(-250, 250, 5000), np.arange(-180, 181, 0.5), np.repeat(np.arange(0, 181, 2.5), 2)])
     el = np.concatenate([rng.uniform(-90, 130, 5000), np.tile([0.0, 5.0, -45.0, 85.0, 95.0], 145)[:721],
                          np.tile([15.0, 45.0], 73)])
+    n = min(az.shape[0], el.shape[0])
+    az, el = az[:n], el[:n]
     full = np.array([kemar.nearest_index(a, e) for a, e in zip(az, el)])
     np.testing.assert_array_equal(kemar.nearest_indices(az, el), full)
