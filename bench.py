@@ -300,14 +300,18 @@ def make_workload(args, rank, local):
                     config=cfg, fill_steps=bank.partitions, reduce=True)
     if w == "c5":   # 10 s IR at 64-sample blocks: N=1 is the named latency case, N=256 replicas give an HBM figure
         N = args.streams or 1
-        bank = pg.ConvolveBank(wl.c5_ir(), N, 1, block=64, max_pull=64, device=local, single_filter_dims=True)
+        bank = pg.ConvolveBank(wl.c5_ir(), N, 1, block=64, max_pull=64, device=local, single_filter_dims=True,
+                               tail_block=args.tail_block or None)
         cfg = {"workload": "C5 10 s IR (441000 taps) @44.1 kHz at 64-sample pulls (6891 uniform partitions), "
                            f"{N} stream(s); voice generation excluded",
                "streams_per_gpu": N, "block": 64, "partitions": bank.partitions, "pull": 64, "sample_rate": wl.SR_441,
                "l2": ("state 7 MB: L2-resident, latency-bound" if N == 1 else
                       f"delay line streamed per step: {N * bank.partitions * 64 * 8 / 1e6:.0f} MB vs 126 MB L2")}
+        if args.tail_block:
+            cfg["partitioning"] = (f"two-level: {bank.partitions} head partitions of 64 + {bank.tail_partitions} tail "
+                                   f"partitions of {args.tail_block}; roofline bytes are still SURVEY's uniform figure")
         return dict(bank=bank, N=N, c_in=1, c_out=1, L=wl.C5_L, B=64, pull=64, sr=wl.SR_441, distinct=False, mix=False,
-                    config=cfg, fill_steps=min(bank.partitions, 400))
+                    config=cfg, fill_steps=400)
     if w == "c5v":  # C5 with its front end: 1024 SuperSawPE voices -> MixPE -> 10 s IR at 64-sample pulls, all in HBM
         V = args.streams or wl.C5_VOICES
         pg.set_sample_rate(wl.SR_441)
@@ -571,6 +575,8 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's named size)")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5v"],
                     help="c2 = BASELINE.json configs[1] (headline); the others are the remaining configs, for profiling")
+    ap.add_argument("--tail-block", type=int, default=0,
+                    help="c5: two-level partitioning, first TAIL_BLOCK taps at 64-sample blocks, the rest at TAIL_BLOCK")
     ap.add_argument("--reverb", action="store_true", help="c2: add ReverbPE's fused wet/dry output stage")
     ap.add_argument("--pcm16", action="store_true",
                     help="e2e leg with int16 PCM host buffers converted on the device (WAV staging, half the PCIe bytes)")

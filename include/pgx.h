@@ -72,6 +72,11 @@ typedef struct pgx_bank_config {
   int32_t block;           /* partition size B: power of two in [16, 8192]; FFT size is 2B */
   int32_t max_pull;        /* largest n accepted by one process call (staging size) */
   uint32_t flags;          /* PGX_FLAG_* */
+  int32_t tail_block;      /* 0 = uniform partitions of `block` (the default).  > 0: two-level partitioning for long
+                              filters pulled in small blocks: the first tail_block taps at `block`, the rest at
+                              tail_block (power of two in [block, 8192]) - same result, the long tail is streamed once
+                              per tail_block samples instead of once per block.  Such a bank keeps its filters and
+                              its filter map, and does not switch between per-stream and mixed pulls without a reset. */
 } pgx_bank_config;
 
 typedef struct pgx_bank_info {
@@ -82,6 +87,7 @@ typedef struct pgx_bank_info {
   int64_t kernel_launches;  /* kernels launched by this handle since creation */
   int64_t block_steps;      /* FFT->MAC->IFFT steps executed since creation */
   int32_t mac_grid, mac_split, mac_stream_tile, mac_occupancy; /* launch plan of the accumulate kernel */
+  int32_t tail_block, tail_partitions; /* two-level partitioning: block and partition count of the tail level (0 = off) */
 } pgx_bank_info;
 
 /* ---- library ------------------------------------------------------------ */

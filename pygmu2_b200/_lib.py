@@ -27,7 +27,7 @@ class Layout(C.Structure):
 class BankConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("device", "n_streams", "c_in", "c_out", "filter_len",
                                           "filter_channels", "n_filters", "block", "max_pull")] + \
-               [("flags", C.c_uint32)]
+               [("flags", C.c_uint32), ("tail_block", C.c_int32)]
 
 
 class BankInfo(C.Structure):
@@ -35,7 +35,8 @@ class BankInfo(C.Structure):
                                           "n_filters", "block", "partitions", "max_pull", "device", "head",
                                           "fill")] + \
                [(n, C.c_int64) for n in ("state_bytes", "kernel_launches", "block_steps")] + \
-               [(n, C.c_int32) for n in ("mac_grid", "mac_split", "mac_stream_tile", "mac_occupancy")]
+               [(n, C.c_int32) for n in ("mac_grid", "mac_split", "mac_stream_tile", "mac_occupancy",
+                                          "tail_block", "tail_partitions")]
 
 
 class OscConfig(C.Structure):

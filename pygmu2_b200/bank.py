@@ -44,7 +44,8 @@ class ConvolveBank:
 
     def __init__(self, filters, n_streams: int, c_in: int = 1, *, block: int | None = None,
                  pull_hint: int | None = None, max_pull: int | None = None, filter_of_stream=None,
-                 device: int = 0, mixdown_input: bool = False, single_filter_dims: bool = False):
+                 device: int = 0, mixdown_input: bool = False, single_filter_dims: bool = False,
+                 tail_block: int | None = None):
         h = np.asarray(filters, dtype=np.float32)
         if single_filter_dims:  # (L,) or (L, C_f)
             h = h[None] if h.ndim >= 1 else h
@@ -68,13 +69,16 @@ class ConvolveBank:
         B = int(block) if block else choose_block(L, pull_hint)
         self.n_streams, self.c_in, self.c_out, self.c_f = int(n_streams), int(c_in), int(c_out), int(c_f)
         self.filter_len, self.n_filters, self.block = int(L), int(F), B
-        self.partitions = -(-L // B)
+        self.tail_block = int(tail_block) if tail_block and L > int(tail_block) else 0
+        # two-level partitioning (extension): the first tail_block taps at block B, the rest at block tail_block
+        self.partitions = -(-(self.tail_block or L) // B)
+        self.tail_partitions = -(-(L - self.tail_block) // self.tail_block) if self.tail_block else 0
         self.max_pull = int(max_pull) if max_pull else max(8 * B, 4096)
         self.device = int(device)
         _lib.require_device()
         cfg = BankConfig(device=self.device, n_streams=self.n_streams, c_in=self.c_in, c_out=self.c_out,
                          filter_len=L, filter_channels=c_f, n_filters=F, block=B, max_pull=self.max_pull,
-                         flags=_lib.PGX_FLAG_MIXDOWN_INPUT if mixdown_input else 0)
+                         flags=_lib.PGX_FLAG_MIXDOWN_INPUT if mixdown_input else 0, tail_block=self.tail_block)
         h_planar = np.ascontiguousarray(np.transpose(h, (0, 2, 1)))  # [F][C_f][L]
         fmap = None
         if filter_of_stream is not None:

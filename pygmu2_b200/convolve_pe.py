@@ -27,15 +27,18 @@ class ConvolvePE(ProcessingElement):
         fft_size: reference-compatible hint; must be >= L when given
         block_size: (extension) partition size B of the device path; default picks
             next_pow2(first pull) clamped to [16, 4096]
+        tail_block: (extension) two-level partitioning for a long filter pulled in small blocks: the first
+            tail_block taps at block_size, the rest at tail_block (same result, far less delay-line traffic)
         device: (extension) CUDA device ordinal, default 0
     """
 
     def __init__(self, src: ProcessingElement, fir: ProcessingElement, *, fft_size: int | None = None,
-                 block_size: int | None = None, device: int = 0):
+                 block_size: int | None = None, tail_block: int | None = None, device: int = 0):
         self._src = src
         self._fir = fir
         self._fft_size = int(fft_size) if fft_size is not None else None
         self._block_size = int(block_size) if block_size is not None else None
+        self._tail_block = int(tail_block) if tail_block else None
         self._device = int(device)
         self._fir_len = None
         self._bank = None
@@ -124,7 +127,8 @@ class ConvolvePE(ProcessingElement):
             raise ValueError(f"fft_size ({self._fft_size}) must be >= filter length ({filt_len})")
         block = self._block_size or choose_block(filt_len, pull_hint)
         # channel-rule violations raise ValueError inside ConvolveBank (convolve_pe.py:219-223)
-        self._bank = ConvolveBank(h, 1, int(src_ch), block=block, device=self._device, single_filter_dims=True)
+        self._bank = ConvolveBank(h, 1, int(src_ch), block=block, device=self._device, single_filter_dims=True,
+                                  tail_block=self._tail_block)
         if self._out_gains is not None:
             self._bank.set_output_gains(*self._out_gains)
         self._fir_len = filt_len

@@ -168,6 +168,7 @@ __device__ __forceinline__ void emit_block(const C2RArgs& a, const int o, const 
   const int s = o / a.c_out, c = o - s * a.c_out;
   float* y = a.y + (int64_t)s * a.ys + (int64_t)c * a.yc;
   const float* xd = a.xdry ? a.xdry + (int64_t)s * a.xs + (int64_t)c * a.xc : nullptr;
+  const float* ad = a.add ? a.add + (int64_t)s * a.as + (int64_t)c * a.ac : nullptr;  // tail level's contribution
   const bool gains = (a.wet != 1.0f) || xd;
   const int lo = N + a.fill, hi = lo + a.take;
   if (a.fast) {  // a whole block into contiguous, 8-byte aligned output: elements N/2.. (m >= 4), vector stores
@@ -176,6 +177,11 @@ __device__ __forceinline__ void emit_block(const C2RArgs& a, const int o, const 
     for (int m = 4; m < 8; ++m) {
       const int i = 2 * (j + m * T8) - N;
       float2 val = v[m];
+      if (ad) {
+        const float2 t = *reinterpret_cast<const float2*>(ad + a.y_off + i);
+        val.x += t.x;
+        val.y += t.y;
+      }
       if (gains) {
         val.x = __fmul_rn(val.x, a.wet);
         val.y = __fmul_rn(val.y, a.wet);
@@ -197,6 +203,7 @@ __device__ __forceinline__ void emit_block(const C2RArgs& a, const int o, const 
       const int i = i0 + h;
       if (i >= lo && i < hi) {
         float val = e[h];
+        if (ad) val += ad[(int64_t)(a.y_off + i - lo) * a.ai];
         if (gains) {
           val = __fmul_rn(val, a.wet);
           if (xd) val = __fadd_rn(__fmul_rn(xd[(int64_t)(a.x_off + i - lo) * a.xi], a.dry), val);

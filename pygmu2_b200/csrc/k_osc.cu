@@ -181,10 +181,27 @@ __global__ void __launch_bounds__(256) k_f32_to_pcm16(const float* __restrict__ 
   }
 }
 
+__global__ void __launch_bounds__(256) k_copy_block(const float* __restrict__ src, const int64_t ss, const int64_t sc,
+                                                    const int64_t si, float* __restrict__ dst, const int64_t ds,
+                                                    const int64_t dc, const int64_t di, const int rows, const int chans,
+                                                    const int n) {
+  const int64_t total = (int64_t)rows * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / n), i = (int)(e - (int64_t)r * n);
+    const int s = r / chans, c = r - s * chans;
+    dst[s * ds + c * dc + i * di] = src[s * ss + c * sc + i * si];
+  }
+}
+
 static int pcm_grid(int64_t n) {
   int64_t b = (n + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
   return (int)(b < 1 ? 1 : b);
+}
+void launch_copy_block(const float* src, int64_t ss, int64_t sc, int64_t si, float* dst, int64_t ds, int64_t dc,
+                       int64_t di, int32_t n_streams, int32_t chans, int32_t n, cudaStream_t st) {
+  const int rows = n_streams * chans;
+  k_copy_block<<<pcm_grid((int64_t)rows * n), 256, 0, st>>>(src, ss, sc, si, dst, ds, dc, di, rows, chans, n);
 }
 void launch_pcm16_to_f32(const int16_t* in, float* out, int64_t n, cudaStream_t st) {
   k_pcm16_to_f32<<<pcm_grid(n), 256, 0, st>>>(in, out, n);

@@ -87,7 +87,11 @@ struct C2RArgs {
   int64_t xs, xc, xi;
   int32_t x_off;
   float wet, dry;
-  int32_t fast;          // whole block into contiguous, 8-byte aligned y (and xdry): vector stores
+  int32_t fast;          // whole block into contiguous, 8-byte aligned y (and xdry, add): vector stores
+  // addend (two-level partitioning: the tail level's contribution to these output samples), added to the
+  // convolution before the output gains; element (s, c, i) at add[s*as + c*ac + (y_off... see emit_block) ], or NULL
+  const float* add;
+  int64_t as, ac, ai;
 };
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st);
 // K1 + K2 in one kernel for single-partition conv banks (P = 1): the spectrum never visits the delay line.
@@ -124,6 +128,10 @@ void launch_blit_bank(const BlitArgs& a, cudaStream_t st);
 // PCM16 <-> float32 staging (k_osc.cu): dense arrays of n elements
 void launch_pcm16_to_f32(const int16_t* in, float* out, int64_t n, cudaStream_t st);
 void launch_f32_to_pcm16(const float* in, int16_t* out, int64_t n, cudaStream_t st);
+
+// Strided gather of (streams x chans x n) samples: dst[s*ds + c*dc + i*di] = src[s*ss + c*sc + i*si]
+void launch_copy_block(const float* src, int64_t ss, int64_t sc, int64_t si, float* dst, int64_t ds, int64_t dc,
+                       int64_t di, int32_t n_streams, int32_t chans, int32_t n, cudaStream_t st);
 
 int fft_smem_bytes(int B);
 

@@ -134,6 +134,17 @@ struct pgx_bank {
   pgx::MacPlan plan_conv{}, plan_mix{}, plan_now{};
   int sm_count = 148;
   float wet = 1.0f, dry = 0.0f;    // fused output stage: y = dry * x + wet * conv
+  // two-level partitioning (cfg.tail_block > 0): this bank convolves with the first tail_B taps at block B; `tail`
+  // convolves with the rest at block tail_B, one big block at a time, and its output is the addend of the next
+  // tail_B output samples (h = [head | tail]: the tail's contribution to y[t .. t+tail_B) only needs x[.. t))
+  pgx_bank* tail = nullptr;
+  int tail_B = 0, tail_fill = 0, tail_cur = 0, tail_mode = -1;   // tail_mode: -1 undecided, 0 conv, 1 mix
+  int full_filter_len = 0;
+  float* xacc = nullptr;           // [N][c_in][tail_B] the big block being filled
+  float* ytail[2] = {nullptr, nullptr};  // [N or 1][c_out][tail_B] tail contribution of the current / next big block
+  size_t xacc_bytes = 0, ytail_bytes = 0;
+  const float* addend = nullptr;   // set by the two-level driver for the next run_pull1 of this (head) bank
+  pgx_layout addend_l{};
   bool serial = false;
   bool use_conv1 = true;           // P = 1 conv pulls: K1 and K2 fused into one kernel (PGX_CONV1=0 disables)
   int64_t launches = 0, steps = 0;
@@ -150,9 +161,14 @@ namespace {
 
 void free_bank(pgx_bank* b) {
   if (!b) return;
+  free_bank(b->tail);
+  b->tail = nullptr;
   cudaSetDevice(b->cfg.device);
   for (cudaStream_t s : {b->s_h2d, b->stream, b->s_in, b->s_bg, b->s_bg2, b->s_d2h})
     if (s) cudaStreamSynchronize(s);
+  cudaFree(b->xacc);
+  cudaFree(b->ytail[0]);
+  cudaFree(b->ytail[1]);
   cudaFree(b->hist);
   cudaFree(b->fdl);
   cudaFree(b->Hd);
@@ -367,10 +383,12 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   k.wet = b->wet; k.dry = b->dry;
   k.xdry = (!mix && b->dry != 0.0f) ? x_dev : nullptr;
   k.xs = xl.stream; k.xc = xl.chan; k.xi = xl.samp; k.x_off = pos;
+  k.add = b->addend; k.as = mix ? 0 : b->addend_l.stream; k.ac = b->addend_l.chan; k.ai = b->addend_l.samp;
   {
     pgx_layout ye = yl;
     if (mix) ye.stream = 0;
-    k.fast = (whole && vec_ok(y_dev, ye) && (!k.xdry || vec_ok(x_dev, xl))) ? 1 : 0;
+    k.fast = (whole && vec_ok(y_dev, ye) && (!k.xdry || vec_ok(x_dev, xl)) &&
+              (!k.add || vec_ok(b->addend, b->addend_l))) ? 1 : 0;
   }
 
   // the block commits with this step: its row is final once K1 has run, so the next block's past pass
@@ -399,8 +417,8 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   return PGX_OK;
 }
 
-// One pull on device buffers, enqueued on crit (no synchronisation).
-int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int n,
+// One pull of one level on device buffers, enqueued on crit (no synchronisation).
+int run_pull1(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int n,
              bool mix, bool input_resident, cudaStream_t crit) {
   if (!input_resident) {
     // x is produced by work queued earlier on the caller's stream: the ingest stream must see it
@@ -426,9 +444,49 @@ int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   return PGX_OK;
 }
 
+// One pull on device buffers, enqueued on crit (no synchronisation).  Two-level banks cut the pull at big-block
+// boundaries: each piece goes through the head level with the tail level's contribution as addend and is
+// gathered into the big block; a completed big block is pushed through the tail level at once.
+int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int n,
+             bool mix, bool input_resident, cudaStream_t crit) {
+  if (!b->tail) return run_pull1(b, x_dev, xl, y_dev, yl, n, mix, input_resident, crit);
+  if (b->tail_mode < 0) b->tail_mode = mix ? 1 : 0;
+  if (b->tail_mode != (mix ? 1 : 0))
+    return fail(PGX_ERR_INVALID, "a two-level bank cannot switch between per-stream and mixed pulls without a reset");
+  const pgx_bank_config& c = b->cfg;
+  const int TB = b->tail_B;
+  const pgx_layout xa{(int64_t)c.c_in * TB, TB, 1};
+  const pgx_layout ya{mix ? 0 : (int64_t)c.c_out * TB, TB, 1};
+  int pos = 0;
+  while (pos < n) {
+    const int take = (TB - b->tail_fill < n - pos) ? (TB - b->tail_fill) : (n - pos);
+    if (!input_resident && pos == 0) {  // x may come from work queued on crit: the head's ingest is ordered by run_pull1
+    }
+    pgx::launch_copy_block(x_dev + (int64_t)pos * xl.samp, xl.stream, xl.chan, xl.samp, b->xacc + b->tail_fill,
+                           xa.stream, xa.chan, 1, c.n_streams, c.c_in, take, crit);
+    b->launches += 1;
+    b->addend = b->ytail[b->tail_cur] + b->tail_fill;
+    b->addend_l = ya;
+    int rc = run_pull1(b, x_dev + (int64_t)pos * xl.samp, xl, y_dev + (int64_t)pos * yl.samp, yl, take, mix,
+                       input_resident, crit);
+    b->addend = nullptr;
+    if (rc != PGX_OK) return rc;
+    b->tail_fill += take;
+    if (b->tail_fill == TB) {  // the big block is complete: its tail contribution lands TB samples later
+      rc = run_pull1(b->tail, b->xacc, xa, b->ytail[b->tail_cur ^ 1], ya, TB, mix, false, crit);
+      if (rc != PGX_OK) return rc;
+      b->tail_cur ^= 1;
+      b->tail_fill = 0;
+    }
+    pos += take;
+  }
+  return PGX_OK;
+}
+
 // State changes outside run_pull (reset, filter reload / re-selection) are rare and synchronous: drain the
 // bank's streams (a caller-owned critical stream is the caller's to drain) and drop the cached past sum.
 void quiesce(pgx_bank* b) {
+  if (b->tail) quiesce(b->tail);
   cudaStreamSynchronize(b->s_h2d);
   cudaStreamSynchronize(b->s_in);
   cudaStreamSynchronize(b->s_bg);
@@ -527,7 +585,7 @@ int pgx_device_zero(int32_t device, void* dst_dev, int64_t bytes) {
   return PGX_OK;
 }
 
-int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, const int32_t* filter_of_stream) {
+static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float* h, const int32_t* filter_of_stream) {
   if (!out || !cfg || !h) return fail(PGX_ERR_INVALID, "pgx_bank_create: NULL argument");
   *out = nullptr;
   const pgx_bank_config& c = *cfg;
@@ -679,7 +737,58 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     free_bank(b);
     return rc;
   }
+  b->full_filter_len = c.filter_len;
   *out = b;
+  return PGX_OK;
+}
+
+int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, const int32_t* filter_of_stream) {
+  if (!out || !cfg || !h) return fail(PGX_ERR_INVALID, "pgx_bank_create: NULL argument");
+  *out = nullptr;
+  const int TB = cfg->tail_block;
+  if (TB <= 0 || cfg->filter_len <= TB) {  // single level (also when the whole filter fits the head)
+    pgx_bank_config c1 = *cfg;
+    c1.tail_block = 0;
+    return create_single(out, &c1, h, filter_of_stream);
+  }
+  if (!is_pow2(TB) || TB > 8192 || TB < cfg->block)
+    return fail(PGX_ERR_INVALID, "tail_block must be a power of two in [block, 8192], got %d", TB);
+  if (cfg->n_filters < 1 || cfg->filter_channels < 1) return fail(PGX_ERR_INVALID, "bad filter set");
+  // h = [head (TB taps) | tail]: two filter sets, two uniformly partitioned banks
+  const size_t rows = (size_t)cfg->n_filters * cfg->filter_channels;
+  const int L = cfg->filter_len, Lt = L - TB;
+  std::vector<float> hh(rows * TB), ht(rows * Lt);
+  for (size_t r = 0; r < rows; ++r) {
+    memcpy(&hh[r * TB], h + r * L, (size_t)TB * sizeof(float));
+    memcpy(&ht[r * Lt], h + r * L + TB, (size_t)Lt * sizeof(float));
+  }
+  pgx_bank_config ch = *cfg, ct = *cfg;
+  ch.filter_len = TB; ch.tail_block = 0;
+  ct.filter_len = Lt; ct.block = TB; ct.max_pull = TB; ct.tail_block = 0;
+  pgx_bank *head = nullptr, *tail = nullptr;
+  int rc = create_single(&head, &ch, hh.data(), filter_of_stream);
+  if (rc != PGX_OK) return rc;
+  rc = create_single(&tail, &ct, ht.data(), filter_of_stream);
+  if (rc != PGX_OK) {
+    free_bank(head);
+    return rc;
+  }
+  head->tail = tail;
+  head->tail_B = TB;
+  head->full_filter_len = L;
+  head->xacc_bytes = (size_t)cfg->n_streams * cfg->c_in * TB * sizeof(float);
+  head->ytail_bytes = (size_t)cfg->n_streams * cfg->c_out * TB * sizeof(float);
+  cudaError_t e = cudaMalloc(&head->xacc, head->xacc_bytes);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMalloc(&head->ytail[i], head->ytail_bytes);
+    if (e == cudaSuccess) e = cudaMemset(head->ytail[i], 0, head->ytail_bytes);
+  }
+  if (e == cudaSuccess) e = cudaMemset(head->xacc, 0, head->xacc_bytes);
+  if (e != cudaSuccess) {
+    free_bank(head);
+    return fail(e == cudaErrorMemoryAllocation ? PGX_ERR_NOMEM : PGX_ERR_CUDA, "two-level buffers: %s", cudaGetErrorString(e));
+  }
+  *out = head;
   return PGX_OK;
 }
 
@@ -692,15 +801,22 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   if (!b || !info) return fail(PGX_ERR_INVALID, "NULL argument");
   const pgx_bank_config& c = b->cfg;
   info->n_streams = c.n_streams; info->c_in = c.c_in; info->c_x = b->c_x; info->c_out = c.c_out;
-  info->filter_len = c.filter_len; info->filter_channels = c.filter_channels; info->n_filters = c.n_filters;
+  info->filter_len = b->full_filter_len; info->filter_channels = c.filter_channels; info->n_filters = c.n_filters;
   info->block = b->B; info->partitions = b->P; info->max_pull = c.max_pull; info->device = c.device;
   info->head = b->head; info->fill = b->fill;
   info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + 2 * b->ypart_bytes + 2 * b->ysum_bytes +
                                 b->ynow_bytes + pgx_bank::kSlots * (b->xs_bytes + b->ys_bytes));
-  info->kernel_launches = b->launches;
   info->block_steps = b->steps;
+  info->tail_block = b->tail ? b->tail_B : 0;
+  info->tail_partitions = b->tail ? b->tail->P : 0;
+  if (b->tail) {
+    const pgx_bank* t = b->tail;
+    info->state_bytes += (int64_t)(t->hist_bytes + t->fdl_bytes + t->Hd_bytes + 2 * t->ypart_bytes + 2 * t->ysum_bytes +
+                                   t->ynow_bytes + b->xacc_bytes + 2 * b->ytail_bytes);
+  }
   info->mac_grid = b->plan_conv.grid; info->mac_split = b->plan_conv.n_split;
   info->mac_stream_tile = b->plan_conv.st; info->mac_occupancy = b->plan_conv.occupancy;
+  info->kernel_launches = b->launches + (b->tail ? b->tail->launches : 0);
   return PGX_OK;
 }
 
@@ -708,6 +824,31 @@ int pgx_bank_reset(pgx_bank* b, const int32_t* stream_ids, int32_t k) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   quiesce(b);
+  if (b->tail) {
+    const bool all = (k <= 0 || !stream_ids);
+    if (!all && b->tail_mode == 1)
+      return fail(PGX_ERR_INVALID, "per-stream reset of a two-level bank is not available in mixed mode: the tail "
+                                   "contribution in flight is already summed over the streams");
+    const int rc = pgx_bank_reset(b->tail, stream_ids, k);
+    if (rc != PGX_OK) return rc;
+    if (all) {
+      PGX_CUDA(cudaMemset(b->xacc, 0, b->xacc_bytes));
+      PGX_CUDA(cudaMemset(b->ytail[0], 0, b->ytail_bytes));
+      PGX_CUDA(cudaMemset(b->ytail[1], 0, b->ytail_bytes));
+      b->tail_fill = 0;
+      b->tail_cur = 0;
+      b->tail_mode = -1;
+    } else {
+      const size_t xr = (size_t)b->cfg.c_in * b->tail_B * sizeof(float), yr = (size_t)b->cfg.c_out * b->tail_B * sizeof(float);
+      for (int i = 0; i < k; ++i) {
+        const int s = stream_ids[i];
+        if (s < 0 || s >= b->cfg.n_streams) return fail(PGX_ERR_INVALID, "stream id %d outside [0,%d)", s, b->cfg.n_streams);
+        PGX_CUDA(cudaMemset(reinterpret_cast<char*>(b->xacc) + s * xr, 0, xr));
+        PGX_CUDA(cudaMemset(reinterpret_cast<char*>(b->ytail[0]) + s * yr, 0, yr));
+        PGX_CUDA(cudaMemset(reinterpret_cast<char*>(b->ytail[1]) + s * yr, 0, yr));
+      }
+    }
+  }
   if (k <= 0 || !stream_ids) {
     PGX_CUDA(cudaMemsetAsync(b->hist, 0, b->hist_bytes, b->stream));
     PGX_CUDA(cudaMemsetAsync(b->fdl, 0, b->fdl_bytes, b->stream));
@@ -734,6 +875,8 @@ int pgx_bank_load_filter(pgx_bank* b, int32_t filter_index, const float* h) {
   const pgx_bank_config& c = b->cfg;
   if (filter_index < 0 || filter_index >= c.n_filters)
     return fail(PGX_ERR_INVALID, "filter_index %d outside [0,%d)", filter_index, c.n_filters);
+  if (b->tail) return fail(PGX_ERR_INVALID, "a two-level bank keeps its filters: the tail contribution in flight was "
+                                          "computed with them (create a new bank, or use tail_block = 0)");
   PGX_CUDA(cudaSetDevice(c.device));
   quiesce(b);
   return prep_filters(b, h, filter_index * c.filter_channels, c.filter_channels);
@@ -741,6 +884,7 @@ int pgx_bank_load_filter(pgx_bank* b, int32_t filter_index, const float* h) {
 
 int pgx_bank_set_filter_map(pgx_bank* b, const int32_t* filter_of_stream) {
   if (!b || !filter_of_stream) return fail(PGX_ERR_INVALID, "NULL argument");
+  if (b->tail) return fail(PGX_ERR_INVALID, "a two-level bank keeps its filter map (use tail_block = 0 for moving sources)");
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   const int N = b->cfg.n_streams;
   for (int s = 0; s < N; ++s)
@@ -783,6 +927,7 @@ int pgx_bank_set_output_gains(pgx_bank* b, float wet, float dry) {
 
 int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  if (b->tail) return fail(PGX_ERR_INVALID, "a two-level bank keeps its filter map");
   b->fmap = fmap_dev ? const_cast<int32_t*>(fmap_dev) : b->fmap_own + (size_t)b->fmap_cur * b->cfg.n_streams;
   b->past_block = -1;  // a cached past sum was computed with the previous map
   return PGX_OK;
@@ -892,6 +1037,10 @@ int pgx_bank_process_device(pgx_bank* b, const float* x_dev, pgx_layout xl, floa
 
 int pgx_bank_synchronize(pgx_bank* b) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  if (b->tail) {
+    const int rc = pgx_bank_synchronize(b->tail);
+    if (rc != PGX_OK) return rc;
+  }
   PGX_CUDA(cudaSetDevice(b->cfg.device));
   PGX_CUDA(cudaStreamSynchronize(b->s_h2d));
   PGX_CUDA(cudaStreamSynchronize(b->stream));
@@ -904,6 +1053,7 @@ int pgx_bank_synchronize(pgx_bank* b) {
 
 int pgx_bank_profile_begin(pgx_bank* b) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  if (b->tail) pgx_bank_profile_begin(b->tail);
   b->profiling = true;
   b->prof_spans.clear();
   b->prof_pool_used = 0;
@@ -955,6 +1105,13 @@ int pgx_bank_profile_end(pgx_bank* b, pgx_profile* out) {
   if (cur1 > cur0) out->ms_mac_union += cur1 - cur0;
   b->prof_spans.clear();
   b->prof_pool_used = 0;
+  if (b->tail) {  // the tail level's kernels belong to the same steps
+    pgx_profile t{};
+    const int rc = pgx_bank_profile_end(b->tail, &t);
+    if (rc != PGX_OK) return rc;
+    out->ms_r2c += t.ms_r2c; out->ms_mac += t.ms_mac; out->ms_c2r += t.ms_c2r; out->ms_fold += t.ms_fold;
+    out->ms_now += t.ms_now; out->ms_conv1 += t.ms_conv1; out->ms_mac_union += t.ms_mac_union; out->n_mac += t.n_mac;
+  }
   return PGX_OK;
 }
 

@@ -936,3 +936,61 @@ def test_random_operation_sequences_match_direct_model(seed, L, B):
     for a in keep:
         a.free()
     bank.close()
+
+
+# ---------------------------------------------------------------------------
+# two-level partitioning (pgx_bank_config.tail_block): head taps at the small block, the rest at a big block.
+# Same contract as the uniform bank -- exact linear convolution, zero latency for any pull size.
+@pytest.mark.parametrize("L,B,TB", [(3000, 64, 512), (700, 32, 128), (5000, 128, 1024), (513, 64, 512)])
+@pytest.mark.parametrize("mix", [False, True])
+def test_two_level_partitioning_matches_oracle_and_uniform(L, B, TB, mix):
+    rng = np.random.default_rng(300 + L)
+    N, C = 3, 2
+    h = (rng.standard_normal((N, L, C)) / np.sqrt(L)).astype(np.float32)
+    pulls = [B] * 5 + [1, B - 1, 17, TB, TB + 3, 2 * B + 5, B // 2, B // 2, 3 * TB - 7] + [B] * 9
+    x = rng.uniform(-1, 1, (N, C, sum(pulls))).astype(np.float32)
+    two = pg.ConvolveBank(h, N, C, block=B, tail_block=TB, max_pull=4 * TB)
+    uni = pg.ConvolveBank(h, N, C, block=B, max_pull=4 * TB)
+    info = two.info()
+    assert (info.tail_block, info.block, info.filter_len) == (TB, B, L)
+    assert info.partitions == TB // B and info.tail_partitions == -(-(L - TB) // TB)
+    y2, y1, pos = [], [], 0
+    for d in pulls:
+        xc = np.ascontiguousarray(x[:, :, pos:pos + d])
+        y2.append(two.process_mix(xc) if mix else two.process(xc))
+        y1.append(uni.process_mix(xc) if mix else uni.process(xc))
+        pos += d
+    y2, y1 = np.concatenate(y2, axis=-1), np.concatenate(y1, axis=-1)
+    per = np.stack([orc.OracleConvolve(h[s], C).render(x[s].T).T for s in range(N)])
+    ref = per.astype(np.float64).sum(axis=0) if mix else per
+    assert rel_err(y2, ref) <= TOL
+    assert rel_err(y2, y1) <= 2e-6
+    # a reset starts a new run on both levels
+    two.reset()
+    xc = np.ascontiguousarray(x[:, :, :TB + 50])
+    y = two.process_mix(xc) if mix else two.process(xc)
+    assert rel_err(y, ref[..., :TB + 50]) <= TOL
+    two.close()
+    uni.close()
+
+
+def test_two_level_contract_restrictions_and_c5_shape():
+    rng = np.random.default_rng(77)
+    ir = (rng.standard_normal(20_000) * np.exp(-np.arange(20_000) / 4000.0) / 30).astype(np.float32)
+    x = rng.uniform(-1, 1, 64 * 400).astype(np.float32)
+    pe = pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(ir), block_size=64, tail_block=4096)   # C5's shape in miniature
+    y = _pull_pe(pe, [64] * 400)[:, 0]
+    ref = orc.OracleConvolve(ir, 1).render(x[:, None])[:, 0]
+    assert rel_err(y, ref) <= TOL
+    bank = pe.bank
+    assert bank.info().tail_block == 4096 and bank.info().partitions == 64
+    with pytest.raises(ValueError):
+        bank.set_filter_map(np.zeros(1, np.int32))
+    with pytest.raises(ValueError):
+        bank.load_filter(0, ir)
+    with pytest.raises(ValueError):                       # mode switch without a reset
+        bank.process_mix(np.zeros((1, 1, 64), np.float32))
+    short = pg.ConvolveBank(ir[:1000], 1, 1, block=64, tail_block=4096, single_filter_dims=True)
+    assert short.info().tail_block == 0                    # the whole filter fits the head: plain uniform bank
+    with pytest.raises(ValueError):
+        pg.ConvolveBank(ir, 1, 1, block=64, tail_block=3000, single_filter_dims=True)

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Layout) == 24
-    assert C.sizeof(_lib.BankConfig) == 40
+    assert C.sizeof(_lib.BankConfig) == 44
     assert C.sizeof(_lib.Profile) == 72
     assert C.sizeof(_lib.OscConfig) == 40
 
