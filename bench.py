@@ -257,10 +257,14 @@ def make_workload(args, rank, local):
         N = args.streams or STREAMS_PER_GPU
         if distinct:
             irs = np.stack([wl.c2_ir(stream=rank * N + s) for s in range(N)])
-            bank = pg.ConvolveBank(irs, N, CH, block=B, max_pull=PULL, device=local)
+            bank = pg.ConvolveBank(irs, N, CH, block=B, max_pull=PULL, device=local, tail_block=args.tail_block or None)
         else:
-            bank = pg.ConvolveBank(wl.c2_ir(), N, CH, block=B, max_pull=PULL, device=local, single_filter_dims=True)
+            bank = pg.ConvolveBank(wl.c2_ir(), N, CH, block=B, max_pull=PULL, device=local, single_filter_dims=True,
+                                   tail_block=args.tail_block or None)
         cfg = _config(args)
+        if args.tail_block:  # NOT the named configuration (uniform partitions): an extra data point
+            cfg["partitioning"] = (f"two-level: {bank.partitions} head partitions of {B} + {bank.tail_partitions} tail "
+                                   f"partitions of {args.tail_block}; roofline bytes are still SURVEY's uniform figure")
         if args.reverb:  # ReverbPE's wet/dry tail fused into the inverse-FFT kernel (reverb_pe.py:82-95)
             bank.set_output_gains(0.3, 0.7)
             cfg["output_stage"] = "fused ReverbPE wet/dry: y = 0.7*x + 0.3*conv (pgx_bank_set_output_gains)"
@@ -317,7 +321,7 @@ def make_workload(args, rank, local):
         pg.set_sample_rate(wl.SR_441)
         voices = [pg.SuperSawPE(frequency=55.0 * 2.0 ** (i / 128.0), amplitude=1.0 / 32.0, seed=i) for i in range(V)]
         mixpe = pg.MixPE(*voices)
-        pe = pg.ConvolvePE(mixpe, pg.ArrayPE(wl.c5_ir()), block_size=64)
+        pe = pg.ConvolvePE(mixpe, pg.ArrayPE(wl.c5_ir()), block_size=64, tail_block=args.tail_block or None)
         pe.render(0, 64)                       # builds the VoiceBank (V x 7 oscillators) and the 6891-partition bank
         bank, vb = pe.bank, mixpe._fused.vb
         cfg = {"workload": f"C5 with its front end on the device: {V} SuperSawPE voices (7 BLIT oscillators each, "
@@ -576,7 +580,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5v"],
                     help="c2 = BASELINE.json configs[1] (headline); the others are the remaining configs, for profiling")
     ap.add_argument("--tail-block", type=int, default=0,
-                    help="c5: two-level partitioning, first TAIL_BLOCK taps at 64-sample blocks, the rest at TAIL_BLOCK")
+                    help="c2 / c5: two-level partitioning (not the named uniform configuration): the first TAIL_BLOCK "
+                         "taps at the pull-sized block, the rest at TAIL_BLOCK")
     ap.add_argument("--reverb", action="store_true", help="c2: add ReverbPE's fused wet/dry output stage")
     ap.add_argument("--pcm16", action="store_true",
                     help="e2e leg with int16 PCM host buffers converted on the device (WAV staging, half the PCIe bytes)")

@@ -70,6 +70,9 @@ def main():
     voices = [pg.SuperSawPE(frequency=55.0 * 2.0 ** (i / 128.0), amplitude=1.0 / 32.0, seed=i) for i in range(wl.C5_VOICES)]
     run("C5 1024 SuperSaw -> MixPE -> 441000-tap IR", pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(wl.c5_ir()), block_size=64),
         wl.SR_441, 64, min(S, 1.0), 1)
+    voices = [pg.SuperSawPE(frequency=55.0 * 2.0 ** (i / 128.0), amplitude=1.0 / 32.0, seed=i) for i in range(wl.C5_VOICES)]
+    run("C5 same, two-level partitions (64 / 4096)",
+        pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(wl.c5_ir()), block_size=64, tail_block=4096), wl.SR_441, 64, min(S, 1.0), 1)
 
 
 if __name__ == "__main__":
