@@ -16,6 +16,8 @@ PGX_MAC=tma ncu --set full --clock-control none --import-source on -k regex:k_fd
 ncu --set full --clock-control none --import-source on -k regex:"k_r2c|k_c2r" -s 524 -c 2 -f -o gpurun_out/${tag}_fft_c2 $B > gpurun_out/${tag}_ncu_f.log 2>&1
 $B --workload c4 > gpurun_out/${tag}_plain_c4.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:k_fdl_mac -s 350 -c 2 -f -o gpurun_out/${tag}_mac_c4 $B --workload c4 > gpurun_out/${tag}_ncu_c4.log 2>&1
+$B --workload c1 > gpurun_out/${tag}_plain_c1.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:k_conv1 -s 10 -c 1 -f -o gpurun_out/${tag}_conv1_c1 $B --workload c1 > gpurun_out/${tag}_ncu_c1.log 2>&1
 $B --workload c5v > gpurun_out/${tag}_plain_c5v.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:"k_blit|k_mix_sum" -s 400 -c 2 -f -o gpurun_out/${tag}_osc_c5v $B --workload c5v > gpurun_out/${tag}_ncu_o.log 2>&1
 tail -n 2 gpurun_out/${tag}_ncu_*.log
