@@ -119,10 +119,12 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
 
   fft_passes<LOG2N, false>(v, sA, sB, 0, j, tw);
 
-  // split step needs Z[N-k]: exchange through shared memory (natural order, padded)
+  // split step needs Z[N-k]: exchange through shared memory, natural order and NOT padded: the natural-order
+  // writes and the mirrored reads are both contiguous runs, conflict-free as they are (with the pad of the FFT
+  // passes a mirrored run straddles a pad slot and two lanes meet in one bank)
   __syncthreads();
 #pragma unroll
-  for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+  for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
   float2 tws[8];  // requested before the barrier
 #pragma unroll
   for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
       if (k == 0) {
         o = make_float2(v[m].x + v[m].y, v[m].x - v[m].y);
       } else {
-        o = r2c_bin(v[m], sA[phys(N - k)], tws[m]);
+        o = r2c_bin(v[m], sA[N - k], tws[m]);
       }
       if (MODE == 1) {
         o.x *= scale;
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
       add_partials(a.ynow, a.n_split_now);
     }
 #pragma unroll
-    for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+    for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
   }
   float2 tws[8];
   if (!C::SMEM_TW) {  // global table: requested before the barrier
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
       if (k == 0) {
         v[m] = make_float2(0.5f * (v[m].x + v[m].y), 0.5f * (v[m].x - v[m].y));
       } else {
-        v[m] = c2r_bin(v[m], sA[phys(N - k)], tws[m]);
+        v[m] = c2r_bin(v[m], sA[N - k], tws[m]);
       }
     }
   }
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
   // split: packed half spectrum X[k], k = j + m*T8, from Z[k] and Z[N-k]
   __syncthreads();
 #pragma unroll
-  for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+  for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
   float2 tws[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const int kk = j + m * T8;
-    X[m] = (kk == 0) ? make_float2(v[m].x + v[m].y, v[m].x - v[m].y) : r2c_bin(v[m], sA[phys(N - kk)], tws[m]);
+    X[m] = (kk == 0) ? make_float2(v[m].x + v[m].y, v[m].x - v[m].y) : r2c_bin(v[m], sA[N - kk], tws[m]);
   }
 
   const int s = active ? (int)(f / a.c_x) : 0, cx = active ? (int)(f - (int64_t)s * a.c_x) : 0;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
       for (int m = 0; m < 8; ++m) v[m] = cmul(X[m], hh[m]);
       if (j == 0) v[0] = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
 #pragma unroll
-      for (int m = 0; m < 8; ++m) sA[phys(j + m * T8)] = v[m];
+      for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
     }
     __syncthreads();
     if (active) {
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
       for (int m = 0; m < 8; ++m) {
         const int kk = j + m * T8;
         v[m] = (kk == 0) ? make_float2(0.5f * (v[m].x + v[m].y), 0.5f * (v[m].x - v[m].y))
-                         : c2r_bin(v[m], sA[phys(N - kk)], tws[m]);
+                         : c2r_bin(v[m], sA[N - kk], tws[m]);
       }
     }
     fft_passes<LOG2N, true>(v, sA, sB, 1, j, tw);  // first exchange goes to sB: sA may still be read above
