@@ -334,6 +334,22 @@ def make_workload(args, rank, local):
     raise SystemExit(f"unknown workload {w}")
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner on stdout when the first communicator comes up; the contract is ONE JSON
+    line on stdout, so file descriptor 1 points at stderr while the process group is being set up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -348,7 +364,9 @@ def run_gpu(args):
         from pygmu2_b200.dist import bind_host_to_gpu
         numa_bound = bind_host_to_gpu(local)   # host staging buffers next to this rank's GPU
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()   # brings the communicator up (and its banner out) now
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
