@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpgx.so")
+LIB_PATH = os.environ.get("PGX_LIB") or os.path.join(_HERE, "csrc", "libpgx.so")  # PGX_LIB: A/B builds
 
 PGX_OK, PGX_ERR_INVALID, PGX_ERR_CUDA, PGX_ERR_NO_DEVICE, PGX_ERR_NOMEM = 0, -1, -2, -3, -4
 PGX_FLAG_MIXDOWN_INPUT = 1

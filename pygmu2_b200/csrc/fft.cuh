@@ -40,6 +40,16 @@ __device__ __forceinline__ float2 tw_get(const float2* tw, int idx) {
 // padded shared-memory index: one pad element per 16 keeps both the contiguous reads and the
 // stride-8 writes of the first pass free of 8-byte bank conflicts
 __device__ __forceinline__ int phys(int i) { return i + (i >> 4); }
+// The exchange after the SECOND pass scatters, per half-warp, two runs of 8 elements that lie 64 apart; with
+// the pad above they land 68 slots apart (4 banks off: a 2-way conflict that no additive pad common to all
+// exchanges removes).  That one exchange therefore uses its own pad, 8 slots per 64 elements (72 apart = 8
+// banks off), under which its contiguous reads stay conflict-free too.  E = index of the exchange.
+// Only the large transforms take it (FftCfg::PAD2): the small ones run beside the resident accumulate CTAs, where
+// the extra shared memory per CTA costs more than the conflicts (measured A/B: C2 +11 % step time with it).
+template <int E>
+__device__ __forceinline__ int phys_x(int i) {
+  return E == 1 ? i + ((i >> 6) << 3) : i + (i >> 4);
+}
 
 template <int LOG2N>
 struct FftCfg {
@@ -47,7 +57,8 @@ struct FftCfg {
   static constexpr int T8 = N / 8;                   // threads per transform
   static constexpr int NP8 = LOG2N / 3;              // radix-8 passes
   static constexpr int RLAST = 1 << (LOG2N % 3);     // 1 = none, else a final radix-2 / radix-4 pass
-  static constexpr int PADN = N + N / 16;            // padded buffer length (elements)
+  static constexpr bool PAD2 = LOG2N >= 11;          // second exchange uses its own pad (see phys_x)
+  static constexpr int PADN = N + N / (PAD2 ? 8 : 16);  // padded buffer length (elements)
   // Small CTAs on purpose: a 64-thread CTA needs ~3K registers, so the latency-critical FFT kernels fit into
   // what the resident accumulate CTAs leave free on an SM instead of displacing one of them.
   static constexpr int CTA = T8 < 64 ? 64 : T8;      // threads per CTA
@@ -114,7 +125,7 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
         w4 = tw_get<INV, GTW>(tw, 4 * m);
       }
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = cur[phys(j + r * T8)];
+      for (int r = 0; r < 8; ++r) v[r] = cur[(C::PAD2 && p == 2) ? phys_x<1>(j + r * T8) : phys_x<0>(j + r * T8)];
       const float2 w3 = cmul(w1, w2);
       v[1] = cmul(v[1], w1);
       v[2] = cmul(v[2], w2);
@@ -136,7 +147,7 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
       float2* d = ((p + first) & 1) ? sB : sA;
       const int j0 = (j - k) * 8 + k;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) d[phys(j0 + r * Ns)] = v[r];
+      for (int r = 0; r < 8; ++r) d[(C::PAD2 && p == 1) ? phys_x<1>(j0 + r * Ns) : phys_x<0>(j0 + r * Ns)] = v[r];
       cur = d;
     }
     Ns *= 8;
@@ -155,7 +166,9 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int jj = j + u * T8;
-      float2 t0 = cur[phys(jj)], t1 = cur[phys(jj + NB)], t2 = cur[phys(jj + 2 * NB)], t3 = cur[phys(jj + 3 * NB)];
+      constexpr int E = (C::PAD2 && C::NP8 - 1 == 1) ? 1 : 0;  // pad of the exchange that filled `cur`
+      float2 t0 = cur[phys_x<E>(jj)], t1 = cur[phys_x<E>(jj + NB)], t2 = cur[phys_x<E>(jj + 2 * NB)],
+             t3 = cur[phys_x<E>(jj + 3 * NB)];
       t1 = cmul(t1, a1[u]);
       t2 = cmul(t2, a2[u]);
       t3 = cmul(t3, cmul(a1[u], a2[u]));
@@ -172,7 +185,8 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int jj = j + u * T8;
-      float2 t0 = cur[phys(jj)], t1 = cur[phys(jj + NB)];
+      constexpr int E = (C::PAD2 && C::NP8 - 1 == 1) ? 1 : 0;
+      float2 t0 = cur[phys_x<E>(jj)], t1 = cur[phys_x<E>(jj + NB)];
       t1 = cmul(t1, a1[u]);
       bfly2<INV>(t0, t1);
       v[u] = t0; v[u + 4] = t1;  // position jj + r*NB = j + (u + 4r)*T8
