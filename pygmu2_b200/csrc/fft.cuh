@@ -138,9 +138,9 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
     if (GTW && p + 1 < C::NP8) {  // issue the next pass's twiddle loads now: their latency hides behind this pass
       const int Nn = Ns * 8;
       const int m = 2 * (j & (Nn - 1)) * (N / (8 * Nn));
-      w1 = tw_get<INV, GTW>(tw, m);
-      w2 = tw_get<INV, GTW>(tw, 2 * m);
-      w4 = tw_get<INV, GTW>(tw, 4 * m);
+      w1 = tw_get<INV, GTW>(tw, m);      // one scattered load; w^2 and w^4 by squaring (2 ulp, far inside 1e-5)
+      w2 = cmul(w1, w1);
+      w4 = cmul(w2, w2);
     }
     bfly8<INV>(v);
     if (p < C::NP8 - 1 || C::RLAST > 1) {
@@ -192,6 +192,20 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[8], float2* sA, float2* s
       v[u] = t0; v[u + 4] = t1;  // position jj + r*NB = j + (u + 4r)*T8
     }
   }
+}
+
+// tw[j + m*N/8] for m = 0..7 from ONE table read: tw[j] times the constant 16th roots exp(-2*pi*i*m/16)
+// (tw is the table of 2N-th roots, so a step of N/8 entries is a 16th of a turn).
+__device__ __forceinline__ void split_twiddles(const float2 t0, float2 (&t)[8]) {
+  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  t[0] = t0;
+  t[1] = cmul(t0, make_float2(c1, -s1));
+  t[2] = cmul(t0, make_float2(h, -h));
+  t[3] = cmul(t0, make_float2(s1, -c1));
+  t[4] = make_float2(t0.y, -t0.x);  // times -i
+  t[5] = cmul(t0, make_float2(-s1, -c1));
+  t[6] = cmul(t0, make_float2(-h, -h));
+  t[7] = cmul(t0, make_float2(-c1, -s1));
 }
 
 // Split step after the forward transform: packed half-spectrum bin k from Z[k] and Z[N-k].

@@ -125,9 +125,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA) k_r2c(const R2CArgs a, con
   __syncthreads();
 #pragma unroll
   for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
-  float2 tws[8];  // requested before the barrier
-#pragma unroll
-  for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
+  float2 tws[8];  // one table read (requested before the barrier), the other seven by constant 16th roots
+  split_twiddles(tw[j], tws);
   __syncthreads();
   if (active) {
     float2 *row0, *row1 = nullptr;
@@ -288,15 +287,11 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
     for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
   }
   float2 tws[8];
-  if (!C::SMEM_TW) {  // global table: requested before the barrier
-#pragma unroll
-    for (int m = 0; m < 8; ++m) tws[m] = __ldg(tw + j + m * T8);
-  }
+  float2 tw0 = make_float2(1.f, 0.f);
+  if (!C::SMEM_TW) tw0 = __ldg(tw + j);  // global table: requested before the barrier
   __syncthreads();
-  if (C::SMEM_TW) {
-#pragma unroll
-    for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
-  }
+  if (C::SMEM_TW) tw0 = tw[j];
+  split_twiddles(tw0, tws);
   if (active) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -347,8 +342,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
 #pragma unroll
   for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
   float2 tws[8];
-#pragma unroll
-  for (int m = 0; m < 8; ++m) tws[m] = tw[j + m * T8];
+  split_twiddles(tw[j], tws);
   __syncthreads();
   float2 X[8];
 #pragma unroll
