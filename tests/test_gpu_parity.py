@@ -994,3 +994,77 @@ def test_two_level_contract_restrictions_and_c5_shape():
     assert short.info().tail_block == 0                    # the whole filter fits the head: plain uniform bank
     with pytest.raises(ValueError):
         pg.ConvolveBank(ir, 1, 1, block=64, tail_block=3000, single_filter_dims=True)
+
+
+# ---------------------------------------------------------------------------
+# cross-feature checks: two-level banks under output gains / PCM16 / device-resident input, and the host-gather
+# path of the fused HRTF mix against the resident-source path
+def test_two_level_with_output_gains_pcm16_and_device_voices():
+    rng = np.random.default_rng(404)
+    L, B, TB, n = 2500, 64, 512, 64 * 30
+    h = (rng.standard_normal((1, L, 2)) / np.sqrt(L)).astype(np.float32)
+    x = rng.uniform(-1, 1, (1, 2, n)).astype(np.float32)
+    two = pg.ConvolveBank(h, 1, 2, block=B, tail_block=TB)
+    uni = pg.ConvolveBank(h, 1, 2, block=B)
+    for bank in (two, uni):
+        bank.set_output_gains(0.6, 0.3)
+    y2 = np.concatenate([two.process(np.ascontiguousarray(x[:, :, p:p + 96])) for p in range(0, n, 96)], axis=2)
+    y1 = np.concatenate([uni.process(np.ascontiguousarray(x[:, :, p:p + 96])) for p in range(0, n, 96)], axis=2)
+    wet = orc.OracleConvolve(h[0], 2).render(x[0].T).T
+    assert rel_err(y2[0], 0.3 * x[0] + 0.6 * wet) <= TOL and rel_err(y2, y1) <= 2e-6
+    # int16 out of a two-level single-stream bank
+    two.reset()
+    from pygmu2_b200.wav_pe import f32_to_pcm16
+    xi = np.ascontiguousarray(x[0].T[:1000])
+    pcm = two.process_interleaved(xi, pcm16_out=True)
+    two.reset()
+    np.testing.assert_array_equal(pcm, f32_to_pcm16(two.process_interleaved(xi)))
+    # device-resident voices into a two-level ConvolvePE (the c5v --tail-block route), against the uniform one
+    ir = (rng.standard_normal(3000) * np.exp(-np.arange(3000) / 600.0) / 12).astype(np.float32)
+    def graph(tail):
+        voices = [pg.SuperSawPE(frequency=80.0 * 2 ** (i / 12.0), amplitude=1.0 / 8, seed=i) for i in range(8)]
+        return pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(ir), block_size=64, tail_block=tail)
+    ya = _pull_pe(graph(512), [64] * 40)
+    yb = _pull_pe(graph(None), [64] * 40)
+    assert rel_err(ya, yb) <= 2e-6 and np.max(np.abs(yb)) > 0.01
+
+
+class _Opaque(pg.ProcessingElement):
+    """Hides an ArrayPE behind a custom PE so the fused mix has to gather on the host."""
+
+    def __init__(self, inner):
+        self._inner = inner
+
+    def inputs(self):
+        return [self._inner]
+
+    def is_pure(self):
+        return True
+
+    def channel_count(self):
+        return self._inner.channel_count()
+
+    def _compute_extent(self):
+        return self._inner.extent()
+
+    def _render(self, start, duration):
+        return self._inner.render(start, duration)
+
+
+def test_fused_hrtf_mix_host_gather_equals_resident_sources():
+    rng = np.random.default_rng(405)
+    xs = [rng.uniform(-1, 1, 1500 + 200 * i).astype(np.float32) / 4 for i in range(5)]
+    az = [-150.0, -40.0, 0.0, 75.0, 180.0]
+
+    def mix(wrap):
+        ins = []
+        for i, (x, a) in enumerate(zip(xs, az)):
+            src = pg.ArrayPE(x)
+            sp = pg.SpatialPE(_Opaque(src) if wrap else src, method=pg.SpatialHRTF(a, 10.0 * i))
+            ins.append(pg.DelayPE(sp, 100 * i) if i % 2 else sp)
+        return pg.MixPE(*ins)
+
+    res, host = mix(False), mix(True)
+    yr, yh = _pull_pe(res, [512] * 6), _pull_pe(host, [512] * 6)
+    assert res._fused._resident is not None and host._fused._resident is None
+    np.testing.assert_array_equal(yr, yh)
