@@ -8,6 +8,7 @@
 // One transform per N/8 threads (see fft.cuh); a CTA hosts FPB transforms.  K1 loads its window
 // straight from global memory into registers (first pass needs no staging), K2 leaves its result in
 // registers and writes only the samples that are new.  Kernels are instantiated per LOG2N = 4..13.
+#include "bulk.cuh"
 #include "fft.cuh"
 #include "kernels.h"
 
@@ -330,6 +331,22 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
   float2* sB = sA + C::PADN;
   const int64_t f = (int64_t)blockIdx.x * C::FPB + g;
   const bool active = f < (int64_t)a.n_fft;
+  // One transform per CTA and one filter row per transform: the row (B*8 bytes of H) is fetched by ONE bulk-async
+  // copy issued before the forward transform starts and waited for on an mbarrier just before the product, so
+  // its HBM latency hides behind the forward FFT and no load instruction is spent on it.
+  constexpr bool HPRE = !FAN && C::FPB == 1;
+  float2* hbuf = bufs + 2 * C::PADN;                                  // [N] staged filter row (HPRE only)
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(hbuf + N);
+  if (HPRE && threadIdx.x == 0) {
+    mbar_init(hbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (active) {
+      const int s0 = (int)(f / a.c_x), c0 = (int)(f - (int64_t)s0 * a.c_x);
+      const float2* hrow = k.Hd + ((size_t)(__ldg(k.fmap + s0) * k.c_f + ((k.c_f == 1) ? 0 : c0)) * 2 * k.R + (k.R - 1)) * N;
+      mbar_expect_tx(hbar, (uint32_t)(N * sizeof(float2)));
+      bulk_g2s(hbuf, hrow, (uint32_t)(N * sizeof(float2)), hbar, l2_policy_evict_first());
+    }
+  }
 
   float2 v[8];
 #pragma unroll
@@ -358,10 +375,16 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
     const int fc = (k.c_f == 1) ? 0 : c;
     __syncthreads();  // every read of sA / sB above (or by the previous channel's inverse passes) is done
     if (active) {
-      const float2* hrow = k.Hd + ((size_t)(__ldg(k.fmap + s) * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N;
       float2 hh[8];
+      if (HPRE) {
+        mbar_wait(hbar, 0);  // the staged row has landed (the barriers above made the mbarrier's init visible)
 #pragma unroll
-      for (int m = 0; m < 8; ++m) hh[m] = __ldg(hrow + j + m * T8);
+        for (int m = 0; m < 8; ++m) hh[m] = hbuf[j + m * T8];
+      } else {
+        const float2* hrow = k.Hd + ((size_t)(__ldg(k.fmap + s) * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) hh[m] = __ldg(hrow + j + m * T8);
+      }
 #pragma unroll
       for (int m = 0; m < 8; ++m) v[m] = cmul(X[m], hh[m]);
       if (j == 0) v[0] = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
@@ -431,11 +454,13 @@ static void launch_c2r_t(const C2RArgs& a, cudaStream_t st) {
 template <int LOG2N, bool FAN>
 static void launch_conv1_t(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
   using C = FftCfg<LOG2N>;
+  // + the staged filter row and its mbarrier when the CTA holds one transform (see HPRE in the kernel)
+  constexpr int smem = C::SMEM_BYTES + ((!FAN && C::FPB == 1) ? C::N * 8 + 16 : 0);
   static bool attr_done[64] = {};
-  if (C::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
-    cudaFuncSetAttribute(k_conv1<LOG2N, FAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  if (smem > 48 * 1024 && need_smem_attr(attr_done))
+    cudaFuncSetAttribute(k_conv1<LOG2N, FAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int grid = (a.n_fft + C::FPB - 1) / C::FPB;
-  k_conv1<LOG2N, FAN><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a, k);
+  k_conv1<LOG2N, FAN><<<grid, C::CTA, smem, st>>>(a, k);
 }
 
 #define PGX_DISPATCH(LOG, CALL)                                                                              \
