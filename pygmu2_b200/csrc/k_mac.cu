@@ -312,9 +312,20 @@ __global__ void __launch_bounds__(1024) k_mix_sum_tall(const float* __restrict__
   const int64_t e = (int64_t)blockIdx.x * 32 + lane;
   const bool live = e < n_elems;
   const int n_chunks = (n_inputs + kTallRows - 1) / kTallRows;
-  auto stage = [&](int c) {
+  auto stage = [&](int c) {  // every load of the warp's rows is issued before the first shared-memory store
     const int r0 = c * kTallRows, nr = min(kTallRows, n_inputs - r0);
-    for (int r = warp - 1; r < nr; r += 31) rows[c & 1][r][lane] = live ? in[(int64_t)(r0 + r) * n_elems + e] : 0.f;
+    constexpr int kPer = (kTallRows + 30) / 31;
+    float t[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int r = warp - 1 + 31 * i;
+      t[i] = (live && r < nr) ? __ldcg(in + (int64_t)(r0 + r) * n_elems + e) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int r = warp - 1 + 31 * i;
+      if (r < nr) rows[c & 1][r][lane] = t[i];
+    }
   };
   if (warp > 0) stage(0);
   __syncthreads();

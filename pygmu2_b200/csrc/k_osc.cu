@@ -62,27 +62,22 @@ __global__ void __launch_bounds__(1024) k_blit_bank(const BlitArgs a) {
   const int v = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int U = a.unison;
   const int o = v * U + w;
-  const double sr = (double)a.sample_rate;
-  const double f = a.freq[o], gain = a.gain[o];
-  const double fm = fmax(f, 1.0);
-  const double inc = f / sr;          // blit_saw_pe.py:189
-  const double P = sr / fm;           // :198
-  const double invP = 1.0 / P;        // :218
-  double M;                           // :167-177
-  if (a.m_fixed && a.m_fixed[o] > 0) {
-    M = (double)a.m_fixed[o];
-  } else {
-    int m = (int)floor(sr / (2.0 * fm));
-    m = m - (1 - m % 2);
-    if (m < 1) m = 1;
-    M = (double)m;
-  }
+  // per-oscillator constants, computed once on the host with the reference's own float64 expressions
+  // (blit_saw_pe.py:167-177,189,198,218): phase increment, period, 1/period, harmonic count
+  const double gain = a.gain[o];
+  const double inc = a.consts[4 * o], P = a.consts[4 * o + 1], invP = a.consts[4 * o + 2], M = a.consts[4 * o + 3];
   const double leak = a.leak;
   double lk[kOscT + 1];  // leak^q
   lk[0] = 1.0;
 #pragma unroll
   for (int q = 1; q <= kOscT; ++q) lk[q] = lk[q - 1] * leak;
-  const double lane_pow = pow(leak, (double)(kOscT * lane));  // weight of the tile's carry-in at this lane
+  // weight of the tile's carry-in at this lane, leak^(kOscT*lane), by binary exponentiation over the lane bits
+  double lane_pow = 1.0, sq = lk[kOscT];
+#pragma unroll
+  for (int b = 0; b < 5; ++b) {
+    if (lane & (1 << b)) lane_pow *= sq;
+    sq *= sq;
+  }
   double ph0 = a.st_phase[o], y0 = a.st_int[o];               // state at the start of the pull
   double ph_last = ph0;
 

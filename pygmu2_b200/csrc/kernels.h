@@ -112,9 +112,8 @@ struct SineArgs {
 void launch_sine_bank(const SineArgs& a, cudaStream_t st);
 
 struct BlitArgs {
-  const double* freq;      // [V*U] oscillator frequency (Hz)
+  const double* consts;    // [V*U][4] phase increment f/sr, period sr/max(f,1), 1/period, harmonic count M
   const double* gain;      // [V*U] oscillator amplitude
-  const int32_t* m_fixed;  // [V*U] harmonics (0 = auto: largest odd M below Nyquist), or NULL
   const double* amp;       // [V] voice amplitude
   double* st_phase;        // [V*U] state: phase in [0,1) at the end of the previous pull
   double* st_int;          // [V*U] state: leaky-integrator output at the end of the previous pull

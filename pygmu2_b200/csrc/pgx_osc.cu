@@ -1,6 +1,7 @@
 // pgx_osc.cu -- C ABI of the device-resident sources (include/pgx.h "sources" section): constant-parameter
 // SinePE banks and BlitSawPE / SuperSawPE voice banks that render straight into device memory, so the
 // convolution path's inputs never exist on the host.
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -13,9 +14,8 @@ struct pgx_osc {
   int n_osc = 0;
   cudaStream_t stream = nullptr;
   double *params = nullptr;                       // sine: [V][3]
-  double *freq = nullptr, *gain = nullptr, *amp = nullptr, *phase_init = nullptr;
+  double *consts = nullptr, *gain = nullptr, *amp = nullptr, *phase_init = nullptr;
   double *st_phase = nullptr, *st_int = nullptr;  // blit state
-  int32_t* m_fixed = nullptr;
   float *out = nullptr, *mix = nullptr;           // [V][C][max_pull], [C][max_pull]
   int64_t last_end = INT64_MIN;
   bool has_last = false;
@@ -28,8 +28,8 @@ void free_osc(pgx_osc* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (void* p : {(void*)h->params, (void*)h->freq, (void*)h->gain, (void*)h->amp, (void*)h->phase_init,
-                  (void*)h->st_phase, (void*)h->st_int, (void*)h->m_fixed, (void*)h->out, (void*)h->mix})
+  for (void* p : {(void*)h->params, (void*)h->consts, (void*)h->gain, (void*)h->amp, (void*)h->phase_init,
+                  (void*)h->st_phase, (void*)h->st_int, (void*)h->out, (void*)h->mix})
     cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -65,7 +65,7 @@ int render_on(pgx_osc* h, int64_t start, int32_t n, int32_t flags, cudaStream_t 
       if (rc != PGX_OK) return rc;
     }
     pgx::BlitArgs a{};
-    a.freq = h->freq; a.gain = h->gain; a.m_fixed = h->m_fixed; a.amp = h->amp;
+    a.consts = h->consts; a.gain = h->gain; a.amp = h->amp;
     a.st_phase = h->st_phase; a.st_int = h->st_int; a.out = h->out;
     a.os = (int64_t)C * n; a.oc = n; a.oi = 1; a.channels = C;
     a.leak = c.leak; a.n_voices = c.n_voices; a.unison = c.unison; a.n = n; a.sample_rate = c.sample_rate;
@@ -118,11 +118,28 @@ int pgx_osc_create(pgx_osc** out, const pgx_osc_config* cfg, const double* freq,
     if (e == cudaSuccess) e = upload(&h->params, p.data(), p.size(), h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // p goes out of scope
   } else {
-    if (e == cudaSuccess) e = upload(&h->freq, freq, no, h->stream);
+    // blit_saw_pe.py:167-177,189,198,218 in the reference's own float64 expressions
+    std::vector<double> cst(4 * no);
+    const double sr = (double)c.sample_rate;
+    for (size_t o = 0; o < no; ++o) {
+      const double f = freq[o], fm = f > 1.0 ? f : 1.0;
+      const double P = sr / fm;
+      double M;
+      if (m_fixed && m_fixed[o] > 0) {
+        M = (double)m_fixed[o];
+      } else {
+        int m = (int)floor(sr / (2.0 * fm));
+        m = m - (1 - m % 2);
+        if (m < 1) m = 1;
+        M = (double)m;
+      }
+      cst[4 * o] = f / sr; cst[4 * o + 1] = P; cst[4 * o + 2] = 1.0 / P; cst[4 * o + 3] = M;
+    }
+    if (e == cudaSuccess) e = upload(&h->consts, cst.data(), cst.size(), h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // cst goes out of scope
     if (e == cudaSuccess) e = upload(&h->gain, gain, no, h->stream);
     if (e == cudaSuccess) e = upload(&h->phase_init, phase, no, h->stream);
     if (e == cudaSuccess) e = upload(&h->amp, amp, (size_t)c.n_voices, h->stream);
-    if (e == cudaSuccess && m_fixed) e = upload(&h->m_fixed, m_fixed, no, h->stream);
     if (e == cudaSuccess) e = cudaMalloc(&h->st_phase, no * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&h->st_int, no * sizeof(double));
   }
