@@ -318,7 +318,12 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
 // 2B*4 (window) + B*4 (hist) + B*8 (H) + B*4 (y) instead of that plus a B*8 row written and read again.
 // FAN: a mono source fanned out to c_out filter channels (convolve_pe.py:300-310): one forward transform,
 // c_out inverse transforms.
-template <int LOG2N, bool FAN>
+// PAST: the bank has a few partitions (2 <= P <= kFusedMaxP, conv mode): the same kernel also writes X to its
+// delay-line row and adds the past partitions sum_{p>=1} X_{t-p} H_p, read straight from the stream's own ring
+// rows (written by earlier launches of this kernel on the same stream) -- one launch per block step instead of
+// K1 + background pass + K2 on three streams, which is what bounds short filters and the head level of a
+// two-level bank.
+template <int LOG2N, bool FAN, bool PAST>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 ? 2 : 1)
     k_conv1(const R2CArgs a, const C2RArgs k) {
   using C = FftCfg<LOG2N>;
@@ -368,6 +373,11 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
     X[m] = (kk == 0) ? make_float2(v[m].x + v[m].y, v[m].x - v[m].y) : r2c_bin(v[m], sA[N - kk], tws[m]);
   }
 
+  if (PAST && active) {  // the open block's spectrum goes to its ring row for the steps to come
+    float2* row = a.fdl + ((size_t)f * a.R + a.slot) * N;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) row[j + m * T8] = X[m];
+  }
   const int s = active ? (int)(f / a.c_x) : 0, cx = active ? (int)(f - (int64_t)s * a.c_x) : 0;
   const int n_c = FAN ? k.c_out : 1;
   for (int ci = 0; ci < n_c; ++ci) {
@@ -387,7 +397,29 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
       }
 #pragma unroll
       for (int m = 0; m < 8; ++m) v[m] = cmul(X[m], hh[m]);
-      if (j == 0) v[0] = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
+      float2 b0 = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
+      if (PAST) {
+        const float2* xring = k.fdl + (size_t)f * k.R * N + j;
+        const float2* hring = k.Hd + ((size_t)(__ldg(k.fmap + s) * k.c_f + fc) * 2 * k.R + k.q0) * N + j;
+        for (int jj = 0; jj < k.n_past; ++jj) {
+          int slot = k.p_off + jj;
+          slot += (slot >= k.p_skip) ? k.p_nskip : 0;
+          float2 xx[8], hp[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            xx[m] = __ldcg(xring + (size_t)slot * N + m * T8);
+            hp[m] = __ldg(hring + (size_t)slot * N + m * T8);
+          }
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            v[m].x = fmaf(xx[m].x, hp[m].x, fmaf(-xx[m].y, hp[m].y, v[m].x));
+            v[m].y = fmaf(xx[m].x, hp[m].y, fmaf(xx[m].y, hp[m].x, v[m].y));
+          }
+          b0.x = fmaf(xx[0].x, hp[0].x, b0.x);
+          b0.y = fmaf(xx[0].y, hp[0].y, b0.y);
+        }
+      }
+      if (j == 0) v[0] = b0;
 #pragma unroll
       for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
     }
@@ -451,16 +483,16 @@ static void launch_c2r_t(const C2RArgs& a, cudaStream_t st) {
   k_c2r<LOG2N, PART><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a);
 }
 
-template <int LOG2N, bool FAN>
+template <int LOG2N, bool FAN, bool PAST>
 static void launch_conv1_t(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
   using C = FftCfg<LOG2N>;
   // + the staged filter row and its mbarrier when the CTA holds one transform (see HPRE in the kernel)
   constexpr int smem = C::SMEM_BYTES + ((!FAN && C::FPB == 1) ? C::N * 8 + 16 : 0);
   static bool attr_done[64] = {};
   if (smem > 48 * 1024 && need_smem_attr(attr_done))
-    cudaFuncSetAttribute(k_conv1<LOG2N, FAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_conv1<LOG2N, FAN, PAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int grid = (a.n_fft + C::FPB - 1) / C::FPB;
-  k_conv1<LOG2N, FAN><<<grid, C::CTA, smem, st>>>(a, k);
+  k_conv1<LOG2N, FAN, PAST><<<grid, C::CTA, smem, st>>>(a, k);
 }
 
 #define PGX_DISPATCH(LOG, CALL)                                                                              \
@@ -489,10 +521,13 @@ void launch_filter_prep(const FilterPrepArgs& fp, cudaStream_t st) {
 }
 
 void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
-  if (a.c_x == 1 && k.c_out > 1) {
-    PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, true>(a, k, st)));
+  const bool fan = (a.c_x == 1 && k.c_out > 1);
+  if (k.n_past > 0) {
+    if (fan) { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, true, true>(a, k, st))); }
+    else { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, false, true>(a, k, st))); }
   } else {
-    PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, false>(a, k, st)));
+    if (fan) { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, true, false>(a, k, st))); }
+    else { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, false, false>(a, k, st))); }
   }
 }
 

@@ -92,6 +92,9 @@ struct C2RArgs {
   // convolution before the output gains; element (s, c, i) at add[s*as + c*ac + (y_off... see emit_block) ], or NULL
   const float* add;
   int64_t as, ac, ai;
+  // fused small-P step (k_conv1<.., PAST>): the past partitions are ring slots p_off + jj (+ p_nskip from p_skip on),
+  // jj < n_past, paired with filter rows q0 + slot -- the same slot walk as MacArgs
+  int32_t n_past, p_off, p_skip, p_nskip, q0;
 };
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st);
 // K1 + K2 in one kernel for single-partition conv banks (P = 1): the spectrum never visits the delay line.

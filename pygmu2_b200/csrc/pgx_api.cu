@@ -147,6 +147,7 @@ struct pgx_bank {
   pgx_layout addend_l{};
   bool serial = false;
   bool use_conv1 = true;           // P = 1 conv pulls: K1 and K2 fused into one kernel (PGX_CONV1=0 disables)
+  int fused_max_p = 16;            // ... and conv pulls of banks with up to this many partitions (PGX_FUSED_MAXP)
   int64_t launches = 0, steps = 0;
   // per-kernel CUDA-event timing
   bool profiling = false;
@@ -309,7 +310,8 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   const int64_t i = b->step, t = b->block;
   const bool completes = (b->fill + take == B);
 
-  const bool fused1 = (R == 1 && !mix && b->use_conv1);
+  // one kernel per step: single-partition banks, and banks with a few partitions (the past sum is added in-kernel)
+  const bool fused1 = (!mix && b->use_conv1 && (R == 1 || P <= b->fused_max_p));
   pgx::R2CArgs r{};
   r.x = x_dev; r.xs = xl.stream; r.xc = xl.chan; r.xi = xl.samp; r.x_off = pos;
   r.hist = b->hist; r.fdl = b->fdl; r.tw = b->tw;
@@ -337,14 +339,15 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     }
     cudaEventRecord(b->ev_k1[i % kRing], b->s_in);
     b->launches += 1;
-  } else if (i >= 1) {
-    cudaStreamWaitEvent(crit, b->ev_k2[(i - 1) % kRing], 0);  // hist of the previous step (no-op on one stream)
+  } else {
+    if (i >= 1) cudaStreamWaitEvent(crit, b->ev_k2[(i - 1) % kRing], 0);  // previous step (no-op on one stream)
+    if (R > 1 && b->fill == 0 && t >= 2) cudaStreamWaitEvent(crit, b->ev_mac[(t - 2) % kRing], 0);  // a mix pass
   }
 
   // ---- background stream: past sum of the open block, if it is not in flight / valid already
   int n_split_past = 0;
   const int par = (int)(t & 1);
-  if (P > 1) {
+  if (P > 1 && !fused1) {
     if (b->past_block != t || b->past_mode != (mix ? 1 : 0)) issue_past(b, mix, t, b->head, b->ev_k1[i % kRing]);
     cudaStreamWaitEvent(crit, b->ev_mac[t % kRing], 0);
     const int ns = (mix ? b->plan_mix : b->plan_conv).n_partials;
@@ -393,7 +396,13 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
 
   // the block commits with this step: its row is final once K1 has run, so the next block's past pass
   // can start now, overlapping this step's K2 and the next step's K1
-  if (completes && P > 1) issue_past(b, mix, t + 1, (b->head + 1) % R, b->ev_k1[i % kRing]);
+  if (completes && P > 1 && !fused1) issue_past(b, mix, t + 1, (b->head + 1) % R, b->ev_k1[i % kRing]);
+  if (fused1 && P > 1) {  // past partitions summed inside the fused kernel: every ring row but the open and the spare
+    k.n_past = R - 2;
+    k.q0 = R - 1 - b->head;
+    if (b->head + 1 < R) { k.p_off = 0; k.p_skip = b->head; k.p_nskip = 2; }
+    else                 { k.p_off = 1; k.p_skip = R; k.p_nskip = 0; }
+  }
 
   {
     ProfScope ps(b, crit, fused1 ? 5 : 2);
@@ -673,6 +682,7 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
     guard(cudaEventCreateWithFlags(&b->ev_bgjoin, cudaEventDisableTiming), "cudaEventCreate");
     if (const char* e = getenv("PGX_BG_STREAMS")) b->two_bg = (e[0] != '1');
     if (const char* e = getenv("PGX_CONV1")) b->use_conv1 = (e[0] != '0');
+    if (const char* e = getenv("PGX_FUSED_MAXP")) b->fused_max_p = atoi(e);
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");
     if (const char* e = getenv("PGX_DEBUG_SERIAL")) {  // debugging aid: no overlap, one stream for everything
