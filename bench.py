@@ -512,8 +512,10 @@ def run_gpu(args):
     dt_e2e = float(te.item())
     checksum = float(np.abs(yp.array.astype(np.float32)).mean()) / (32768.0 if args.pcm16 else 1.0)
 
-    # audio-seconds x channels per step: every rank's streams for independent outputs, ONE mix when mixed
-    units = (c_out if (mix and (do_reduce or world == 1)) else world * n_out_ch) * pull / sr
+    # audio-seconds x channels per step, SURVEY.md §8d: N_streams x C_out x duration / sample_rate -- the stream-channels
+    # CONVOLVED, also when they are then summed into one mix (C3: 256 sources x 2 ears, C4: 512 streams per GPU); the
+    # number of mixed output channels is reported beside it in config
+    units = world * N * c_out * pull / sr
     value = units * K / (ms_max * 1e-3)
     e2e_value = units * ke / dt_e2e
 
@@ -535,6 +537,9 @@ def run_gpu(args):
             traffic = None
 
     if rank == 0:
+        if mix:
+            spec["config"]["mixed_output"] = (f"{c_out} channel(s) per GPU per pull" +
+                                              (", reduced over the GPUs with NCCL" if do_reduce else ""))
         achieved = mac_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
