@@ -437,6 +437,84 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
   }
 }
 
+// K1 + present-slot accumulate fused for single-partition MIXES of mono transforms (SpatialHRTF banks, C3): a CTA
+// holds G sources; each group ingests and transforms its source, multiplies the spectrum by that source's
+// filter row per output channel (the HRTF pair chosen by fmap) and the G products are summed through shared
+// memory -- FFT, HRTF multiply and the MixPE sum over the CTA's sources in one kernel.  Writes one partial row per
+// (CTA, channel) that K2 folds; replaces k_r2c + k_fdl_mac<MIX> of the three-kernel step.
+template <int LOG2N>
+struct Mix1Cfg {
+  using C = FftCfg<LOG2N>;
+  static constexpr int G = (1024 / C::T8) < 16 ? (1024 / C::T8) : 16;   // sources per CTA
+  static constexpr int CTA = G * C::T8;
+  static constexpr int SMEM_BYTES = (C::SMEM_TW ? 2 * C::N : 0) * 8 + G * 2 * C::PADN * 8;
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, const C2RArgs k, float2* __restrict__ ynow) {
+  using C = FftCfg<LOG2N>;
+  using M = Mix1Cfg<LOG2N>;
+  constexpr int N = C::N, T8 = C::T8;
+  extern __shared__ float2 sm[];
+  const float2* tw = stage_twiddles<LOG2N>(sm, a.tw);
+  float2* bufs = sm + (C::SMEM_TW ? 2 * N : 0);
+  const int g = threadIdx.x / T8, j = threadIdx.x - g * T8;
+  float2* sA = bufs + (size_t)g * 2 * C::PADN;
+  float2* sB = sA + C::PADN;
+  const int64_t f = (int64_t)blockIdx.x * M::G + g;   // c_x == 1: transform f is stream f
+  const bool active = f < (int64_t)a.n_fft;
+
+  float2 v[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
+  if (active) ingest_window<LOG2N>(a, f, j, v);
+  fft_passes<LOG2N, false>(v, sA, sB, 0, j, tw);
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
+  float2 tws[8];
+  split_twiddles(tw[j], tws);
+  __syncthreads();
+  float2 X[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int kk = j + m * T8;
+    X[m] = (kk == 0) ? make_float2(v[m].x + v[m].y, v[m].x - v[m].y) : r2c_bin(v[m], sA[N - kk], tws[m]);
+  }
+  const int fid = active ? __ldg(k.fmap + (int)f) : 0;
+  for (int c = 0; c < k.c_out; ++c) {
+    const int fc = (k.c_f == 1) ? 0 : c;
+    __syncthreads();  // the reads of sA above / by the previous channel's sum are done
+    float2 y[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) y[m] = make_float2(0.f, 0.f);
+    if (active) {
+      const float2* hrow = k.Hd + ((size_t)(fid * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N + j;
+      float2 hh[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) hh[m] = __ldg(hrow + m * T8);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) y[m] = cmul(X[m], hh[m]);
+      if (j == 0) y[0] = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) sA[j + m * T8] = y[m];
+    __syncthreads();
+    // the MixPE sum over this CTA's sources, in source order
+    float2* out = ynow + ((size_t)blockIdx.x * k.c_out + c) * N;
+    for (int bin = threadIdx.x; bin < N; bin += M::CTA) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int gg = 0; gg < M::G; ++gg) {
+        const float2 t = bufs[(size_t)gg * 2 * C::PADN + bin];
+        acc.x += t.x;
+        acc.y += t.y;
+      }
+      out[bin] = acc;
+    }
+  }
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 // cudaFuncSetAttribute is per device: remember it per (kernel instantiation, device), not once per process
 static bool need_smem_attr(bool (&done)[64]) {
@@ -528,6 +606,37 @@ void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
   } else {
     if (fan) { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, true, false>(a, k, st))); }
     else { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, false, false>(a, k, st))); }
+  }
+}
+
+template <int LOG2N>
+static void launch_mix1_t(const R2CArgs& a, const C2RArgs& k, float2* ynow, cudaStream_t st) {
+  using M = Mix1Cfg<LOG2N>;
+  static bool attr_done[64] = {};
+  if (M::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
+    cudaFuncSetAttribute(k_mix1<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, M::SMEM_BYTES);
+  k_mix1<LOG2N><<<(a.n_fft + M::G - 1) / M::G, M::CTA, M::SMEM_BYTES, st>>>(a, k, ynow);
+}
+
+int mix1_sources_per_cta(int B) {
+  switch (ilog2(B)) {
+    case 4: return Mix1Cfg<4>::G; case 5: return Mix1Cfg<5>::G; case 6: return Mix1Cfg<6>::G;
+    case 7: return Mix1Cfg<7>::G; case 8: return Mix1Cfg<8>::G; case 9: return Mix1Cfg<9>::G;
+    case 10: return Mix1Cfg<10>::G;
+    default: return 0;  // larger transforms keep the three-kernel step
+  }
+}
+
+void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, cudaStream_t st) {
+  switch (ilog2(a.B)) {
+    case 4: launch_mix1_t<4>(a, k, ynow, st); break;
+    case 5: launch_mix1_t<5>(a, k, ynow, st); break;
+    case 6: launch_mix1_t<6>(a, k, ynow, st); break;
+    case 7: launch_mix1_t<7>(a, k, ynow, st); break;
+    case 8: launch_mix1_t<8>(a, k, ynow, st); break;
+    case 9: launch_mix1_t<9>(a, k, ynow, st); break;
+    case 10: launch_mix1_t<10>(a, k, ynow, st); break;
+    default: break;
   }
 }
 

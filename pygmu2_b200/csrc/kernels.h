@@ -135,6 +135,11 @@ void launch_f32_to_pcm16(const float* in, int16_t* out, int64_t n, cudaStream_t 
 void launch_copy_block(const float* src, int64_t ss, int64_t sc, int64_t si, float* dst, int64_t ds, int64_t dc,
                        int64_t di, int32_t n_streams, int32_t chans, int32_t n, cudaStream_t st);
 
+// K1 + present-slot accumulate in one kernel for single-partition mixes of mono transforms (k_mix1): writes
+// ceil(n_fft / mix1_sources_per_cta(B)) partial rows per channel to ynow; 0 sources per CTA = not available for B.
+int mix1_sources_per_cta(int B);
+void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, cudaStream_t st);
+
 int fft_smem_bytes(int B);
 
 }  // namespace pgx

@@ -148,6 +148,8 @@ struct pgx_bank {
   bool serial = false;
   bool use_conv1 = true;           // P = 1 conv pulls: K1 and K2 fused into one kernel (PGX_CONV1=0 disables)
   int fused_max_p = 16;            // ... and conv pulls of banks with up to this many partitions (PGX_FUSED_MAXP)
+  bool use_mix1 = true;            // P = 1 mixes of mono transforms: K1 + present-slot accumulate fused (PGX_MIX1=0)
+  int mix1_rows = 0;               // partial rows per channel written by k_mix1 (= CTAs)
   int64_t launches = 0, steps = 0;
   // per-kernel CUDA-event timing
   bool profiling = false;
@@ -325,8 +327,10 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   };
   r.fast = (whole && !r.mixdown && vec_ok(x_dev, xl)) ? 1 : 0;
 
+  // single-partition mixes of mono transforms: K1 and the present-slot accumulate are one kernel, on the critical stream
+  const bool mix1 = (mix && R == 1 && b->use_mix1 && b->mix1_rows > 0);
   // ---- ingest stream: K1 (single-partition conv pulls run K1 and K2 as one kernel on the critical stream)
-  if (!fused1) {
+  if (!fused1 && !mix1) {
     if (b->fill > 0 || R == 1) {  // same ring row (and open half) as the previous step
       if (i >= 1) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 1) % kRing], 0);
     } else {
@@ -355,11 +359,29 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   }
 
   // ---- critical stream: [NOW] + K2
-  if (!fused1) cudaStreamWaitEvent(crit, b->ev_k1[i % kRing], 0);
+  if (!fused1 && !mix1) cudaStreamWaitEvent(crit, b->ev_k1[i % kRing], 0);
   pgx::C2RArgs k{};
   k.yspec = b->ypast[par]; k.n_split = n_split_past;
   k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
-  if (mix) {  // present term of every stream: K3 restricted to the open slot
+  if (mix1) {
+    k.Hd = b->Hd; k.fmap = b->fmap; k.c_f = c.filter_channels; k.R = R; k.c_out = c.c_out;
+    {
+      ProfScope ps(b, crit, 4);
+      pgx::launch_mix1(r, k, b->ynow, crit);
+    }
+    b->launches += 1;
+    cudaEventRecord(b->ev_k1[i % kRing], crit);
+    k.ynow = b->ynow; k.n_split_now = b->mix1_rows;
+    if (b->mix1_rows > 32) {  // many CTAs: fold their rows with the wide kernel instead of inside K2
+      float2* folded = b->ynow + (size_t)b->mix1_rows * c.c_out * B;
+      ProfScope ps(b, crit, 3);
+      pgx::launch_reduce_partials(reinterpret_cast<const float4*>(b->ynow), reinterpret_cast<float4*>(folded),
+                                  b->mix1_rows, c.c_out, B / 2, crit);
+      b->launches += 1;
+      k.ynow = folded; k.n_split_now = 1;
+    }
+    k.fdl = nullptr;
+  } else if (mix) {  // present term of every stream: K3 restricted to the open slot
     pgx::MacArgs m{};
     fill_mac_common(b, m, true, b->head);
     m.mix = b->plan_now.layout;  // always the flattened layout: one term per stream
@@ -663,7 +685,12 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   b->ypart_bytes = (y_conv > y_mix ? y_conv : y_mix) * B * sizeof(float2);
   if (b->ypart_bytes == 0) b->ypart_bytes = sizeof(float2);
   b->ysum_bytes = n_out_max * B * sizeof(float2) * kFoldAbove;
-  b->ynow_bytes = (size_t)b->plan_now.n_split * c.c_out * B * sizeof(float2);
+  {
+    const int g = pgx::mix1_sources_per_cta(B);
+    b->mix1_rows = (g > 0 && P == 1 && c_x == 1) ? (c.n_streams + g - 1) / g : 0;
+    const int rows = b->plan_now.n_split > b->mix1_rows ? b->plan_now.n_split : b->mix1_rows;
+    b->ynow_bytes = (size_t)(rows + 1) * c.c_out * B * sizeof(float2);  // + one folded row block
+  }
   b->xs_bytes = (size_t)c.n_streams * c.c_in * c.max_pull * sizeof(float);
   b->ys_bytes = (size_t)c.n_streams * c.c_out * c.max_pull * sizeof(float);
 
@@ -683,6 +710,7 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
     if (const char* e = getenv("PGX_BG_STREAMS")) b->two_bg = (e[0] != '1');
     if (const char* e = getenv("PGX_CONV1")) b->use_conv1 = (e[0] != '0');
     if (const char* e = getenv("PGX_FUSED_MAXP")) b->fused_max_p = atoi(e);
+    if (const char* e = getenv("PGX_MIX1")) b->use_mix1 = (e[0] != '0');
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");
     if (const char* e = getenv("PGX_DEBUG_SERIAL")) {  // debugging aid: no overlap, one stream for everything
