@@ -899,7 +899,10 @@ def test_random_operation_sequences_match_direct_model(seed, L, B):
     def drain():
         for tk, yp, ref, label in pending:
             bank.wait(tk)
-            assert rel_err(yp.array, ref) <= TOL, label
+            # full scale: inputs are uniform(-1,1), filters unit-energy -> outputs O(1); a 1-sample pull can have a
+            # tiny maximum by chance, which is not the scale of the signal
+            err = float(np.max(np.abs(yp.array.astype(np.float64) - ref)) / max(float(np.max(np.abs(ref))), 0.25))
+            assert err <= TOL, label
         pending.clear()
 
     for step in range(70):
