@@ -450,8 +450,11 @@ struct Mix1Cfg {
   static constexpr int SMEM_BYTES = (C::SMEM_TW ? 2 * C::N : 0) * 8 + G * 2 * C::PADN * 8;
 };
 
-template <int LOG2N>
-__global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, const C2RArgs k, float2* __restrict__ ynow) {
+// LAST: the CTA that finishes last (ticket counter) also folds the partial rows of all CTAs, runs the c_out
+// inverse transforms and emits -- the whole block step of a small mix is then ONE launch.
+template <int LOG2N, bool LAST>
+__global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, const C2RArgs k, float2* __restrict__ ynow,
+                                                              unsigned int* __restrict__ ticket) {
   using C = FftCfg<LOG2N>;
   using M = Mix1Cfg<LOG2N>;
   constexpr int N = C::N, T8 = C::T8;
@@ -513,6 +516,61 @@ __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, c
       out[bin] = acc;
     }
   }
+  if (!LAST) return;
+  // ---- last CTA: fold + inverse transforms + emit (K2's work), groups 0..c_out-1 carry one output channel each
+  __shared__ unsigned int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch (launches of one bank are stream-ordered)
+  __threadfence();
+  const bool emit = g < k.c_out;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
+  if (emit) {
+    const float2* part = ynow + (size_t)g * N + j;   // rows written by other CTAs: read through L2 (__ldcg)
+    const size_t rs = (size_t)k.c_out * N;
+    const int nr = (int)gridDim.x;
+    int r = 0;
+    for (; r + 4 <= nr; r += 4) {  // 32 loads in flight, summed in row order
+      float2 t[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) t[u][m] = __ldcg(part + (size_t)(r + u) * rs + m * T8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          v[m].x += t[u][m].x;
+          v[m].y += t[u][m].y;
+        }
+    }
+    for (; r < nr; ++r) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float2 t = __ldcg(part + (size_t)r * rs + m * T8);
+        v[m].x += t.x;
+        v[m].y += t.y;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
+  __syncthreads();
+  if (emit) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int kk = j + m * T8;
+      v[m] = (kk == 0) ? make_float2(0.5f * (v[m].x + v[m].y), 0.5f * (v[m].x - v[m].y))
+                       : c2r_bin(v[m], sA[N - kk], tws[m]);
+    }
+  }
+  fft_passes<LOG2N, true>(v, sA, sB, 1, j, tw);
+  if (emit) emit_block<LOG2N>(k, g, j, v);
 }
 
 // ---- launchers ---------------------------------------------------------------------------------
@@ -609,13 +667,13 @@ void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
   }
 }
 
-template <int LOG2N>
-static void launch_mix1_t(const R2CArgs& a, const C2RArgs& k, float2* ynow, cudaStream_t st) {
+template <int LOG2N, bool LAST>
+static void launch_mix1_t(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st) {
   using M = Mix1Cfg<LOG2N>;
   static bool attr_done[64] = {};
   if (M::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
-    cudaFuncSetAttribute(k_mix1<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, M::SMEM_BYTES);
-  k_mix1<LOG2N><<<(a.n_fft + M::G - 1) / M::G, M::CTA, M::SMEM_BYTES, st>>>(a, k, ynow);
+    cudaFuncSetAttribute(k_mix1<LOG2N, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, M::SMEM_BYTES);
+  k_mix1<LOG2N, LAST><<<(a.n_fft + M::G - 1) / M::G, M::CTA, M::SMEM_BYTES, st>>>(a, k, ynow, ticket);
 }
 
 int mix1_sources_per_cta(int B) {
@@ -627,17 +685,17 @@ int mix1_sources_per_cta(int B) {
   }
 }
 
-void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, cudaStream_t st) {
+void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st) {
+#define PGX_MIX1_CASE(L)                                                     \
+  case L:                                                                    \
+    if (ticket) launch_mix1_t<L, true>(a, k, ynow, ticket, st);              \
+    else launch_mix1_t<L, false>(a, k, ynow, nullptr, st);                   \
+    break;
   switch (ilog2(a.B)) {
-    case 4: launch_mix1_t<4>(a, k, ynow, st); break;
-    case 5: launch_mix1_t<5>(a, k, ynow, st); break;
-    case 6: launch_mix1_t<6>(a, k, ynow, st); break;
-    case 7: launch_mix1_t<7>(a, k, ynow, st); break;
-    case 8: launch_mix1_t<8>(a, k, ynow, st); break;
-    case 9: launch_mix1_t<9>(a, k, ynow, st); break;
-    case 10: launch_mix1_t<10>(a, k, ynow, st); break;
+    PGX_MIX1_CASE(4) PGX_MIX1_CASE(5) PGX_MIX1_CASE(6) PGX_MIX1_CASE(7) PGX_MIX1_CASE(8) PGX_MIX1_CASE(9) PGX_MIX1_CASE(10)
     default: break;
   }
+#undef PGX_MIX1_CASE
 }
 
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st) {

@@ -138,7 +138,9 @@ void launch_copy_block(const float* src, int64_t ss, int64_t sc, int64_t si, flo
 // K1 + present-slot accumulate in one kernel for single-partition mixes of mono transforms (k_mix1): writes
 // ceil(n_fft / mix1_sources_per_cta(B)) partial rows per channel to ynow; 0 sources per CTA = not available for B.
 int mix1_sources_per_cta(int B);
-void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, cudaStream_t st);
+// ticket != NULL: the last CTA to finish also does K2's work (fold, inverse transforms, emit): one launch per step.
+// Needs c_out <= mix1_sources_per_cta(B); *ticket must be 0 before the first launch (the kernel re-arms it).
+void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st);
 
 int fft_smem_bytes(int B);
 

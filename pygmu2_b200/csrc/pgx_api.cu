@@ -150,6 +150,7 @@ struct pgx_bank {
   int fused_max_p = 16;            // ... and conv pulls of banks with up to this many partitions (PGX_FUSED_MAXP)
   bool use_mix1 = true;            // P = 1 mixes of mono transforms: K1 + present-slot accumulate fused (PGX_MIX1=0)
   int mix1_rows = 0;               // partial rows per channel written by k_mix1 (= CTAs)
+  unsigned int* mix1_ticket = nullptr;  // last-CTA ticket counter (k_mix1<LAST>)
   int64_t launches = 0, steps = 0;
   // per-kernel CUDA-event timing
   bool profiling = false;
@@ -169,6 +170,7 @@ void free_bank(pgx_bank* b) {
   cudaSetDevice(b->cfg.device);
   for (cudaStream_t s : {b->s_h2d, b->stream, b->s_in, b->s_bg, b->s_bg2, b->s_d2h})
     if (s) cudaStreamSynchronize(s);
+  cudaFree(b->mix1_ticket);
   cudaFree(b->xacc);
   cudaFree(b->ytail[0]);
   cudaFree(b->ytail[1]);
@@ -363,14 +365,26 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   pgx::C2RArgs k{};
   k.yspec = b->ypast[par]; k.n_split = n_split_past;
   k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
+  bool step_done = false;  // the whole step ran inside k_mix1<LAST>: no K2 launch
   if (mix1) {
-    k.Hd = b->Hd; k.fmap = b->fmap; k.c_f = c.filter_channels; k.R = R; k.c_out = c.c_out;
+    k.Hd = b->Hd; k.fmap = b->fmap; k.c_f = c.filter_channels; k.R = R; k.c_out = c.c_out; k.head = b->head;
+    k.y = y_dev; k.ys = 0; k.yc = yl.chan; k.yi = yl.samp; k.y_off = pos;
+    k.B = B; k.fill = b->fill; k.take = take; k.tw = b->tw; k.wet = b->wet; k.dry = 0.0f; k.xdry = nullptr;
+    k.add = nullptr; k.fast = 0;
     {
-      ProfScope ps(b, crit, 4);
-      pgx::launch_mix1(r, k, b->ynow, crit);
+      pgx_layout ye = yl;
+      ye.stream = 0;
+      k.fast = (whole && vec_ok(y_dev, ye)) ? 1 : 0;
+    }
+    // few CTAs: the last one to finish folds their rows and does the inverse transforms itself
+    const bool last = (b->mix1_rows <= 32 && c.c_out <= pgx::mix1_sources_per_cta(B));
+    {
+      ProfScope ps(b, crit, last ? 5 : 4);
+      pgx::launch_mix1(r, k, b->ynow, last ? b->mix1_ticket : nullptr, crit);
     }
     b->launches += 1;
     cudaEventRecord(b->ev_k1[i % kRing], crit);
+    step_done = last;
     k.ynow = b->ynow; k.n_split_now = b->mix1_rows;
     if (b->mix1_rows > 32) {  // many CTAs: fold their rows with the wide kernel instead of inside K2
       float2* folded = b->ynow + (size_t)b->mix1_rows * c.c_out * B;
@@ -426,15 +440,15 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     else                 { k.p_off = 1; k.p_skip = R; k.p_nskip = 0; }
   }
 
-  {
+  if (!step_done) {
     ProfScope ps(b, crit, fused1 ? 5 : 2);
     if (fused1) pgx::launch_conv1(r, k, crit);
     else pgx::launch_c2r_emit(k, crit);
+    b->launches += 1;
   }
   if (fused1) cudaEventRecord(b->ev_k1[i % kRing], crit);
   cudaEventRecord(b->ev_k2[i % kRing], crit);
   b->last_k2_of_par[par] = i;
-  b->launches += 1;
   b->steps += 1;
   if (b->profiling) b->prof_steps += 1;
   b->step += 1;
@@ -737,6 +751,8 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   guard(cudaMalloc(&b->ypart[0], b->ypart_bytes), "cudaMalloc(ypart)");
   guard(cudaMalloc(&b->ypart[1], b->ypart_bytes), "cudaMalloc(ypart)");
   guard(cudaMalloc(&b->ynow, b->ynow_bytes), "cudaMalloc(ynow)");
+  guard(cudaMalloc(&b->mix1_ticket, sizeof(unsigned int)), "cudaMalloc(ticket)");
+  guard(cudaMemset(b->mix1_ticket, 0, sizeof(unsigned int)), "memset ticket");
   guard(cudaMalloc(&b->tw, (size_t)2 * B * sizeof(float2)), "cudaMalloc(tw)");
   guard(cudaMalloc(&b->fmap_own, (size_t)pgx_bank::kMapSlots * c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
   for (int i = 0; i < pgx_bank::kSlots; ++i) {
