@@ -60,6 +60,13 @@ class HrtfMixBank:
         self.c_in = 1 if self.host_mixdown else int(chans.pop())
         self.pan_index = {i: k for k, i in enumerate(i for i, m in enumerate(self.methods) if _is_pan(m))}
         self._pan_loaded = {}
+        # methods that can announce a changed direction (SpatialHRTF) let the per-pull re-selection be skipped
+        # while nothing moved; anything else (duck-typed methods, pan laws) is re-read on every pull
+        self._dirty = [True]
+        self._all_watched = all(hasattr(m, "_watchers") for m in self.methods)
+        for m in self.methods:
+            if hasattr(m, "_watchers"):
+                m._watchers.append(self._dirty)
         # [e] as measured, [E + e] ears swapped, [2E] silence: the filter of a source MixPE does not render
         both = np.concatenate([table, table[:, :, ::-1], np.zeros_like(table[:1]),
                                np.zeros((len(self.pan_index),) + table.shape[1:], np.float32)], axis=0)
@@ -85,6 +92,9 @@ class HrtfMixBank:
     def _select(self) -> np.ndarray:
         """Filter-table row of every source for the CURRENT azimuth / elevation attributes (re-resolved on every
         pull like spatial_pe.py:446-449), vectorised over the sources."""
+        if self._all_watched and not self._dirty[0] and getattr(self, "_sel_cache", None) is not None:
+            return self._sel_cache.copy()
+        self._dirty[0] = False
         n = len(self.methods)
         az = np.fromiter((float(m.azimuth) for m in self.methods), dtype=np.float64, count=n)
         if self.n_entries == len(kemar.KEMAR_HRTF_ENTRIES):
@@ -100,6 +110,7 @@ class HrtfMixBank:
         idx = (e + np.where(az < 0, self.n_entries, 0)).astype(np.int32)
         for i, k in self.pan_index.items():
             idx[i] = 2 * self.n_entries + 1 + k
+        self._sel_cache = idx.copy()
         return idx
 
     def _refresh_pans(self) -> None:

@@ -142,6 +142,7 @@ class SpatialHRTF(SpatialMethod):
                 "SpatialHRTF: azimuth and elevation must be static (float or int). "
                 "Dynamic values would switch impulse responses during rendering and cause discontinuities."
             )
+        self._watchers = []            # one-element lists owned by fused banks: [True] = "a direction changed"
         self.azimuth = float(azimuth)
         self.elevation = float(elevation)
         self._block_size, self._device = block_size, int(device)
@@ -150,6 +151,23 @@ class SpatialHRTF(SpatialMethod):
         self._loaded = None  # (table index, swapped) resident in the bank
         self._last_render_end = None
         self._warned_sr_mismatch = False
+
+    # azimuth / elevation stay plain public attributes to the user (spatial_pe.py:434-435: mutate them between
+    # pulls to move the source); as properties they can tell a fused bank that its cached selection is stale
+    azimuth = property(lambda self: self._azimuth)
+    elevation = property(lambda self: self._elevation)
+
+    @azimuth.setter
+    def azimuth(self, value):
+        self._azimuth = value
+        for w in self._watchers:
+            w[0] = True
+
+    @elevation.setter
+    def elevation(self, value):
+        self._elevation = value
+        for w in self._watchers:
+            w[0] = True
 
     @property
     def output_channels(self) -> int:
