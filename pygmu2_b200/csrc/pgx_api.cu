@@ -119,6 +119,14 @@ struct pgx_bank {
   float* y_stage[kSlots] = {};
   int16_t* xpcm_stage[kSlots] = {};  // PCM16 staging, allocated on first use
   int16_t* ypcm_stage[kSlots] = {};
+  // small pulls (a single PE graph: a few KB per pull) bounce through pinned host buffers owned by the bank, so that
+  // the copies are truly asynchronous whatever memory the caller's arrays live in (a cudaMemcpyAsync from / to
+  // pageable memory is staged by the driver and, device-to-host, blocks the calling thread)
+  static constexpr size_t kBounceMax = 256 * 1024;
+  char* hx_bounce[kSlots] = {};
+  char* hy_bounce[kSlots] = {};
+  void* y_user[kSlots] = {};       // pending copy-back: hy_bounce[slot] -> y_user[slot] once ev_done[slot] has fired
+  size_t y_user_bytes[kSlots] = {};
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[kSlots] = {}, ev_y[kSlots] = {}, ev_done[kSlots] = {};
   int64_t next_ticket = 0;
@@ -189,6 +197,8 @@ void free_bank(pgx_bank* b) {
     cudaFree(b->y_stage[i]);
     cudaFree(b->xpcm_stage[i]);
     cudaFree(b->ypcm_stage[i]);
+    if (b->hx_bounce[i]) cudaFreeHost(b->hx_bounce[i]);
+    if (b->hy_bounce[i]) cudaFreeHost(b->hy_bounce[i]);
     for (cudaEvent_t e : {b->ev_h2d[i], b->ev_y[i], b->ev_done[i]})
       if (e) cudaEventDestroy(e);
   }
@@ -1008,17 +1018,38 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   const int slot = (int)(tk % pgx_bank::kSlots);
   // the slot's previous pull is over once its D2H has completed (its K1s read x_stage before that)
   if (tk >= pgx_bank::kSlots) PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
+  if (b->y_user[slot]) {  // that pull was never waited for: its result still has to reach the caller's array
+    memcpy(b->y_user[slot], b->hy_bounce[slot], b->y_user_bytes[slot]);
+    b->y_user[slot] = nullptr;
+  }
+  const size_t xb_host = x_pcm ? xb / 2 : xb, yb_host = y_pcm ? yb / 2 : yb;
+  const bool bounce_x = !x_device && xb_host <= pgx_bank::kBounceMax;
+  const bool bounce_y = yb_host <= pgx_bank::kBounceMax;
+  if (bounce_x && !b->hx_bounce[slot]) {
+    size_t cap = b->xs_bytes < pgx_bank::kBounceMax ? b->xs_bytes : pgx_bank::kBounceMax;
+    PGX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b->hx_bounce[slot]), cap, cudaHostAllocDefault));
+  }
+  if (bounce_y && !b->hy_bounce[slot]) {
+    size_t cap = b->ys_bytes < pgx_bank::kBounceMax ? b->ys_bytes : pgx_bank::kBounceMax;
+    PGX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b->hy_bounce[slot]), cap, cudaHostAllocDefault));
+  }
+  const void* x_src = x;
+  if (bounce_x) {
+    memcpy(b->hx_bounce[slot], x, xb_host);
+    x_src = b->hx_bounce[slot];
+  }
+  void* y_dst = bounce_y ? static_cast<void*>(b->hy_bounce[slot]) : static_cast<void*>(y);
   if (x_pcm && !b->xpcm_stage[slot]) PGX_CUDA(cudaMalloc(&b->xpcm_stage[slot], b->xs_bytes / 2));
   if (y_pcm && !b->ypcm_stage[slot]) PGX_CUDA(cudaMalloc(&b->ypcm_stage[slot], b->ys_bytes / 2));
   if (x_device) {  // produced by work already queued on the bank's stream: run_pull orders the ingest after it
     rc = run_pull(b, x, xl, b->y_stage[slot], yd, n, mix, false, b->stream);
   } else {
     if (x_pcm) {   // half the H2D bytes; int16 / 32768 on the device, on the copy-in stream
-      PGX_CUDA(cudaMemcpyAsync(b->xpcm_stage[slot], x, xb / 2, cudaMemcpyHostToDevice, b->s_h2d));
+      PGX_CUDA(cudaMemcpyAsync(b->xpcm_stage[slot], x_src, xb / 2, cudaMemcpyHostToDevice, b->s_h2d));
       pgx::launch_pcm16_to_f32(b->xpcm_stage[slot], b->x_stage[slot], (int64_t)(xb / sizeof(float)), b->s_h2d);
       b->launches += 1;
     } else
-    PGX_CUDA(cudaMemcpyAsync(b->x_stage[slot], x, xb, cudaMemcpyHostToDevice, b->s_h2d));
+    PGX_CUDA(cudaMemcpyAsync(b->x_stage[slot], x_src, xb, cudaMemcpyHostToDevice, b->s_h2d));
     PGX_CUDA(cudaEventRecord(b->ev_h2d[slot], b->s_h2d));
     PGX_CUDA(cudaStreamWaitEvent(b->s_in, b->ev_h2d[slot], 0));
     PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
@@ -1031,10 +1062,14 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   }
   PGX_CUDA(cudaEventRecord(b->ev_y[slot], b->stream));
   PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_y[slot], 0));
-  if (y_pcm) PGX_CUDA(cudaMemcpyAsync(y, b->ypcm_stage[slot], yb / 2, cudaMemcpyDeviceToHost, b->s_d2h));
+  if (y_pcm) PGX_CUDA(cudaMemcpyAsync(y_dst, b->ypcm_stage[slot], yb / 2, cudaMemcpyDeviceToHost, b->s_d2h));
   else
-  PGX_CUDA(cudaMemcpyAsync(y, b->y_stage[slot], yb, cudaMemcpyDeviceToHost, b->s_d2h));
+  PGX_CUDA(cudaMemcpyAsync(y_dst, b->y_stage[slot], yb, cudaMemcpyDeviceToHost, b->s_d2h));
   PGX_CUDA(cudaEventRecord(b->ev_done[slot], b->s_d2h));
+  if (bounce_y) {
+    b->y_user[slot] = y;
+    b->y_user_bytes[slot] = yb_host;
+  }
   b->next_ticket = tk + 1;
   if (ticket) *ticket = tk;
   return PGX_OK;
@@ -1045,7 +1080,12 @@ static int submit_wait(pgx_bank* b, int64_t ticket) {
   if (ticket < 0 || ticket >= b->next_ticket) return fail(PGX_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
   if (ticket + pgx_bank::kSlots < b->next_ticket) return PGX_OK;  // its slot was recycled: long complete
   PGX_CUDA(cudaSetDevice(b->cfg.device));
-  PGX_CUDA(cudaEventSynchronize(b->ev_done[ticket % pgx_bank::kSlots]));
+  const int slot = (int)(ticket % pgx_bank::kSlots);
+  PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
+  if (b->y_user[slot]) {  // small result: out of the bank's pinned bounce buffer into the caller's array
+    memcpy(b->y_user[slot], b->hy_bounce[slot], b->y_user_bytes[slot]);
+    b->y_user[slot] = nullptr;
+  }
   return PGX_OK;
 }
 
