@@ -93,6 +93,10 @@ class ConvolveBank:
 
     # -- lifetime ------------------------------------------------------------
     def close(self) -> None:
+        res = getattr(self, "_resident", None)
+        if res is not None:
+            res.close()
+            self._resident = None
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().pgx_bank_destroy(self._h)
             self._h = None

@@ -129,6 +129,17 @@ class HrtfMixBank:
         self.bank.reset()
         self._pos = None
 
+    def close(self) -> None:
+        """Release the device state (bank, resident sources) and stop watching the methods."""
+        for m in self.methods:
+            w = getattr(m, "_watchers", None)
+            if w is not None and self._dirty in w:
+                w.remove(self._dirty)
+        if self._resident is not None:
+            self._resident.close()
+            self._resident = None
+        self.bank.close()
+
     def render(self, start: int, duration: int) -> np.ndarray:
         """One lockstep pull of every source -> (2, duration) float32 stereo mix."""
         sr = self.sources[0].sample_rate
