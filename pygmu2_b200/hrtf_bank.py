@@ -133,8 +133,8 @@ class HrtfMixBank:
         """Release the device state (bank, resident sources) and stop watching the methods."""
         for m in self.methods:
             w = getattr(m, "_watchers", None)
-            if w is not None and self._dirty in w:
-                w.remove(self._dirty)
+            if w is not None:
+                w[:] = [cell for cell in w if cell is not self._dirty]   # by identity: other banks keep theirs
         if self._resident is not None:
             self._resident.close()
             self._resident = None
