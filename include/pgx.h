@@ -28,7 +28,9 @@
 extern "C" {
 #endif
 
-#define PGX_ABI_VERSION 1
+/* 2: pgx_bank_config grew tail_block (round 1, unversioned at the time); multi-GPU mix reduce (pgx_comm_*,
+ *    pgx_mix_reduce), filter trajectories, graph replay.  The binding refuses a library of another version. */
+#define PGX_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PGX_API __attribute__((visibility("default")))
@@ -92,6 +94,10 @@ typedef struct pgx_bank_info {
 
 /* ---- library ------------------------------------------------------------ */
 PGX_API int pgx_abi_version(void);
+/* sizeof() of the structs of this header as the library was compiled, so that a binding can check its own
+ * mirror at load time: which = 0 pgx_layout, 1 pgx_bank_config, 2 pgx_bank_info, 3 pgx_profile, 4 pgx_osc_config;
+ * -1 for an unknown index. */
+PGX_API int pgx_struct_size(int32_t which);
 PGX_API const char* pgx_last_error(void);
 PGX_API int pgx_device_count(int* count);
 /* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */

@@ -17,7 +17,7 @@ PGX_OK, PGX_ERR_INVALID, PGX_ERR_CUDA, PGX_ERR_NO_DEVICE, PGX_ERR_NOMEM = 0, -1,
 PGX_FLAG_MIXDOWN_INPUT = 1
 PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16 = 1, 2, 4, 8, 16
 PGX_OSC_SINE, PGX_OSC_BLIT = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Layout(C.Structure):
@@ -56,6 +56,7 @@ _i32p = C.POINTER(C.c_int32)
 # name -> (restype, argtypes): every symbol include/pgx.h declares
 PROTOTYPES = {
     "pgx_abi_version": (C.c_int, []),
+    "pgx_struct_size": (C.c_int, [C.c_int32]),
     "pgx_last_error": (C.c_char_p, []),
     "pgx_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pgx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
@@ -113,6 +114,10 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if h.pgx_abi_version() != ABI_VERSION:
             raise RuntimeError(f"libpgx ABI {h.pgx_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+        for which, st in enumerate((Layout, BankConfig, BankInfo, Profile, OscConfig)):
+            if h.pgx_struct_size(which) != C.sizeof(st):
+                raise RuntimeError(f"libpgx struct {st.__name__}: library {h.pgx_struct_size(which)} bytes, "
+                                   f"binding {C.sizeof(st)} bytes")
         _lib = h
     return _lib
 

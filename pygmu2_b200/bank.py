@@ -24,12 +24,19 @@ def next_pow2(n: int) -> int:
 def choose_block(filter_len: int, pull_hint: int | None) -> int:
     """Partition size B for a filter of ``filter_len`` taps pulled ``pull_hint`` samples at a time.
 
-    Delay-line traffic per second is ~ L*sr/B rows and every pull costs at least one block step
-    (three launches), so B = next_pow2(pull) is the sweet spot whatever L is: a longer filter just
-    has more partitions, a shorter one a single zero-padded partition.
+    Delay-line traffic per second is ~ L*sr/B rows and every pull costs at least one block step, so
+    B = next_pow2(pull) is the sweet spot for the steady state.  The hint is only the FIRST pull of a PE, though,
+    and that may be a probe (``render(0, 1)`` -- ConvolvePE issues one itself on sources without a channel
+    count, convolve_pe.py:203-205): B is sticky, so it gets a floor of min(256, next_pow2(L)) and is raised until
+    the filter has at most 2048 partitions.  Pulls shorter than B stay exact and zero-latency (partial block
+    steps); pass ``block_size=`` to pin a smaller B (the named 64-sample configuration does).
     """
     want = next_pow2(int(pull_hint)) if pull_hint else 512
-    return int(min(max(16, want), 4096))
+    B = int(min(max(16, want), 4096))
+    B = max(B, min(256, next_pow2(int(filter_len))))
+    while B < 4096 and -(-int(filter_len) // B) > 2048:
+        B *= 2
+    return B
 
 
 class ConvolveBank:
@@ -297,7 +304,7 @@ class ConvolveBank:
         return out
 
     # -- batched renderer support ------------------------------------------------
-    def attach_sources(self, sources, delays=None, gains=None) -> None:
+    def attach_sources(self, sources, delays=None, gains=None, extents=None) -> None:
         """N host PEs feeding the N streams; enables ``render`` for BankRenderer.  ``delays`` (integer samples:
         the source is pulled that much earlier, delay_pe.py:153-160) and ``gains`` (float32, applied to the
         source samples, gain_pe.py:123-125) fold per-stream DelayPE / GainPE wrappers into the pull."""
@@ -307,6 +314,15 @@ class ConvolveBank:
         self.sources = sources
         self._src_delays = [0] * len(sources) if delays is None else [int(d) for d in delays]
         self._src_gains = [None] * len(sources) if gains is None else [None if g is None else np.float32(g) for g in gains]
+        # ``extents`` (one Extent per stream, in output time): MixPE's gating (mix_pe.py:81-85) -- a stream whose
+        # extent does not meet the request is not rendered (zero input) and starts a new run when it comes back
+        self._gate = None
+        if extents is not None:
+            lo = np.array([-np.inf if e.start is None else e.start for e in extents], dtype=np.float64)
+            hi = np.array([np.inf if e.end is None else e.end for e in extents], dtype=np.float64)
+            empty = np.array([e.is_empty() for e in extents], dtype=bool)
+            self._gate = (lo, hi, empty)
+            self._was_active = np.ones(len(sources), dtype=bool)
         self._resident = None
         from .resident import ResidentSources  # plain in-memory sources are uploaded once and stay in HBM
         if ResidentSources.eligible(sources, self._src_delays, self.c_in, False):
@@ -348,8 +364,19 @@ class ConvolveBank:
                 pos += d
             self._pos = start + duration
             return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=-1)
+        active = None
+        if getattr(self, "_gate", None) is not None:
+            lo, hi, empty = self._gate
+            active = ~empty & (lo < start + duration) & (hi > start)        # Extent.intersects
+            back = np.flatnonzero(active & ~self._was_active)
+            if back.size and self._pos == start:                           # (a full reset just happened otherwise)
+                self.reset(back)
+            self._was_active = active
         x = np.empty((self.n_streams, self.c_in, duration), dtype=np.float32)
         for s, pe in enumerate(self.sources):
+            if active is not None and not active[s]:
+                x[s] = 0.0
+                continue
             data = pe.render(start - self._src_delays[s], duration).data
             if self._src_gains[s] is not None:
                 data = data * self._src_gains[s]

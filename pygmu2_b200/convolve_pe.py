@@ -15,7 +15,7 @@ from __future__ import annotations
 import numpy as np
 
 from .bank import ConvolveBank, choose_block, next_pow2
-from .core import Extent, ProcessingElement, Snippet
+from .core import Extent, ProcessingElement, Snippet, log
 
 
 class ConvolvePE(ProcessingElement):
@@ -144,6 +144,10 @@ class ConvolvePE(ProcessingElement):
 
     def _render(self, start: int, duration: int, pcm16_out: bool = False):
         self._ensure_filter_prepared(duration)
+        if duration >= 32 * self._bank.block and not getattr(self, "_warned_block", False):
+            self._warned_block = True   # B is fixed at the first pull; correct, but every pull is many block steps
+            log.warning("ConvolvePE: pull of %d samples on a bank partitioned at B=%d (chosen at the first pull); "
+                        "pass block_size= to pin a larger partition", duration, self._bank.block)
         if self._last_render_end is None or start != self._last_render_end:
             self._bank.reset()  # non-contiguous pull: prior samples are zeros (convolve_pe.py:255-256)
         dev = None if pcm16_out else getattr(self._src, "device_block", None)

@@ -139,6 +139,7 @@ struct pgx_bank {
   int64_t past_block = -1;         // block whose past sum was last issued ...
   int past_mode = -1;              // ... for this mode (0 conv, 1 mix)
   int64_t last_k2_of_par[2] = {-1, -1};  // last step whose K2 read ypast[par]
+  bool prev_on_crit = false;       // the previous step ran ingest + output as one kernel on the critical stream
   pgx::MacPlan plan_conv{}, plan_mix{}, plan_now{};
   int sm_count = 148;
   float wet = 1.0f, dry = 0.0f;    // fused output stage: y = dry * x + wet * conv
@@ -343,9 +344,13 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   const bool mix1 = (mix && R == 1 && b->use_mix1 && b->mix1_rows > 0);
   // ---- ingest stream: K1 (single-partition conv pulls run K1 and K2 as one kernel on the critical stream)
   if (!fused1 && !mix1) {
-    if (b->fill > 0 || R == 1) {  // same ring row (and open half) as the previous step
+    if (b->fill > 0 || R == 1 || b->prev_on_crit) {
+      // same ring row (and open half) as the previous step -- or the previous step was a fused kernel on the
+      // critical stream (k_conv1 / k_mix1), which WROTE hist and its ring row there: this K1 and the past pass
+      // ordered after it must not start before that kernel is done (conv -> mix switch with pulls queued)
       if (i >= 1) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 1) % kRing], 0);
-    } else {
+    }
+    if (!(b->fill > 0 || R == 1)) {
       if (i >= 2) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 2) % kRing], 0);
       if (t >= 2) cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);  // every block had its past pass issued
     }
@@ -459,6 +464,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   if (fused1) cudaEventRecord(b->ev_k1[i % kRing], crit);
   cudaEventRecord(b->ev_k2[i % kRing], crit);
   b->last_k2_of_par[par] = i;
+  b->prev_on_crit = fused1 || mix1;
   b->steps += 1;
   if (b->profiling) b->prof_steps += 1;
   b->step += 1;
@@ -504,6 +510,8 @@ int run_pull1(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_de
 // gathered into the big block; a completed big block is pushed through the tail level at once.
 int run_pull(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int n,
              bool mix, bool input_resident, cudaStream_t crit) {
+  if (mix && b->dry != 0.0f)
+    return fail(PGX_ERR_INVALID, "a fused-mix pull has no dry path (dry = %g): set dry = 0 or pull per stream", (double)b->dry);
   if (!b->tail) return run_pull1(b, x_dev, xl, y_dev, yl, n, mix, input_resident, crit);
   if (b->tail_mode < 0) b->tail_mode = mix ? 1 : 0;
   if (b->tail_mode != (mix ? 1 : 0))
@@ -587,6 +595,17 @@ extern "C" {
 
 int pgx_abi_version(void) { return PGX_ABI_VERSION; }
 
+int pgx_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return (int)sizeof(pgx_layout);
+    case 1: return (int)sizeof(pgx_bank_config);
+    case 2: return (int)sizeof(pgx_bank_info);
+    case 3: return (int)sizeof(pgx_profile);
+    case 4: return (int)sizeof(pgx_osc_config);
+    default: return -1;
+  }
+}
+
 const char* pgx_last_error(void) { return g_err.c_str(); }
 
 int pgx_device_count(int* count) {
@@ -630,6 +649,9 @@ int pgx_device_upload(int32_t device, void* dst_dev, const void* src_host, int64
   if (!dst_dev || (!src_host && bytes > 0) || bytes < 0) return fail(PGX_ERR_INVALID, "pgx_device_upload: bad arguments");
   PGX_CUDA(cudaSetDevice(device));
   if (src_host) PGX_CUDA(cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+  // a pageable-memory copy may return before its DMA has landed, and the banks read from non-blocking streams
+  // that are not ordered with the legacy stream: make the data visible to every stream before returning
+  PGX_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
   return PGX_OK;
 }
 
@@ -637,6 +659,7 @@ int pgx_device_zero(int32_t device, void* dst_dev, int64_t bytes) {
   if (!dst_dev || bytes < 0) return fail(PGX_ERR_INVALID, "pgx_device_zero: bad arguments");
   PGX_CUDA(cudaSetDevice(device));
   PGX_CUDA(cudaMemset(dst_dev, 0, (size_t)bytes));
+  PGX_CUDA(cudaStreamSynchronize(cudaStreamLegacy));  // cudaMemset is asynchronous with respect to the host
   return PGX_OK;
 }
 
@@ -919,6 +942,7 @@ int pgx_bank_reset(pgx_bank* b, const int32_t* stream_ids, int32_t k) {
     b->head = b->fill = b->half = 0;
     b->step = b->block = 0;
     b->last_k2_of_par[0] = b->last_k2_of_par[1] = -1;
+    b->prev_on_crit = false;
     PGX_CUDA(cudaStreamSynchronize(b->stream));
     return PGX_OK;
   }
@@ -1055,7 +1079,12 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
     PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
     rc = run_pull(b, b->x_stage[slot], xl, b->y_stage[slot], yd, n, mix, true, b->stream);
   }
-  if (rc != PGX_OK) return rc;
+  if (rc != PGX_OK) {  // part of the pull may be enqueued and reading x_stage[slot]: drain before the slot is reused
+    const std::string msg = g_err;
+    quiesce(b);
+    g_err = msg;
+    return rc;
+  }
   if (y_pcm) {     // clip(lrint(y * 32768)) on the device, half the D2H bytes
     pgx::launch_f32_to_pcm16(b->y_stage[slot], b->ypcm_stage[slot], (int64_t)(yb / sizeof(float)), b->stream);
     b->launches += 1;

@@ -86,9 +86,13 @@ class MixPE(ProcessingElement):
         return False
 
     def _adopt_convolves(self, duration: int, ins, delays, gains):
-        taps, src_ch = [], set()
-        for p in ins:
+        taps, src_ch, exts = [], set(), []
+        for p, d in zip(ins, delays):
+            # settings of the PE that a shared bank would silently drop: keep such inputs on their own banks
+            if p._device != self._device or p._block_size is not None or p._tail_block or p._out_gains is not None:
+                raise _NotFusable
             ext = p.extent()  # validates the filter contract (raises ValueError like the reference)
+            exts.append(Extent(None if ext.start is None else ext.start + d, None if ext.end is None else ext.end + d))
             fe = p.fir.extent()
             if fe.start != 0 or fe.end is None or fe.end < 1:
                 raise _NotFusable
@@ -102,7 +106,7 @@ class MixPE(ProcessingElement):
             raise _NotFusable
         bank = ConvolveBank(np.stack(taps), len(ins), int(src_ch.pop()),
                             block=choose_block(taps[0].shape[0], duration), device=self._device)
-        bank.attach_sources([p.src for p in ins], delays=delays, gains=gains)
+        bank.attach_sources([p.src for p in ins], delays=delays, gains=gains, extents=exts)
         bank.mix_output = True
         return bank
 

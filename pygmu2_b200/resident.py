@@ -7,6 +7,12 @@ copy -- is replaced by ONE upload: the arrays are stacked into a device buffer `
 source's integer delay baked into its position, its constant gain applied and, where the bank wants a mono
 input, its channels averaged (all float32, exactly what the per-pull path computes).  A pull is then just a
 pointer into that buffer (``PGX_PULL_X_DEVICE``): no host samples at all.
+
+The buffer is a SNAPSHOT of ``ArrayPE.data`` taken when the bank adopts the sources: the reference's ArrayPE
+re-reads the caller's array on every render (array_pe.py:46,94-111), so a caller that mutates the array in place
+after the first pull must rebuild the graph here (rendered data is meant to be immutable,
+processing_element.py:109-111).  ``pgx_device_upload`` / ``pgx_device_zero`` return only when the bytes are visible to every
+CUDA stream.
 """
 from __future__ import annotations
 

@@ -37,6 +37,30 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.OscConfig) == 40
 
 
+def test_integration_md_stub_matches_the_library():
+    """The reference-side ctypes stub printed in INTEGRATION.md is executed as written against the built library:
+    its structs must have the sizes the library was compiled with (round 1 shipped a stub without tail_block)."""
+    import ctypes as C
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", md, flags=re.S)
+    stub = next(b for b in blocks if "class BankConfig" in b)
+    os.environ["PYGMU2_PGX"] = _lib.LIB_PATH
+    ns = {}
+    try:
+        exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    finally:
+        del os.environ["PYGMU2_PGX"]
+    h = _lib.lib()
+    assert C.sizeof(ns["Layout"]) == h.pgx_struct_size(0) == C.sizeof(_lib.Layout)
+    assert C.sizeof(ns["BankConfig"]) == h.pgx_struct_size(1) == C.sizeof(_lib.BankConfig)
+    assert [f[0] for f in ns["BankConfig"]._fields_] == [f[0] for f in _lib.BankConfig._fields_]
+    hdr = open(os.path.join(ROOT, "include", "pgx.h")).read()
+    body = re.search(r"typedef struct pgx_bank_config \{(.*?)\} pgx_bank_config;", hdr, flags=re.S).group(1)
+    fields = re.findall(r"^\s*u?int32_t\s+(\w+);", body, flags=re.M)
+    assert fields == [f[0] for f in ns["BankConfig"]._fields_]
+    assert h.pgx_struct_size(99) == -1
+
+
 def test_no_silent_cpu_path():
     """Without a CUDA device the device-backed PEs raise; nothing falls back to numpy."""
     if _lib.device_count() > 0:
@@ -260,8 +284,12 @@ def test_kernel_model_matches_oracle():
 
 def test_choose_block_and_workload_bytes():
     from pygmu2_b200 import workloads as wl
-    assert pg.choose_block(132300, 512) == 512 and pg.choose_block(441000, 64) == 64
-    assert pg.choose_block(3, 6) == 16 and pg.choose_block(4096, 441000) == 4096
+    assert pg.choose_block(132300, 512) == 512 and pg.choose_block(4096, 441000) == 4096
+    assert pg.choose_block(3, 6) == 16 and pg.choose_block(100, 64) == 128
+    # B is sticky from the first pull: a probing render(0, 1) must not lock a long filter into thousands of tiny
+    # partitions (floor of 256, at most 2048 partitions); block_size= pins anything smaller (the named C5 does)
+    assert pg.choose_block(132300, 1) == 256 and pg.choose_block(441000, 64) == 256
+    assert pg.choose_block(3_000_000, 16) == 2048
     # bytes per output sample.channel
     assert round(wl.bytes_per_block_step(256, 2, 2, 132300, 512, False) / (256 * 2 * 512)) == 2092
     assert round(wl.bytes_per_block_step(256, 2, 2, 132300, 512, True) / (256 * 2 * 512)) == 4168
