@@ -190,14 +190,18 @@ PGX_API int pgx_bank_set_output_gains(pgx_bank* bank, float wet, float dry);
                                       device - libsndfile's float -> PCM_16 rule with clipping on, as python-soundfile
                                       writes for WavWriterPE (wav_writer_pe.py:153) - half the D2H bytes */
 
+#define PGX_PULL_REDUCE 32u        /* with PGX_PULL_MIX on a bank that has a communicator attached (pgx_bank_attach_comm):
+                                      this rank's mix is a partial one; it is summed over the ranks onto the root behind
+                                      the pull's output stage (pgx_mix_reduce) and only the root delivers y */
+
 /*
  * Pipelined host-buffer pulls (the batched renderer loop, renderer.py:297-327, with more than one pull in
  * flight): submit stages x (H2D on a copy stream), enqueues the pull and the D2H of y, and returns a ticket
  * without waiting; pgx_bank_wait(ticket) returns when that pull's y is complete in host memory.  Pulls
  * execute in submission order.  x and y must stay valid (and should be pinned, pgx_host_alloc) until the
  * wait returns; at most 3 pulls are in flight - a further submit first waits for the oldest.
- * flags: PGX_PULL_MIX, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16.  pgx_bank_process[_mix] =
- * submit + wait.
+ * flags: PGX_PULL_MIX, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16, PGX_PULL_REDUCE (on the ranks
+ * other than the root y is not written: there is no D2H copy).  pgx_bank_process[_mix] = submit + wait.
  */
 PGX_API int pgx_bank_submit(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y, pgx_layout y_layout,
                     int32_t n, int32_t flags, int64_t* ticket);
@@ -210,6 +214,30 @@ PGX_API void* pgx_bank_stream(pgx_bank* bank);
 PGX_API int pgx_bank_process_device(pgx_bank* bank, const float* x_dev, pgx_layout x_layout, float* y_dev,
                             pgx_layout y_layout, int32_t n, int32_t flags, void* cuda_stream);
 PGX_API int pgx_bank_synchronize(pgx_bank* bank);
+
+/* ---- multi-GPU: the one exchange step of the path, the MixPE sum (mix_pe.py:92-94) over stream shards ------------
+ * Streams are sharded over the GPUs of one box (one process per GPU, or several devices in one process); every
+ * rank's fused mix pull yields a partial (C_out, n) mix and the partials are summed onto `root` in RANK ORDER
+ * (float32, deterministic) through peer memory over NVLink: a non-root rank stores its partial into the root's
+ * mailbox and raises a flag, the root's gather kernel waits for the flags, adds and acknowledges -- one small
+ * kernel per rank and pull on the bank's stream, no host synchronisation, no library collective.
+ *   1. every rank: pgx_comm_create -> a PGX_COMM_HANDLE_BYTES blob describing its mailbox
+ *   2. the host's plumbing all-gathers the blobs (torch.distributed / MPI / a pipe: any byte transport)
+ *   3. every rank: pgx_comm_connect(all blobs in rank order) maps the peers (CUDA IPC across processes)
+ * Every rank must issue the same sequence of reduces.  A rank that waits 20 s for a peer gives up and the next
+ * pgx_comm_check / pgx_bank_wait reports it. */
+#define PGX_COMM_HANDLE_BYTES 128
+typedef struct pgx_comm pgx_comm;
+PGX_API int pgx_comm_create(pgx_comm** out, int32_t device, int32_t rank, int32_t world, int32_t root,
+                            int32_t max_floats, void* handle_out);
+PGX_API int pgx_comm_connect(pgx_comm* comm, const void* handles);
+PGX_API int pgx_comm_check(pgx_comm* comm);
+PGX_API int pgx_comm_destroy(pgx_comm* comm);
+/* Sum the ranks' partials part_dev[0..n) onto the root's y_dev (device pointers; y_dev may alias part_dev and is
+ * ignored on the other ranks), enqueued on cuda_stream.  n <= max_floats. */
+PGX_API int pgx_mix_reduce(pgx_comm* comm, const float* part_dev, float* y_dev, int32_t n, void* cuda_stream);
+/* Mix pulls of this bank that carry PGX_PULL_REDUCE are reduced through `comm` (NULL detaches). */
+PGX_API int pgx_bank_attach_comm(pgx_bank* bank, pgx_comm* comm);
 
 /* ---- measurement: per-kernel device time, CUDA events on the launching stream ---- */
 typedef struct pgx_profile {

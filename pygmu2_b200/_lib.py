@@ -16,6 +16,8 @@ LIB_PATH = os.environ.get("PGX_LIB") or os.path.join(_HERE, "csrc", "libpgx.so")
 PGX_OK, PGX_ERR_INVALID, PGX_ERR_CUDA, PGX_ERR_NO_DEVICE, PGX_ERR_NOMEM = 0, -1, -2, -3, -4
 PGX_FLAG_MIXDOWN_INPUT = 1
 PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16 = 1, 2, 4, 8, 16
+PGX_PULL_REDUCE = 32
+PGX_COMM_HANDLE_BYTES = 128
 PGX_OSC_SINE, PGX_OSC_BLIT = 0, 1
 ABI_VERSION = 2
 
@@ -92,6 +94,13 @@ PROTOTYPES = {
     "pgx_bank_synchronize": (C.c_int, [C.c_void_p]),
     "pgx_bank_profile_begin": (C.c_int, [C.c_void_p]),
     "pgx_bank_profile_end": (C.c_int, [C.c_void_p, C.POINTER(Profile)]),
+    "pgx_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p]),
+    "pgx_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pgx_comm_check": (C.c_int, [C.c_void_p]),
+    "pgx_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pgx_mix_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pgx_bank_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgx_mix_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pgx_mix_sum_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
 }

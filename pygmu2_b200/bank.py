@@ -220,7 +220,13 @@ class ConvolveBank:
         return y
 
     # -- pipelined host-buffer pulls (several in flight; copies overlap the kernels) ------------
-    def submit(self, x: np.ndarray, out: np.ndarray, *, mix: bool = False) -> int:
+    def attach_comm(self, comm) -> None:
+        """Mix pulls submitted with ``reduce=True`` are summed over the ranks of ``comm`` (a ``dist.MixComm``)
+        onto its root; None detaches."""
+        self._comm = comm  # keep it alive as long as the bank uses it
+        check(lib().pgx_bank_attach_comm(self._h, comm._h if comm is not None else None))
+
+    def submit(self, x: np.ndarray, out: np.ndarray, *, mix: bool = False, reduce: bool = False) -> int:
         """Enqueue one pull: x (N, C_in, n) -> out (N, C_out, n), or (C_out, n) when ``mix``.  Returns a
         ticket for ``wait``.  x and out must be C-contiguous float32 (pinned for real overlap: ``PinnedArray``)
         and must not be touched until the wait returns; at most 3 pulls are in flight."""
@@ -236,7 +242,8 @@ class ConvolveBank:
         tk = C.c_int64(-1)
         check(lib().pgx_bank_submit(self._h, _lib.f32_ptr(x), Layout(self.c_in * n, n, 1), _lib.f32_ptr(out),
                                     Layout(0 if mix else self.c_out * n, n, 1), n,
-                                    (1 if mix else 0) | (_lib.PGX_PULL_X_PCM16 if x.dtype == np.int16 else 0)
+                                    (1 if mix else 0) | (_lib.PGX_PULL_REDUCE if reduce else 0)
+                                    | (_lib.PGX_PULL_X_PCM16 if x.dtype == np.int16 else 0)
                                     | (_lib.PGX_PULL_Y_PCM16 if out.dtype == np.int16 else 0), C.byref(tk)))
         self._inflight = getattr(self, "_inflight", {})
         self._inflight[tk.value] = (x, out)  # keep the buffers alive until waited
@@ -281,12 +288,12 @@ class ConvolveBank:
     # -- device-resident pulls (pointers from torch / cuda-python; not synchronised) ------------
     def process_device(self, x_ptr: int, y_ptr: int, n: int, *, mix: bool = False, cuda_stream: int = 0,
                        input_resident: bool = False, x_layout: Layout | None = None,
-                       y_layout: Layout | None = None) -> None:
+                       y_layout: Layout | None = None, reduce: bool = False) -> None:
         """Enqueue one pull on device buffers (planar by default). ``input_resident``: x is already complete
         in memory, so its ingest may overlap the output stage of pulls queued earlier."""
         xl = x_layout or Layout(self.c_in * n, n, 1)
         yl = y_layout or Layout(0 if mix else self.c_out * n, n, 1)
-        flags = (1 if mix else 0) | (2 if input_resident else 0)
+        flags = (1 if mix else 0) | (2 if input_resident else 0) | (_lib.PGX_PULL_REDUCE if reduce else 0)
         check(lib().pgx_bank_process_device(self._h, C.c_void_p(x_ptr), xl, C.c_void_p(y_ptr), yl, int(n),
                                             flags, C.c_void_p(cuda_stream)))
 
@@ -304,7 +311,7 @@ class ConvolveBank:
         return out
 
     # -- batched renderer support ------------------------------------------------
-    def attach_sources(self, sources, delays=None, gains=None, extents=None) -> None:
+    def attach_sources(self, sources, delays=None, gains=None, extents=None, silent_filter=None) -> None:
         """N host PEs feeding the N streams; enables ``render`` for BankRenderer.  ``delays`` (integer samples:
         the source is pulled that much earlier, delay_pe.py:153-160) and ``gains`` (float32, applied to the
         source samples, gain_pe.py:123-125) fold per-stream DelayPE / GainPE wrappers into the pull."""
@@ -315,7 +322,8 @@ class ConvolveBank:
         self._src_delays = [0] * len(sources) if delays is None else [int(d) for d in delays]
         self._src_gains = [None] * len(sources) if gains is None else [None if g is None else np.float32(g) for g in gains]
         # ``extents`` (one Extent per stream, in output time): MixPE's gating (mix_pe.py:81-85) -- a stream whose
-        # extent does not meet the request is not rendered (zero input) and starts a new run when it comes back
+        # extent does not meet the request is not rendered: zero input AND the all-zero filter ``silent_filter``
+        # (its carried history must not ring on), and it starts a new run when it comes back
         self._gate = None
         if extents is not None:
             lo = np.array([-np.inf if e.start is None else e.start for e in extents], dtype=np.float64)
@@ -323,6 +331,9 @@ class ConvolveBank:
             empty = np.array([e.is_empty() for e in extents], dtype=bool)
             self._gate = (lo, hi, empty)
             self._was_active = np.ones(len(sources), dtype=bool)
+            self._silent = None if silent_filter is None else int(silent_filter)
+            self._own_map = np.arange(len(sources), dtype=np.int32)
+            self._cur_map = self._own_map.copy()
         self._resident = None
         from .resident import ResidentSources  # plain in-memory sources are uploaded once and stay in HBM
         if ResidentSources.eligible(sources, self._src_delays, self.c_in, False):
@@ -372,6 +383,11 @@ class ConvolveBank:
             if back.size and self._pos == start:                           # (a full reset just happened otherwise)
                 self.reset(back)
             self._was_active = active
+            if self._silent is not None:
+                sel = np.where(active, self._own_map, np.int32(self._silent)).astype(np.int32)
+                if not np.array_equal(sel, self._cur_map):
+                    self.set_filter_map(sel)
+                    self._cur_map = sel
         x = np.empty((self.n_streams, self.c_in, duration), dtype=np.float32)
         for s, pe in enumerate(self.sources):
             if active is not None and not active[s]:

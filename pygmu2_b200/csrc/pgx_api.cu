@@ -161,6 +161,7 @@ struct pgx_bank {
   int mix1_rows = 0;               // partial rows per channel written by k_mix1 (= CTAs)
   unsigned int* mix1_ticket = nullptr;  // last-CTA ticket counter (k_mix1<LAST>)
   int64_t launches = 0, steps = 0;
+  pgx_comm* comm = nullptr;        // cross-GPU mix reduce for pulls that carry PGX_PULL_REDUCE (not owned)
   // per-kernel CUDA-event timing
   bool profiling = false;
   struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3 (past pass), 2 = K2, 3 = fold, 4 = K3 (present slot, mix), 5 = fused K1+K2 (P = 1)
@@ -1024,10 +1025,19 @@ int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
 // Host-buffer pull, asynchronous: stage x into the next slot (H2D on the copy-in stream), enqueue the block
 // steps, copy y back on the copy-out stream.  Returns a ticket; y is complete after submit_wait(ticket).
 static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, bool mix,
-                       int64_t* ticket, bool x_device = false, bool x_pcm = false, bool y_pcm = false) {
+                       int64_t* ticket, bool x_device = false, bool x_pcm = false, bool y_pcm = false,
+                       bool reduce = false) {
   int rc = check_pull_args(b, x, y, n);
   if (rc != PGX_OK) return rc;
   const pgx_bank_config& c = b->cfg;
+  if (reduce) {
+    if (!mix) return fail(PGX_ERR_INVALID, "PGX_PULL_REDUCE needs PGX_PULL_MIX: only a mix is summed over the ranks");
+    if (!b->comm) return fail(PGX_ERR_INVALID, "PGX_PULL_REDUCE: no communicator attached (pgx_bank_attach_comm)");
+    if (c.c_out * n > pgx_comm_max_floats(b->comm))
+      return fail(PGX_ERR_INVALID, "PGX_PULL_REDUCE: %d floats exceed the communicator's %d", c.c_out * n,
+                  pgx_comm_max_floats(b->comm));
+  }
+  const bool deliver = !reduce || pgx_comm_is_root(b->comm);  // only the root of a reduce copies y back
   // host x is staged with one copy, so it has to be one dense block; device-resident x is read in place
   if (!x_device && !layout_dense(xl, c.n_streams, c.c_in, n))
     return fail(PGX_ERR_INVALID, "x layout does not tile a dense block");
@@ -1048,7 +1058,7 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   }
   const size_t xb_host = x_pcm ? xb / 2 : xb, yb_host = y_pcm ? yb / 2 : yb;
   const bool bounce_x = !x_device && xb_host <= pgx_bank::kBounceMax;
-  const bool bounce_y = yb_host <= pgx_bank::kBounceMax;
+  const bool bounce_y = deliver && yb_host <= pgx_bank::kBounceMax;
   if (bounce_x && !b->hx_bounce[slot]) {
     size_t cap = b->xs_bytes < pgx_bank::kBounceMax ? b->xs_bytes : pgx_bank::kBounceMax;
     PGX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b->hx_bounce[slot]), cap, cudaHostAllocDefault));
@@ -1085,15 +1095,22 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
     g_err = msg;
     return rc;
   }
-  if (y_pcm) {     // clip(lrint(y * 32768)) on the device, half the D2H bytes
+  if (reduce) {    // sum of the ranks' partial mixes onto the root, behind this pull's output stage
+    rc = pgx_comm_enqueue(b->comm, b->y_stage[slot], b->y_stage[slot], c.c_out * n, b->stream);
+    if (rc != PGX_OK) return rc;
+    b->launches += 1;
+  }
+  if (y_pcm && deliver) {  // clip(lrint(y * 32768)) on the device, half the D2H bytes
     pgx::launch_f32_to_pcm16(b->y_stage[slot], b->ypcm_stage[slot], (int64_t)(yb / sizeof(float)), b->stream);
     b->launches += 1;
   }
   PGX_CUDA(cudaEventRecord(b->ev_y[slot], b->stream));
   PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_y[slot], 0));
-  if (y_pcm) PGX_CUDA(cudaMemcpyAsync(y_dst, b->ypcm_stage[slot], yb / 2, cudaMemcpyDeviceToHost, b->s_d2h));
-  else
-  PGX_CUDA(cudaMemcpyAsync(y_dst, b->y_stage[slot], yb, cudaMemcpyDeviceToHost, b->s_d2h));
+  if (deliver) {
+    if (y_pcm) PGX_CUDA(cudaMemcpyAsync(y_dst, b->ypcm_stage[slot], yb / 2, cudaMemcpyDeviceToHost, b->s_d2h));
+    else
+    PGX_CUDA(cudaMemcpyAsync(y_dst, b->y_stage[slot], yb, cudaMemcpyDeviceToHost, b->s_d2h));
+  }
   PGX_CUDA(cudaEventRecord(b->ev_done[slot], b->s_d2h));
   if (bounce_y) {
     b->y_user[slot] = y;
@@ -1115,6 +1132,7 @@ static int submit_wait(pgx_bank* b, int64_t ticket) {
     memcpy(b->y_user[slot], b->hy_bounce[slot], b->y_user_bytes[slot]);
     b->y_user[slot] = nullptr;
   }
+  if (b->comm) return pgx_comm_check(b->comm);  // a reduce whose peer never arrived gave up instead of hanging
   return PGX_OK;
 }
 
@@ -1130,7 +1148,7 @@ int pgx_bank_submit(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_la
   if ((flags & PGX_PULL_X_DEVICE) && (flags & PGX_PULL_X_PCM16))
     return fail(PGX_ERR_INVALID, "PGX_PULL_X_DEVICE and PGX_PULL_X_PCM16 exclude each other");
   return submit_host(b, x, xl, y, yl, n, (flags & PGX_PULL_MIX) != 0, ticket, (flags & PGX_PULL_X_DEVICE) != 0,
-                     (flags & PGX_PULL_X_PCM16) != 0, (flags & PGX_PULL_Y_PCM16) != 0);
+                     (flags & PGX_PULL_X_PCM16) != 0, (flags & PGX_PULL_Y_PCM16) != 0, (flags & PGX_PULL_REDUCE) != 0);
 }
 
 void* pgx_bank_stream(pgx_bank* b) { return b ? static_cast<void*>(b->stream) : nullptr; }
@@ -1155,7 +1173,24 @@ int pgx_bank_process_device(pgx_bank* b, const float* x_dev, pgx_layout xl, floa
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->stream;
   pgx_layout yd = yl;
   if (mix) yd.stream = 0;
-  return run_pull(b, x_dev, xl, y_dev, yd, n, mix, (flags & PGX_PULL_INPUT_RESIDENT) != 0, st);
+  const bool reduce = (flags & PGX_PULL_REDUCE) != 0;
+  if (reduce) {
+    if (!mix) return fail(PGX_ERR_INVALID, "PGX_PULL_REDUCE needs PGX_PULL_MIX: only a mix is summed over the ranks");
+    if (!b->comm) return fail(PGX_ERR_INVALID, "PGX_PULL_REDUCE: no communicator attached (pgx_bank_attach_comm)");
+    if (!layout_dense(yd, 1, b->cfg.c_out, n)) return fail(PGX_ERR_INVALID, "PGX_PULL_REDUCE: y must be one dense block");
+  }
+  const int rc = run_pull(b, x_dev, xl, y_dev, yd, n, mix, (flags & PGX_PULL_INPUT_RESIDENT) != 0, st);
+  if (rc != PGX_OK || !reduce) return rc;
+  b->launches += 1;
+  return pgx_comm_enqueue(b->comm, y_dev, y_dev, b->cfg.c_out * n, st);  // in place: the root's y_dev becomes the sum
+}
+
+int pgx_bank_attach_comm(pgx_bank* b, pgx_comm* comm) {
+  if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
+  if (comm && pgx_comm_device(comm) != b->cfg.device)
+    return fail(PGX_ERR_INVALID, "communicator lives on device %d, bank on device %d", pgx_comm_device(comm), b->cfg.device);
+  b->comm = comm;
+  return PGX_OK;
 }
 
 int pgx_bank_synchronize(pgx_bank* b) {

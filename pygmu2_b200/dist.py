@@ -5,9 +5,13 @@ One process per GPU (torchrun), ``torch.distributed`` for the plumbing.  Streams
 independent until the final MixPE sum (reference mix_pe.py:92-94), so rank g owns the
 contiguous slice [g*N/G, (g+1)*N/G) of the stream index with its filter spectra and delay
 lines resident, computes its partial mix locally (fused in the accumulate kernel) and the
-only collective is one sum-reduce of the (C_out, n) float32 mix per pull -- NCCL over
-NVLink on GPUs, gloo in the CPU tests.  Configurations without a mix (C2: independent
-reverbs) shard with no collective at all.
+only exchange is one sum of the (C_out, n) float32 partial mixes per pull.  On GPUs that sum
+is ``MixComm`` / ``pgx_mix_reduce``: the ranks store their partials into the root's memory over
+NVLink and the root adds them in rank order, one small kernel per rank on the bank's stream
+(csrc/pgx_comm.cu) -- ``torch.distributed`` only carries the 128-byte mailbox handles at set-up.
+``reduce_mix`` (a library collective: NCCL on GPUs, gloo in the CPU tests) stays as the baseline
+the kernel path is measured against.  Configurations without a mix (C2: independent reverbs)
+shard with no collective at all.
 """
 from __future__ import annotations
 
@@ -78,6 +82,76 @@ def reduce_mix(mix, root: int | None = 0, group=None):
     return mix
 
 
+class MixComm:
+    """The cross-GPU mix reduce of ``libpgx`` (pgx_comm_*): mailboxes in peer memory, rank-ordered float32 sum.
+
+    ``exchange(blob: bytes) -> list[bytes]`` all-gathers the per-rank handle blobs in rank order; the default uses
+    ``torch.distributed.all_gather_object`` on the initialised process group.  Several devices inside ONE process
+    connect with ``MixComm.connect_local([comm0, comm1, ...])`` instead.
+    """
+
+    def __init__(self, device: int, rank: int, world: int, root: int = 0, max_floats: int = 2 * 8192, exchange=None,
+                 connect: bool = True):
+        import ctypes as C
+
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.device, self.rank, self.world, self.root = int(device), int(rank), int(world), int(root)
+        self.max_floats = int(max_floats)
+        _lib.require_device()
+        self._h = C.c_void_p()
+        blob = (C.c_char * _lib.PGX_COMM_HANDLE_BYTES)()
+        _lib.check(_lib.lib().pgx_comm_create(C.byref(self._h), self.device, self.rank, self.world, self.root,
+                                              self.max_floats, blob))
+        self.handle = bytes(blob)
+        if connect and self.world > 1:
+            if exchange is None:
+                import torch.distributed as dist
+
+                def exchange(b):
+                    out = [None] * self.world
+                    dist.all_gather_object(out, b)
+                    return out
+            self.connect(exchange(self.handle))
+
+    def connect(self, handles) -> None:
+        blob = b"".join(handles)
+        if len(blob) != self.world * self._lib.PGX_COMM_HANDLE_BYTES:
+            raise ValueError("need one handle blob per rank")
+        self._lib.check(self._lib.lib().pgx_comm_connect(self._h, blob))
+
+    @staticmethod
+    def connect_local(comms) -> None:
+        """Ranks living in one process (one device each): hand every communicator all the handles."""
+        handles = [c.handle for c in sorted(comms, key=lambda c: c.rank)]
+        for c in comms:
+            c.connect(handles)
+
+    @property
+    def is_root(self) -> bool:
+        return self.rank == self.root
+
+    def reduce_device(self, part_ptr: int, y_ptr: int, n: int, cuda_stream: int = 0) -> None:
+        """Enqueue the sum of the ranks' ``n``-float partials (device pointers) onto the root's ``y_ptr``."""
+        C = self._C
+        self._lib.check(self._lib.lib().pgx_mix_reduce(self._h, C.c_void_p(part_ptr), C.c_void_p(y_ptr), int(n),
+                                                       C.c_void_p(cuda_stream)))
+
+    def check(self) -> None:
+        self._lib.check(self._lib.lib().pgx_comm_check(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.lib().pgx_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedMix:
     """N streams sharded over the ranks of a process group, mixed to one (C_out, n) signal.
 
@@ -109,11 +183,26 @@ class ShardedMix:
         reduce_mix(t, self.root)
         return t.numpy()
 
-    # device tensors (nccl): everything is enqueued on torch's current stream, no host sync
+    # device tensors: everything is enqueued on torch's current stream, no host sync.  With a MixComm attached
+    # to the bank (``attach_comm``) the sum is the peer-memory kernel path; otherwise the library collective.
+    def attach_comm(self, comm: "MixComm") -> None:
+        self.comm = comm
+        self.bank.attach_comm(comm)
+
     def render_mix_device(self, x_local, y_mix, n: int):
         import torch
 
         st = torch.cuda.current_stream().cuda_stream
+        if getattr(self, "comm", None) is not None:
+            self.bank.process_device(x_local.data_ptr(), y_mix.data_ptr(), n, mix=True, cuda_stream=st, reduce=True)
+            return y_mix
         self.bank.process_device(x_local.data_ptr(), y_mix.data_ptr(), n, mix=True, cuda_stream=st)
         reduce_mix(y_mix, self.root)
         return y_mix
+
+    # host buffers, pipelined: pinned x_local (hi-lo, C_in, n) -> the root's pinned out (C_out, n); returns a ticket
+    def submit_mix(self, x_local: np.ndarray, out: np.ndarray) -> int:
+        return self.bank.submit(x_local, out, mix=True, reduce=True)
+
+    def wait(self, ticket: int) -> None:
+        self.bank.wait(ticket)

@@ -104,9 +104,11 @@ class MixPE(ProcessingElement):
             del ext
         if len({h.shape for h in taps}) != 1 or len(src_ch) != 1 or None in src_ch:
             raise _NotFusable
-        bank = ConvolveBank(np.stack(taps), len(ins), int(src_ch.pop()),
-                            block=choose_block(taps[0].shape[0], duration), device=self._device)
-        bank.attach_sources([p.src for p in ins], delays=delays, gains=gains, extents=exts)
+        # one resident filter per input + an all-zero one for inputs MixPE does not render (mix_pe.py:81-85)
+        bank = ConvolveBank(np.stack(taps + [np.zeros_like(taps[0])]), len(ins), int(src_ch.pop()),
+                            block=choose_block(taps[0].shape[0], duration), device=self._device,
+                            filter_of_stream=np.arange(len(ins), dtype=np.int32))
+        bank.attach_sources([p.src for p in ins], delays=delays, gains=gains, extents=exts, silent_filter=len(ins))
         bank.mix_output = True
         return bank
 

@@ -242,7 +242,8 @@ def test_golden_c5_voicebank_long_ir_64_blocks():
     v = wl.c5_voices(n, nv)
     vm = pg.MixPE(*[pg.ArrayPE(v[i]) for i in range(nv)])
     assert np.array_equal(vm.render(0, n).data, g["voice_mix"])  # K5 is bit-exact
-    pe = pg.ConvolvePE(pg.MixPE(*[pg.ArrayPE(v[i]) for i in range(nv)]), pg.ArrayPE(wl.c5_ir(L)))
+    # block_size=64: the NAMED low-latency partitioning (the default would pick B=256 for a 64-sample first pull)
+    pe = pg.ConvolvePE(pg.MixPE(*[pg.ArrayPE(v[i]) for i in range(nv)]), pg.ArrayPE(wl.c5_ir(L)), block_size=64)
     y = _pull_pe(pe, (wl.C5_PULL,) * npull)
     assert pe.bank.block == 64 and pe.bank.partitions == 6891
     assert rel_err(y, g["y"]) <= TOL
@@ -352,6 +353,162 @@ def test_full_size_c2_impulse_and_linearity():
     assert np.max(np.abs(y[0, :, L:])) <= TOL * np.max(np.abs(ir))
     lin = 0.5 * y[1].astype(np.float64) + 0.25 * y[0].astype(np.float64)
     assert rel_err(y[2], lin) <= TOL
+
+
+def _fftconv64(x, h, n):
+    """Exact linear convolution in float64 (the definition both the reference and the device path implement,
+    SURVEY.md Appendix A), first n samples."""
+    from scipy.signal import fftconvolve
+    return fftconvolve(np.asarray(x, np.float64), np.asarray(h, np.float64))[:n]
+
+
+def test_full_plan_c2_256_streams_shared_ir_every_partition():
+    """The BENCHMARKED launch plan (256 stereo streams, one shared 132300-tap IR, B=512, P=259: k_fdl_mac<false,4,4>,
+    5 term splits) with noise over n > L samples, so every one of the 259 partitions of every stream carries data
+    when the last pulls are produced; streams {0, 1, N/2, N-1} against the float64 convolution."""
+    pg.set_sample_rate(wl.SR_48)
+    ir = wl.c2_ir()
+    L, N, pull = ir.shape[0], 256, 512
+    bank = pg.ConvolveBank(ir, N, 2, block=512, single_filter_dims=True, max_pull=pull)
+    info = bank.info()
+    assert info.partitions == 259 and info.mac_stream_tile == 4          # the plan bench.py times
+    pulls = 259 + 3
+    n = pulls * pull
+    rng = np.random.default_rng(77)
+    sample = (0, 1, N // 2, N - 1)
+    ys = {s: [] for s in sample}
+    xs = {s: [] for s in sample}
+    for i in range(pulls):
+        x = rng.uniform(-1, 1, (N, 2, pull)).astype(np.float32)
+        y = bank.process(x)
+        for s in sample:
+            xs[s].append(x[s].copy())
+            ys[s].append(y[s].copy())
+    for s in sample:
+        x = np.concatenate(xs[s], axis=1)
+        y = np.concatenate(ys[s], axis=1)
+        for c in range(2):
+            ref = _fftconv64(x[c], ir[:, c], n)
+            assert rel_err(y[c], ref) <= TOL, (s, c)
+            assert rel_err(y[c, -pull:], ref[-pull:]) <= TOL * max(1.0, np.max(np.abs(ref)) / np.max(np.abs(ref[-pull:])))
+    bank.close()
+
+
+def test_full_plan_c2_distinct_irs_64_streams():
+    """Distinct-filter plan (k_fdl_mac<false,1,8>) at the named filter length, n > L."""
+    pg.set_sample_rate(wl.SR_48)
+    N, pull = 64, 2048
+    irs = np.stack([wl.c2_ir(stream=s) for s in range(N)])
+    L = irs.shape[1]
+    bank = pg.ConvolveBank(irs, N, 2, block=512, max_pull=pull)
+    assert bank.info().mac_stream_tile == 1
+    pulls = -(-(L + 1024) // pull)
+    n = pulls * pull
+    rng = np.random.default_rng(78)
+    sample = (0, 31, N - 1)
+    x = rng.uniform(-1, 1, (N, 2, n)).astype(np.float32)
+    y = np.concatenate([bank.process(np.ascontiguousarray(x[:, :, i * pull:(i + 1) * pull])) for i in range(pulls)], axis=2)
+    for s in sample:
+        for c in range(2):
+            assert rel_err(y[s, c], _fftconv64(x[s, c], irs[s, :, c], n)) <= TOL, (s, c)
+    bank.close()
+
+
+def test_full_plan_c4_512_streams_all_173_partitions_fused_mix():
+    """C4 per-GPU size (512 mono streams x distinct 88200-tap IRs, fused mix, the per-stream mix layout) over
+    n > L samples.  Every stream gets a scaled impulse at its own offset -- its spectrum marches through all 173
+    partitions of THAT stream's filter, and its exact contribution is the shifted IR -- and 8 streams get noise on
+    top (float64 convolution).  The fused mix must equal the sum."""
+    N, pull = 512, 512
+    irs = np.stack([wl.c4_ir(s) for s in range(N)])
+    L = irs.shape[1]
+    bank = pg.ConvolveBank(irs, N, 1, block=512, max_pull=pull)
+    assert bank.info().partitions == 173
+    pulls = 173 + 3
+    n = pulls * pull
+    rng = np.random.default_rng(79)
+    amp = rng.uniform(0.5, 1.0, N) * rng.choice([-1.0, 1.0], N)
+    off = rng.integers(0, 2048, N)
+    noisy = rng.choice(N, 8, replace=False)
+    x = np.zeros((N, 1, n), np.float32)
+    x[np.arange(N), 0, off] = amp.astype(np.float32)
+    ref = np.zeros(n)
+    for s in range(N):
+        a = float(np.float32(amp[s]))
+        m = min(L, n - off[s])
+        ref[off[s]:off[s] + m] += a * irs[s, :m].astype(np.float64)
+    for s in noisy:
+        nz = (rng.uniform(-1, 1, n) / 8).astype(np.float32)
+        nz[off[s]] = 0.0
+        x[s, 0] += nz
+        ref += _fftconv64(nz, irs[s], n)
+    y = np.concatenate([bank.process_mix(np.ascontiguousarray(x[:, :, i * pull:(i + 1) * pull])) for i in range(pulls)], axis=1)
+    assert rel_err(y[0], ref) <= TOL
+    tail = slice(n - 4 * pull, n)                          # produced when all 173 partitions are live
+    assert np.max(np.abs(y[0, tail] - ref[tail])) <= TOL * np.max(np.abs(ref))
+    bank.close()
+
+
+def test_full_plan_c5_single_stream_all_6891_partitions():
+    """C5 as named (one stream, 441000 taps, B=64: 6891 partitions), noise over n > L samples pulled 4096 at a
+    time (64 block steps per pull), against the float64 convolution."""
+    ir = wl.c5_ir()
+    L = ir.shape[0]
+    bank = pg.ConvolveBank(ir, 1, 1, block=64, single_filter_dims=True, max_pull=4096)
+    assert bank.info().partitions == 6891
+    pulls = -(-(L + 4096) // 4096)
+    n = pulls * 4096
+    x = (np.random.default_rng(80).uniform(-1, 1, n) / 4).astype(np.float32)
+    y = np.concatenate([bank.process(x[None, None, i * 4096:(i + 1) * 4096])[0, 0] for i in range(pulls)])
+    ref = _fftconv64(x, ir, n)
+    assert rel_err(y, ref) <= TOL
+    assert np.max(np.abs(y[-4096:] - ref[-4096:])) <= TOL * np.max(np.abs(ref))
+    assert bank.info().block_steps >= 6891
+    bank.close()
+
+
+@pytest.mark.parametrize("P,B", [(2, 64), (7, 128), (16, 64)])
+def test_conv_to_mix_switch_back_to_back_on_a_block_boundary(P, B):
+    """Banks with 2..16 partitions run conv pulls as ONE fused kernel on the critical stream; a mix pull queued
+    right behind (no host synchronisation: pipelined submits, resident input) must see what that kernel wrote."""
+    rng = np.random.default_rng(P)
+    N, L = 5, P * B - 3
+    h = (rng.standard_normal((N, L)) / np.sqrt(L)).astype(np.float32)
+    n_conv, n_mix = 3 * B, 4 * B
+    x = rng.uniform(-1, 1, (N, 1, n_conv + n_mix)).astype(np.float32)
+    for trial in range(8):                       # a race needs several tries to show
+        bank = pg.ConvolveBank(h, N, 1, block=B, max_pull=B)
+        y1 = [np.empty((N, 1, B), np.float32) for _ in range(3)]
+        y2 = [np.empty((1, B), np.float32) for _ in range(4)]
+        tks = [bank.submit(np.ascontiguousarray(x[:, :, i * B:(i + 1) * B]), y1[i]) for i in range(3)]
+        tks += [bank.submit(np.ascontiguousarray(x[:, :, n_conv + i * B:n_conv + (i + 1) * B]), y2[i], mix=True)
+                for i in range(4)]
+        for t in tks:
+            bank.wait(t)
+        ref = np.stack([orc.OracleConvolve(h[s], 1).render(x[s, 0])[:, 0] for s in range(N)])
+        assert rel_err(np.concatenate(y1, axis=2)[:, 0], ref[:, :n_conv]) <= TOL
+        assert rel_err(np.concatenate(y2, axis=1)[0], ref[:, n_conv:].astype(np.float64).sum(axis=0)) <= TOL, trial
+        bank.close()
+
+
+def test_adopted_convolve_mix_gates_on_extents_like_the_reference():
+    """MixPE over ConvolvePEs adopts them into one bank; inputs whose extent misses the request are not rendered
+    (mix_pe.py:81-85) -- a HOLD_LAST source therefore stops contributing where its ConvolvePE's extent ends."""
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-1, 1, 700).astype(np.float32)
+    b = rng.uniform(-1, 1, 300).astype(np.float32)
+    h = (rng.standard_normal(40) / 6).astype(np.float32)
+
+    def graph(fuse):
+        return pg.MixPE(pg.ConvolvePE(pg.ArrayPE(a), pg.ArrayPE(h)),
+                        pg.ConvolvePE(pg.ArrayPE(b, extend_mode=pg.ExtendMode.HOLD_LAST), pg.ArrayPE(h)), fuse=fuse)
+    pulls = (256,) * 4
+    y_f, y_u = _pull_pe(graph(True), pulls), _pull_pe(graph(False), pulls)
+    assert rel_err(y_f, y_u) <= TOL
+    assert np.max(np.abs(y_u[512:, 0])) > 0          # stream a still sounds ...
+    # ... and past its extent (300 + 39) stream b is silent although its source holds its last value forever
+    ca = orc.OracleConvolve(h, 1).render(np.concatenate([a, np.zeros(324, np.float32)]))[:, 0]
+    assert rel_err(y_f[512:, 0], ca[512:]) <= TOL
 
 
 def test_full_size_c5_impulse_response():
