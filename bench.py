@@ -467,6 +467,7 @@ def parity_leg(spec, bank, dev, stream, world, rank, do_reduce, traj_dev, traj):
         x_all *= keep.view(1, N, 1, 1)
     n_out_ch = c_out if mix else N * c_out
     y_all = torch.empty((n_p, n_out_ch, pull), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)   # x_all was produced on torch's stream; the bank's streams are not ordered with it
     sh = stream.cuda_stream
     blk = N * c_in * pull * 4
     for i in range(n_p):

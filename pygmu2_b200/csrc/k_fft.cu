@@ -600,35 +600,41 @@ int fft_smem_bytes(int B) {
 }
 
 template <int LOG2N, int MODE>
-static void launch_r2c_t(const R2CArgs& a, const FilterPrepArgs& fp, int64_t total, cudaStream_t st) {
+static void describe_r2c_t(int64_t total, LaunchDesc* d) {
   using C = FftCfg<LOG2N>;
   static bool attr_done[64] = {};
   if (C::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
     cudaFuncSetAttribute(k_r2c<LOG2N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  const int grid = (int)((total + C::FPB - 1) / C::FPB);
-  k_r2c<LOG2N, MODE><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a, fp);
+  d->func = reinterpret_cast<const void*>(k_r2c<LOG2N, MODE>);
+  d->grid = dim3((unsigned)((total + C::FPB - 1) / C::FPB));
+  d->block = dim3(C::CTA);
+  d->smem = C::SMEM_BYTES;
 }
 
 template <int LOG2N, bool PART>
-static void launch_c2r_t(const C2RArgs& a, cudaStream_t st) {
+static void describe_c2r_t(const C2RArgs& a, LaunchDesc* d) {
   using C = FftCfg<LOG2N>;
   static bool attr_done[64] = {};
   if (C::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
     cudaFuncSetAttribute(k_c2r<LOG2N, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  const int grid = (a.n_out + C::FPB - 1) / C::FPB;
-  k_c2r<LOG2N, PART><<<grid, C::CTA, C::SMEM_BYTES, st>>>(a);
+  d->func = reinterpret_cast<const void*>(k_c2r<LOG2N, PART>);
+  d->grid = dim3((unsigned)((a.n_out + C::FPB - 1) / C::FPB));
+  d->block = dim3(C::CTA);
+  d->smem = C::SMEM_BYTES;
 }
 
 template <int LOG2N, bool FAN, bool PAST>
-static void launch_conv1_t(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
+static void describe_conv1_t(const R2CArgs& a, LaunchDesc* d) {
   using C = FftCfg<LOG2N>;
   // + the staged filter row and its mbarrier when the CTA holds one transform (see HPRE in the kernel)
   constexpr int smem = C::SMEM_BYTES + ((!FAN && C::FPB == 1) ? C::N * 8 + 16 : 0);
   static bool attr_done[64] = {};
   if (smem > 48 * 1024 && need_smem_attr(attr_done))
     cudaFuncSetAttribute(k_conv1<LOG2N, FAN, PAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int grid = (a.n_fft + C::FPB - 1) / C::FPB;
-  k_conv1<LOG2N, FAN, PAST><<<grid, C::CTA, smem, st>>>(a, k);
+  d->func = reinterpret_cast<const void*>(k_conv1<LOG2N, FAN, PAST>);
+  d->grid = dim3((unsigned)((a.n_fft + C::FPB - 1) / C::FPB));
+  d->block = dim3(C::CTA);
+  d->smem = smem;
 }
 
 #define PGX_DISPATCH(LOG, CALL)                                                                              \
@@ -646,34 +652,63 @@ static void launch_conv1_t(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) 
     default: break;                                                                                          \
   }
 
+static void launch_desc(const LaunchDesc& d, void** params, cudaStream_t st) {
+  if (d.func) cudaLaunchKernel(d.func, d.grid, d.block, params, d.smem, st);
+}
+
+bool describe_r2c_ingest(const R2CArgs& a, LaunchDesc* d) {
+  d->func = nullptr;
+  PGX_DISPATCH(ilog2(a.B), (describe_r2c_t<L_, 0>(a.n_fft, d)));
+  return d->func != nullptr;
+}
+
 void launch_r2c_ingest(const R2CArgs& a, cudaStream_t st) {
   FilterPrepArgs fp{};
-  PGX_DISPATCH(ilog2(a.B), (launch_r2c_t<L_, 0>(a, fp, a.n_fft, st)));
+  LaunchDesc d;
+  describe_r2c_ingest(a, &d);
+  void* params[] = {const_cast<R2CArgs*>(&a), &fp};
+  launch_desc(d, params, st);
 }
 
 void launch_filter_prep(const FilterPrepArgs& fp, cudaStream_t st) {
   R2CArgs a{};
-  PGX_DISPATCH(ilog2(fp.B), (launch_r2c_t<L_, 1>(a, fp, (int64_t)fp.n_rows * fp.P, st)));
+  LaunchDesc d;
+  PGX_DISPATCH(ilog2(fp.B), (describe_r2c_t<L_, 1>((int64_t)fp.n_rows * fp.P, &d)));
+  void* params[] = {&a, const_cast<FilterPrepArgs*>(&fp)};
+  launch_desc(d, params, st);
+}
+
+bool describe_conv1(const R2CArgs& a, const C2RArgs& k, LaunchDesc* d) {
+  d->func = nullptr;
+  if (describe_conv1_r16(a, k, d)) return true;
+  const bool fan = (a.c_x == 1 && k.c_out > 1);
+  if (k.n_past > 0) {
+    if (fan) { PGX_DISPATCH(ilog2(a.B), (describe_conv1_t<L_, true, true>(a, d))); }
+    else { PGX_DISPATCH(ilog2(a.B), (describe_conv1_t<L_, false, true>(a, d))); }
+  } else {
+    if (fan) { PGX_DISPATCH(ilog2(a.B), (describe_conv1_t<L_, true, false>(a, d))); }
+    else { PGX_DISPATCH(ilog2(a.B), (describe_conv1_t<L_, false, false>(a, d))); }
+  }
+  return d->func != nullptr;
 }
 
 void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
-  const bool fan = (a.c_x == 1 && k.c_out > 1);
-  if (k.n_past > 0) {
-    if (fan) { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, true, true>(a, k, st))); }
-    else { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, false, true>(a, k, st))); }
-  } else {
-    if (fan) { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, true, false>(a, k, st))); }
-    else { PGX_DISPATCH(ilog2(a.B), (launch_conv1_t<L_, false, false>(a, k, st))); }
-  }
+  LaunchDesc d;
+  describe_conv1(a, k, &d);
+  void* params[] = {const_cast<R2CArgs*>(&a), const_cast<C2RArgs*>(&k)};
+  launch_desc(d, params, st);
 }
 
 template <int LOG2N, bool LAST>
-static void launch_mix1_t(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st) {
+static void describe_mix1_t(const R2CArgs& a, LaunchDesc* d) {
   using M = Mix1Cfg<LOG2N>;
   static bool attr_done[64] = {};
   if (M::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
     cudaFuncSetAttribute(k_mix1<LOG2N, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, M::SMEM_BYTES);
-  k_mix1<LOG2N, LAST><<<(a.n_fft + M::G - 1) / M::G, M::CTA, M::SMEM_BYTES, st>>>(a, k, ynow, ticket);
+  d->func = reinterpret_cast<const void*>(k_mix1<LOG2N, LAST>);
+  d->grid = dim3((unsigned)((a.n_fft + M::G - 1) / M::G));
+  d->block = dim3(M::CTA);
+  d->smem = M::SMEM_BYTES;
 }
 
 int mix1_sources_per_cta(int B) {
@@ -685,25 +720,43 @@ int mix1_sources_per_cta(int B) {
   }
 }
 
-void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st) {
-#define PGX_MIX1_CASE(L)                                                     \
-  case L:                                                                    \
-    if (ticket) launch_mix1_t<L, true>(a, k, ynow, ticket, st);              \
-    else launch_mix1_t<L, false>(a, k, ynow, nullptr, st);                   \
+bool describe_mix1(const R2CArgs& a, bool last, LaunchDesc* d) {
+  d->func = nullptr;
+#define PGX_MIX1_CASE(L)                                  \
+  case L:                                                 \
+    if (last) describe_mix1_t<L, true>(a, d);             \
+    else describe_mix1_t<L, false>(a, d);                 \
     break;
   switch (ilog2(a.B)) {
     PGX_MIX1_CASE(4) PGX_MIX1_CASE(5) PGX_MIX1_CASE(6) PGX_MIX1_CASE(7) PGX_MIX1_CASE(8) PGX_MIX1_CASE(9) PGX_MIX1_CASE(10)
     default: break;
   }
 #undef PGX_MIX1_CASE
+  return d->func != nullptr;
+}
+
+void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st) {
+  LaunchDesc d;
+  describe_mix1(a, ticket != nullptr, &d);
+  void* params[] = {const_cast<R2CArgs*>(&a), const_cast<C2RArgs*>(&k), &ynow, &ticket};
+  launch_desc(d, params, st);
+}
+
+bool describe_c2r_emit(const C2RArgs& a, LaunchDesc* d) {
+  d->func = nullptr;
+  if (a.n_split > 0 || a.n_split_now > 0) {
+    PGX_DISPATCH(ilog2(a.B), (describe_c2r_t<L_, true>(a, d)));
+  } else {
+    PGX_DISPATCH(ilog2(a.B), (describe_c2r_t<L_, false>(a, d)));
+  }
+  return d->func != nullptr;
 }
 
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st) {
-  if (a.n_split > 0 || a.n_split_now > 0) {
-    PGX_DISPATCH(ilog2(a.B), (launch_c2r_t<L_, true>(a, st)));
-  } else {
-    PGX_DISPATCH(ilog2(a.B), (launch_c2r_t<L_, false>(a, st)));
-  }
+  LaunchDesc d;
+  describe_c2r_emit(a, &d);
+  void* params[] = {const_cast<C2RArgs*>(&a)};
+  launch_desc(d, params, st);
 }
 
 }  // namespace pgx

@@ -228,19 +228,28 @@ MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_fi
   return p;
 }
 
+bool describe_fdl_mac(const MacArgs& a, LaunchDesc* d) {
+  d->func = nullptr;
+  if (a.variant == 1) return false;  // the bulk-async kernel has its own launcher
+  const int lanes = a.W4 < kMacThreads ? a.W4 : kMacThreads;
+  d->grid = dim3((unsigned)(a.n_otiles * (a.W4 / lanes) * a.n_split));
+  d->block = dim3(kMacThreads);
+  d->smem = 0;
+  if (a.mix == 1) d->func = reinterpret_cast<const void*>(k_fdl_mac<true, 1, 8>);
+  else if (a.st == 4) d->func = reinterpret_cast<const void*>(k_fdl_mac<false, 4, 4>);
+  else d->func = reinterpret_cast<const void*>(k_fdl_mac<false, 1, 8>);
+  return true;
+}
+
 void launch_fdl_mac(const MacArgs& a, cudaStream_t st) {
   if (a.variant == 1) {
     launch_fdl_mac_tma(a, a.persistent_ctas, st);
     return;
   }
-  const int lanes = a.W4 < kMacThreads ? a.W4 : kMacThreads;
-  const int grid = a.n_otiles * (a.W4 / lanes) * a.n_split;
-  if (a.mix == 1)
-    k_fdl_mac<true, 1, 8><<<grid, kMacThreads, 0, st>>>(a);
-  else if (a.st == 4)
-    k_fdl_mac<false, 4, 4><<<grid, kMacThreads, 0, st>>>(a);
-  else
-    k_fdl_mac<false, 1, 8><<<grid, kMacThreads, 0, st>>>(a);
+  LaunchDesc d;
+  describe_fdl_mac(a, &d);
+  void* params[] = {const_cast<MacArgs*>(&a)};
+  cudaLaunchKernel(d.func, d.grid, d.block, params, d.smem, st);
 }
 
 // Second stage of the split accumulation: out[e] = sum_sp in[sp][e], e over n_out*W4 float4 columns.
@@ -279,6 +288,15 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float4* __restric
     }
     out[col] = acc;
   }
+}
+
+bool describe_reduce_partials(int n_out, int W4, LaunchDesc* d) {
+  const int64_t n_cols = (int64_t)n_out * W4;
+  d->func = reinterpret_cast<const void*>(k_reduce_partials);
+  d->grid = dim3((unsigned)((n_cols + 31) / 32));
+  d->block = dim3(256);
+  d->smem = 0;
+  return true;
 }
 
 void launch_reduce_partials(const float4* in, float4* out, int n_split, int n_out, int W4, cudaStream_t st) {

@@ -95,10 +95,15 @@ struct C2RArgs {
   // fused small-P step (k_conv1<.., PAST>): the past partitions are ring slots p_off + jj (+ p_nskip from p_skip on),
   // jj < n_past, paired with filter rows q0 + slot -- the same slot walk as MacArgs
   int32_t n_past, p_off, p_skip, p_nskip, q0;
+  int32_t fft16;         // B = 4096 fused step: 0 radix-8 kernel, 1 radix-16 (shared-memory exchanges), 2 radix-16 + shuffles
 };
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st);
 // K1 + K2 in one kernel for single-partition conv banks (P = 1): the spectrum never visits the delay line.
 void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st);
+// Radix-16 variant of the same step for B = 4096 (k_fft16.cu): 16 elements per thread, two exchanges per transform, the
+// half-warp exchange by warp shuffles.  Returns false when the pull is not its shape (the general kernel runs then).
+bool launch_conv1_r16(const R2CArgs& a, const C2RArgs& k, cudaStream_t st);
+int conv1_r16_default();  // PGX_FFT16 or the measured default, read when a bank is created
 
 // K5: MixPE left-to-right float32 sum of n_inputs dense arrays.
 void launch_mix_sum(const float* in, int32_t n_inputs, int64_t n_elems, float* out, cudaStream_t st);
@@ -143,5 +148,22 @@ int mix1_sources_per_cta(int B);
 void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st);
 
 int fft_smem_bytes(int B);
+
+// What a launch_* call launches: the kernel instantiation, its grid and its dynamic shared memory.  The launchers
+// are describe_* + cudaLaunchKernel; the CUDA-graph replay of a whole pull (pgx_api.cu) builds its kernel nodes
+// from the same descriptions, so both paths run identical kernels.  describe_* also raises the kernel's dynamic
+// shared-memory limit when it needs more than 48 KB.  false = no such kernel for these arguments.
+struct LaunchDesc {
+  const void* func = nullptr;
+  dim3 grid{1, 1, 1}, block{1, 1, 1};
+  unsigned smem = 0;
+};
+bool describe_r2c_ingest(const R2CArgs& a, LaunchDesc* d);                    // params: (R2CArgs, FilterPrepArgs)
+bool describe_c2r_emit(const C2RArgs& a, LaunchDesc* d);                      // params: (C2RArgs)
+bool describe_conv1(const R2CArgs& a, const C2RArgs& k, LaunchDesc* d);       // params: (R2CArgs, C2RArgs)
+bool describe_mix1(const R2CArgs& a, bool last, LaunchDesc* d);               // params: (R2CArgs, C2RArgs, float2*, unsigned*)
+bool describe_fdl_mac(const MacArgs& a, LaunchDesc* d);                       // params: (MacArgs); LDG kernel only
+bool describe_reduce_partials(int n_out, int W4, LaunchDesc* d);              // params: (in, out, int n_split, int64 n_cols)
+bool describe_conv1_r16(const R2CArgs& a, const C2RArgs& k, LaunchDesc* d);   // params: (R2CArgs, C2RArgs)
 
 }  // namespace pgx

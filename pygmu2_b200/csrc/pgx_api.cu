@@ -156,6 +156,7 @@ struct pgx_bank {
   pgx_layout addend_l{};
   bool serial = false;
   bool use_conv1 = true;           // P = 1 conv pulls: K1 and K2 fused into one kernel (PGX_CONV1=0 disables)
+  int fft16 = 0;                   // B = 4096 fused step: radix-16 kernel variant (PGX_FFT16; see k_fft16.cu)
   int fused_max_p = 16;            // ... and conv pulls of banks with up to this many partitions (PGX_FUSED_MAXP)
   bool use_mix1 = true;            // P = 1 mixes of mono transforms: K1 + present-slot accumulate fused (PGX_MIX1=0)
   int mix1_rows = 0;               // partial rows per channel written by k_mix1 (= CTAs)
@@ -436,6 +437,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   k.y = y_dev; k.ys = mix ? 0 : yl.stream; k.yc = yl.chan; k.yi = yl.samp; k.y_off = pos;
   k.c_out = c.c_out; k.B = B; k.fill = b->fill; k.take = take; k.tw = b->tw;
   k.wet = b->wet; k.dry = b->dry;
+  k.fft16 = b->fft16;
   k.xdry = (!mix && b->dry != 0.0f) ? x_dev : nullptr;
   k.xs = xl.stream; k.xc = xl.chan; k.xi = xl.samp; k.x_off = pos;
   k.add = b->addend; k.as = mix ? 0 : b->addend_l.stream; k.ac = b->addend_l.chan; k.ai = b->addend_l.samp;
@@ -758,6 +760,7 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
     if (const char* e = getenv("PGX_BG_STREAMS")) b->two_bg = (e[0] != '1');
     if (const char* e = getenv("PGX_CONV1")) b->use_conv1 = (e[0] != '0');
     if (const char* e = getenv("PGX_FUSED_MAXP")) b->fused_max_p = atoi(e);
+    b->fft16 = pgx::conv1_r16_default();
     if (const char* e = getenv("PGX_MIX1")) b->use_mix1 = (e[0] != '0');
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");

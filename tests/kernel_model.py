@@ -220,3 +220,62 @@ def stockham8(z: np.ndarray, twM: np.ndarray, inverse: bool) -> np.ndarray:
         a, b = b, a
         Ns *= R
     return a
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Register-level model of the radix-16 kernel (csrc/k_fft16.cu): 256 threads x 16 registers, the same index maps,
+# exchanges (shared-memory gather / 16 x 16 half-warp transpose) and twiddles, vectorised over the threads.  The
+# CUDA kernel was transcribed from this model once it agreed with numpy.fft.
+FFT16_N = N = 4096; T = 256
+P=lambda q: ((q&3)<<2)|(q>>2)
+Pv=np.array([P(q) for q in range(16)])
+def bfly16(v, inv):
+    # v[:, n] natural logical input; output logical k at phys P(k)
+    s = 1 if inv else -1
+    n=np.arange(16); W=np.exp(s*2j*np.pi*np.outer(n,n)/16)
+    X = v @ W.T   # X[:,k] = sum_n v[:,n] W[k,n]
+    out=np.empty_like(v); out[:,Pv]=X
+    return out
+def tw(i): return np.exp(-2j*np.pi*(i%(2*N))/(2*N))   # table of 2N-th roots
+def fft16_forward(z):
+    j=np.arange(T); lo=j&15; hi=j>>4
+    v=np.stack([z[j+256*a] for a in range(16)],axis=1)
+    v=bfly16(v,False)
+    A=np.empty(N,complex)
+    for k0 in range(16): A[256*k0+j]=v[:,P(k0)]
+    v=np.stack([A[256*hi+16*b+lo] for b in range(16)],axis=1)
+    for b in range(16): v[:,b]*=tw(32*b*hi)
+    v=bfly16(v,False)
+    # transpose within 16-lane groups on physical regs
+    nv=np.empty_like(v)
+    for l in range(16):
+        for p in range(16):
+            nv[hi*16+l if False else (np.arange(16)*16+l), p]=v[np.arange(16)*16+p, l]
+    v=nv
+    k0=hi; k1=Pv[lo]
+    e=k0+16*k1
+    for c in range(16): v[:,c]*=tw(2*c*e)
+    v=bfly16(v,False)
+    Z=np.empty(N,complex)
+    for k2 in range(16): Z[k0+16*k1+256*k2]=v[:,P(k2)]
+    return Z
+def fft16_inverse(Wk):
+    j=np.arange(T); lo=j&15; hi=j>>4   # lo=b, hi=c
+    v=np.stack([Wk[256*a+16*lo+hi] for a in range(16)],axis=1)
+    v=bfly16(v,True)
+    for n0 in range(16): v[:,P(n0)]*=np.conj(tw(32*lo*n0))
+    nv=np.empty_like(v)
+    for l in range(16):
+        for p in range(16):
+            nv[np.arange(16)*16+l, p]=v[np.arange(16)*16+p, l]
+    v=nv   # lane l <-> n0=P(l), reg p <-> b
+    v=bfly16(v,True)  # logical n1 at phys P(n1)
+    n0=Pv[lo]
+    Bf=np.empty(N,complex)
+    for n1 in range(16): Bf[256*hi+16*n1+n0]=v[:,P(n1)]
+    v=np.stack([Bf[256*c+j] for c in range(16)],axis=1)
+    for c in range(16): v[:,c]*=np.conj(tw(2*c*j))
+    v=bfly16(v,True)
+    z=np.empty(N,complex)
+    for n2 in range(16): z[j+256*n2]=v[:,P(n2)]
+    return z

@@ -511,6 +511,34 @@ def test_adopted_convolve_mix_gates_on_extents_like_the_reference():
     assert rel_err(y_f[512:, 0], ca[512:]) <= TOL
 
 
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_c1_block4096_fft_kernel_variants_agree_with_oracle(variant, monkeypatch):
+    """B = 4096 single-partition step: the radix-8 kernel (0), the radix-16 kernel with shared-memory exchanges (1)
+    and with the half-warp exchange by warp shuffles (2; the default) against the oracle -- whole blocks (the
+    radix-16 fast path), then ragged pulls (general kernel), with a wet/dry output stage, mono and stereo."""
+    monkeypatch.setenv("PGX_FFT16", variant)
+    rng = np.random.default_rng(int(variant) + 40)
+    for c in (1, 2):
+        N, L, B = 5, 4096, 4096
+        h = (rng.standard_normal((N, L, 1)) / 64).astype(np.float32)
+        x = rng.uniform(-1, 1, (N, c, 6 * B + 777)).astype(np.float32)
+        bank = pg.ConvolveBank(h, N, c, block=B, max_pull=B)
+        if c == 2:
+            bank.set_output_gains(0.25, 0.5)
+        pulls = (B,) * 4 + (100, B - 100, 777, B)
+        ys, pos = [], 0
+        for d in pulls:
+            ys.append(bank.process(np.ascontiguousarray(x[:, :, pos:pos + d])))
+            pos += d
+        y = np.concatenate(ys, axis=2)
+        for s_ in (0, N - 1):
+            ref = orc.OracleConvolve(h[s_], c).render(x[s_].T).astype(np.float64)
+            if c == 2:
+                ref = 0.5 * x[s_].T + 0.25 * ref
+            assert rel_err(y[s_].T, ref) <= TOL, (variant, c, s_)
+        bank.close()
+
+
 def test_full_size_c5_impulse_response():
     ir = wl.c5_ir()
     L = ir.shape[0]

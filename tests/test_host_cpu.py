@@ -422,3 +422,13 @@ def test_vectorised_hrtf_lookup_equals_the_reference_rule():
     az, el = az[:n], el[:n]
     full = np.array([kemar.nearest_index(a, e) for a, e in zip(az, el)])
     np.testing.assert_array_equal(kemar.nearest_indices(az, el), full)
+
+
+def test_fft16_register_model_matches_numpy_fft():
+    """The index maps of the radix-16 kernel (thread digit <-> register exchanges, digit-reversed butterfly outputs,
+    twiddle exponents), as modelled in tests/kernel_model.py, are an exact 4096-point DFT / inverse DFT."""
+    import kernel_model as km
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal(km.FFT16_N) + 1j * rng.standard_normal(km.FFT16_N)
+    assert np.max(np.abs(km.fft16_forward(z) - np.fft.fft(z))) < 1e-9
+    assert np.max(np.abs(km.fft16_inverse(z) - np.fft.ifft(z) * km.FFT16_N)) < 1e-9
