@@ -90,6 +90,8 @@ typedef struct pgx_bank_info {
   int64_t block_steps;      /* FFT->MAC->IFFT steps executed since creation */
   int32_t mac_grid, mac_split, mac_stream_tile, mac_occupancy; /* launch plan of the accumulate kernel */
   int32_t tail_block, tail_partitions; /* two-level partitioning: block and partition count of the tail level (0 = off) */
+  int64_t graph_pulls;      /* host pulls that ran as ONE CUDA-graph replay (small whole-block pulls in the steady state:
+                               copies and kernels of the pull as one launch; PGX_GRAPH=0 disables) */
 } pgx_bank_info;
 
 /* ---- library ------------------------------------------------------------ */
@@ -283,6 +285,18 @@ PGX_API int pgx_osc_render_device(pgx_osc* osc, int64_t start, int32_t n, int32_
 /* Same pull delivered to host memory (D2H inside, returns when y is complete). */
 PGX_API int pgx_osc_render(pgx_osc* osc, int64_t start, int32_t n, int32_t flags, float* y);
 PGX_API int pgx_osc_launches(pgx_osc* osc, int64_t* launches);
+/* Modulated SinePE: any of frequency / amplitude / phase is a PE (sine_pe.py:134-142,188-232: the stateful branch --
+ * phase[i] = cumsum(2 pi f[i] / sr)[i] + carried phase (+ phase_mod[i]), float64, np.cumsum's left-to-right order).
+ * freq / amp / phase: float32 [n_voices][n], what the parameter PEs rendered for this pull (widened to float64 on the
+ * device), or NULL for a parameter that is the constant given to pgx_osc_create.  ctl_flags & PGX_CTL_HOST: the vectors
+ * are host memory (staged by the call, which then returns once they have been consumed); otherwise device pointers
+ * whose producer was enqueued on cuda_stream.  The phase carries over from pull to pull (the reference's base class
+ * only allows contiguous pulls of a stateful PE); pgx_osc_reset starts over.  Output as pgx_osc_render_device
+ * (*out_dev, may be NULL) and / or, when y_host is not NULL, copied to host memory before the call returns. */
+#define PGX_CTL_HOST 1
+PGX_API int pgx_osc_render_modulated(pgx_osc* osc, int32_t n, int32_t flags, const float* freq, const float* amp,
+                                     const float* phase, int32_t ctl_flags, void* cuda_stream, const float** out_dev,
+                                     float* y_host);
 
 /* ---- MixPE: replaces the float32 left-to-right sum of mix_pe.py:92-94 ------ */
 /*

@@ -6,6 +6,7 @@ TEST INFRASTRUCTURE ONLY (same rule as pygmu2_oracle.py: nothing under ``pygmu2_
 
 A numpy/scipy restatement, function by function, of
   sine_pe.py:119-175       (pure sine: float64 phase from the sample index)
+  sine_pe.py:135-232       (modulated sine, PE-valued parameters: running float64 phase, carried between pulls)
   blit_saw_pe.py:152-264   (BLIT: Dirichlet kernel / period, DC removed, leaky integrator via lfilter)
   super_saw_pe.py:128-318  (detune ratios, mix gains, rng phases, float64 sum of float32 voices)
 Parity pinned: ``tests/test_oracle_golden.py`` checks it against ``tests/golden/src_*.npz`` produced by the
@@ -23,6 +24,41 @@ def sine(frequency: float, amplitude: float, phase: float, sample_rate: int, sta
     time = idx / sample_rate                                            # :174
     ph = phase + 2.0 * np.pi * frequency * time                         # :175
     return (np.float64(amplitude) * np.sin(ph)).astype(np.float32)      # :146,157
+
+
+class OracleSineModulated:
+    """sine_pe.py:135-232, the stateful branch taken when any of frequency / amplitude / phase is a PE.  ``freq`` /
+    ``amp`` / ``phase`` given to render() are the control vectors the parameter PEs rendered for the pull (float32,
+    channel 0), or None where the parameter is the constant passed to the constructor."""
+
+    def __init__(self, frequency=440.0, amplitude=1.0, phase=0.0, sample_rate=44100, channels=1):
+        self.f0, self.a0, self.p0, self.sr, self.channels = float(frequency), float(amplitude), float(phase), int(sample_rate), channels
+        self.reset()
+
+    def reset(self):                                                    # :110-118
+        self.acc, self.init = 0.0, False
+
+    def render(self, duration, freq=None, amp=None, phase=None):
+        f = np.full(duration, self.f0) if freq is None else np.asarray(freq, np.float32).astype(np.float64)   # :135
+        a = (np.full(duration, self.a0) if amp is None else np.asarray(amp, np.float32).astype(np.float64)).reshape(-1, 1)
+        inc = (2.0 * np.pi * f.reshape(-1, 1) / self.sr)                # :198
+        if not self.init:                                               # :203-210
+            initial = self.p0 if phase is None else 0.0
+            self.init = True
+        else:
+            initial = self.acc
+        cum = np.cumsum(inc, axis=0) + initial                          # :216
+        # :137,219-222: _scalar_or_pe_values turns a CONSTANT phase into a constant array too (processing_element.py:
+        # 360-365), so "isinstance(phase_mod, np.ndarray)" always holds and the constant is added to every sample -- on
+        # top of its use as the initial phase -- and, through :229, again on every later pull.  Reference behaviour,
+        # restated as it is.
+        pm = np.full(duration, self.p0) if phase is None else np.asarray(phase, np.float32).astype(np.float64)
+        cum = cum + pm.reshape(-1, 1)
+        self.acc = float(cum[-1, 0])                                    # :229
+        y = a * np.sin(cum)                                             # :146
+        if self.channels > 1:
+            y = np.tile(y, (1, self.channels))                          # :153-155
+        return y.astype(np.float32)                                     # :157
 
 
 class OracleBlitSaw:

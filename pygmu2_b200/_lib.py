@@ -17,6 +17,7 @@ PGX_OK, PGX_ERR_INVALID, PGX_ERR_CUDA, PGX_ERR_NO_DEVICE, PGX_ERR_NOMEM = 0, -1,
 PGX_FLAG_MIXDOWN_INPUT = 1
 PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16 = 1, 2, 4, 8, 16
 PGX_PULL_REDUCE = 32
+PGX_CTL_HOST = 1
 PGX_COMM_HANDLE_BYTES = 128
 PGX_OSC_SINE, PGX_OSC_BLIT = 0, 1
 ABI_VERSION = 2
@@ -38,7 +39,7 @@ class BankInfo(C.Structure):
                                           "fill")] + \
                [(n, C.c_int64) for n in ("state_bytes", "kernel_launches", "block_steps")] + \
                [(n, C.c_int32) for n in ("mac_grid", "mac_split", "mac_stream_tile", "mac_occupancy",
-                                          "tail_block", "tail_partitions")]
+                                          "tail_block", "tail_partitions")] + [("graph_pulls", C.c_int64)]
 
 
 class OscConfig(C.Structure):
@@ -89,6 +90,8 @@ PROTOTYPES = {
                                         C.POINTER(C.c_void_p)]),
     "pgx_osc_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "pgx_osc_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "pgx_osc_render_modulated": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "pgx_bank_process_device": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32,
                                           C.c_int32, C.c_void_p]),
     "pgx_bank_synchronize": (C.c_int, [C.c_void_p]),

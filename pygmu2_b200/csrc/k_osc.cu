@@ -30,6 +30,50 @@ __global__ void __launch_bounds__(256) k_sine_bank(const SineArgs a) {
   }
 }
 
+// Modulated SinePE: the reference's STATEFUL branch (sine_pe.py:139-142,188-232), taken as soon as any of
+// frequency / amplitude / phase is a PE.  One CTA per voice.  phase[i] = cumsum(2 pi f[i] / sr)[i] + initial
+// (+ phase_mod[i]); np.cumsum is a left-to-right float64 sum, so ONE thread walks the increments (staged by all
+// threads first: the walk is a chain of dependent DADDs, ~2 us for a 512-sample pull) -- bit-identical phases, not a
+// re-associated scan.  The accumulated phase handed to the next pull is the last sample's phase INCLUDING its phase
+// modulation, exactly like :229.
+__global__ void __launch_bounds__(256) k_sine_mod(const SineModArgs a) {
+  const int v = blockIdx.x;
+  double* ph = a.scratch + (size_t)v * a.max_pull;
+  const float* fq = a.freq ? a.freq + (size_t)v * a.n : nullptr;
+  const float* am = a.amp ? a.amp + (size_t)v * a.n : nullptr;
+  const float* pm = a.phase ? a.phase + (size_t)v * a.n : nullptr;
+  const double f0 = a.params[3 * v], a0 = a.params[3 * v + 1], p0 = a.params[3 * v + 2];
+  const double sr = (double)a.sample_rate;
+  for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+    const double f = fq ? (double)fq[i] : f0;
+    ph[i] = ((2.0 * 3.141592653589793) * f) / sr;                 // :198 phase_increment (left-to-right product, then / sr)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < a.n; ++i) {                                // :216 np.cumsum
+      acc += ph[i];
+      ph[i] = acc;
+    }
+  }
+  __syncthreads();
+  // :203-213 first render: the constant phase (0 when the phase is a PE); afterwards the accumulated phase
+  const double initial = a.first ? (pm ? 0.0 : p0) : a.state[v];
+  __syncthreads();                                                 // everyone has read the carried phase before it is replaced
+  for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+    double p = ph[i] + initial;                                    // :216
+    p = p + (pm ? (double)pm[i] : p0);                             // :219-222 (a constant phase is a constant ARRAY there:
+                                                                   // processing_element.py:360-365 -- it is added to every
+                                                                   // sample and, through :229, carried into the next pull)
+    const double amp = am ? (double)am[i] : a0;
+    const float y = (float)(amp * sin(p));                         // :146,157
+    for (int c = 0; c < a.channels; ++c) a.out[(int64_t)v * a.os + (int64_t)c * a.oc + (int64_t)i * a.oi] = y;
+    if (i == a.n - 1) a.state[v] = p;                              // :229
+  }
+}
+
+void launch_sine_mod(const SineModArgs& a, cudaStream_t st) { k_sine_mod<<<a.n_voices, 256, 0, st>>>(a); }
+
 void launch_sine_bank(const SineArgs& a, cudaStream_t st) {
   const int64_t total = (int64_t)a.n_streams * a.n;
   int64_t blocks = (total + 255) / 256;

@@ -119,6 +119,19 @@ struct SineArgs {
 };
 void launch_sine_bank(const SineArgs& a, cudaStream_t st);
 
+struct SineModArgs {
+  const double* params;     // [V][3] constants: frequency, amplitude, phase (used where the control vector is NULL)
+  const float* freq;        // [V][n] per-sample controls (device), or NULL
+  const float* amp;
+  const float* phase;
+  double* state;            // [V] accumulated phase carried between pulls
+  double* scratch;          // [V][max_pull]
+  float* out;
+  int64_t os, oc, oi;
+  int32_t n_voices, channels, n, sample_rate, max_pull, first;
+};
+void launch_sine_mod(const SineModArgs& a, cudaStream_t st);
+
 struct BlitArgs {
   const double* consts;    // [V*U][4] phase increment f/sr, period sr/max(f,1), 1/period, harmonic count M
   const double* gain;      // [V*U] oscillator amplitude

@@ -163,6 +163,23 @@ struct pgx_bank {
   unsigned int* mix1_ticket = nullptr;  // last-CTA ticket counter (k_mix1<LAST>)
   int64_t launches = 0, steps = 0;
   pgx_comm* comm = nullptr;        // cross-GPU mix reduce for pulls that carry PGX_PULL_REDUCE (not owned)
+  // CUDA-graph replay of a whole small host pull (see graph_pull): one instantiated graph per staging slot and
+  // shape; kernel-node arguments are refreshed before every launch, the topology never changes
+  struct PullGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t n_h2d = nullptr, n_a = nullptr, n_mac = nullptr, n_fold = nullptr, n_k2 = nullptr, n_d2h = nullptr;
+    const void* f_a = nullptr; const void* f_mac = nullptr; const void* f_k2 = nullptr;
+    int shape = -1;                // 1 one fused kernel (k_conv1 / k_mix1<LAST>), 3 K1 -> K2 with the next block's past pass beside it
+    bool fold = false;
+    size_t xb = 0, yb = 0;
+  };
+  PullGraph pgraph[kSlots][2][2];  // [slot][mix][x already on the device]
+  bool use_graph = true;           // PGX_GRAPH=0 disables
+  bool after_graph = false;        // the previous step was a graph replay: the event ring must be re-armed before the
+                                   // multi-stream schedule continues
+  cudaEvent_t ev_join[4] = {};
+  int64_t graph_pulls = 0;
   // per-kernel CUDA-event timing
   bool profiling = false;
   struct ProfSpan { int kind; cudaEvent_t a, b; };  // kind 0 = K1, 1 = K3 (past pass), 2 = K2, 3 = fold, 4 = K3 (present slot, mix), 5 = fused K1+K2 (P = 1)
@@ -213,6 +230,14 @@ void free_bank(pgx_bank* b) {
   for (int i = 0; i < pgx_bank::kMapSlots; ++i)
     for (cudaEvent_t e : {b->fmap_ev[i], b->fmap_ret_crit[i], b->fmap_ret_bg[i]})
       if (e) cudaEventDestroy(e);
+  for (int i = 0; i < pgx_bank::kSlots; ++i)
+    for (int m = 0; m < 2; ++m)
+      for (int d = 0; d < 2; ++d) {
+        if (b->pgraph[i][m][d].exec) cudaGraphExecDestroy(b->pgraph[i][m][d].exec);
+        if (b->pgraph[i][m][d].graph) cudaGraphDestroy(b->pgraph[i][m][d].graph);
+      }
+  for (cudaEvent_t e : b->ev_join)
+    if (e) cudaEventDestroy(e);
   if (b->ev_call) cudaEventDestroy(b->ev_call);
   if (b->ev_bgjoin) cudaEventDestroy(b->ev_bgjoin);
   for (cudaStream_t s : {b->stream, b->s_in, b->s_bg, b->s_bg2, b->s_h2d, b->s_d2h})
@@ -326,6 +351,16 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   const int B = b->B, P = b->P, R = b->R;
   const int64_t i = b->step, t = b->block;
   const bool completes = (b->fill + take == B);
+  if (b->after_graph) {
+    // the steps before this one were graph replays on the bank's stream: whatever the schedule below waits for
+    // (ev_k1 / ev_k2 / ev_mac of earlier steps and blocks) is complete once that stream reaches this point
+    for (int e = 0; e < kRing; ++e) {
+      cudaEventRecord(b->ev_k1[e], b->stream);
+      cudaEventRecord(b->ev_k2[e], b->stream);
+      cudaEventRecord(b->ev_mac[e], b->stream);
+    }
+    b->after_graph = false;
+  }
 
   // one kernel per step: single-partition banks, and banks with a few partitions (the past sum is added in-kernel)
   const bool fused1 = (!mix && b->use_conv1 && (R == 1 || P <= b->fused_max_p));
@@ -762,6 +797,8 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
     if (const char* e = getenv("PGX_FUSED_MAXP")) b->fused_max_p = atoi(e);
     b->fft16 = pgx::conv1_r16_default();
     if (const char* e = getenv("PGX_MIX1")) b->use_mix1 = (e[0] != '0');
+    if (const char* e = getenv("PGX_GRAPH")) b->use_graph = (e[0] != '0');
+    for (cudaEvent_t& e : b->ev_join) guard(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate(join)");
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");
     if (const char* e = getenv("PGX_DEBUG_SERIAL")) {  // debugging aid: no overlap, one stream for everything
@@ -908,6 +945,7 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->mac_grid = b->plan_conv.grid; info->mac_split = b->plan_conv.n_split;
   info->mac_stream_tile = b->plan_conv.st; info->mac_occupancy = b->plan_conv.occupancy;
   info->kernel_launches = b->launches + (b->tail ? b->tail->launches : 0);
+  info->graph_pulls = b->graph_pulls;
   return PGX_OK;
 }
 
@@ -1025,6 +1063,230 @@ int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
   return PGX_OK;
 }
 
+// ---- CUDA-graph replay of a small host pull ------------------------------------------------------------------
+// A single-stream (or small) bank pulled one block at a time is a latency chain: H2D copy, two to four small kernels
+// on three streams joined by events, D2H copy -- ~20 driver calls and several cross-stream hand-overs for a few
+// microseconds of work (the reference's loop being replaced: renderer.py:297-327 / audio_renderer.py:214-236, one
+// pull per callback).  For whole-block pulls in the steady state the SAME work is one instantiated graph
+//     [H2D] -> A -> [K2] -> D2H           A = K1, or the fused k_conv1 / k_mix1<LAST> (then there is no K2)
+//               \-> MAC(t+1) [-> fold]    the next block's past-partition pass, beside K2 as in the streamed schedule
+// replayed with cudaGraphLaunch after its kernel-node arguments (ring position, block parity, x / filter-map
+// pointers, gains) have been refreshed with cudaGraphExecKernelNodeSetParams: same kernels, same arguments, same
+// buffers as run_step, one launch call.  Successive replays are ordered by the bank's stream, which is what the
+// cross-block hazards of run_step need (every earlier step is complete).
+struct StepArgs {
+  pgx::R2CArgs r{};
+  pgx::C2RArgs k{};
+  pgx::MacArgs m{};
+  const float4* fold_in = nullptr; float4* fold_out = nullptr; int fold_n = 0; int64_t fold_cols = 0;
+  float2* ynow = nullptr; unsigned int* ticket = nullptr;
+  pgx::FilterPrepArgs fp{};
+};
+
+static bool vec_ok2(const void* p, const pgx_layout& l, int pos) {
+  return l.samp == 1 && (l.stream % 2) == 0 && (l.chan % 2) == 0 && (pos % 2) == 0 && (reinterpret_cast<uintptr_t>(p) % 8) == 0;
+}
+
+// Which graph shape a whole-block pull of this bank is (0 = none: the streamed schedule handles it).
+static int graph_shape(const pgx_bank* b, bool mix) {
+  const int R = b->R, P = b->P;
+  if (!mix) {
+    if (b->use_conv1 && (R == 1 || P <= b->fused_max_p)) return 1;
+    if (P > 1 && b->plan_conv.variant == 0) return 3;
+    return 0;
+  }
+  const bool mix1 = (R == 1 && b->use_mix1 && b->mix1_rows > 0);
+  if (mix1 && b->mix1_rows <= 32 && b->cfg.c_out <= pgx::mix1_sources_per_cta(b->B)) return 1;
+  return 0;
+}
+
+// The arguments run_step would hand to its kernels for the whole-block step that is about to run.
+static void graph_args(pgx_bank* b, int shape, bool mix, const float* x_dev, const pgx_layout& xl, float* y_dev,
+                       const pgx_layout& yl, StepArgs* a) {
+  const pgx_bank_config& c = b->cfg;
+  const int B = b->B, R = b->R;
+  const int64_t t = b->block;
+  const int par = (int)(t & 1);
+  pgx::R2CArgs& r = a->r;
+  r.x = x_dev; r.xs = xl.stream; r.xc = xl.chan; r.xi = xl.samp; r.x_off = 0;
+  r.hist = b->hist; r.fdl = b->fdl; r.tw = b->tw;
+  r.n_fft = c.n_streams * b->c_x; r.c_in = c.c_in; r.c_x = b->c_x; r.B = B; r.R = R;
+  r.slot = b->head; r.half = b->half; r.fill = 0; r.take = B;
+  r.mixdown = (c.flags & PGX_FLAG_MIXDOWN_INPUT) ? 1 : 0;
+  r.fast = (!r.mixdown && vec_ok2(x_dev, xl, 0)) ? 1 : 0;
+  pgx::C2RArgs& k = a->k;
+  k.yspec = b->ypast[par]; k.n_split = 0;
+  k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
+  k.Hd = b->Hd; k.fmap = b->fmap; k.c_f = c.filter_channels; k.R = R; k.c_out = c.c_out; k.head = b->head;
+  k.y = y_dev; k.ys = mix ? 0 : yl.stream; k.yc = yl.chan; k.yi = yl.samp; k.y_off = 0;
+  k.B = B; k.fill = 0; k.take = B; k.tw = b->tw; k.wet = b->wet; k.fft16 = b->fft16;
+  k.add = nullptr;
+  pgx_layout ye = yl;
+  if (mix) ye.stream = 0;
+  if (mix) {  // k_mix1<LAST>: exactly the fields run_step's mix1 branch sets
+    k.dry = 0.0f; k.xdry = nullptr;
+    k.fast = vec_ok2(y_dev, ye, 0) ? 1 : 0;
+    k.ynow = b->ynow; k.n_split_now = b->mix1_rows; k.fdl = nullptr;
+    a->ynow = b->ynow; a->ticket = b->mix1_ticket;
+    return;
+  }
+  k.c_x = b->c_x; k.dry = b->dry;
+  k.xdry = (b->dry != 0.0f) ? x_dev : nullptr;
+  k.xs = xl.stream; k.xc = xl.chan; k.xi = xl.samp; k.x_off = 0;
+  k.fast = (vec_ok2(y_dev, ye, 0) && (!k.xdry || vec_ok2(x_dev, xl, 0))) ? 1 : 0;
+  k.ynow = nullptr; k.n_split_now = 0; k.fdl = b->fdl;
+  if (shape == 1) {
+    if (b->P > 1) {  // past partitions summed inside the fused kernel
+      k.n_past = R - 2;
+      k.q0 = R - 1 - b->head;
+      if (b->head + 1 < R) { k.p_off = 0; k.p_skip = b->head; k.p_nskip = 2; }
+      else                 { k.p_off = 1; k.p_skip = R; k.p_nskip = 0; }
+    }
+    return;
+  }
+  // shape 3: K2 sums the past pass of THIS block (issued by the previous step) ...
+  const pgx::MacPlan& pl = b->plan_conv;
+  k.n_split = pl.n_partials > kFoldAbove ? 1 : pl.n_partials;
+  // ... and the past pass of the NEXT block runs beside it
+  const int nhead = (b->head + 1) % R, npar = par ^ 1;
+  pgx::MacArgs& m = a->m;
+  fill_mac_common(b, m, false, nhead);
+  const bool fold = pl.n_partials > kFoldAbove;
+  m.mix = pl.layout;
+  m.yspec = reinterpret_cast<float4*>(fold ? b->ypart[npar] : b->ypast[npar]);
+  m.Pt = R - 2; m.jfix = -1;
+  if (nhead + 1 < R) { m.off = 0; m.skip = nhead; m.nskip = 2; }
+  else               { m.off = 1; m.skip = R; m.nskip = 0; }
+  m.n_terms = m.Pt;
+  m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
+  m.variant = pl.variant; m.persistent_ctas = pl.persistent_ctas;
+  a->fold_in = reinterpret_cast<const float4*>(b->ypart[npar]);
+  a->fold_out = reinterpret_cast<float4*>(b->ypast[npar]);
+  a->fold_n = pl.n_partials;
+  a->fold_cols = (int64_t)m.n_out * (B / 2);
+}
+
+static cudaKernelNodeParams knode(const pgx::LaunchDesc& d, void** params) {
+  cudaKernelNodeParams p{};
+  p.func = const_cast<void*>(d.func);
+  p.gridDim = d.grid; p.blockDim = d.block; p.sharedMemBytes = d.smem;
+  p.kernelParams = params; p.extra = nullptr;
+  return p;
+}
+
+// One whole-block host pull as a graph replay.  Returns PGX_OK and *done = true when the pull was enqueued this way;
+// *done = false (nothing enqueued) when the pull is not graph material.
+static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slot, const pgx_layout& yd, int32_t n, bool mix,
+                      bool x_device, size_t xb, size_t yb, bool* done) {
+  *done = false;
+  const pgx_bank_config& c = b->cfg;
+  if (!b->use_graph || b->tail || b->profiling || b->serial || b->fill != 0 || n != b->B) return PGX_OK;
+  if ((size_t)c.n_streams * b->c_x * b->B > (size_t)(1 << 18)) return PGX_OK;   // big banks: the streamed schedule overlaps better
+  const int shape = graph_shape(b, mix);
+  if (shape == 0) return PGX_OK;
+  if (shape == 3 && !(b->past_block == b->block && b->past_mode == 0)) return PGX_OK;  // this block's past sum must exist
+  if (b->block < 2) return PGX_OK;                                    // steady state only
+  const float* x_dev = x_device ? x : b->x_stage[slot];
+  float* y_dev = b->y_stage[slot];
+  StepArgs a;
+  graph_args(b, shape, mix, x_dev, xl, y_dev, yd, &a);
+  pgx::LaunchDesc dA, dMac, dFold, dK2;
+  bool ok = true;
+  if (shape == 1) ok = mix ? pgx::describe_mix1(a.r, true, &dA) : pgx::describe_conv1(a.r, a.k, &dA);
+  else ok = pgx::describe_r2c_ingest(a.r, &dA) && pgx::describe_fdl_mac(a.m, &dMac) && pgx::describe_c2r_emit(a.k, &dK2);
+  const bool fold = shape == 3 && b->plan_conv.n_partials > kFoldAbove;
+  if (fold) ok = ok && pgx::describe_reduce_partials(a.m.n_out, b->B / 2, &dFold);
+  if (!ok) return PGX_OK;
+  void* pA_fused_conv[] = {&a.r, &a.k};
+  void* pA_mix1[] = {&a.r, &a.k, &a.ynow, &a.ticket};
+  void* pA_k1[] = {&a.r, &a.fp};
+  void** pA = shape == 3 ? pA_k1 : (mix ? pA_mix1 : pA_fused_conv);
+  void* pMac[] = {&a.m};
+  void* pFold[] = {&a.fold_in, &a.fold_out, &a.fold_n, &a.fold_cols};
+  void* pK2[] = {&a.k};
+
+  pgx_bank::PullGraph& g = b->pgraph[slot][mix ? 1 : 0][x_device ? 1 : 0];
+  const bool stale = g.exec && (g.shape != shape || g.f_a != dA.func || g.f_mac != dMac.func || g.f_k2 != dK2.func ||
+                                g.fold != fold || g.xb != xb || g.yb != yb);
+  if (stale) {
+    cudaGraphExecDestroy(g.exec);
+    cudaGraphDestroy(g.graph);
+    g = pgx_bank::PullGraph{};
+  }
+  if (!g.exec) {
+    PGX_CUDA(cudaGraphCreate(&g.graph, 0));
+    cudaGraphNode_t dep = nullptr;
+    if (!x_device) {
+      PGX_CUDA(cudaGraphAddMemcpyNode1D(&g.n_h2d, g.graph, nullptr, 0, b->x_stage[slot], b->hx_bounce[slot], xb,
+                                        cudaMemcpyHostToDevice));
+      dep = g.n_h2d;
+    }
+    cudaKernelNodeParams kp = knode(dA, pA);
+    PGX_CUDA(cudaGraphAddKernelNode(&g.n_a, g.graph, dep ? &dep : nullptr, dep ? 1 : 0, &kp));
+    cudaGraphNode_t last = g.n_a;
+    if (shape == 3) {
+      kp = knode(dK2, pK2);
+      PGX_CUDA(cudaGraphAddKernelNode(&g.n_k2, g.graph, &g.n_a, 1, &kp));
+      last = g.n_k2;
+      kp = knode(dMac, pMac);
+      PGX_CUDA(cudaGraphAddKernelNode(&g.n_mac, g.graph, &g.n_a, 1, &kp));
+      if (fold) {
+        kp = knode(dFold, pFold);
+        PGX_CUDA(cudaGraphAddKernelNode(&g.n_fold, g.graph, &g.n_mac, 1, &kp));
+      }
+    }
+    PGX_CUDA(cudaGraphAddMemcpyNode1D(&g.n_d2h, g.graph, &last, 1, b->hy_bounce[slot], b->y_stage[slot], yb,
+                                      cudaMemcpyDeviceToHost));
+    PGX_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+    g.shape = shape; g.f_a = dA.func; g.f_mac = dMac.func; g.f_k2 = dK2.func; g.fold = fold; g.xb = xb; g.yb = yb;
+  } else {  // refresh the arguments that move from step to step
+    cudaKernelNodeParams kp = knode(dA, pA);
+    PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_a, &kp));
+    if (shape == 3) {
+      kp = knode(dK2, pK2);
+      PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_k2, &kp));
+      kp = knode(dMac, pMac);
+      PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_mac, &kp));
+      if (fold) {
+        kp = knode(dFold, pFold);
+        PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_fold, &kp));
+      }
+    }
+  }
+  // entering from the streamed schedule: everything it left on the other streams comes first
+  if (!b->after_graph) {
+    int e = 0;
+    for (cudaStream_t s : {b->s_in, b->s_bg, b->s_bg2, b->s_h2d}) {
+      PGX_CUDA(cudaEventRecord(b->ev_join[e], s));
+      PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_join[e], 0));
+      ++e;
+    }
+    // (a caller-owned critical stream may be gone by now: its last output stage recorded ev_k2)
+    if (b->step >= 1) PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_k2[(b->step - 1) % kRing], 0));
+  }
+  if (b->fmap_pending) {
+    PGX_CUDA(cudaStreamWaitEvent(b->stream, b->fmap_ev[b->fmap_cur], 0));
+    b->fmap_pending = false;
+  }
+  PGX_CUDA(cudaGraphLaunch(g.exec, b->stream));
+  // bookkeeping of run_step for a completed block
+  const int par = (int)(b->block & 1);
+  b->last_crit = b->stream;
+  b->last_k2_of_par[par] = b->step;
+  b->prev_on_crit = (shape == 1);
+  b->launches += shape == 1 ? 1 : (fold ? 4 : 3);
+  b->steps += 1;
+  b->step += 1;
+  if (shape == 3) { b->past_block = b->block + 1; b->past_mode = 0; }
+  b->head = (b->head + 1) % b->R;
+  b->half ^= 1;
+  b->block += 1;
+  b->after_graph = true;
+  b->graph_pulls += 1;
+  *done = true;
+  return PGX_OK;
+}
+
 // Host-buffer pull, asynchronous: stage x into the next slot (H2D on the copy-in stream), enqueue the block
 // steps, copy y back on the copy-out stream.  Returns a ticket; y is complete after submit_wait(ticket).
 static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, bool mix,
@@ -1078,6 +1340,19 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   void* y_dst = bounce_y ? static_cast<void*>(b->hy_bounce[slot]) : static_cast<void*>(y);
   if (x_pcm && !b->xpcm_stage[slot]) PGX_CUDA(cudaMalloc(&b->xpcm_stage[slot], b->xs_bytes / 2));
   if (y_pcm && !b->ypcm_stage[slot]) PGX_CUDA(cudaMalloc(&b->ypcm_stage[slot], b->ys_bytes / 2));
+  if ((bounce_x || x_device) && bounce_y && !x_pcm && !y_pcm && !reduce) {  // small whole-block pull: one graph replay
+    bool done = false;
+    rc = graph_pull(b, x, xl, slot, yd, n, mix, x_device, xb, yb, &done);
+    if (rc != PGX_OK) return rc;
+    if (done) {
+      PGX_CUDA(cudaEventRecord(b->ev_done[slot], b->stream));
+      b->y_user[slot] = y;
+      b->y_user_bytes[slot] = yb_host;
+      b->next_ticket = tk + 1;
+      if (ticket) *ticket = tk;
+      return PGX_OK;
+    }
+  }
   if (x_device) {  // produced by work already queued on the bank's stream: run_pull orders the ingest after it
     rc = run_pull(b, x, xl, b->y_stage[slot], yd, n, mix, false, b->stream);
   } else {

@@ -17,6 +17,9 @@ struct pgx_osc {
   double *consts = nullptr, *gain = nullptr, *amp = nullptr, *phase_init = nullptr;
   double *st_phase = nullptr, *st_int = nullptr;  // blit state
   float *out = nullptr, *mix = nullptr;           // [V][C][max_pull], [C][max_pull]
+  double *mod_state = nullptr, *mod_scratch = nullptr;  // modulated sine: accumulated phase [V], phases [V][max_pull]
+  float *ctl[3] = {nullptr, nullptr, nullptr};    // staged control vectors (host-supplied), [V][max_pull] each
+  bool mod_started = false;
   int64_t last_end = INT64_MIN;
   bool has_last = false;
   int64_t launches = 0;
@@ -29,7 +32,8 @@ void free_osc(pgx_osc* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : {(void*)h->params, (void*)h->consts, (void*)h->gain, (void*)h->amp, (void*)h->phase_init,
-                  (void*)h->st_phase, (void*)h->st_int, (void*)h->out, (void*)h->mix})
+                  (void*)h->st_phase, (void*)h->st_int, (void*)h->out, (void*)h->mix, (void*)h->mod_state,
+                  (void*)h->mod_scratch, (void*)h->ctl[0], (void*)h->ctl[1], (void*)h->ctl[2]})
     cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -164,8 +168,57 @@ int pgx_osc_destroy(pgx_osc* h) {
   return PGX_OK;
 }
 
+int pgx_osc_render_modulated(pgx_osc* h, int32_t n, int32_t flags, const float* freq, const float* amp,
+                             const float* phase, int32_t ctl_flags, void* cuda_stream, const float** out_dev,
+                             float* y_host) {
+  if (!h || (!out_dev && !y_host)) return pgx_fail(PGX_ERR_INVALID, "NULL argument");
+  const pgx_osc_config& c = h->cfg;
+  if (c.kind != PGX_OSC_SINE) return pgx_fail(PGX_ERR_INVALID, "pgx_osc_render_modulated is for PGX_OSC_SINE handles");
+  if (n < 1 || n > c.max_pull) return pgx_fail(PGX_ERR_INVALID, "pull of %d samples outside [1, max_pull=%d]", n, c.max_pull);
+  PGX_CUDA(cudaSetDevice(c.device));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  const size_t V = (size_t)c.n_voices;
+  if (!h->mod_state) {
+    PGX_CUDA(cudaMalloc(&h->mod_state, V * sizeof(double)));
+    PGX_CUDA(cudaMalloc(&h->mod_scratch, V * c.max_pull * sizeof(double)));
+  }
+  const float* ctl[3] = {freq, amp, phase};
+  if (ctl_flags & PGX_CTL_HOST) {  // what the parameter PEs rendered on the host: staged, in stream order
+    for (int i = 0; i < 3; ++i) {
+      if (!ctl[i]) continue;
+      if (!h->ctl[i]) PGX_CUDA(cudaMalloc(&h->ctl[i], V * c.max_pull * sizeof(float)));
+      PGX_CUDA(cudaMemcpyAsync(h->ctl[i], ctl[i], V * n * sizeof(float), cudaMemcpyHostToDevice, st));
+      ctl[i] = h->ctl[i];
+    }
+  }
+  pgx::SineModArgs a{};
+  a.params = h->params; a.freq = ctl[0]; a.amp = ctl[1]; a.phase = ctl[2];
+  a.state = h->mod_state; a.scratch = h->mod_scratch; a.out = h->out;
+  a.os = (int64_t)c.channels * n; a.oc = n; a.oi = 1;
+  a.n_voices = c.n_voices; a.channels = c.channels; a.n = n; a.sample_rate = c.sample_rate; a.max_pull = c.max_pull;
+  a.first = h->mod_started ? 0 : 1;
+  pgx::launch_sine_mod(a, st);
+  h->mod_started = true;
+  h->launches += 1;
+  const float* res = h->out;
+  if (flags & PGX_PULL_MIX) {
+    pgx::launch_mix_sum(h->out, c.n_voices, (int64_t)c.channels * n, h->mix, st);
+    h->launches += 1;
+    res = h->mix;
+  }
+  if (out_dev) *out_dev = res;
+  PGX_CUDA(cudaGetLastError());
+  if (y_host) {
+    const size_t rows = (flags & PGX_PULL_MIX) ? 1 : V;
+    PGX_CUDA(cudaMemcpyAsync(y_host, res, rows * c.channels * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (y_host || (ctl_flags & PGX_CTL_HOST)) PGX_CUDA(cudaStreamSynchronize(st));  // y complete / the control arrays may go away
+  return PGX_OK;
+}
+
 int pgx_osc_reset(pgx_osc* h) {
   if (!h) return pgx_fail(PGX_ERR_INVALID, "osc is NULL");
+  h->mod_started = false;  // modulated sine: the next pull starts from the constant phase again (sine_pe.py:110-118)
   h->has_last = false;  // the next pull re-initialises the state on its own stream, in order
   return PGX_OK;
 }

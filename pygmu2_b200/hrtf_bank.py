@@ -83,6 +83,12 @@ class HrtfMixBank:
         self._ext_lo = np.array([-np.inf if e.start is None else e.start for e in ext])
         self._ext_hi = np.array([np.inf if e.end is None else e.end for e in ext])
         self._ext_empty = np.array([e.is_empty() for e in ext], dtype=bool)
+        # scalar fast test: a request inside [max lo, min hi) meets every source's extent
+        self._lo_max = float(np.max(self._ext_lo)) if not self._ext_empty.any() else np.inf
+        self._hi_min = float(np.min(self._ext_hi)) if not self._ext_empty.any() else -np.inf
+        self._all_active_last = False
+        self._sr_checked = False
+        self._traj = None   # (device table handle, n_rows, hop, t0) of set_trajectory
         # plain in-memory sources are uploaded once and stay in HBM (no per-pull host samples)
         self._resident = None
         if ResidentSources.eligible(self.sources, self.delays, self.c_in, self.host_mixdown):
@@ -129,8 +135,55 @@ class HrtfMixBank:
         self.bank.reset()
         self._pos = None
 
+    # -- trajectories: moving sources without per-pull host work ---------------------------------------------------
+    def set_trajectory(self, azimuth, elevation=None, *, hop: int, start: int = 0) -> None:
+        """Directions of every source for a whole run, handed over once (extension; the reference moves a source by
+        assigning ``method.azimuth`` between pulls, spatial_pe.py:434-449 -- N attribute writes, N table searches and
+        one map upload per pull).  ``azimuth`` is (n_rows, N) degrees, ``elevation`` (n_rows, N), (N,) or None (the
+        methods' current elevations); row r applies to the pulls that start in [start + r*hop, start + (r+1)*hop) --
+        the same hard switch at pull boundaries -- and the first / last row holds outside the table.  The filter
+        choice of every row (nearest KEMAR entry, ears swapped for negative azimuth, spatial_pe.py:395-426,486-489)
+        is resolved here, vectorised, and uploaded as one int32 table; a pull then just points the bank at its row
+        (pgx_bank_use_filter_map_device).  ``set_trajectory(None)`` returns to the methods' attributes."""
+        import ctypes as C
+
+        from . import _lib
+        if self._traj is not None:
+            self.bank.use_filter_map_device(None)
+            _lib.lib().pgx_device_free(self.bank.device, self._traj[0])
+            self._traj = None
+            self._selected = None
+        if azimuth is None:
+            return
+        if self.pan_index:
+            raise ValueError("set_trajectory: every source must be an HRTF source (pan laws keep their attribute)")
+        n = len(self.methods)
+        az = np.asarray(azimuth, dtype=np.float64)
+        if az.ndim != 2 or az.shape[1] != n:
+            raise ValueError(f"azimuth must be (n_rows, {n}), got {az.shape}")
+        if elevation is None:
+            el = np.fromiter((float(getattr(m, "elevation", 0.0)) for m in self.methods), dtype=np.float64, count=n)
+        else:
+            el = np.asarray(elevation, dtype=np.float64)
+        el = np.broadcast_to(el, az.shape)
+        if self.n_entries != len(kemar.KEMAR_HRTF_ENTRIES):
+            raise ValueError("set_trajectory needs the KEMAR table (directions are resolved against its grid)")
+        e = kemar.nearest_indices(az.reshape(-1), el.reshape(-1)).reshape(az.shape)
+        table = np.ascontiguousarray(e + np.where(az < 0, self.n_entries, 0), dtype=np.int32)
+        ptr = C.c_void_p()
+        _lib.check(_lib.lib().pgx_device_alloc(self.bank.device, table.nbytes, C.byref(ptr)))
+        _lib.check(_lib.lib().pgx_device_upload(self.bank.device, ptr, table.ctypes.data, table.nbytes))
+        self._traj = (ptr, int(table.shape[0]), int(hop), int(start))
+        self._traj_host = table
+        self._traj_row = None
+
     def close(self) -> None:
         """Release the device state (bank, resident sources) and stop watching the methods."""
+        if self._traj is not None:
+            try:
+                self.set_trajectory(None)
+            except Exception:
+                pass
         for m in self.methods:
             w = getattr(m, "_watchers", None)
             if w is not None:
@@ -142,32 +195,58 @@ class HrtfMixBank:
 
     def render(self, start: int, duration: int) -> np.ndarray:
         """One lockstep pull of every source -> (2, duration) float32 stereo mix."""
-        sr = self.sources[0].sample_rate
-        has_hrtf = len(self.pan_index) < len(self.methods)
-        if has_hrtf and self.table_sample_rate is not None and sr != self.table_sample_rate and not self._warned:
-            handle_error(
-                f"SpatialHRTF: IR sample rate is {self.table_sample_rate} Hz but source is {sr} Hz. "
-                "Proceeding without resampling.",
-                fatal=False,
-            )
-            self._warned = True
+        if not self._sr_checked:
+            sr = self.sources[0].sample_rate
+            has_hrtf = len(self.pan_index) < len(self.methods)
+            if has_hrtf and self.table_sample_rate is not None and sr != self.table_sample_rate and not self._warned:
+                handle_error(
+                    f"SpatialHRTF: IR sample rate is {self.table_sample_rate} Hz but source is {sr} Hz. "
+                    "Proceeding without resampling.",
+                    fatal=False,
+                )
+                self._warned = True
+            self._sr_checked = True
+        contiguous = self._pos is not None and start == self._pos
         # MixPE renders only the inputs whose extent meets the request (mix_pe.py:81-85; a SpatialPE's extent is
         # its source's, spatial_pe.py:640-642).  A skipped source contributes nothing - the silent filter - and
         # its next render starts a new run (spatial_pe.py:461-463): its history is cleared when it comes back.
-        active = ~self._ext_empty & (self._ext_lo < start + duration) & (self._ext_hi > start)   # Extent.intersects
-        self._refresh_pans()
-        sel = self._select()
-        sel[~active] = 2 * self.n_entries
-        if self._pos is None or start != self._pos:
-            self.bank.reset()
+        all_active = start >= self._lo_max and start + duration <= self._hi_min   # scalar test first: the common case
+        if all_active and self._all_active_last and contiguous and self._traj is None \
+                and self._all_watched and not self._dirty[0] and not self.pan_index and self._selected is not None:
+            active = self._was_active    # nothing moved, nothing came or went: the resident selection stands
         else:
-            back = np.flatnonzero(active & ~self._was_active)
-            if back.size:
-                self.bank.reset(back)
-        if not np.array_equal(sel, self._selected):
-            self.bank.set_filter_map(sel)
-            self._selected = sel
-        self._was_active = active
+            if all_active:
+                active = np.ones(len(self.sources), dtype=bool)
+            else:
+                active = ~self._ext_empty & (self._ext_lo < start + duration) & (self._ext_hi > start)   # Extent.intersects
+            if not contiguous:
+                self.bank.reset()
+            else:
+                back = np.flatnonzero(active & ~self._was_active)
+                if back.size:
+                    self.bank.reset(back)
+            if self._traj is not None and all_active:
+                ptr, n_rows, hop, t0 = self._traj
+                row = min(max((start - t0) // hop, 0), n_rows - 1)
+                if row != self._traj_row or self._selected is not None:
+                    self.bank.use_filter_map_device(ptr.value + row * len(self.sources) * 4)
+                    self._traj_row, self._selected = row, None
+            else:
+                if self._traj is not None:      # a source is outside its extent: this pull's row, silenced where needed
+                    ptr, n_rows, hop, t0 = self._traj
+                    sel = self._traj_host[min(max((start - t0) // hop, 0), n_rows - 1)].copy()
+                    self._traj_row = None
+                else:
+                    self._refresh_pans()
+                    sel = self._select()
+                sel[~active] = 2 * self.n_entries
+                if self._selected is None or not np.array_equal(sel, self._selected):
+                    if self._traj is not None:
+                        self.bank.use_filter_map_device(None)
+                    self.bank.set_filter_map(sel)
+                    self._selected = sel
+            self._was_active = active
+            self._all_active_last = all_active
         if self._resident is not None:  # sources live in HBM: a pull is a pointer into the resident buffer
             self._pos = start + duration
             outs, pos = [], 0

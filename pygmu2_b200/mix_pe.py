@@ -56,6 +56,7 @@ class MixPE(ProcessingElement):
         self._device = int(device)
         self._fused = None       # None = undecided, False = general path, else the adopted bank
         self._fused_pos = None
+        self._rest = []          # inputs that stay outside an adopted bank
 
     def inputs(self) -> list:
         return self._inputs
@@ -65,24 +66,39 @@ class MixPE(ProcessingElement):
 
     # -- fusion ----------------------------------------------------------------
     def _try_adopt(self, duration: int):
+        """-> the device bank the bank-able inputs were adopted into, or False.  ``self._rest`` then holds the inputs
+        that stay on the general path (e.g. a source wrapped in a PE-valued GainPE, whose per-sample gain applies AFTER
+        its convolution and so cannot ride in a frequency-domain sum): one un-bankable input no longer drops the
+        whole mix to N separate pulls."""
+        self._rest = []
         if not self._fuse:
             return False
         ins = self._inputs
-        try:
-            cores, delays, gains = zip(*[_unwrap(p) for p in ins])
-            if all(type(p) is ConvolvePE and p.bank is None for p in cores):
-                return self._adopt_convolves(duration, cores, delays, gains)
-            if all(type(p) is SpatialPE and _foldable_method(p.method) for p in cores):
-                if None not in {p.source.channel_count() for p in cores}:
-                    return HrtfMixBank([p.source for p in cores], [p.method for p in cores], pull_hint=duration,
+        if len({type(p) for p in ins}) == 1 and type(ins[0]) in (SuperSawPE, BlitSawPE, SinePE) \
+                and all(p.is_pure() or type(p) is not SinePE for p in ins):
+            try:
+                return _VoiceMix(VoiceBank(ins, device=self._device))
+            except ValueError:
+                return False  # voices of different shapes: general path
+        un = [_unwrap(p) for p in ins]
+        conv = [i for i, (c, _, _) in enumerate(un) if type(c) is ConvolvePE and c.bank is None]
+        spat = [i for i, (c, _, _) in enumerate(un) if type(c) is SpatialPE and _foldable_method(c.method)
+                and c.source.channel_count() is not None]
+        for group in sorted((conv, spat), key=len, reverse=True):
+            if len(group) < 2:
+                continue
+            cores, delays, gains = zip(*[un[i] for i in group])
+            try:
+                if group is conv:
+                    bank = self._adopt_convolves(duration, cores, delays, gains)
+                else:
+                    bank = HrtfMixBank([p.source for p in cores], [p.method for p in cores], pull_hint=duration,
                                        device=self._device, delays=delays, gains=gains)
-            if len({type(p) for p in ins}) == 1 and type(ins[0]) in (SuperSawPE, BlitSawPE, SinePE):
-                try:
-                    return _VoiceMix(VoiceBank(ins, device=self._device))
-                except ValueError:
-                    return False  # voices of different shapes: general path
-        except _NotFusable:
-            return False
+            except _NotFusable:
+                continue
+            taken = set(group)
+            self._rest = [p for i, p in enumerate(ins) if i not in taken]
+            return bank
         return False
 
     def _adopt_convolves(self, duration: int, ins, delays, gains):
@@ -117,7 +133,17 @@ class MixPE(ProcessingElement):
             self._fused = self._try_adopt(duration)
         if self._fused is not False:
             y = self._fused.render(start, duration)  # (C_out, n); resets itself on a non-contiguous pull
-            return Snippet(start, np.ascontiguousarray(y.T))
+            out = np.ascontiguousarray(y.T)
+            if self._rest:                           # inputs outside the bank: rendered as they are, added in order
+                req = Extent(start, start + duration)
+                for p in self._rest:
+                    if p.extent().intersects(req):
+                        d = p.render(start, duration).data
+                        if d.shape[1] != out.shape[1]:
+                            raise ValueError(f"MixPE input channel mismatch: fused inputs have {out.shape[1]} channels, "
+                                             f"{p.__class__.__name__} has {d.shape[1]} channels")
+                        out += d
+            return Snippet(start, out)
         # general path: mix_pe.py:80-96
         req = Extent(start, start + duration)
         rendered = [p.render(start, duration).data for p in self._inputs if p.extent().intersects(req)]
@@ -126,6 +152,21 @@ class MixPE(ProcessingElement):
         if len(rendered) == 1:
             return Snippet(start, rendered[0].copy())
         return Snippet(start, device_mix_sum(rendered, self._device))
+
+    @property
+    def fused_bank(self):
+        """The device bank the inputs were adopted into (None before the first pull / when the inputs are not
+        bank-able): ``HrtfMixBank``, ``ConvolveBank`` or the voice mix."""
+        return self._fused if self._fused not in (None, False) else None
+
+    def set_trajectory(self, azimuth, elevation=None, *, hop: int, start: int = 0) -> None:
+        """Moving HRTF sources without per-pull host work (extension): see ``HrtfMixBank.set_trajectory``.  Adopts
+        the inputs first if that has not happened yet (``hop`` doubles as the pull-size hint)."""
+        if self._fused is None:
+            self._fused = self._try_adopt(int(hop))
+        if not isinstance(self._fused, HrtfMixBank):
+            raise ValueError("set_trajectory needs a MixPE whose inputs are all SpatialPE(..., SpatialHRTF) sources")
+        self._fused.set_trajectory(azimuth, elevation, hop=hop, start=start)
 
     def device_block(self, start: int, duration: int, cuda_stream: int = 0):
         """The mix left in HBM (only when the inputs are oscillator voices fused into one VoiceBank)."""
@@ -201,6 +242,21 @@ class _VoiceMix:
 
     def render(self, start: int, duration: int) -> np.ndarray:
         return self.vb.render(start, duration, mix=True)
+
+    @property
+    def fused_bank(self):
+        """The device bank the inputs were adopted into (None before the first pull / when the inputs are not
+        bank-able): ``HrtfMixBank``, ``ConvolveBank`` or the voice mix."""
+        return self._fused if self._fused not in (None, False) else None
+
+    def set_trajectory(self, azimuth, elevation=None, *, hop: int, start: int = 0) -> None:
+        """Moving HRTF sources without per-pull host work (extension): see ``HrtfMixBank.set_trajectory``.  Adopts
+        the inputs first if that has not happened yet (``hop`` doubles as the pull-size hint)."""
+        if self._fused is None:
+            self._fused = self._try_adopt(int(hop))
+        if not isinstance(self._fused, HrtfMixBank):
+            raise ValueError("set_trajectory needs a MixPE whose inputs are all SpatialPE(..., SpatialHRTF) sources")
+        self._fused.set_trajectory(azimuth, elevation, hop=hop, start=start)
 
     def device_block(self, start: int, duration: int, cuda_stream: int = 0):
         return self.vb.device_block(start, duration, mix=True, cuda_stream=cuda_stream)

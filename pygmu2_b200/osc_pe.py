@@ -101,6 +101,45 @@ class OscBank:
             pos += d
         return y
 
+    def _modulated(self, duration: int, freq, amp, phase, mix: bool, cuda_stream: int, y_host):
+        n = int(duration)
+        ptrs, keep, on_host, on_dev = [], [], False, False
+        for ctl in (freq, amp, phase):
+            if ctl is None:
+                ptrs.append(None)
+            elif isinstance(ctl, DeviceBlock):
+                if ctl.n_streams * ctl.channels != self.n_voices or ctl.duration != n or ctl.layout.samp != 1:
+                    raise ValueError("control block must be (n_voices, n) planar")
+                ptrs.append(C.c_void_p(ctl.ptr))
+                on_dev = True
+            else:
+                a = np.ascontiguousarray(ctl, dtype=np.float32).reshape(self.n_voices, n)
+                keep.append(a)
+                ptrs.append(a.ctypes.data_as(C.c_void_p))
+                on_host = True
+        if on_host and on_dev:
+            raise ValueError("control vectors must be all host arrays or all device blocks")
+        out = C.c_void_p()
+        check(lib().pgx_osc_render_modulated(self._h, n, 1 if mix else 0, ptrs[0], ptrs[1], ptrs[2],
+                                             _lib.PGX_CTL_HOST if on_host else 0,
+                                             C.c_void_p(cuda_stream) if cuda_stream else None, C.byref(out),
+                                             y_host.ctypes.data_as(C.c_void_p) if y_host is not None else None))
+        return DeviceBlock(int(out.value), Layout(self.channels * n, n, 1), 1 if mix else self.n_voices,
+                           self.channels, n)
+
+    def render_modulated_device(self, duration: int, freq=None, amp=None, phase=None, *, mix: bool = False,
+                                cuda_stream: int = 0) -> DeviceBlock:
+        """Modulated sine pull (stateful branch of sine_pe.py): ``freq`` / ``amp`` / ``phase`` are per-sample control
+        vectors -- host float32 arrays (n_voices, n) or ``DeviceBlock``s produced on ``cuda_stream`` -- or None for a
+        parameter that is constant."""
+        return self._modulated(duration, freq, amp, phase, mix, cuda_stream, None)
+
+    def render_modulated(self, duration: int, freq=None, amp=None, phase=None) -> np.ndarray:
+        """Same pull delivered to the host: (n_voices, channels, n) float32."""
+        y = np.empty((self.n_voices, self.channels, int(duration)), dtype=np.float32)
+        self._modulated(duration, freq, amp, phase, False, 0, y)
+        return y
+
     def render_device(self, start: int, duration: int, mix: bool = False, cuda_stream: int = 0) -> DeviceBlock:
         """Enqueue one pull (duration <= max_pull) on ``cuda_stream``; the block lives in the handle's buffer
         until the next render."""
@@ -162,33 +201,78 @@ class _OscPE(ProcessingElement):
 
 
 class SinePE(_OscPE):
-    """sine_pe.py:18-270 with constant frequency / amplitude / phase (pure)."""
+    """sine_pe.py:18-270.  Constant frequency / amplitude / phase: pure, phase from the sample index.  Any of them a
+    PE (FM / AM / PM): the reference's stateful branch (:188-232) -- the parameter PEs are rendered for the pull
+    (``_scalar_or_pe_values``: channel 0, widened to float64) and the phase is the running float64 sum of
+    2 pi f / sr, carried from pull to pull; on the device that sum is walked left to right like np.cumsum."""
 
     def __init__(self, frequency=440.0, amplitude=1.0, phase=0.0, channels: int = 1, *, device: int = 0):
-        self._frequency = float(_const("frequency", frequency))
-        self._amplitude = float(_const("amplitude", amplitude))
-        self._phase = float(_const("phase", phase))
+        self._params = {"frequency": frequency, "amplitude": amplitude, "phase": phase}
+        self._pe_params = {k: v for k, v in self._params.items() if isinstance(v, ProcessingElement)}
+        self._frequency = frequency if "frequency" in self._pe_params else float(frequency)
+        self._amplitude = amplitude if "amplitude" in self._pe_params else float(amplitude)
+        self._phase = phase if "phase" in self._pe_params else float(phase)
         self._channels, self._device = int(channels), int(device)
 
     frequency = property(lambda self: self._frequency)
     amplitude = property(lambda self: self._amplitude)
     initial_phase = property(lambda self: self._phase)
 
+    def inputs(self) -> list:
+        return [self._params[k] for k in ("frequency", "amplitude", "phase") if k in self._pe_params]   # sine_pe.py:91-100
+
     def is_pure(self) -> bool:
-        return True
+        return not self._pe_params                                   # sine_pe.py:102-107
+
+    def _compute_extent(self) -> Extent:
+        result = Extent(None, None)                                  # sine_pe.py:234-245
+        for pe in self.inputs():
+            result = result.intersection(pe.extent())
+        return result
+
+    def _const_or_zero(self, name):
+        return 0.0 if name in self._pe_params else float(self._params[name])
 
     def _make_bank(self) -> OscBank:
-        return OscBank(_lib.PGX_OSC_SINE, [self._frequency], [self._amplitude], [self._phase],
-                       channels=self._channels, sample_rate=self.sample_rate, max_pull=self._max_pull,
-                       device=self._device)
+        return OscBank(_lib.PGX_OSC_SINE, [self._const_or_zero("frequency")], [self._const_or_zero("amplitude")],
+                       [self._const_or_zero("phase")], channels=self._channels, sample_rate=self.sample_rate,
+                       max_pull=self._max_pull, device=self._device)
 
-    def _reset_state(self) -> None:  # stateless
-        pass
+    def _controls(self, start: int, duration: int):
+        """The PE-valued parameters rendered for this pull: channel 0 of each (processing_element.py:296-340)."""
+        return {k: np.ascontiguousarray(pe.render(start, duration).data[:, 0], dtype=np.float32)
+                for k, pe in self._pe_params.items()}
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        if not self._pe_params:
+            return super()._render(start, duration)
+        bank, outs, pos = self._bank(), [], 0
+        while pos < duration:
+            d = min(self._max_pull, duration - pos)
+            ctl = self._controls(start + pos, d)
+            outs.append(bank.render_modulated(d, ctl.get("frequency"), ctl.get("amplitude"), ctl.get("phase"))[0].T)
+            pos += d
+        return Snippet(start, np.ascontiguousarray(outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)))
+
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0) -> DeviceBlock | None:
+        if duration > self._max_pull:
+            return None
+        if not self._pe_params:
+            return self._bank().render_device(start, duration, cuda_stream=cuda_stream)
+        ctl = self._controls(start, duration)
+        return self._bank().render_modulated_device(duration, ctl.get("frequency"), ctl.get("amplitude"),
+                                                    ctl.get("phase"), cuda_stream=cuda_stream)
+
+    def _reset_state(self) -> None:
+        if self._pe_params and self._osc is not None:                # sine_pe.py:110-118: the accumulated phase starts over
+            self._osc.reset()
 
     _on_start = _on_stop = _reset_state
 
     def __repr__(self):
-        return f"SinePE(frequency={self._frequency}, amplitude={self._amplitude})"
+        f = self._frequency.__class__.__name__ if "frequency" in self._pe_params else self._frequency
+        a = self._amplitude.__class__.__name__ if "amplitude" in self._pe_params else self._amplitude
+        return f"SinePE(frequency={f}, amplitude={a})"
 
 
 class BlitSawPE(_OscPE):
@@ -319,6 +403,8 @@ class VoiceBank:
         if sr is None:
             raise RuntimeError("Sample rate not set. Call pg.set_sample_rate() first.")
         p0 = pes[0]
+        if isinstance(p0, SinePE) and any(p._pe_params for p in pes):
+            raise ValueError("VoiceBank voices must have constant parameters (a modulated SinePE renders on its own)")
         if isinstance(p0, SinePE):
             self.bank = OscBank(_lib.PGX_OSC_SINE, [p._frequency for p in pes], [p._amplitude for p in pes],
                                 [p._phase for p in pes], channels=self.channels, sample_rate=sr,

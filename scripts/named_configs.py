@@ -66,6 +66,12 @@ def main():
             sp.method.azimuth = az_tab[p, i]
 
     run("C3 256 MOVING HRTF sources -> MixPE", pg.MixPE(*srcs), wl.SR_441, 512, S, 2, before_pull=move)
+    # the same motion handed over once as a table (extension): no per-pull host work at all
+    srcs = [pg.SpatialPE(pg.ArrayPE(wl.c3_source(n3, i)), method=pg.SpatialHRTF(wl.c3_azimuth(i, 0, 2), el[i]))
+            for i in range(wl.C3_SOURCES)]
+    mix = pg.MixPE(*srcs)
+    mix.set_trajectory(az_tab, el, hop=512)
+    run("C3 256 MOVING HRTF sources -> MixPE, trajectory table", mix, wl.SR_441, 512, S, 2)
     # C5: 1024 SuperSawPE voices -> MixPE -> 10 s IR at 64-sample pulls
     voices = [pg.SuperSawPE(frequency=55.0 * 2.0 ** (i / 128.0), amplitude=1.0 / 32.0, seed=i) for i in range(wl.C5_VOICES)]
     run("C5 1024 SuperSaw -> MixPE -> 441000-tap IR", pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(wl.c5_ir()), block_size=64),

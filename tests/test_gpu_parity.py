@@ -539,6 +539,119 @@ def test_c1_block4096_fft_kernel_variants_agree_with_oracle(variant, monkeypatch
         bank.close()
 
 
+@pytest.mark.parametrize("L,B,c", [(5000, 64, 1), (700, 64, 2), (100, 128, 1), (132300, 512, 2)])
+def test_graph_replay_of_whole_block_pulls_is_bit_identical_to_the_streamed_schedule(L, B, c, monkeypatch):
+    """Small whole-block host pulls run as ONE CUDA-graph replay (H2D, kernels, D2H; kernel-node arguments refreshed
+    per step).  Same kernels, same arguments: the output must equal the multi-stream schedule's BIT FOR BIT -- through
+    whole blocks, ragged pulls in between (which leave and re-enter graph mode), resets and a gain change -- and both
+    must match the oracle."""
+    rng = np.random.default_rng(L)
+    h = (rng.standard_normal((L, c)) / np.sqrt(L)).astype(np.float32)
+    pulls = (B,) * 9 + (B // 2, B // 2 - 3, 3) + (B,) * 6 + (2 * B,) + (B,) * 4
+    n = sum(pulls)
+    x = rng.uniform(-1, 1, (n, c)).astype(np.float32)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PGX_GRAPH", mode)
+        bank = pg.ConvolveBank(h, 1, c, block=B, single_filter_dims=True, max_pull=2 * B)
+        ys, pos = [], 0
+        for rnd in range(2):
+            for i, d in enumerate(pulls):
+                if rnd == 1 and i == 5:
+                    bank.set_output_gains(0.5, 0.25)
+                ys.append(bank.process_interleaved(x[pos % n:pos % n + d]))
+                pos += d
+            if rnd == 0:
+                bank.reset()
+        outs[mode] = np.concatenate(ys)
+        info = bank.info()
+        assert (info.graph_pulls > 0) == (mode == "1"), (mode, info.graph_pulls)
+        bank.close()
+    assert np.array_equal(outs["0"], outs["1"])
+    ref = orc.OracleConvolve(h, c).render(x)
+    assert rel_err(outs["1"][:n], ref) <= TOL
+
+
+def test_graph_replay_fused_hrtf_mix_matches_streamed(monkeypatch):
+    """The one-launch HRTF mix step (k_mix1<LAST>) with resident sources as a graph replay, directions re-selected
+    between pulls: bit-identical to the streamed schedule."""
+    rng = np.random.default_rng(11)
+    srcs = [rng.uniform(-1, 1, 512 * 12).astype(np.float32) / 8 for _ in range(24)]
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PGX_GRAPH", mode)
+        methods = [pg.SpatialHRTF(-170.0 + 14 * i, 10.0 * (i % 5)) for i in range(24)]
+        mix = pg.MixPE(*[pg.SpatialPE(pg.ArrayPE(s_), method=m) for s_, m in zip(srcs, methods)])
+        ys = []
+        for p in range(12):
+            if p % 3 == 2:
+                for i, m in enumerate(methods):
+                    m.azimuth = ((m.azimuth + 25.0 + i + 180.0) % 360.0) - 180.0
+            ys.append(mix.render(p * 512, 512).data.copy())
+        outs[mode] = np.concatenate(ys)
+        gp = mix._fused.bank.info().graph_pulls
+        assert (gp > 0) == (mode == "1"), (mode, gp)
+    assert np.array_equal(outs["0"], outs["1"])
+
+
+def test_trajectory_table_equals_per_pull_attribute_assignment():
+    """MixPE.set_trajectory (directions of every pull resolved once, one device-resident int32 table) gives exactly
+    what assigning method.azimuth / .elevation before every pull gives -- including sources that start late or end
+    early (extent gating) and a non-contiguous pull."""
+    rng = np.random.default_rng(21)
+    N, pull, n_p = 20, 256, 14
+    lens = rng.integers(pull * 6, pull * n_p, N)
+    data = [rng.uniform(-1, 1, int(l)).astype(np.float32) / 4 for l in lens]
+    delays = [0] * (N - 3) + [300, 700, 1500]
+    az = rng.uniform(-180, 180, (n_p, N))
+    el = rng.uniform(-40, 90, (n_p, N))
+
+    def graph():
+        ms = [pg.SpatialHRTF(az[0, i], el[0, i]) for i in range(N)]
+        return pg.MixPE(*[pg.DelayPE(pg.SpatialPE(pg.ArrayPE(d), method=m), delay=dl) if dl else
+                          pg.SpatialPE(pg.ArrayPE(d), method=m) for d, m, dl in zip(data, ms, delays)]), ms
+    order = list(range(n_p)) + [3, 4, 5]                     # ... then jump back: a non-contiguous pull
+    mix_a, ms = graph()
+    ya = []
+    for p in order:
+        for i, m in enumerate(ms):
+            m.azimuth, m.elevation = az[p, i], el[p, i]
+        ya.append(mix_a.render(p * pull, pull).data.copy())
+    mix_b, _ = graph()
+    mix_b.set_trajectory(az, el, hop=pull)
+    yb = [mix_b.render(p * pull, pull).data.copy() for p in order]
+    assert np.array_equal(np.concatenate(ya), np.concatenate(yb))
+    assert np.max(np.abs(np.concatenate(ya))) > 0
+    mix_b.set_trajectory(None, hop=pull)                     # back to the attributes (still those of construction)
+    yc = mix_b.render(0, pull).data
+    mix_c, _ = graph()
+    assert np.array_equal(yc, mix_c.render(0, pull).data)
+
+
+def test_mix_with_one_unbankable_input_still_fuses_the_rest():
+    """A MixPE whose inputs are ConvolvePEs except one wrapped in a PE-VALUED GainPE (its per-sample gain applies after
+    the convolution, gain_pe.py:92-127, so it cannot ride in the frequency-domain sum) and one plain ArrayPE: the
+    bank-able inputs are adopted into one bank, the others are rendered as they are and added -- equal to the
+    unfused graph, and the bank really exists."""
+    rng = np.random.default_rng(8)
+    n = 2048
+    xs = [rng.uniform(-1, 1, n).astype(np.float32) / 3 for _ in range(5)]
+    hs = [(rng.standard_normal(200) / 14).astype(np.float32) for _ in range(5)]
+    gain_ctl = (0.5 + 0.5 * np.sin(np.arange(n) / 50.0)).astype(np.float32)
+
+    def graph(fuse):
+        convs = [pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(h)) for x, h in zip(xs, hs)]
+        ins = convs[:3] + [pg.GainPE(convs[3], pg.ArrayPE(gain_ctl)), pg.DelayPE(pg.GainPE(convs[4], 0.5), delay=100),
+                           pg.ArrayPE(xs[0])]
+        return pg.MixPE(*ins, fuse=fuse)
+    mf, mu = graph(True), graph(False)
+    pulls = (512, 100, 412, 1024)
+    yf, yu = _pull_pe(mf, pulls), _pull_pe(mu, pulls)
+    assert rel_err(yf, yu) <= TOL
+    assert isinstance(mf.fused_bank, pg.ConvolveBank) and mf.fused_bank.n_streams == 4 and len(mf._rest) == 2
+    assert mu.fused_bank is None
+
+
 def test_full_size_c5_impulse_response():
     ir = wl.c5_ir()
     L = ir.shape[0]

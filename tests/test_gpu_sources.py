@@ -146,3 +146,52 @@ def test_bank_with_device_voice_source_lockstep():
     for s in range(N):
         x = osrc.sine(200.0 * (s + 1), 0.5, 0.1 * s, SR, 0, 1024)
         assert rel_err(y[s, 0], orc.OracleConvolve(hs[s], 1).render(x[:, None])[:, 0]) <= TOL
+
+
+def test_modulated_sine_fm_am_pm_matches_reference_golden():
+    """SinePE with PE-valued frequency / amplitude / phase (sine_pe.py:134-232) on the device against outputs of the
+    REAL reference: the float64 phase is walked left to right like np.cumsum and carried between pulls, so the result
+    may differ from the reference only where CUDA's and the host libm's float64 sin differ in the last bit before the
+    float32 rounding: <= 1 float32 ulp, and exact almost everywhere."""
+    g = golden("src_modulated.npz")
+    pulls = [int(d) for d in g["pulls"]]
+    A = lambda k: pg.ArrayPE(g["ctl_" + k])  # noqa: E731
+
+    def close(y, ref):
+        assert y.shape == ref.shape
+        ulp = np.spacing(np.maximum(np.abs(ref), np.float32(1e-3)).astype(np.float32))
+        assert np.all(np.abs(y.astype(np.float64) - ref.astype(np.float64)) <= ulp), float(np.max(np.abs(y - ref)))
+        assert np.mean(y == ref) > 0.98
+
+    close(_pull(pg.SinePE(frequency=A("fm_freq")), pulls), g["fm"])
+    close(_pull(pg.SinePE(frequency=A("fm_freq"), amplitude=0.5, phase=0.7), pulls), g["fm_phase0p7_amp0p5"])
+    close(_pull(pg.SinePE(frequency=1000.0, amplitude=A("am_amp"), phase=0.25), pulls), g["am"])
+    close(_pull(pg.SinePE(frequency=220.0, phase=A("pm_phase")), pulls), g["pm"])
+    close(_pull(pg.SinePE(frequency=A("sweep_freq"), amplitude=A("am_amp"), phase=A("pm_phase"), channels=2), pulls),
+          g["all3_stereo"])
+    pe = pg.SinePE(frequency=A("fm_freq"), phase=A("pm_phase"))
+    assert not pe.is_pure() and len(pe.inputs()) == 2 and pe.extent().end == g["ctl_fm_freq"].shape[0]
+    r = pg.NullRenderer(sample_rate=44_100)
+    r.set_source(pe)
+    r.start()
+    a = _pull(pe, [256, 256])
+    r.stop()
+    r.start()
+    b = _pull(pe, [256, 256])
+    r.stop()
+    close(np.concatenate([a, b]), g["restart"])
+
+
+def test_modulated_sine_feeds_convolve_on_the_device():
+    """An FM SinePE as the source of a ConvolvePE: the modulated block is produced in HBM on the bank's stream and
+    consumed there (device_block protocol); against the oracle chain."""
+    import pygmu2_oracle as orc
+    import pygmu2_oracle_sources as osrc
+    g = golden("src_modulated.npz")
+    rng = np.random.default_rng(5)
+    h = (rng.standard_normal(300) / 17).astype(np.float32)
+    pe = pg.ConvolvePE(pg.SinePE(frequency=pg.ArrayPE(g["ctl_fm_freq"]), amplitude=0.5), pg.ArrayPE(h), block_size=256)
+    y = _pull(pe, [256] * 8)
+    o, c = osrc.OracleSineModulated(amplitude=0.5), orc.OracleConvolve(h, 1)
+    ref = np.concatenate([c.render(o.render(256, g["ctl_fm_freq"][i * 256:(i + 1) * 256])) for i in range(8)])
+    assert np.max(np.abs(y - ref)) <= 1e-5 * np.max(np.abs(ref))

@@ -60,3 +60,30 @@ def test_c5_voice_mix_bit_exact():
         out.append(acc)
         pos += 64
     np.testing.assert_array_equal(np.concatenate(out), g["c5_voicemix16"][:, 0])
+
+
+def test_oracle_modulated_sine_is_the_reference_bit_for_bit():
+    """OracleSineModulated against tests/golden/src_modulated.npz (real reference, oracle/gen_golden_modulated.py)."""
+    import pygmu2_oracle_sources as osrc
+    g = golden("src_modulated.npz")
+    pulls = [int(d) for d in g["pulls"]]
+
+    def run(o, f=None, a=None, p=None, pulls=pulls):
+        out, pos = [], 0
+        for d in pulls:
+            sl = slice(pos, pos + d)
+            out.append(o.render(d, None if f is None else g[f][sl], None if a is None else g[a][sl],
+                                None if p is None else g[p][sl]))
+            pos += d
+        return np.concatenate(out)
+    assert np.array_equal(run(osrc.OracleSineModulated(), f="ctl_fm_freq"), g["fm"])
+    assert np.array_equal(run(osrc.OracleSineModulated(amplitude=0.5, phase=0.7), f="ctl_fm_freq"), g["fm_phase0p7_amp0p5"])
+    assert np.array_equal(run(osrc.OracleSineModulated(frequency=1000.0, phase=0.25), a="ctl_am_amp"), g["am"])
+    assert np.array_equal(run(osrc.OracleSineModulated(frequency=220.0), p="ctl_pm_phase"), g["pm"])
+    assert np.array_equal(run(osrc.OracleSineModulated(channels=2), f="ctl_sweep_freq", a="ctl_am_amp", p="ctl_pm_phase"),
+                          g["all3_stereo"])
+    o = osrc.OracleSineModulated()
+    a = run(o, f="ctl_fm_freq", p="ctl_pm_phase", pulls=[256, 256])
+    o.reset()
+    b = run(o, f="ctl_fm_freq", p="ctl_pm_phase", pulls=[256, 256])
+    assert np.array_equal(np.concatenate([a, b]), g["restart"])
