@@ -208,6 +208,10 @@ PGX_API int pgx_bank_set_output_gains(pgx_bank* bank, float wet, float dry);
 PGX_API int pgx_bank_submit(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y, pgx_layout y_layout,
                     int32_t n, int32_t flags, int64_t* ticket);
 PGX_API int pgx_bank_wait(pgx_bank* bank, int64_t ticket);
+/* pgx_bank_submit + pgx_bank_wait of that ticket in one call (one FFI crossing per pull for callers that do not
+ * pipeline: the PE shims' render()).  Same flags. */
+PGX_API int pgx_bank_pull(pgx_bank* bank, const float* x, pgx_layout x_layout, float* y, pgx_layout y_layout,
+                  int32_t n, int32_t flags);
 /* The bank's own (critical) CUDA stream as a cudaStream_t: producers of device-resident input enqueue on it. */
 PGX_API void* pgx_bank_stream(pgx_bank* bank);
 

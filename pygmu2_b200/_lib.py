@@ -81,6 +81,7 @@ PROTOTYPES = {
     "pgx_bank_submit": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32, C.c_int32,
                                   C.POINTER(C.c_int64)]),
     "pgx_bank_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "pgx_bank_pull": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32, C.c_int32]),
     "pgx_bank_stream": (C.c_void_p, [C.c_void_p]),
     "pgx_osc_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(OscConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),

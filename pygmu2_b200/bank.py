@@ -213,10 +213,8 @@ class ConvolveBank:
                 check(lib().pgx_bank_process(self._h, _lib.f32_ptr(xc), Layout(0, 1, self.c_in),
                                              _lib.f32_ptr(yc), Layout(0, 1, self.c_out), d))
             else:
-                tk = C.c_int64(-1)
-                check(lib().pgx_bank_submit(self._h, _lib.f32_ptr(xc), Layout(0, 1, self.c_in), _lib.f32_ptr(yc),
-                                            Layout(0, 1, self.c_out), d, flags, C.byref(tk)))
-                check(lib().pgx_bank_wait(self._h, tk.value))
+                check(lib().pgx_bank_pull(self._h, _lib.f32_ptr(xc), Layout(0, 1, self.c_in), _lib.f32_ptr(yc),
+                                          Layout(0, 1, self.c_out), d, flags))
         return y
 
     # -- pipelined host-buffer pulls (several in flight; copies overlap the kernels) ------------
@@ -278,11 +276,8 @@ class ConvolveBank:
             y, yl = np.empty((self.c_out, n), dtype=np.float32), Layout(0, n, 1)
         else:
             y, yl = np.empty((self.n_streams, self.c_out, n), dtype=np.float32), Layout(self.c_out * n, n, 1)
-        tk = C.c_int64(-1)
         flags = (_lib.PGX_PULL_MIX if mix else 0) | _lib.PGX_PULL_X_DEVICE
-        check(lib().pgx_bank_submit(self._h, C.c_void_p(blk.ptr), blk.layout, _lib.f32_ptr(y), yl, n, flags,
-                                    C.byref(tk)))
-        check(lib().pgx_bank_wait(self._h, tk.value))
+        check(lib().pgx_bank_pull(self._h, blk.ptr, blk.layout, y.ctypes.data, yl, n, flags))
         return y
 
     # -- device-resident pulls (pointers from torch / cuda-python; not synchronised) ------------

@@ -445,13 +445,20 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
 template <int LOG2N>
 struct Mix1Cfg {
   using C = FftCfg<LOG2N>;
-  static constexpr int G = (1024 / C::T8) < 16 ? (1024 / C::T8) : 16;   // sources per CTA
+  // sources per CTA: at most 512 threads, so that a thread may keep the filter rows of two output channels in flight
+  // in registers behind the forward transform (128 registers per thread) and a small mix spreads over more SMs
+  static constexpr int G = (512 / C::T8) < 16 ? ((512 / C::T8) < 1 ? 1 : (512 / C::T8)) : 16;
   static constexpr int CTA = G * C::T8;
   static constexpr int SMEM_BYTES = (C::SMEM_TW ? 2 * C::N : 0) * 8 + G * 2 * C::PADN * 8;
 };
 
 // LAST: the CTA that finishes last (ticket counter) also folds the partial rows of all CTAs, runs the c_out
 // inverse transforms and emits -- the whole block step of a small mix is then ONE launch.
+// The kernel is a latency chain (ncu, profiles/r02_mix1_c3_ncu_full.txt: 16 CTAs, 4.1 long-scoreboard and 2.7 barrier
+// stall cycles per issue), so its global-memory round trips are overlapped instead of queued: the filter-map entry and
+// the filter rows of the first two output channels are requested BEFORE the forward transform and consumed after
+// it, and the last CTA folds the partial rows with all its thread groups at once (one round trip per channel) instead
+// of two groups walking them four rows at a time.
 template <int LOG2N, bool LAST>
 __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, const C2RArgs k, float2* __restrict__ ynow,
                                                               unsigned int* __restrict__ ticket) {
@@ -466,11 +473,21 @@ __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, c
   float2* sB = sA + C::PADN;
   const int64_t f = (int64_t)blockIdx.x * M::G + g;   // c_x == 1: transform f is stream f
   const bool active = f < (int64_t)a.n_fft;
+  const int fid = active ? __ldg(k.fmap + (int)f) : 0;
 
   float2 v[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
   if (active) ingest_window<LOG2N>(a, f, j, v);
+  // the source's filter rows of the first two output channels: in flight while the forward transform runs
+  float2 hpre[2][8];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int fc = (k.c_f == 1) ? 0 : c;
+    const float2* hrow = k.Hd + ((size_t)(fid * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N + j;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) hpre[c][m] = (active && c < k.c_out) ? __ldg(hrow + m * T8) : make_float2(0.f, 0.f);
+  }
   fft_passes<LOG2N, false>(v, sA, sB, 0, j, tw);
   __syncthreads();
 #pragma unroll
@@ -484,22 +501,12 @@ __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, c
     const int kk = j + m * T8;
     X[m] = (kk == 0) ? make_float2(v[m].x + v[m].y, v[m].x - v[m].y) : r2c_bin(v[m], sA[N - kk], tws[m]);
   }
-  const int fid = active ? __ldg(k.fmap + (int)f) : 0;
-  for (int c = 0; c < k.c_out; ++c) {
-    const int fc = (k.c_f == 1) ? 0 : c;
+  auto channel = [&](const int c, const float2 (&hh)[8]) {
     __syncthreads();  // the reads of sA above / by the previous channel's sum are done
     float2 y[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) y[m] = make_float2(0.f, 0.f);
-    if (active) {
-      const float2* hrow = k.Hd + ((size_t)(fid * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N + j;
-      float2 hh[8];
-#pragma unroll
-      for (int m = 0; m < 8; ++m) hh[m] = __ldg(hrow + m * T8);
-#pragma unroll
-      for (int m = 0; m < 8; ++m) y[m] = cmul(X[m], hh[m]);
-      if (j == 0) y[0] = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
-    }
+    for (int m = 0; m < 8; ++m) y[m] = active ? cmul(X[m], hh[m]) : make_float2(0.f, 0.f);
+    if (active && j == 0) y[0] = make_float2(X[0].x * hh[0].x, X[0].y * hh[0].y);  // packed bin 0: two real bins
 #pragma unroll
     for (int m = 0; m < 8; ++m) sA[j + m * T8] = y[m];
     __syncthreads();
@@ -515,6 +522,16 @@ __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, c
       }
       out[bin] = acc;
     }
+  };
+  channel(0, hpre[0]);
+  if (k.c_out > 1) channel(1, hpre[1]);
+  for (int c = 2; c < k.c_out; ++c) {
+    const int fc = (k.c_f == 1) ? 0 : c;
+    const float2* hrow = k.Hd + ((size_t)(fid * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N + j;
+    float2 hh[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) hh[m] = active ? __ldg(hrow + m * T8) : make_float2(0.f, 0.f);
+    channel(c, hh);
   }
   if (!LAST) return;
   // ---- last CTA: fold + inverse transforms + emit (K2's work), groups 0..c_out-1 carry one output channel each
@@ -527,36 +544,62 @@ __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, c
   if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch (launches of one bank are stream-ordered)
   __threadfence();
   const bool emit = g < k.c_out;
+  const int nr = (int)gridDim.x;
+  const size_t rs = (size_t)k.c_out * N;
+  float2 mine[8];
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
-  if (emit) {
-    const float2* part = ynow + (size_t)g * N + j;   // rows written by other CTAs: read through L2 (__ldcg)
-    const size_t rs = (size_t)k.c_out * N;
-    const int nr = (int)gridDim.x;
-    int r = 0;
-    for (; r + 4 <= nr; r += 4) {  // 32 loads in flight, summed in row order
+  for (int m = 0; m < 8; ++m) mine[m] = make_float2(0.f, 0.f);
+  for (int c = 0; c < k.c_out; ++c) {
+    // group g sums rows g, g+G, ... of channel c (rows written by other CTAs: read through L2), every load of a batch
+    // of 4 rows in flight at once; then the G group sums are added in group order -- a fixed order, so the result
+    // does not depend on which CTA happened to be last
+    float2 acc[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] = make_float2(0.f, 0.f);
+    const float2* part = ynow + (size_t)c * N + j;
+    int r = g;
+    for (; r + 3 * M::G < nr; r += 4 * M::G) {
       float2 t[4][8];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int m = 0; m < 8; ++m) t[u][m] = __ldcg(part + (size_t)(r + u) * rs + m * T8);
+        for (int m = 0; m < 8; ++m) t[u][m] = __ldcg(part + (size_t)(r + u * M::G) * rs + m * T8);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-          v[m].x += t[u][m].x;
-          v[m].y += t[u][m].y;
+          acc[m].x += t[u][m].x;
+          acc[m].y += t[u][m].y;
         }
     }
-    for (; r < nr; ++r) {
+    for (; r < nr; r += M::G) {
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         const float2 t = __ldcg(part + (size_t)r * rs + m * T8);
-        v[m].x += t.x;
-        v[m].y += t.y;
+        acc[m].x += t.x;
+        acc[m].y += t.y;
+      }
+    }
+    __syncthreads();  // the previous channel's group sums have been read
+#pragma unroll
+    for (int m = 0; m < 8; ++m) bufs[(size_t)g * 2 * C::PADN + j + m * T8] = acc[m];
+    __syncthreads();
+    if (g == c) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        float2 sacc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int gg = 0; gg < M::G; ++gg) {
+          const float2 t = bufs[(size_t)gg * 2 * C::PADN + j + m * T8];
+          sacc.x += t.x;
+          sacc.y += t.y;
+        }
+        mine[m] = sacc;
       }
     }
   }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = mine[m];
   __syncthreads();
 #pragma unroll
   for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];

@@ -139,7 +139,7 @@ __device__ __forceinline__ float2 w32(const float2 t0, const int m) {
 
 }  // namespace
 
-template <bool SHFL>
+template <bool SHFL, bool PAIR>
 __global__ void __launch_bounds__(kT, 3) k_conv1_r16(const R2CArgs a, const C2RArgs k) {
   extern __shared__ float2 sm[];
   float2* sA = sm;
@@ -200,10 +200,73 @@ __global__ void __launch_bounds__(kT, 3) k_conv1_r16(const R2CArgs a, const C2RA
 
   // ================= split: packed half spectrum X[k], natural layout k = j + 256 m =================
   float2* sS = SHFL ? sB : sA;   // (no barrier since exchange 1's reads in the SHFL variant: A may still be read)
+  if constexpr (PAIR) {
+    // pair layout: bins below N/2 at swz(k), bins from N/2 up at N/2 + swz(N - k) -- the mirror partner of bin k then
+    // sits at N/2 + swz(k): both reads of a pair are natural-order runs (no run straddles a swizzle group, which cost
+    // every mirrored read a 2-way bank conflict), and the stride-16 writes stay conflict-free
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) sS[swz(hi + 16 * k1 + 256 * k2)] = v[P16(k2)];
+    for (int k2 = 0; k2 < 8; ++k2) sS[swz(hi + 16 * k1 + 256 * k2)] = v[P16(k2)];
+#pragma unroll
+    for (int k2 = 8; k2 < 16; ++k2) sS[kN / 2 + swz((kN - (hi + 16 * k1 + 256 * k2)) & (kN / 2 - 1))] = v[P16(k2)];
+  } else {
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) sS[swz(hi + 16 * k1 + 256 * k2)] = v[P16(k2)];
+  }
   const float2 twj = __ldg(tw + j);
+  float2* sM = SHFL ? sA : sB;
+  const int kb = 16 * lo + hi;
+  const float2 twb = __ldg(tw + kb);
+  float2 hA[8], hB[8];
+  if constexpr (PAIR) {  // the filter row (in L2 by now): requested before the barrier, consumed after it
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+      const int kA = j + 256 * sl, kB = (sl == 0 && j == 0) ? kN / 2 : kN - kA;
+      hA[sl] = __ldg(hrow + kA);
+      hB[sl] = __ldg(hrow + kB);
+    }
+  }
   __syncthreads();
+  if constexpr (PAIR) {
+    // ---- split, product and merge on mirror PAIRS (k, N-k), all in registers: thread j owns the 8 pairs
+    // (j + 256 s, N - j - 256 s), s < 8 (each pair exactly once over the CTA; thread 0 owns bins 0 and N/2 instead of a
+    // pair).  X[k] = E + w O and X[N-k] = conj(E - w O) share E, O and the twiddle; so do W[k] = e + i o and
+    // W[N-k] = conj(e - i o): half the shared-memory reads of the one-bin-per-thread form, and no merge exchange --
+    // only the redistribution of W into the inverse transform's input layout.
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+      const int kA = j + 256 * sl;
+      const float2 zA = sS[swz(kA)], zB = sS[kN / 2 + swz(kA)];
+      float2 wa, wb;
+      if (sl == 0 && j == 0) {
+        // bin 0 (packed DC / Nyquist, two real products) and bin N/2 (its own mirror, twiddle -i)
+        const float2 x0 = make_float2(zA.x + zA.y, zA.x - zA.y);
+        const float2 y0 = make_float2(x0.x * hA[sl].x, x0.y * hA[sl].y);
+        wa = make_float2(0.5f * (y0.x + y0.y), 0.5f * (y0.x - y0.y));
+        const float2 wq = make_float2(0.f, -1.f);
+        const float2 yq = cmul(r2c_bin(zB, zB, wq), hB[sl]);
+        wb = c2r_bin(yq, yq, wq);
+      } else {
+        const float2 w = w32(twj, sl);
+        const float2 E = make_float2(0.5f * (zA.x + zB.x), 0.5f * (zA.y - zB.y));
+        const float2 O = make_float2(0.5f * (zA.y + zB.y), -0.5f * (zA.x - zB.x));   // -i/2 (zA - conj zB)
+        const float2 t = cmul(w, O);
+        const float2 xA = make_float2(E.x + t.x, E.y + t.y), xB = make_float2(E.x - t.x, -(E.y - t.y));
+        const float2 yA = cmul(xA, hA[sl]), yB = cmul(xB, hB[sl]);
+        const float2 e = make_float2(0.5f * (yA.x + yB.x), 0.5f * (yA.y - yB.y));
+        const float2 d = make_float2(yA.x - yB.x, yA.y + yB.y);                       // yA - conj yB
+        const float2 o = cmul(make_float2(0.5f * w.x, -0.5f * w.y), d);
+        wa = make_float2(e.x - o.y, e.y + o.x);                                       // e + i o
+        wb = make_float2(e.x + o.y, -(e.y - o.x));                                    // conj(e - i o)
+      }
+      sM[swz(kA)] = wa;                    // same pair layout: W[k] at swz(k), W[N-k] at N/2 + swz(k)
+      sM[kN / 2 + swz(kA)] = wb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sM[swz(kb + 256 * q)];
+#pragma unroll
+    for (int q = 8; q < 16; ++q) v[q] = sM[kN / 2 + swz((kN - (kb + 256 * q)) & (kN / 2 - 1))];
+  } else {
   float2 X[16];
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
@@ -229,11 +292,8 @@ __global__ void __launch_bounds__(kT, 3) k_conv1_r16(const R2CArgs a, const C2RA
     }
   }
   // ================= merge: W[k] for the inverse transform, thread (b = lo, c = hi), k = 256a + 16b + c ==========
-  float2* sM = SHFL ? sA : sB;
 #pragma unroll
   for (int m = 0; m < 16; ++m) sM[swz(j + m * kT)] = X[m];
-  const int kb = 16 * lo + hi;
-  const float2 twb = __ldg(tw + kb);
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -244,6 +304,7 @@ __global__ void __launch_bounds__(kT, 3) k_conv1_r16(const R2CArgs a, const C2RA
     } else {
       v[q] = c2r_bin(yk, sM[swz(kN - kk)], w32(twb, q));
     }
+  }
   }
 
   // ================= inverse =================
@@ -311,11 +372,11 @@ __global__ void __launch_bounds__(kT, 3) k_conv1_r16(const R2CArgs a, const C2RA
 }
 
 // PGX_FFT16 = 0 (radix-8 kernel of k_fft.cu), 1 (radix-16, both exchanges through shared memory), 2 (radix-16 with the
-// half-warp exchange done by shuffles).  Read when a bank is created, so one process can A/B the variants.
+// half-warp exchange done by shuffles), 3 / 4 = 1 / 2 with split, product and merge on mirror pairs in registers.  Read when a bank is created, so one process can A/B the variants.
 int conv1_r16_default() {
   const char* e = getenv("PGX_FFT16");
-  const int v = e ? atoi(e) : 1;  // measured A/B on one box (profiles/r02_ab_fft_c1.txt): 0.153 / 0.127 / 0.141 ms per step
-  return (v < 0 || v > 2) ? 0 : v;
+  const int v = e ? atoi(e) : 3;  // measured A/B on one box (profiles/r02_ab_fft_c1.txt)
+  return (v < 0 || v > 4) ? 0 : v;
 }
 
 bool describe_conv1_r16(const R2CArgs& a, const C2RArgs& k, LaunchDesc* d) {
@@ -328,11 +389,16 @@ bool describe_conv1_r16(const R2CArgs& a, const C2RArgs& k, LaunchDesc* d) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!done[dev & 63]) {
-    cudaFuncSetAttribute(k_conv1_r16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_conv1_r16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_conv1_r16<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_conv1_r16<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_conv1_r16<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_conv1_r16<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     done[dev & 63] = true;
   }
-  d->func = variant == 2 ? reinterpret_cast<const void*>(k_conv1_r16<true>) : reinterpret_cast<const void*>(k_conv1_r16<false>);
+  d->func = variant == 1 ? reinterpret_cast<const void*>(k_conv1_r16<false, false>)
+          : variant == 2 ? reinterpret_cast<const void*>(k_conv1_r16<true, false>)
+          : variant == 3 ? reinterpret_cast<const void*>(k_conv1_r16<false, true>)
+                         : reinterpret_cast<const void*>(k_conv1_r16<true, true>);
   d->grid = dim3((unsigned)a.n_fft);
   d->block = dim3(kT);
   d->smem = smem;

@@ -429,7 +429,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
       k.fast = (whole && vec_ok(y_dev, ye)) ? 1 : 0;
     }
     // few CTAs: the last one to finish folds their rows and does the inverse transforms itself
-    const bool last = (b->mix1_rows <= 32 && c.c_out <= pgx::mix1_sources_per_cta(B));
+    const bool last = (b->mix1_rows <= 64 && c.c_out <= pgx::mix1_sources_per_cta(B));
     {
       ProfScope ps(b, crit, last ? 5 : 4);
       pgx::launch_mix1(r, k, b->ynow, last ? b->mix1_ticket : nullptr, crit);
@@ -438,7 +438,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     cudaEventRecord(b->ev_k1[i % kRing], crit);
     step_done = last;
     k.ynow = b->ynow; k.n_split_now = b->mix1_rows;
-    if (b->mix1_rows > 32) {  // many CTAs: fold their rows with the wide kernel instead of inside K2
+    if (b->mix1_rows > 64) {  // many CTAs: fold their rows with the wide kernel instead of inside K2
       float2* folded = b->ynow + (size_t)b->mix1_rows * c.c_out * B;
       ProfScope ps(b, crit, 3);
       pgx::launch_reduce_partials(reinterpret_cast<const float4*>(b->ynow), reinterpret_cast<float4*>(folded),
@@ -1096,7 +1096,7 @@ static int graph_shape(const pgx_bank* b, bool mix) {
     return 0;
   }
   const bool mix1 = (R == 1 && b->use_mix1 && b->mix1_rows > 0);
-  if (mix1 && b->mix1_rows <= 32 && b->cfg.c_out <= pgx::mix1_sources_per_cta(b->B)) return 1;
+  if (mix1 && b->mix1_rows <= 64 && b->cfg.c_out <= pgx::mix1_sources_per_cta(b->B)) return 1;
   return 0;
 }
 
@@ -1427,6 +1427,12 @@ int pgx_bank_submit(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_la
     return fail(PGX_ERR_INVALID, "PGX_PULL_X_DEVICE and PGX_PULL_X_PCM16 exclude each other");
   return submit_host(b, x, xl, y, yl, n, (flags & PGX_PULL_MIX) != 0, ticket, (flags & PGX_PULL_X_DEVICE) != 0,
                      (flags & PGX_PULL_X_PCM16) != 0, (flags & PGX_PULL_Y_PCM16) != 0, (flags & PGX_PULL_REDUCE) != 0);
+}
+
+int pgx_bank_pull(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx_layout yl, int32_t n, int32_t flags) {
+  int64_t tk = 0;
+  const int rc = pgx_bank_submit(b, x, xl, y, yl, n, flags, &tk);
+  return rc != PGX_OK ? rc : submit_wait(b, tk);
 }
 
 void* pgx_bank_stream(pgx_bank* b) { return b ? static_cast<void*>(b->stream) : nullptr; }

@@ -52,6 +52,7 @@ class ResidentSources:
         self._ptr = C.c_void_p()
         check(lib().pgx_device_alloc(self.device, nbytes, C.byref(self._ptr)))
         check(lib().pgx_device_zero(self.device, self._ptr, nbytes))
+        self._base = int(self._ptr.value)
         row = self.T * 4
         for s, (pe, d, g) in enumerate(zip(sources, delays, gains)):
             data = pe.data                                                   # (n_s, C_s) float32
@@ -72,8 +73,10 @@ class ResidentSources:
             return None
         pos = int(start) - self.t0 + MARGIN
         pos = min(max(pos, 0), self.T - duration)          # beyond either end everything is zero anyway
-        return DeviceBlock(self._ptr.value + pos * 4, Layout(self.c_in * self.T, self.T, 1), self.n, self.c_in,
-                           int(duration))
+        lay = getattr(self, "_layout", None)
+        if lay is None:
+            lay = self._layout = Layout(self.c_in * self.T, self.T, 1)
+        return DeviceBlock(self._base + pos * 4, lay, self.n, self.c_in, int(duration))
 
     def close(self) -> None:
         if getattr(self, "_ptr", None) is not None and self._ptr.value:

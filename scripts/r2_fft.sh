@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "c1 or 4096" > gpurun_out/${tag}_tests.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_tests.log
 tail -15 gpurun_out/${tag}_tests.log
 for rep in 1 2; do
-for v in 0 1 2; do
+for v in 0 1 2 3 4; do
   PGX_FFT16=$v timeout 300 python bench.py --steps 200 --warmup 20 --workload c1 --no-cpu > gpurun_out/${tag}_c1_v${v}_$rep.json 2> gpurun_out/${tag}_c1_v${v}_$rep.err; echo "v$v rc=$?"
 done
 done

@@ -4,7 +4,7 @@ tag=${1:-r02}
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 B="python bench.py --steps 20 --warmup 3 --no-cpu --reps 3"
-for v in 0 1 2; do
+for v in 0 1 3; do
   PGX_FFT16=$v $B --workload c1 > gpurun_out/${tag}_plain_c1_v$v.log 2>&1 || { echo "plain c1 v$v failed"; tail -3 gpurun_out/${tag}_plain_c1_v$v.log; }
   PGX_FFT16=$v ncu --set full --clock-control none --import-source on -k regex:k_conv1 -s 10 -c 1 -f -o gpurun_out/${tag}_conv1_c1_v$v $B --workload c1 > gpurun_out/${tag}_ncu_c1_v$v.log 2>&1
 done

@@ -511,10 +511,11 @@ def test_adopted_convolve_mix_gates_on_extents_like_the_reference():
     assert rel_err(y_f[512:, 0], ca[512:]) <= TOL
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4"])
 def test_c1_block4096_fft_kernel_variants_agree_with_oracle(variant, monkeypatch):
     """B = 4096 single-partition step: the radix-8 kernel (0), the radix-16 kernel with shared-memory exchanges (1)
-    and with the half-warp exchange by warp shuffles (2; the default) against the oracle -- whole blocks (the
+    and with the half-warp exchange by warp shuffles (2), and both with split / product / merge on mirror pairs in
+    registers (3, 4) against the oracle -- whole blocks (the
     radix-16 fast path), then ragged pulls (general kernel), with a wet/dry output stage, mono and stereo."""
     monkeypatch.setenv("PGX_FFT16", variant)
     rng = np.random.default_rng(int(variant) + 40)

@@ -92,11 +92,14 @@ def test_voice_mix_fused_matches_reference_golden():
     assert isinstance(mix._fused, _VoiceMix) and mix._fused.vb.bank.launches == 2 * 12
 
 
-def test_modulated_parameters_are_rejected_loudly():
-    with pytest.raises(NotImplementedError):
-        pg.SinePE(frequency=pg.ConstantPE(440.0))
+def test_modulated_saw_parameters_are_rejected_loudly():
+    """SinePE takes PE-valued parameters on the device (test_modulated_sine_*); the BLIT oscillators do not yet and
+    say so instead of falling back to anything."""
+    assert not pg.SinePE(frequency=pg.ConstantPE(440.0)).is_pure()
     with pytest.raises(NotImplementedError):
         pg.SuperSawPE(frequency=pg.ConstantPE(440.0))
+    with pytest.raises(NotImplementedError):
+        pg.BlitSawPE(frequency=pg.ConstantPE(440.0))
 
 
 def test_c1_sine_source_stays_on_device_through_convolve():
