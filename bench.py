@@ -752,8 +752,10 @@ def measure(args, wname, world, rank, local, numa_bound):
         if mac_per_step > 0:
             kname, kbytes, klaunch_ms = "k_fdl_mac", mac_bytes, (ms_med / K) / mac_per_step
         elif prof.ms_conv1 > 0:
-            kname = "k_conv1 (fused K1+K2)" if not mix else "k_mix1 (fused ingest+FFT+HRTF+mix)"
-            kbytes = (N * info.c_x * Bw * 12 + N * c_out * Bw * 12) if not mix else (N * Bw * 8 + N * c_out * Bw * 8)
+            # one fused launch IS the block step: SURVEY 8d's per-step figure (which still counts the delay-line row the
+            # fused kernel never writes or re-reads: its own minimum traffic is lower, see "fused_kernel_min_bytes")
+            kname = "k_conv1 / k_conv1_r16 (fused K1+K2)" if not mix else "k_mix1 (fused ingest+FFT+HRTF+mix)"
+            kbytes = step_bytes
             klaunch_ms = ms_med / K
         else:
             kname, kbytes, klaunch_ms = "block step", step_bytes, ms_med / K
@@ -787,6 +789,8 @@ def measure(args, wname, world, rank, local, numa_bound):
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kbytes, "mean_launch_ms": klaunch_ms,
+                         "fused_kernel_min_bytes": ((N * info.c_x * Bw * 12 + N * c_out * Bw * 12) if not mix else
+                                                    (N * Bw * 8 + N * c_out * Bw * 8)) if (mac_per_step == 0 and prof.ms_conv1 > 0) else None,
                          "timing": "UN-instrumented timed loop (CUDA events on the launching stream around K steps, median "
                                    "repetition): the kernel is launched once per step and its launches run back to back, so "
                                    "time per launch = ms_per_step; K1/K2 overlap it on other streams, whatever they do not "

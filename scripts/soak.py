@@ -35,6 +35,7 @@ def one(seed, L, B, TB, steps):
     two = bank.info().tail_block > 0
     hist = [np.zeros(0, np.float32) for _ in range(N)]
     pending, keep, worst, mode = [], [], 0.0, None
+    fill = [0]   # samples in the open block: whole-block pulls on a block boundary are what runs as a graph replay
 
     def model(n, mix):
         per = np.zeros((N, C, n))
@@ -54,9 +55,33 @@ def one(seed, L, B, TB, steps):
             assert e <= TOL, f"{label}: {e:.3e}"
         pending.clear()
 
-    ops = ["pull"] * 5 + ["mix"] * 3 + ["reset_all", "reset_some", "map"]
+    def pull(op, n, step):
+        top = 4 * max(B, TB or B)
+        x = rng.uniform(-1, 1, (N, 1, n)).astype(np.float32)
+        for s in range(N):
+            hist[s] = np.concatenate([hist[s], x[s, 0]])[-(L + top):]
+        xp = PinnedArray((N, 1, n))
+        xp.array[...] = x
+        yp = PinnedArray((C, n) if op == "mix" else (N, C, n))
+        tk = bank.submit(xp.array, yp.array, mix=(op == "mix"))
+        pending.append((tk, yp, model(n, op == "mix"), f"seed {seed} L={L} B={B} TB={TB} step {step} {op} n={n}"))
+        keep.extend([xp, yp])
+        fill[0] = (fill[0] + n) % B
+        if len(pending) >= 3:
+            drain()
+
+    ops = ["pull"] * 5 + ["mix"] * 3 + ["burst"] * 3 + ["reset_all", "reset_some", "map"]
     for step in range(steps):
         op = str(rng.choice(ops))
+        if op == "burst":   # align to a block boundary, then a run of whole-block pulls (graph replays), conv or mix
+            kind = mode if (two and mode) else str(rng.choice(["pull", "mix"]))
+            if two and mode is None:
+                mode = kind
+            if fill[0]:
+                pull(kind, B - fill[0], step)
+            for _ in range(int(rng.integers(2, 7))):
+                pull(kind, B, step)
+            continue
         if two:  # two-level banks keep their map and their mode between resets
             if op == "map":
                 op = "pull"
@@ -69,23 +94,14 @@ def one(seed, L, B, TB, steps):
         if op in ("pull", "mix"):
             top = 4 * max(B, TB or B)
             n = int(rng.choice([1, 7, B - 1, B, B + 1, 2 * B, 3 * B + 5, int(rng.integers(1, top))]))
-            x = rng.uniform(-1, 1, (N, 1, n)).astype(np.float32)
-            for s in range(N):
-                hist[s] = np.concatenate([hist[s], x[s, 0]])[-(L + top):]
-            xp = PinnedArray((N, 1, n))
-            xp.array[...] = x
-            yp = PinnedArray((C, n) if op == "mix" else (N, C, n))
-            tk = bank.submit(xp.array, yp.array, mix=(op == "mix"))
-            pending.append((tk, yp, model(n, op == "mix"), f"seed {seed} L={L} B={B} TB={TB} step {step} {op} n={n}"))
-            keep += [xp, yp]
-            if len(pending) >= 3:
-                drain()
+            pull(op, n, step)
         else:
             drain()
             if op == "reset_all":
                 bank.reset()
                 hist = [np.zeros(0, np.float32) for _ in range(N)]
                 mode = None
+                fill[0] = 0
             elif op == "reset_some":
                 ids = [int(s) for s in range(N) if rng.random() < 0.5] or [0]
                 bank.reset(ids)
@@ -95,10 +111,11 @@ def one(seed, L, B, TB, steps):
                 fmap = rng.integers(0, F, N).astype(np.int32)
                 bank.set_filter_map(fmap)
     drain()
+    gp = int(bank.info().graph_pulls)
     for a in keep:
         a.free()
     bank.close()
-    return worst
+    return worst, gp
 
 
 def main():
@@ -111,11 +128,13 @@ def main():
     t0 = time.time()
     total = 0
     for L, B, TB in shapes:
-        worst = 0.0
+        worst, graphs = 0.0, 0
         for seed in range(a.seeds):
-            worst = max(worst, one(1000 * B + seed, L, B, TB, a.steps))
+            w, gp = one(1000 * B + seed, L, B, TB, a.steps)
+            worst, graphs = max(worst, w), graphs + gp
             total += 1
-        print(f"L={L:6d} B={B:5d} tail={TB}: {a.seeds} sequences x {a.steps} operations ok, worst error {worst:.2e}", flush=True)
+        print(f"L={L:6d} B={B:5d} tail={TB}: {a.seeds} sequences x {a.steps} operations ok, worst error {worst:.2e}, "
+              f"{graphs} pulls ran as graph replays", flush=True)
     print(f"soak ok: {total} sequences in {time.time() - t0:.0f} s")
 
 
