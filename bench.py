@@ -658,7 +658,7 @@ def measure(args, wname, world, rank, local, numa_bound):
 
     # ---- e2e: public host API, pinned host buffers, H2D + step + D2H every step
     io_dt = np.int16 if args.pcm16 else np.float32   # --pcm16: WAV staging, int16 over PCIe, converted in HBM
-    xp = PinnedArray((N_INPUT_BLOCKS, N, c_in, pull), io_dt)
+    xp = PinnedArray((N_INPUT_BLOCKS, N, c_in, pull), io_dt, write_combined=args.wc)
     yp = PinnedArray((c_out, pull) if mix else (N, c_out, pull), io_dt)
     xp.array[...] = np.clip(np.rint(x_host * 32768.0), -32768, 32767).astype(np.int16) if args.pcm16 else x_host
     E2E_DEPTH = 3  # pulls in flight: H2D of pull i+1 and D2H of pull i-1 overlap the kernels of pull i
@@ -782,7 +782,7 @@ def measure(args, wname, world, rank, local, numa_bound):
                             if vb is not None else "ConvolveBank.submit/wait (pgx_bank_submit / pgx_bank_wait): pinned host buffers, "
                             f"{E2E_DEPTH} pulls in flight, every pull's H2D and D2H inside the timed region"
                             + ("; PGX_PULL_REDUCE: the mix is summed over the ranks on the device, D2H on rank 0 only" if do_reduce else "")),
-                    "host_affinity_bound": numa_bound,
+                    "host_affinity_bound": numa_bound, "x_write_combined": bool(args.wc),
                     "checksum_mean_abs_y": checksum},
             "gpu_launches": launches, "host_enqueue_ms_per_step": float(np.median(host_reps)),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -877,6 +877,7 @@ def main():
     ap.add_argument("--pcm16", action="store_true",
                     help="e2e leg with int16 PCM host buffers converted on the device (WAV staging, half the PCIe bytes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--wc", action="store_true", help="e2e leg: input staging buffers in write-combined pinned memory")
     ap.add_argument("--reps", type=int, default=0, help="repetitions of the K-step timed loop (default: ~4 s worth, 5..60)")
     ap.add_argument("--no-c4", action="store_true", help="--gpus N>1: skip the sharded-mix (c4) sub-record")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],

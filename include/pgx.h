@@ -17,7 +17,8 @@
  *     calls cudaSetDevice itself: reference audio_renderer.py:214-236 pulls from
  *     PortAudio's thread);
  *   - "stream" below means an audio stream (one ConvolvePE / one HRTF source),
- *     "cuda_stream" is a cudaStream_t passed as void* (NULL = the bank's own).
+ *     "cuda_stream" is a cudaStream_t passed as void* (NULL = the bank's own; the legacy default stream, whose
+ *     handle is 0, therefore cannot be named: callers on it use a side stream, see dist.ShardedMix).
  */
 #ifndef PGX_H_
 #define PGX_H_
@@ -104,6 +105,10 @@ PGX_API const char* pgx_last_error(void);
 PGX_API int pgx_device_count(int* count);
 /* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
 PGX_API int pgx_host_alloc(void** ptr, int64_t bytes);
+/* Same with flags: PGX_HOST_WRITE_COMBINED = write-combined pinned memory for buffers the host only WRITES and the device
+ * reads (input staging): not snooped on its way over PCIe, at the price of very slow host reads. */
+#define PGX_HOST_WRITE_COMBINED 1
+PGX_API int pgx_host_alloc_flags(void** ptr, int64_t bytes, int32_t flags);
 PGX_API int pgx_host_free(void* ptr);
 
 /* device memory for inputs that stay resident (ArrayPE sources uploaded once; see PGX_PULL_X_DEVICE).
@@ -295,9 +300,16 @@ PGX_API int pgx_osc_launches(pgx_osc* osc, int64_t* launches);
  * device), or NULL for a parameter that is the constant given to pgx_osc_create.  ctl_flags & PGX_CTL_HOST: the vectors
  * are host memory (staged by the call, which then returns once they have been consumed); otherwise device pointers
  * whose producer was enqueued on cuda_stream.  The phase carries over from pull to pull (the reference's base class
- * only allows contiguous pulls of a stateful PE); pgx_osc_reset starts over.  Output as pgx_osc_render_device
+ * only allows contiguous pulls of a stateful PE); pgx_osc_reset starts over.
+ * PGX_OSC_BLIT handles (BlitSawPE / SuperSawPE with a PE-valued frequency and / or amplitude, blit_saw_pe.py:161-262,
+ * super_saw_pe.py:223-246,287-303): `freq` is the voice's frequency control, each oscillator using float32(freq * ratio)
+ * with ratio = its `freq` entry at creation (GainPE(frequency_pe, ratio); pass the detune ratios -- 1 for a BlitSawPE --
+ * when the frequency will be a PE); `amp` see PGX_CTL_AMP_OSC; `phase` must be NULL.  Output as pgx_osc_render_device
  * (*out_dev, may be NULL) and / or, when y_host is not NULL, copied to host memory before the call returns. */
 #define PGX_CTL_HOST 1
+#define PGX_CTL_AMP_OSC 2 /* BLIT handles: the amplitude control replaces the OSCILLATOR amplitude (BlitSawPE: saw * 2 * amp,
+                             blit_saw_pe.py:252-256); without it, it replaces the VOICE amplitude that multiplies the
+                             float64 sum of the oscillators (SuperSawPE, super_saw_pe.py:287-303) */
 PGX_API int pgx_osc_render_modulated(pgx_osc* osc, int32_t n, int32_t flags, const float* freq, const float* amp,
                                      const float* phase, int32_t ctl_flags, void* cuda_stream, const float** out_dev,
                                      float* y_host);

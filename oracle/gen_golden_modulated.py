@@ -66,6 +66,25 @@ def main():
     b = pull(pe, [256, 256])
     r.stop()
     out["restart"] = np.concatenate([a, b])
+    # ---- BLIT oscillators with PE-valued parameters (blit_saw_pe.py:161-262, super_saw_pe.py:223-246,287-303)
+    ctl2 = {
+        "vib_freq": (220.0 * 2.0 ** (0.5 * np.sin(2 * np.pi * 6.0 * t) / 12.0)).astype(np.float32),   # +-50 cent vibrato
+        "glide_freq": np.geomspace(55.0, 3520.0, n).astype(np.float32),                                 # harmonic count changes
+        "env_amp": np.minimum(1.0, np.arange(n) / 800.0).astype(np.float32) * 0.8,
+    }
+    out.update({f"ctl_{k}": v for k, v in ctl2.items()})
+    B = lambda k: pg.ArrayPE(ctl2[k])  # noqa: E731
+    out["blit_vib"] = pull(pg.BlitSawPE(frequency=B("vib_freq"), amplitude=0.7, initial_phase=0.3), PULLS)
+    out["blit_glide_env"] = pull(pg.BlitSawPE(frequency=B("glide_freq"), amplitude=B("env_amp")), PULLS)
+    out["blit_amp_only_m12"] = pull(pg.BlitSawPE(frequency=330.0, amplitude=B("env_amp"), m=12, leak=0.995), PULLS)
+    out["ssaw_vib"] = pull(pg.SuperSawPE(frequency=B("vib_freq"), amplitude=0.5, seed=3), PULLS)
+    out["ssaw_glide_env_stereo"] = pull(pg.SuperSawPE(frequency=B("glide_freq"), amplitude=B("env_amp"), voices=5,
+                                                     detune_cents=35.0, mix_mode="linear", channels=2, seed=4), PULLS)
+    out["ssaw_amp_only"] = pull(pg.SuperSawPE(frequency=110.0, amplitude=B("env_amp"), seed=5), PULLS)
+    pe = pg.BlitSawPE(frequency=B("vib_freq"), amplitude=B("env_amp"))
+    a = pull(pe, [256, 256])
+    b = pull(pe, [256, 256], start=1024)            # non-contiguous: state resets (blit_saw_pe.py:183-186)
+    out["blit_gap"] = np.concatenate([a, b])
     np.savez_compressed(os.path.join(GOLD, "src_modulated.npz"), **out)
     print("wrote src_modulated.npz", {k: v.shape for k, v in out.items()})
 

@@ -73,9 +73,13 @@ class OracleBlitSaw:
     def reset(self):                                                    # :137-142
         self.phase, self.integ, self.last_end = self.initial_phase, 0.0, None
 
-    def render(self, start: int, duration: int) -> np.ndarray:
-        freq = np.full(duration, self.f, dtype=np.float64)              # :163
-        amp = np.full(duration, self.amp, dtype=np.float64)
+    def render(self, start: int, duration: int, freq_ctl=None, amp_ctl=None) -> np.ndarray:
+        """freq_ctl / amp_ctl: what a PE-valued frequency / amplitude rendered for this pull (float32, widened by
+        _scalar_or_pe_values, :162-163), or None for the constants."""
+        freq = np.full(duration, self.f, dtype=np.float64) if freq_ctl is None else \
+            np.asarray(freq_ctl, np.float32).astype(np.float64)         # :162
+        amp = np.full(duration, self.amp, dtype=np.float64) if amp_ctl is None else \
+            np.asarray(amp_ctl, np.float32).astype(np.float64)          # :163
         if self.m is None:                                              # :167-174
             m = np.floor(self.sr / (2.0 * np.maximum(freq, 1.0))).astype(np.int32)
             m = m - (1 - m % 2)
@@ -145,8 +149,14 @@ class OracleSuperSaw:
         for o in self.osc:
             o.reset()
 
-    def render(self, start: int, duration: int) -> np.ndarray:
+    def render(self, start: int, duration: int, freq_ctl=None, amp_ctl=None) -> np.ndarray:
+        """freq_ctl: the frequency PE's float32 output for the pull -- every oscillator then runs at
+        GainPE(frequency_pe, ratio) = freq_ctl * float32(ratio) (super_saw_pe.py:236-240, gain_pe.py:123-125), construct
+        the oracle with frequency=1.0 so that its oscillator frequencies ARE the ratios; amp_ctl: the amplitude PE's
+        output, applied to the float64 sum (:287,300)."""
         result = np.zeros(duration, dtype=np.float64)                   # :292
         for o in self.osc:                                              # :295-297 (float32 snippets summed in f64)
-            result += o.render(start, duration)
-        return (result * np.float64(self.amp)).astype(np.float32)       # :300-303
+            fc = None if freq_ctl is None else np.asarray(freq_ctl, np.float32) * np.float32(o.f)
+            result += o.render(start, duration, freq_ctl=fc)
+        amp = np.float64(self.amp) if amp_ctl is None else np.asarray(amp_ctl, np.float32).astype(np.float64)
+        return (result * amp).astype(np.float32)                        # :300-303

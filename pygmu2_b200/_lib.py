@@ -18,6 +18,7 @@ PGX_FLAG_MIXDOWN_INPUT = 1
 PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16 = 1, 2, 4, 8, 16
 PGX_PULL_REDUCE = 32
 PGX_CTL_HOST = 1
+PGX_CTL_AMP_OSC = 2
 PGX_COMM_HANDLE_BYTES = 128
 PGX_OSC_SINE, PGX_OSC_BLIT = 0, 1
 ABI_VERSION = 2
@@ -63,6 +64,7 @@ PROTOTYPES = {
     "pgx_last_error": (C.c_char_p, []),
     "pgx_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pgx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "pgx_host_alloc_flags": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32]),
     "pgx_host_free": (C.c_int, [C.c_void_p]),
     "pgx_device_alloc": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
     "pgx_device_free": (C.c_int, [C.c_int32, C.c_void_p]),
@@ -165,12 +167,12 @@ def f32_ptr(a: np.ndarray):
 class PinnedArray:
     """A numpy view (float32, or int16 for PCM staging) over cudaHostAlloc'ed memory (pinned, for async H2D/D2H)."""
 
-    def __init__(self, shape, dtype=np.float32):
+    def __init__(self, shape, dtype=np.float32, write_combined: bool = False):
         self.shape = tuple(int(s) for s in shape)
         dt = np.dtype(dtype)
         n = int(np.prod(self.shape)) if self.shape else 1
         self._ptr = C.c_void_p()
-        check(lib().pgx_host_alloc(C.byref(self._ptr), max(n, 1) * dt.itemsize))
+        check(lib().pgx_host_alloc_flags(C.byref(self._ptr), max(n, 1) * dt.itemsize, 1 if write_combined else 0))
         buf = (C.c_char * (max(n, 1) * dt.itemsize)).from_address(self._ptr.value)
         self.array = np.frombuffer(buf, dtype=dt, count=n).reshape(self.shape)
 

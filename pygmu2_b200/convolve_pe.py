@@ -132,6 +132,16 @@ class ConvolvePE(ProcessingElement):
         if self._out_gains is not None:
             self._bank.set_output_gains(*self._out_gains)
         self._fir_len = filt_len
+        # a plain in-memory source (ArrayPE, zero outside its data) is uploaded once and stays in HBM: a pull is then a
+        # pointer into that buffer instead of a host render + H2D copy per pull (same samples; see resident.py)
+        from .resident import ResidentSources
+        from .sources import CachePE
+        self._resident = None
+        inner = self._src
+        while type(inner) is CachePE:          # a pure memo of the source (ReverbPE wraps its source in one): same samples
+            inner = inner.source
+        if ResidentSources.eligible([inner], [0], int(src_ch), False):
+            self._resident = ResidentSources([inner], [0], [None], int(src_ch), False, device=self._device)
 
     def render_pcm16_out(self, start: int, duration: int) -> np.ndarray:
         """One pull delivered as (duration, channels) int16 PCM, converted on the device (WAV staging; what
@@ -150,6 +160,11 @@ class ConvolvePE(ProcessingElement):
                         "pass block_size= to pin a larger partition", duration, self._bank.block)
         if self._last_render_end is None or start != self._last_render_end:
             self._bank.reset()  # non-contiguous pull: prior samples are zeros (convolve_pe.py:255-256)
+        res = None if pcm16_out else getattr(self, "_resident", None)
+        if res is not None and duration <= min(self._bank.max_pull, res.max_pull):
+            y = self._bank.process_device_block(res.device_block(start, duration), interleaved=True)
+            self._last_render_end = start + duration
+            return Snippet(start, y)
         dev = None if pcm16_out else getattr(self._src, "device_block", None)
         if dev is not None:  # device-resident source: its samples never visit the host
             y = self._render_from_device(dev, start, duration)

@@ -420,6 +420,22 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
         }
       }
       if (j == 0) v[0] = b0;
+      if (PAST && k.n_split > 0) {
+        // past partitions summed OUTSIDE the kernel (the background pass of a many-partition bank, folded to
+        // n_split <= 8 rows): K2's job, done here so that a small bank's step is one launch on the latency chain
+        const float2* p0 = k.yspec + (size_t)(s * k.c_out + c) * N + j;
+        const size_t ss = (size_t)k.n_out * N;
+        for (int sp = 0; sp < k.n_split; ++sp) {
+          float2 t[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) t[m] = p0[(size_t)sp * ss + m * T8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            v[m].x += t[m].x;
+            v[m].y += t[m].y;
+          }
+        }
+      }
 #pragma unroll
       for (int m = 0; m < 8; ++m) sA[j + m * T8] = v[m];
     }
@@ -725,7 +741,7 @@ bool describe_conv1(const R2CArgs& a, const C2RArgs& k, LaunchDesc* d) {
   d->func = nullptr;
   if (describe_conv1_r16(a, k, d)) return true;
   const bool fan = (a.c_x == 1 && k.c_out > 1);
-  if (k.n_past > 0) {
+  if (k.n_past > 0 || k.n_split > 0) {
     if (fan) { PGX_DISPATCH(ilog2(a.B), (describe_conv1_t<L_, true, true>(a, d))); }
     else { PGX_DISPATCH(ilog2(a.B), (describe_conv1_t<L_, false, true>(a, d))); }
   } else {

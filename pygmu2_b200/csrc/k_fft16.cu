@@ -382,7 +382,7 @@ int conv1_r16_default() {
 bool describe_conv1_r16(const R2CArgs& a, const C2RArgs& k, LaunchDesc* d) {
   const int variant = k.fft16;
   // B = 4096, one partition, no fan-out, whole aligned blocks: everything else keeps the general kernel
-  if (variant == 0 || a.B != kN || k.n_past > 0 || (a.c_x == 1 && k.c_out > 1) || !a.fast || !k.fast || a.mixdown)
+  if (variant == 0 || a.B != kN || k.n_past > 0 || k.n_split > 0 || (a.c_x == 1 && k.c_out > 1) || !a.fast || !k.fast || a.mixdown)
     return false;
   constexpr int smem = 2 * kN * (int)sizeof(float2);
   static bool done[64] = {};

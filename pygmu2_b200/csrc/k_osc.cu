@@ -188,6 +188,95 @@ __global__ void __launch_bounds__(1024) k_blit_bank(const BlitArgs a) {
   }
 }
 
+// Modulated BLIT oscillators: BlitSawPE / SuperSawPE with a PE-valued frequency and / or amplitude
+// (blit_saw_pe.py:161-262 with per-sample control vectors; super_saw_pe.py:223-246: every oscillator's frequency is
+// GainPE(frequency_pe, ratio) -- a FLOAT32 product -- and :287-303: the voice amplitude multiplies the float64 sum).
+// Same structure as k_blit_bank (one CTA per voice, one warp per oscillator, 128-sample tiles), but the harmonic
+// count, the period and the phase increment change from sample to sample, so the two recurrences are walked in the
+// reference's own order by lane 0 -- the phase is np.cumsum of the increments over the whole pull (:186-192), the
+// leaky integrator is lfilter's  y[k] = x[k] + (leak * y[k-1])  (:225-236; product and sum rounded separately) --
+// while all lanes evaluate the Dirichlet kernel in between.
+__global__ void __launch_bounds__(1024) k_blit_mod(const BlitModArgs a) {
+  constexpr int kTile = 128;
+  extern __shared__ double mod_sm[];           // [U][2][kTile] doubles, then [U][kTile] floats
+  const int v = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int U = a.unison;
+  const int o = v * U + w;
+  double* s_a = mod_sm + (size_t)w * 2 * kTile;   // increments -> cumulative phase
+  double* s_b = s_a + kTile;                      // blit_ac -> saw
+  float* tile = reinterpret_cast<float*>(mod_sm + (size_t)U * 2 * kTile);
+  const float* fq = a.freq ? a.freq + (size_t)v * a.n : nullptr;
+  const float* am = a.amp ? a.amp + (size_t)v * a.n : nullptr;
+  const double sr = (double)a.sample_rate, leak = a.leak;
+  const float ratio = (float)a.osc_freq[o];       // detune ratio when the frequency is a PE, else the frequency itself
+  const double f_const = a.osc_freq[o];
+  const double gain = a.gain[o];
+  const int m_fixed = a.m_fixed ? a.m_fixed[o] : 0;
+  const double ph0 = a.st_phase[o];
+  double acc = 0.0, y = a.st_int[o], ph_last = ph0;
+  auto freq_at = [&](int k) -> double {
+    return fq ? (double)(__fmul_rn(fq[k], ratio)) : f_const;      // GainPE: float32 product (gain_pe.py:123-125)
+  };
+  for (int t0 = 0; t0 < a.n; t0 += kTile) {
+    const int nt = min(kTile, a.n - t0);
+    for (int i = lane; i < nt; i += 32) s_a[i] = freq_at(t0 + i) / sr;                 // :186
+    __syncwarp();
+    if (lane == 0)
+      for (int i = 0; i < nt; ++i) { acc += s_a[i]; s_a[i] = acc; }                    // :189 np.cumsum
+    __syncwarp();
+    for (int i = lane; i < nt; i += 32) {
+      const double f = freq_at(t0 + i);
+      double ph = ph0 + s_a[i];                                                        // :189
+      ph = fmod(ph, 1.0);                                                              // :192 np.mod: sign of the divisor
+      if (ph < 0.0) ph += 1.0;
+      const double fm = fmax(f, 1.0);
+      double m;
+      if (m_fixed > 0) {
+        m = (double)m_fixed;
+      } else {
+        int mi = (int)floor(sr / (2.0 * fm));                                          // :169-174
+        mi = mi - (1 - mi % 2);
+        if (mi < 1) mi = 1;
+        m = (double)mi;
+      }
+      const double P = sr / fm;                                                        // :195
+      const double theta = 3.141592653589793 * ph, sden = sin(theta);
+      const double blit = fabs(sden) < 1e-9 ? m / P : sin(m * theta) / (P * sden);     // :200-211
+      s_b[i] = blit - 1.0 / P;                                                         // :215
+      if (t0 + i == a.n - 1) ph_last = ph;
+    }
+    __syncwarp();
+    if (lane == 0)
+      for (int i = 0; i < nt; ++i) { y = __dadd_rn(s_b[i], __dmul_rn(leak, y)); s_b[i] = y; }   // :225-236 lfilter
+    __syncwarp();
+    for (int i = lane; i < nt; i += 32) {
+      const double amp_o = (am && a.amp_per_osc) ? (double)am[t0 + i] : gain;
+      tile[w * kTile + i] = (float)((s_b[i] * 2.0) * amp_o);                           // :252-259 the oscillator's float32 Snippet
+    }
+    __syncthreads();
+    // voice output: float64 sum of the float32 oscillator outputs, x the voice amplitude (super_saw_pe.py:287-303)
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+      double sum = 0.0;
+      for (int u = 0; u < U; ++u) sum += (double)tile[u * kTile + i];
+      const double va = (am && !a.amp_per_osc) ? (double)am[t0 + i] : a.vamp[v];
+      const float val = (float)(sum * va);
+      for (int c = 0; c < a.channels; ++c) a.out[(int64_t)v * a.os + (int64_t)c * a.oc + (int64_t)(t0 + i) * a.oi] = val;
+    }
+    __syncthreads();
+  }
+  ph_last = shfl_d(ph_last, (a.n - 1) % 32);     // the lane that owned the last sample (i = lane + 32 q)
+  y = shfl_d(y, 0);
+  if (lane == 0) {                               // :249-250
+    a.st_phase[o] = ph_last;
+    a.st_int[o] = y;
+  }
+}
+
+void launch_blit_mod(const BlitModArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)a.unison * (2 * 128 * sizeof(double) + 128 * sizeof(float));
+  k_blit_mod<<<a.n_voices, a.unison * 32, smem, st>>>(a);
+}
+
 void launch_blit_bank(const BlitArgs& a, cudaStream_t st) {
   const int threads = a.unison * 32;
   if (a.n <= 32) k_blit_bank<1><<<a.n_voices, threads, (size_t)a.unison * 32 * sizeof(float), st>>>(a);

@@ -145,6 +145,23 @@ struct BlitArgs {
 };
 void launch_blit_bank(const BlitArgs& a, cudaStream_t st);
 
+struct BlitModArgs {
+  const double* osc_freq;  // [V*U] the oscillator's frequency -- its detune RATIO when a frequency control is given
+  const double* gain;      // [V*U] oscillator amplitude
+  const double* vamp;      // [V] voice amplitude
+  const int32_t* m_fixed;  // [V*U] fixed harmonic count (0 = auto)
+  const float* freq;       // [V][n] frequency control of the voice (what the frequency PE rendered), or NULL
+  const float* amp;        // [V][n] amplitude control, or NULL: replaces the oscillator amplitude when amp_per_osc
+                           // (BlitSawPE), else the voice amplitude (SuperSawPE)
+  double* st_phase;        // [V*U] state: wrapped phase / integrator output at the end of the previous pull
+  double* st_int;
+  float* out;
+  int64_t os, oc, oi;
+  double leak;
+  int32_t n_voices, unison, channels, n, sample_rate, amp_per_osc;
+};
+void launch_blit_mod(const BlitModArgs& a, cudaStream_t st);
+
 // PCM16 <-> float32 staging (k_osc.cu): dense arrays of n elements
 void launch_pcm16_to_f32(const int16_t* in, float* out, int64_t n, cudaStream_t st);
 void launch_f32_to_pcm16(const float* in, int16_t* out, int64_t n, cudaStream_t st);

@@ -123,6 +123,7 @@ struct pgx_bank {
   // the copies are truly asynchronous whatever memory the caller's arrays live in (a cudaMemcpyAsync from / to
   // pageable memory is staged by the driver and, device-to-host, blocks the calling thread)
   static constexpr size_t kBounceMax = 256 * 1024;
+  static constexpr size_t kZeroCopyMax = 32 * 1024;  // graph replays of pulls this small read / write the bounce buffers in place
   char* hx_bounce[kSlots] = {};
   char* hy_bounce[kSlots] = {};
   void* y_user[kSlots] = {};       // pending copy-back: hy_bounce[slot] -> y_user[slot] once ev_done[slot] has fired
@@ -176,6 +177,8 @@ struct pgx_bank {
   };
   PullGraph pgraph[kSlots][2][2];  // [slot][mix][x already on the device]
   bool use_graph = true;           // PGX_GRAPH=0 disables
+  bool graph_fuse = true;          // graph shape 3: K1 and K2 as ONE k_conv1 launch that also adds the folded past sum
+                                   // (PGX_GRAPH_FUSE=0 keeps the two kernels)
   bool after_graph = false;        // the previous step was a graph replay: the event ring must be re-armed before the
                                    // multi-stream schedule continues
   cudaEvent_t ev_join[4] = {};
@@ -664,6 +667,12 @@ int pgx_host_alloc(void** ptr, int64_t bytes) {
   return PGX_OK;
 }
 
+int pgx_host_alloc_flags(void** ptr, int64_t bytes, int32_t flags) {
+  if (!ptr || bytes <= 0) return fail(PGX_ERR_INVALID, "pgx_host_alloc_flags: bad arguments");
+  PGX_CUDA(cudaHostAlloc(ptr, (size_t)bytes, (flags & PGX_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return PGX_OK;
+}
+
 int pgx_host_free(void* ptr) {
   if (ptr) PGX_CUDA(cudaFreeHost(ptr));
   return PGX_OK;
@@ -798,6 +807,7 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
     b->fft16 = pgx::conv1_r16_default();
     if (const char* e = getenv("PGX_MIX1")) b->use_mix1 = (e[0] != '0');
     if (const char* e = getenv("PGX_GRAPH")) b->use_graph = (e[0] != '0');
+    if (const char* e = getenv("PGX_GRAPH_FUSE")) b->graph_fuse = (e[0] != '0');
     for (cudaEvent_t& e : b->ev_join) guard(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate(join)");
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");
@@ -1186,13 +1196,21 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
   if (shape == 0) return PGX_OK;
   if (shape == 3 && !(b->past_block == b->block && b->past_mode == 0)) return PGX_OK;  // this block's past sum must exist
   if (b->block < 2) return PGX_OK;                                    // steady state only
-  const float* x_dev = x_device ? x : b->x_stage[slot];
-  float* y_dev = b->y_stage[slot];
+  // tiny pulls skip the copy engines altogether: the kernels read x from / write y to the pinned bounce buffers
+  // directly (zero-copy over PCIe: a few KB of independent, coalesced accesses), which takes two dependent copies
+  // and their hand-overs off the latency chain
+  const bool zc_x = !x_device && xb <= pgx_bank::kZeroCopyMax, zc_y = yb <= pgx_bank::kZeroCopyMax;
+  const float* x_dev = x_device ? x : (zc_x ? reinterpret_cast<const float*>(b->hx_bounce[slot]) : b->x_stage[slot]);
+  float* y_dev = zc_y ? reinterpret_cast<float*>(b->hy_bounce[slot]) : b->y_stage[slot];
   StepArgs a;
   graph_args(b, shape, mix, x_dev, xl, y_dev, yd, &a);
   pgx::LaunchDesc dA, dMac, dFold, dK2;
   bool ok = true;
+  // shape 3 on a bank whose output stage sums at most kFoldAbove past rows: ingest, transforms, present term, past rows
+  // and emit as ONE fused launch (k_conv1<.., PAST> with n_past = 0 and the folded rows), K2 drops off the chain
+  const bool fuse3 = shape == 3 && b->graph_fuse && b->use_conv1;
   if (shape == 1) ok = mix ? pgx::describe_mix1(a.r, true, &dA) : pgx::describe_conv1(a.r, a.k, &dA);
+  else if (fuse3) ok = pgx::describe_conv1(a.r, a.k, &dA) && pgx::describe_fdl_mac(a.m, &dMac);
   else ok = pgx::describe_r2c_ingest(a.r, &dA) && pgx::describe_fdl_mac(a.m, &dMac) && pgx::describe_c2r_emit(a.k, &dK2);
   const bool fold = shape == 3 && b->plan_conv.n_partials > kFoldAbove;
   if (fold) ok = ok && pgx::describe_reduce_partials(a.m.n_out, b->B / 2, &dFold);
@@ -1200,7 +1218,7 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
   void* pA_fused_conv[] = {&a.r, &a.k};
   void* pA_mix1[] = {&a.r, &a.k, &a.ynow, &a.ticket};
   void* pA_k1[] = {&a.r, &a.fp};
-  void** pA = shape == 3 ? pA_k1 : (mix ? pA_mix1 : pA_fused_conv);
+  void** pA = (shape == 3 && !fuse3) ? pA_k1 : (mix ? pA_mix1 : pA_fused_conv);
   void* pMac[] = {&a.m};
   void* pFold[] = {&a.fold_in, &a.fold_out, &a.fold_n, &a.fold_cols};
   void* pK2[] = {&a.k};
@@ -1216,7 +1234,7 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
   if (!g.exec) {
     PGX_CUDA(cudaGraphCreate(&g.graph, 0));
     cudaGraphNode_t dep = nullptr;
-    if (!x_device) {
+    if (!x_device && !zc_x) {
       PGX_CUDA(cudaGraphAddMemcpyNode1D(&g.n_h2d, g.graph, nullptr, 0, b->x_stage[slot], b->hx_bounce[slot], xb,
                                         cudaMemcpyHostToDevice));
       dep = g.n_h2d;
@@ -1225,9 +1243,11 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
     PGX_CUDA(cudaGraphAddKernelNode(&g.n_a, g.graph, dep ? &dep : nullptr, dep ? 1 : 0, &kp));
     cudaGraphNode_t last = g.n_a;
     if (shape == 3) {
-      kp = knode(dK2, pK2);
-      PGX_CUDA(cudaGraphAddKernelNode(&g.n_k2, g.graph, &g.n_a, 1, &kp));
-      last = g.n_k2;
+      if (!fuse3) {
+        kp = knode(dK2, pK2);
+        PGX_CUDA(cudaGraphAddKernelNode(&g.n_k2, g.graph, &g.n_a, 1, &kp));
+        last = g.n_k2;
+      }
       kp = knode(dMac, pMac);
       PGX_CUDA(cudaGraphAddKernelNode(&g.n_mac, g.graph, &g.n_a, 1, &kp));
       if (fold) {
@@ -1235,16 +1255,19 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
         PGX_CUDA(cudaGraphAddKernelNode(&g.n_fold, g.graph, &g.n_mac, 1, &kp));
       }
     }
-    PGX_CUDA(cudaGraphAddMemcpyNode1D(&g.n_d2h, g.graph, &last, 1, b->hy_bounce[slot], b->y_stage[slot], yb,
-                                      cudaMemcpyDeviceToHost));
+    if (!zc_y)
+      PGX_CUDA(cudaGraphAddMemcpyNode1D(&g.n_d2h, g.graph, &last, 1, b->hy_bounce[slot], b->y_stage[slot], yb,
+                                        cudaMemcpyDeviceToHost));
     PGX_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
     g.shape = shape; g.f_a = dA.func; g.f_mac = dMac.func; g.f_k2 = dK2.func; g.fold = fold; g.xb = xb; g.yb = yb;
   } else {  // refresh the arguments that move from step to step
     cudaKernelNodeParams kp = knode(dA, pA);
     PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_a, &kp));
     if (shape == 3) {
-      kp = knode(dK2, pK2);
-      PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_k2, &kp));
+      if (!fuse3) {
+        kp = knode(dK2, pK2);
+        PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_k2, &kp));
+      }
       kp = knode(dMac, pMac);
       PGX_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.n_mac, &kp));
       if (fold) {
@@ -1274,7 +1297,7 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
   b->last_crit = b->stream;
   b->last_k2_of_par[par] = b->step;
   b->prev_on_crit = (shape == 1);
-  b->launches += shape == 1 ? 1 : (fold ? 4 : 3);
+  b->launches += shape == 1 ? 1 : (fold ? 4 : 3) - (fuse3 ? 1 : 0);
   b->steps += 1;
   b->step += 1;
   if (shape == 3) { b->past_block = b->block + 1; b->past_mode = 0; }

@@ -20,6 +20,8 @@ struct pgx_osc {
   double *mod_state = nullptr, *mod_scratch = nullptr;  // modulated sine: accumulated phase [V], phases [V][max_pull]
   float *ctl[3] = {nullptr, nullptr, nullptr};    // staged control vectors (host-supplied), [V][max_pull] each
   bool mod_started = false;
+  double* osc_freq = nullptr;                     // BLIT: per-oscillator frequency as given (the detune ratio when modulated)
+  int32_t* m_fixed_dev = nullptr;                 // BLIT: fixed harmonic counts (0 = auto)
   int64_t last_end = INT64_MIN;
   bool has_last = false;
   int64_t launches = 0;
@@ -33,7 +35,8 @@ void free_osc(pgx_osc* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : {(void*)h->params, (void*)h->consts, (void*)h->gain, (void*)h->amp, (void*)h->phase_init,
                   (void*)h->st_phase, (void*)h->st_int, (void*)h->out, (void*)h->mix, (void*)h->mod_state,
-                  (void*)h->mod_scratch, (void*)h->ctl[0], (void*)h->ctl[1], (void*)h->ctl[2]})
+                  (void*)h->mod_scratch, (void*)h->ctl[0], (void*)h->ctl[1], (void*)h->ctl[2], (void*)h->osc_freq,
+                  (void*)h->m_fixed_dev})
     cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -141,6 +144,13 @@ int pgx_osc_create(pgx_osc** out, const pgx_osc_config* cfg, const double* freq,
     }
     if (e == cudaSuccess) e = upload(&h->consts, cst.data(), cst.size(), h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // cst goes out of scope
+    if (e == cudaSuccess) e = upload(&h->osc_freq, freq, no, h->stream);
+    {
+      std::vector<int32_t> mf(no, 0);
+      if (m_fixed) for (size_t o = 0; o < no; ++o) mf[o] = m_fixed[o] > 0 ? m_fixed[o] : 0;
+      if (e == cudaSuccess) e = upload(&h->m_fixed_dev, mf.data(), no, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // mf goes out of scope
+    }
     if (e == cudaSuccess) e = upload(&h->gain, gain, no, h->stream);
     if (e == cudaSuccess) e = upload(&h->phase_init, phase, no, h->stream);
     if (e == cudaSuccess) e = upload(&h->amp, amp, (size_t)c.n_voices, h->stream);
@@ -173,12 +183,12 @@ int pgx_osc_render_modulated(pgx_osc* h, int32_t n, int32_t flags, const float* 
                              float* y_host) {
   if (!h || (!out_dev && !y_host)) return pgx_fail(PGX_ERR_INVALID, "NULL argument");
   const pgx_osc_config& c = h->cfg;
-  if (c.kind != PGX_OSC_SINE) return pgx_fail(PGX_ERR_INVALID, "pgx_osc_render_modulated is for PGX_OSC_SINE handles");
+  if (c.kind == PGX_OSC_BLIT && phase) return pgx_fail(PGX_ERR_INVALID, "BLIT oscillators have no phase control");
   if (n < 1 || n > c.max_pull) return pgx_fail(PGX_ERR_INVALID, "pull of %d samples outside [1, max_pull=%d]", n, c.max_pull);
   PGX_CUDA(cudaSetDevice(c.device));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
   const size_t V = (size_t)c.n_voices;
-  if (!h->mod_state) {
+  if (c.kind == PGX_OSC_SINE && !h->mod_state) {
     PGX_CUDA(cudaMalloc(&h->mod_state, V * sizeof(double)));
     PGX_CUDA(cudaMalloc(&h->mod_scratch, V * c.max_pull * sizeof(double)));
   }
@@ -191,14 +201,33 @@ int pgx_osc_render_modulated(pgx_osc* h, int32_t n, int32_t flags, const float* 
       ctl[i] = h->ctl[i];
     }
   }
-  pgx::SineModArgs a{};
-  a.params = h->params; a.freq = ctl[0]; a.amp = ctl[1]; a.phase = ctl[2];
-  a.state = h->mod_state; a.scratch = h->mod_scratch; a.out = h->out;
-  a.os = (int64_t)c.channels * n; a.oc = n; a.oi = 1;
-  a.n_voices = c.n_voices; a.channels = c.channels; a.n = n; a.sample_rate = c.sample_rate; a.max_pull = c.max_pull;
-  a.first = h->mod_started ? 0 : 1;
-  pgx::launch_sine_mod(a, st);
-  h->mod_started = true;
+  if (c.kind == PGX_OSC_SINE) {
+    pgx::SineModArgs a{};
+    a.params = h->params; a.freq = ctl[0]; a.amp = ctl[1]; a.phase = ctl[2];
+    a.state = h->mod_state; a.scratch = h->mod_scratch; a.out = h->out;
+    a.os = (int64_t)c.channels * n; a.oc = n; a.oi = 1;
+    a.n_voices = c.n_voices; a.channels = c.channels; a.n = n; a.sample_rate = c.sample_rate; a.max_pull = c.max_pull;
+    a.first = h->mod_started ? 0 : 1;
+    pgx::launch_sine_mod(a, st);
+    h->mod_started = true;
+  } else {
+    // stateful like the constant-parameter path; a modulated BLIT PE is only ever pulled contiguously (the
+    // reference's renderer enforces it for stateful PEs) and pgx_osc_reset starts over (blit_saw_pe.py:137-142)
+    if (!h->has_last) {
+      const int rc = reset_state(h, st);
+      if (rc != PGX_OK) return rc;
+    }
+    pgx::BlitModArgs a{};
+    a.osc_freq = h->osc_freq; a.gain = h->gain; a.vamp = h->amp; a.m_fixed = h->m_fixed_dev;
+    a.freq = ctl[0]; a.amp = ctl[1];
+    a.st_phase = h->st_phase; a.st_int = h->st_int; a.out = h->out;
+    a.os = (int64_t)c.channels * n; a.oc = n; a.oi = 1; a.leak = c.leak;
+    a.n_voices = c.n_voices; a.unison = c.unison; a.channels = c.channels; a.n = n; a.sample_rate = c.sample_rate;
+    a.amp_per_osc = (ctl_flags & PGX_CTL_AMP_OSC) ? 1 : 0;
+    pgx::launch_blit_mod(a, st);
+    h->has_last = true;
+    h->last_end = (h->last_end == INT64_MIN ? 0 : h->last_end) + n;
+  }
   h->launches += 1;
   const float* res = h->out;
   if (flags & PGX_PULL_MIX) {

@@ -192,13 +192,30 @@ class ShardedMix:
     def render_mix_device(self, x_local, y_mix, n: int):
         import torch
 
-        st = torch.cuda.current_stream().cuda_stream
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream == 0:
+            # the legacy default stream has handle 0, which the C ABI reads as "the bank's own stream": work enqueued
+            # there would not be ordered with torch's.  Run the pull (and the collective) on a side stream that is
+            # fenced against the current one on both sides.
+            side = getattr(self, "_side", None)
+            if side is None:
+                side = self._side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._render_on(side.cuda_stream, x_local, y_mix, n)
+            cur.wait_stream(side)
+            x_local.record_stream(side)
+            y_mix.record_stream(side)
+            return y_mix
+        self._render_on(cur.cuda_stream, x_local, y_mix, n)
+        return y_mix
+
+    def _render_on(self, st: int, x_local, y_mix, n: int) -> None:
         if getattr(self, "comm", None) is not None:
             self.bank.process_device(x_local.data_ptr(), y_mix.data_ptr(), n, mix=True, cuda_stream=st, reduce=True)
-            return y_mix
+            return
         self.bank.process_device(x_local.data_ptr(), y_mix.data_ptr(), n, mix=True, cuda_stream=st)
         reduce_mix(y_mix, self.root)
-        return y_mix
 
     # host buffers, pipelined: pinned x_local (hi-lo, C_in, n) -> the root's pinned out (C_out, n); returns a ticket
     def submit_mix(self, x_local: np.ndarray, out: np.ndarray) -> int:

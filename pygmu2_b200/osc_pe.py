@@ -101,7 +101,7 @@ class OscBank:
             pos += d
         return y
 
-    def _modulated(self, duration: int, freq, amp, phase, mix: bool, cuda_stream: int, y_host):
+    def _modulated(self, duration: int, freq, amp, phase, mix: bool, cuda_stream: int, y_host, amp_osc: bool = False):
         n = int(duration)
         ptrs, keep, on_host, on_dev = [], [], False, False
         for ctl in (freq, amp, phase):
@@ -121,23 +121,23 @@ class OscBank:
             raise ValueError("control vectors must be all host arrays or all device blocks")
         out = C.c_void_p()
         check(lib().pgx_osc_render_modulated(self._h, n, 1 if mix else 0, ptrs[0], ptrs[1], ptrs[2],
-                                             _lib.PGX_CTL_HOST if on_host else 0,
+                                             (_lib.PGX_CTL_HOST if on_host else 0) | (_lib.PGX_CTL_AMP_OSC if amp_osc else 0),
                                              C.c_void_p(cuda_stream) if cuda_stream else None, C.byref(out),
                                              y_host.ctypes.data_as(C.c_void_p) if y_host is not None else None))
         return DeviceBlock(int(out.value), Layout(self.channels * n, n, 1), 1 if mix else self.n_voices,
                            self.channels, n)
 
     def render_modulated_device(self, duration: int, freq=None, amp=None, phase=None, *, mix: bool = False,
-                                cuda_stream: int = 0) -> DeviceBlock:
+                                cuda_stream: int = 0, amp_osc: bool = False) -> DeviceBlock:
         """Modulated sine pull (stateful branch of sine_pe.py): ``freq`` / ``amp`` / ``phase`` are per-sample control
         vectors -- host float32 arrays (n_voices, n) or ``DeviceBlock``s produced on ``cuda_stream`` -- or None for a
         parameter that is constant."""
-        return self._modulated(duration, freq, amp, phase, mix, cuda_stream, None)
+        return self._modulated(duration, freq, amp, phase, mix, cuda_stream, None, amp_osc)
 
-    def render_modulated(self, duration: int, freq=None, amp=None, phase=None) -> np.ndarray:
+    def render_modulated(self, duration: int, freq=None, amp=None, phase=None, *, amp_osc: bool = False) -> np.ndarray:
         """Same pull delivered to the host: (n_voices, channels, n) float32."""
         y = np.empty((self.n_voices, self.channels, int(duration)), dtype=np.float32)
-        self._modulated(duration, freq, amp, phase, False, 0, y)
+        self._modulated(duration, freq, amp, phase, False, 0, y, amp_osc)
         return y
 
     def render_device(self, start: int, duration: int, mix: bool = False, cuda_stream: int = 0) -> DeviceBlock:
@@ -275,13 +275,80 @@ class SinePE(_OscPE):
         return f"SinePE(frequency={f}, amplitude={a})"
 
 
-class BlitSawPE(_OscPE):
-    """blit_saw_pe.py:26-299 with constant frequency / amplitude / m (never pure: integrator state)."""
+class _ModulatedBlit(_OscPE):
+    """BLIT oscillators whose frequency and / or amplitude may be PEs (blit_saw_pe.py:161-163, super_saw_pe.py:223-246,
+    287): the parameter PEs are rendered for the pull (channel 0, float32) and handed to the device as control
+    vectors; the phase and the leaky integrator are walked in the reference's order and carried between pulls."""
+
+    _amp_per_osc = False     # BlitSawPE: the amplitude scales the oscillator; SuperSawPE: the float64 voice sum
+    _pe_params: dict = {}
+    _last_end = None
+
+    def _split_params(self, frequency, amplitude):
+        self._pe_params = {k: v for k, v in (("frequency", frequency), ("amplitude", amplitude))
+                           if isinstance(v, ProcessingElement)}
+        f = frequency if "frequency" in self._pe_params else float(frequency)
+        a = amplitude if "amplitude" in self._pe_params else float(amplitude)
+        return f, a
+
+    def inputs(self) -> list:
+        return [self._pe_params[k] for k in ("frequency", "amplitude") if k in self._pe_params]
+
+    def _compute_extent(self) -> Extent:
+        result = Extent(None, None)
+        for pe in self.inputs():
+            result = result.intersection(pe.extent())
+        return result
+
+    def _controls(self, start: int, duration: int):
+        return {k: np.ascontiguousarray(pe.render(start, duration).data[:, 0], dtype=np.float32)
+                for k, pe in self._pe_params.items()}
+
+    def _render(self, start: int, duration: int) -> Snippet:
+        if not self._pe_params:
+            return super()._render(start, duration)
+        bank = self._bank()
+        if self._last_end is None or start != self._last_end:      # blit_saw_pe.py:183-186: a new run
+            bank.reset()
+        outs, pos = [], 0
+        while pos < duration:
+            d = min(self._max_pull, duration - pos)
+            ctl = self._controls(start + pos, d)
+            outs.append(bank.render_modulated(d, ctl.get("frequency"), ctl.get("amplitude"),
+                                              amp_osc=self._amp_per_osc)[0].T)
+            pos += d
+        self._last_end = start + duration
+        return Snippet(start, np.ascontiguousarray(outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)))
+
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0) -> DeviceBlock | None:
+        if duration > self._max_pull:
+            return None
+        if not self._pe_params:
+            return self._bank().render_device(start, duration, cuda_stream=cuda_stream)
+        bank = self._bank()
+        if self._last_end is None or start != self._last_end:
+            bank.reset()
+        ctl = self._controls(start, duration)
+        self._last_end = start + duration
+        return bank.render_modulated_device(duration, ctl.get("frequency"), ctl.get("amplitude"),
+                                            cuda_stream=cuda_stream, amp_osc=self._amp_per_osc)
+
+    def _reset_state(self) -> None:
+        self._last_end = None
+        if self._osc is not None:
+            self._osc.reset()
+
+    _on_start = _on_stop = _reset_state
+
+
+class BlitSawPE(_ModulatedBlit):
+    """blit_saw_pe.py:26-299; frequency / amplitude constant or PE-valued, m constant (never pure: integrator state)."""
+
+    _amp_per_osc = True
 
     def __init__(self, frequency, amplitude=1.0, initial_phase: float = 0.0, m=None, leak: float = 0.999,
                  channels: int = 1, *, device: int = 0):
-        self._frequency = float(_const("frequency", frequency))
-        self._amplitude = float(_const("amplitude", amplitude))
+        self._frequency, self._amplitude = self._split_params(frequency, amplitude)
         self._initial_phase = float(np.asarray(initial_phase, dtype=np.float64).reshape(-1)[0]) % 1.0
         self._m = None if m is None else int(_const("m", m))
         self._leak, self._channels, self._device = float(leak), int(channels), int(device)
@@ -297,7 +364,10 @@ class BlitSawPE(_OscPE):
 
     def _make_bank(self) -> OscBank:
         m_fixed = None if self._m is None else [max(self._m, 1)]     # blit_saw_pe.py:176-177
-        return OscBank(_lib.PGX_OSC_BLIT, [self._frequency], [self._amplitude], [self._initial_phase], unison=1,
+        # a PE-valued frequency is used as it is (ratio 1), a PE-valued amplitude replaces the oscillator amplitude
+        f = 1.0 if "frequency" in self._pe_params else self._frequency
+        a = 1.0 if "amplitude" in self._pe_params else self._amplitude
+        return OscBank(_lib.PGX_OSC_BLIT, [f], [a], [self._initial_phase], unison=1,
                        m_fixed=m_fixed, channels=self._channels, sample_rate=self.sample_rate, leak=self._leak,
                        max_pull=self._max_pull, device=self._device)
 
@@ -307,8 +377,9 @@ class BlitSawPE(_OscPE):
                 f"leak={self._leak}, channels={self._channels})")
 
 
-class SuperSawPE(_OscPE):
-    """super_saw_pe.py:26-342 with constant frequency / amplitude: ``voices`` detuned BlitSaw oscillators."""
+class SuperSawPE(_ModulatedBlit):
+    """super_saw_pe.py:26-342: ``voices`` detuned BlitSaw oscillators; frequency / amplitude constant or PE-valued
+    (each oscillator then runs at float32(frequency * ratio), GainPE's product, super_saw_pe.py:236-240)."""
 
     MIX_EQUAL = "equal"
     MIX_CENTER_HEAVY = "center_heavy"
@@ -319,8 +390,7 @@ class SuperSawPE(_OscPE):
                  seed: int | None = None, *, device: int = 0):
         if voices < 1:
             voices = 1
-        self._frequency = float(_const("frequency", frequency))
-        self._amplitude = float(_const("amplitude", amplitude))
+        self._frequency, self._amplitude = self._split_params(frequency, amplitude)
         self._voices, self._detune_cents, self._mix_mode = int(voices), detune_cents, mix_mode
         self._channels, self._device = int(channels), int(device)
         self._randomize_phase = bool(randomize_phase)
@@ -329,7 +399,9 @@ class SuperSawPE(_OscPE):
         self._mix_gains = self._compute_mix_gains()
         # one oscillator per detune ratio; its initial phase is drawn at construction, in order
         # (super_saw_pe.py:219-231)
-        self._osc_freq = [float(self._frequency * r) for r in self._detune_ratios]
+        # a PE-valued frequency: the oscillators carry their detune RATIOS, the product is taken per sample on the device
+        self._osc_freq = [float(r) if "frequency" in self._pe_params else float(self._frequency * r)
+                          for r in self._detune_ratios]
         self._osc_gain = [float(self._mix_gains[i]) for i in range(len(self._detune_ratios))]
         self._osc_phase = [float(self._rng.random(1)[0]) % 1.0 if self._randomize_phase else 0.0
                            for _ in self._detune_ratios]
@@ -376,11 +448,13 @@ class SuperSawPE(_OscPE):
 
     def _make_bank(self) -> OscBank:
         return OscBank(_lib.PGX_OSC_BLIT, self._osc_freq, self._osc_gain, self._osc_phase,
-                       unison=self.n_oscillators, amp=[self._amplitude], channels=self._channels,
+                       unison=self.n_oscillators, amp=[1.0 if "amplitude" in self._pe_params else self._amplitude],
+                       channels=self._channels,
                        sample_rate=self.sample_rate, max_pull=self._max_pull, device=self._device)
 
     def __repr__(self):
-        return (f"SuperSawPE(frequency={self._frequency}, voices={self._voices}, "
+        f = self._frequency.__class__.__name__ if "frequency" in self._pe_params else self._frequency
+        return (f"SuperSawPE(frequency={f}, voices={self._voices}, "
                 f"detune_cents={self._detune_cents}, mix_mode={self._mix_mode!r})")
 
 
@@ -403,8 +477,8 @@ class VoiceBank:
         if sr is None:
             raise RuntimeError("Sample rate not set. Call pg.set_sample_rate() first.")
         p0 = pes[0]
-        if isinstance(p0, SinePE) and any(p._pe_params for p in pes):
-            raise ValueError("VoiceBank voices must have constant parameters (a modulated SinePE renders on its own)")
+        if any(getattr(p, "_pe_params", None) for p in pes):
+            raise ValueError("VoiceBank voices must have constant parameters (a modulated oscillator renders on its own)")
         if isinstance(p0, SinePE):
             self.bank = OscBank(_lib.PGX_OSC_SINE, [p._frequency for p in pes], [p._amplitude for p in pes],
                                 [p._phase for p in pes], channels=self.channels, sample_rate=sr,

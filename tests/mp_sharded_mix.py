@@ -57,7 +57,7 @@ def main():
         np.stack([wl.c4_ir(s, L) for s in range(lo, hi)]), hi - lo, 1, block=B, max_pull=pull, device=local))
     xd = torch.from_numpy(x_loc).cuda(local)
     yd = torch.empty((pulls, 1, pull), dtype=torch.float32, device=f"cuda:{local}")
-    for i in range(pulls):
+    for i in range(pulls):       # on torch's DEFAULT stream: ShardedMix moves the pull to a fenced side stream
         sm2.render_mix_device(xd[:, :, i * pull:(i + 1) * pull].contiguous(), yd[i], pull)
     torch.cuda.synchronize()
     ok = True

@@ -92,14 +92,40 @@ def test_voice_mix_fused_matches_reference_golden():
     assert isinstance(mix._fused, _VoiceMix) and mix._fused.vb.bank.launches == 2 * 12
 
 
-def test_modulated_saw_parameters_are_rejected_loudly():
-    """SinePE takes PE-valued parameters on the device (test_modulated_sine_*); the BLIT oscillators do not yet and
-    say so instead of falling back to anything."""
+def test_pe_valued_harmonic_count_is_rejected_loudly():
+    """Frequency and amplitude of every oscillator may be PEs (test_modulated_*); a PE-valued harmonic count `m` is
+    the one modulated parameter outside the device path, and it says so instead of falling back to anything."""
     assert not pg.SinePE(frequency=pg.ConstantPE(440.0)).is_pure()
+    assert pg.SuperSawPE(frequency=pg.ConstantPE(440.0)).inputs()
     with pytest.raises(NotImplementedError):
-        pg.SuperSawPE(frequency=pg.ConstantPE(440.0))
-    with pytest.raises(NotImplementedError):
-        pg.BlitSawPE(frequency=pg.ConstantPE(440.0))
+        pg.BlitSawPE(frequency=440.0, m=pg.ConstantPE(5.0))
+
+
+def test_modulated_blit_and_supersaw_match_reference_goldens():
+    """BlitSawPE / SuperSawPE with PE-valued frequency and / or amplitude (blit_saw_pe.py:161-262,
+    super_saw_pe.py:223-246,287-303) against outputs of the REAL reference: vibrato, a six-octave glide (the harmonic
+    count and the period change from sample to sample), an amplitude envelope, fixed m, stereo, and a non-contiguous
+    pull.  Same tolerance as the constant-parameter oscillators (1e-5 of full scale)."""
+    g = golden("src_modulated.npz")
+    pulls = [int(d) for d in g["pulls"]]
+    A = lambda k: pg.ArrayPE(g["ctl_" + k])  # noqa: E731
+
+    def check(y, ref, scale, what):
+        assert y.shape == ref.shape, what
+        err = float(np.max(np.abs(y.astype(np.float64) - ref)) / max(float(np.max(np.abs(ref))), scale))
+        assert err <= TOL, f"{what}: {err:.3e}"
+
+    check(_pull(pg.BlitSawPE(frequency=A("vib_freq"), amplitude=0.7, initial_phase=0.3), pulls), g["blit_vib"], 0.7, "blit_vib")
+    check(_pull(pg.BlitSawPE(frequency=A("glide_freq"), amplitude=A("env_amp")), pulls), g["blit_glide_env"], 0.8, "blit_glide_env")
+    check(_pull(pg.BlitSawPE(frequency=330.0, amplitude=A("env_amp"), m=12, leak=0.995), pulls), g["blit_amp_only_m12"], 0.8, "m12")
+    check(_pull(pg.SuperSawPE(frequency=A("vib_freq"), amplitude=0.5, seed=3), pulls), g["ssaw_vib"], 0.5, "ssaw_vib")
+    check(_pull(pg.SuperSawPE(frequency=A("glide_freq"), amplitude=A("env_amp"), voices=5, detune_cents=35.0,
+                              mix_mode="linear", channels=2, seed=4), pulls), g["ssaw_glide_env_stereo"], 0.8, "ssaw_glide")
+    check(_pull(pg.SuperSawPE(frequency=110.0, amplitude=A("env_amp"), seed=5), pulls), g["ssaw_amp_only"], 0.8, "ssaw_amp")
+    pe = pg.BlitSawPE(frequency=A("vib_freq"), amplitude=A("env_amp"))
+    y = np.concatenate([_pull(pe, [256, 256]), _pull(pe, [256, 256], start=1024)])
+    check(y, g["blit_gap"], 0.8, "blit_gap")
+    assert pe.extent().end == g["ctl_vib_freq"].shape[0] and not pe.is_pure()
 
 
 def test_c1_sine_source_stays_on_device_through_convolve():

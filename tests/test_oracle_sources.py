@@ -87,3 +87,29 @@ def test_oracle_modulated_sine_is_the_reference_bit_for_bit():
     o.reset()
     b = run(o, f="ctl_fm_freq", p="ctl_pm_phase", pulls=[256, 256])
     assert np.array_equal(np.concatenate([a, b]), g["restart"])
+
+
+def test_oracle_modulated_blit_and_supersaw_are_the_reference_bit_for_bit():
+    import pygmu2_oracle_sources as osrc
+    g = golden("src_modulated.npz")
+    pulls = [int(d) for d in g["pulls"]]
+
+    def run(o, f=None, a=None, pulls=pulls, start=0, off=0):
+        out, pos = [], 0
+        for d in pulls:
+            sl = slice(off + pos, off + pos + d)
+            out.append(o.render(start + pos, d, None if f is None else g[f][sl], None if a is None else g[a][sl]))
+            pos += d
+        return np.concatenate(out)
+    assert np.array_equal(run(osrc.OracleBlitSaw(1.0, 0.7, 0.3), f="ctl_vib_freq"), g["blit_vib"][:, 0])
+    assert np.array_equal(run(osrc.OracleBlitSaw(1.0, 1.0), f="ctl_glide_freq", a="ctl_env_amp"), g["blit_glide_env"][:, 0])
+    assert np.array_equal(run(osrc.OracleBlitSaw(330.0, 1.0, m=12, leak=0.995), a="ctl_env_amp"), g["blit_amp_only_m12"][:, 0])
+    assert np.array_equal(run(osrc.OracleSuperSaw(1.0, 0.5, seed=3), f="ctl_vib_freq"), g["ssaw_vib"][:, 0])
+    y = run(osrc.OracleSuperSaw(1.0, 1.0, voices=5, detune_cents=35.0, mix_mode="linear", seed=4),
+            f="ctl_glide_freq", a="ctl_env_amp")
+    assert np.array_equal(np.stack([y, y], axis=1), g["ssaw_glide_env_stereo"])
+    assert np.array_equal(run(osrc.OracleSuperSaw(110.0, 1.0, seed=5), a="ctl_env_amp"), g["ssaw_amp_only"][:, 0])
+    o = osrc.OracleBlitSaw(1.0, 1.0)
+    a = run(o, f="ctl_vib_freq", a="ctl_env_amp", pulls=[256, 256])
+    b = run(o, f="ctl_vib_freq", a="ctl_env_amp", pulls=[256, 256], start=1024, off=1024)
+    assert np.array_equal(np.concatenate([a, b]), g["blit_gap"][:, 0])
