@@ -600,6 +600,8 @@ def measure(args, wname, world, rank, local, numa_bound):
         torch.cuda.synchronize(dev)
 
     # fill the delay line so the timed steps stream real (non-zero) spectra, then W warm-up steps
+    if do_reduce:
+        barrier()   # banks are built at different speeds: the ranks enter the exchange together
     for i in range(spec["fill_steps"]):
         step(i)
     for i in range(W):

@@ -304,7 +304,8 @@ PGX_API int pgx_osc_launches(pgx_osc* osc, int64_t* launches);
  * PGX_OSC_BLIT handles (BlitSawPE / SuperSawPE with a PE-valued frequency and / or amplitude, blit_saw_pe.py:161-262,
  * super_saw_pe.py:223-246,287-303): `freq` is the voice's frequency control, each oscillator using float32(freq * ratio)
  * with ratio = its `freq` entry at creation (GainPE(frequency_pe, ratio); pass the detune ratios -- 1 for a BlitSawPE --
- * when the frequency will be a PE); `amp` see PGX_CTL_AMP_OSC; `phase` must be NULL.  Output as pgx_osc_render_device
+ * when the frequency will be a PE); `amp` see PGX_CTL_AMP_OSC; the third vector (`phase`) is the harmonic-count control of a
+ * PE-valued `m` (blit_saw_pe.py:175-177: max(int32(m), 1) per sample), or NULL.  Output as pgx_osc_render_device
  * (*out_dev, may be NULL) and / or, when y_host is not NULL, copied to host memory before the call returns. */
 #define PGX_CTL_HOST 1
 #define PGX_CTL_AMP_OSC 2 /* BLIT handles: the amplitude control replaces the OSCILLATOR amplitude (BlitSawPE: saw * 2 * amp,

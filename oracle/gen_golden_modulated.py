@@ -81,6 +81,9 @@ def main():
     out["ssaw_glide_env_stereo"] = pull(pg.SuperSawPE(frequency=B("glide_freq"), amplitude=B("env_amp"), voices=5,
                                                      detune_cents=35.0, mix_mode="linear", channels=2, seed=4), PULLS)
     out["ssaw_amp_only"] = pull(pg.SuperSawPE(frequency=110.0, amplitude=B("env_amp"), seed=5), PULLS)
+    ctl2["m_steps"] = np.repeat(np.array([1, 3, 7.9, 0.2, 15, 40], np.float32), n // 6 + 1)[:n]   # truncation, clamp to >= 1
+    out["ctl_m_steps"] = ctl2["m_steps"]
+    out["blit_m_pe"] = pull(pg.BlitSawPE(frequency=B("vib_freq"), amplitude=0.6, m=B("m_steps")), PULLS)
     pe = pg.BlitSawPE(frequency=B("vib_freq"), amplitude=B("env_amp"))
     a = pull(pe, [256, 256])
     b = pull(pe, [256, 256], start=1024)            # non-contiguous: state resets (blit_saw_pe.py:183-186)

@@ -73,14 +73,16 @@ class OracleBlitSaw:
     def reset(self):                                                    # :137-142
         self.phase, self.integ, self.last_end = self.initial_phase, 0.0, None
 
-    def render(self, start: int, duration: int, freq_ctl=None, amp_ctl=None) -> np.ndarray:
-        """freq_ctl / amp_ctl: what a PE-valued frequency / amplitude rendered for this pull (float32, widened by
-        _scalar_or_pe_values, :162-163), or None for the constants."""
+    def render(self, start: int, duration: int, freq_ctl=None, amp_ctl=None, m_ctl=None) -> np.ndarray:
+        """freq_ctl / amp_ctl / m_ctl: what a PE-valued frequency / amplitude / m rendered for this pull (float32,
+        widened by _scalar_or_pe_values, :162-163,176), or None for the constants."""
         freq = np.full(duration, self.f, dtype=np.float64) if freq_ctl is None else \
             np.asarray(freq_ctl, np.float32).astype(np.float64)         # :162
         amp = np.full(duration, self.amp, dtype=np.float64) if amp_ctl is None else \
             np.asarray(amp_ctl, np.float32).astype(np.float64)          # :163
-        if self.m is None:                                              # :167-174
+        if m_ctl is not None:                                           # :175-177
+            m = np.maximum(np.asarray(m_ctl, np.float32).astype(np.float64).astype(np.int32), 1).astype(np.float64)
+        elif self.m is None:                                            # :167-174
             m = np.floor(self.sr / (2.0 * np.maximum(freq, 1.0))).astype(np.int32)
             m = m - (1 - m % 2)
             m = np.maximum(m, 1)

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(1024) k_blit_mod(const BlitModArgs a) {
   float* tile = reinterpret_cast<float*>(mod_sm + (size_t)U * 2 * kTile);
   const float* fq = a.freq ? a.freq + (size_t)v * a.n : nullptr;
   const float* am = a.amp ? a.amp + (size_t)v * a.n : nullptr;
+  const float* mc = a.m_ctl ? a.m_ctl + (size_t)v * a.n : nullptr;
   const double sr = (double)a.sample_rate, leak = a.leak;
   const float ratio = (float)a.osc_freq[o];       // detune ratio when the frequency is a PE, else the frequency itself
   const double f_const = a.osc_freq[o];
@@ -231,7 +232,10 @@ __global__ void __launch_bounds__(1024) k_blit_mod(const BlitModArgs a) {
       if (ph < 0.0) ph += 1.0;
       const double fm = fmax(f, 1.0);
       double m;
-      if (m_fixed > 0) {
+      if (mc) {                                                                        // :175-177 a PE-valued m
+        const int mi = (int)(double)mc[t0 + i];                                        // astype(int32): toward zero
+        m = (double)(mi < 1 ? 1 : mi);
+      } else if (m_fixed > 0) {
         m = (double)m_fixed;
       } else {
         int mi = (int)floor(sr / (2.0 * fm));                                          // :169-174
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(1024) k_blit_mod(const BlitModArgs a) {
 
 void launch_blit_mod(const BlitModArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)a.unison * (2 * 128 * sizeof(double) + 128 * sizeof(float));
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_blit_mod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // unison > 18
   k_blit_mod<<<a.n_voices, a.unison * 32, smem, st>>>(a);
 }
 

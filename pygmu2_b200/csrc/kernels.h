@@ -153,6 +153,7 @@ struct BlitModArgs {
   const float* freq;       // [V][n] frequency control of the voice (what the frequency PE rendered), or NULL
   const float* amp;        // [V][n] amplitude control, or NULL: replaces the oscillator amplitude when amp_per_osc
                            // (BlitSawPE), else the voice amplitude (SuperSawPE)
+  const float* m_ctl;      // [V][n] harmonic-count control (a PE-valued m, blit_saw_pe.py:175-177), or NULL
   double* st_phase;        // [V*U] state: wrapped phase / integrator output at the end of the previous pull
   double* st_int;
   float* out;

@@ -177,8 +177,10 @@ struct pgx_bank {
   };
   PullGraph pgraph[kSlots][2][2];  // [slot][mix][x already on the device]
   bool use_graph = true;           // PGX_GRAPH=0 disables
-  bool graph_fuse = true;          // graph shape 3: K1 and K2 as ONE k_conv1 launch that also adds the folded past sum
-                                   // (PGX_GRAPH_FUSE=0 keeps the two kernels)
+  bool graph_fuse = false;         // graph shape 3: K1 and K2 as ONE k_conv1 launch that also adds the folded past sum
+                                   // (PGX_GRAPH_FUSE=1).  Off by default: measured slower in a pull loop -- the next
+                                   // block's past pass then waits for the whole fused kernel instead of K1 alone and the
+                                   // replays serialise on it (C2 through the PE API 29.5 vs 26.9 us per pull)
   bool after_graph = false;        // the previous step was a graph replay: the event ring must be re-armed before the
                                    // multi-stream schedule continues
   cudaEvent_t ev_join[4] = {};
@@ -807,7 +809,7 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
     b->fft16 = pgx::conv1_r16_default();
     if (const char* e = getenv("PGX_MIX1")) b->use_mix1 = (e[0] != '0');
     if (const char* e = getenv("PGX_GRAPH")) b->use_graph = (e[0] != '0');
-    if (const char* e = getenv("PGX_GRAPH_FUSE")) b->graph_fuse = (e[0] != '0');
+    if (const char* e = getenv("PGX_GRAPH_FUSE")) b->graph_fuse = (e[0] == '1');
     for (cudaEvent_t& e : b->ev_join) guard(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate(join)");
     guard(cudaStreamCreateWithPriority(&b->s_h2d, cudaStreamNonBlocking, hi), "cudaStreamCreate(h2d)");
     guard(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, hi), "cudaStreamCreate(d2h)");

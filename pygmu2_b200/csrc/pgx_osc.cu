@@ -183,7 +183,6 @@ int pgx_osc_render_modulated(pgx_osc* h, int32_t n, int32_t flags, const float* 
                              float* y_host) {
   if (!h || (!out_dev && !y_host)) return pgx_fail(PGX_ERR_INVALID, "NULL argument");
   const pgx_osc_config& c = h->cfg;
-  if (c.kind == PGX_OSC_BLIT && phase) return pgx_fail(PGX_ERR_INVALID, "BLIT oscillators have no phase control");
   if (n < 1 || n > c.max_pull) return pgx_fail(PGX_ERR_INVALID, "pull of %d samples outside [1, max_pull=%d]", n, c.max_pull);
   PGX_CUDA(cudaSetDevice(c.device));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
@@ -219,7 +218,7 @@ int pgx_osc_render_modulated(pgx_osc* h, int32_t n, int32_t flags, const float* 
     }
     pgx::BlitModArgs a{};
     a.osc_freq = h->osc_freq; a.gain = h->gain; a.vamp = h->amp; a.m_fixed = h->m_fixed_dev;
-    a.freq = ctl[0]; a.amp = ctl[1];
+    a.freq = ctl[0]; a.amp = ctl[1]; a.m_ctl = ctl[2];
     a.st_phase = h->st_phase; a.st_int = h->st_int; a.out = h->out;
     a.os = (int64_t)c.channels * n; a.oc = n; a.oi = 1; a.leak = c.leak;
     a.n_voices = c.n_voices; a.unison = c.unison; a.channels = c.channels; a.n = n; a.sample_rate = c.sample_rate;

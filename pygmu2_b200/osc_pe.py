@@ -5,8 +5,9 @@ Drop-ins for the constant-parameter forms of src/pygmu2/sine_pe.py, blit_saw_pe.
 super_saw_pe.py.  Host logic (detune ratios, mix gains, the seeded initial phases, harmonic
 count rules) is the reference's, parameter for parameter; the samples are produced by the
 sm_100a kernels of ``csrc/k_osc.cu`` through ``pgx_osc_*`` -- float64 arithmetic, float32
-rounding exactly where the reference rounds.  A PE-valued (modulated) parameter is outside the
-path and raises ``NotImplementedError``.
+rounding exactly where the reference rounds.  PE-valued (modulated) parameters -- frequency, amplitude,
+phase, harmonic count -- are rendered for the pull and handed to the device as control vectors
+(``pgx_osc_render_modulated``); the stateful recurrences are walked in the reference's own order.
 
 Besides ``render()`` (host Snippet, as the PE protocol demands) every class offers
 ``device_block(start, duration, cuda_stream)``: the same samples left in HBM, which is how
@@ -151,12 +152,6 @@ class OscBank:
                            self.channels, n)
 
 
-def _const(name: str, v):
-    if isinstance(v, ProcessingElement):
-        raise NotImplementedError(f"pygmu2_b200: a PE-valued {name} (modulation) is outside the device path")
-    return v
-
-
 class _OscPE(ProcessingElement):
     """Shared plumbing: lazy device handle, host render, device block, start/stop reset."""
 
@@ -284,15 +279,15 @@ class _ModulatedBlit(_OscPE):
     _pe_params: dict = {}
     _last_end = None
 
-    def _split_params(self, frequency, amplitude):
-        self._pe_params = {k: v for k, v in (("frequency", frequency), ("amplitude", amplitude))
+    def _split_params(self, frequency, amplitude, m=None):
+        self._pe_params = {k: v for k, v in (("frequency", frequency), ("amplitude", amplitude), ("m", m))
                            if isinstance(v, ProcessingElement)}
         f = frequency if "frequency" in self._pe_params else float(frequency)
         a = amplitude if "amplitude" in self._pe_params else float(amplitude)
         return f, a
 
     def inputs(self) -> list:
-        return [self._pe_params[k] for k in ("frequency", "amplitude") if k in self._pe_params]
+        return [self._pe_params[k] for k in ("frequency", "amplitude", "m") if k in self._pe_params]   # blit_saw_pe.py:110-119
 
     def _compute_extent(self) -> Extent:
         result = Extent(None, None)
@@ -314,7 +309,7 @@ class _ModulatedBlit(_OscPE):
         while pos < duration:
             d = min(self._max_pull, duration - pos)
             ctl = self._controls(start + pos, d)
-            outs.append(bank.render_modulated(d, ctl.get("frequency"), ctl.get("amplitude"),
+            outs.append(bank.render_modulated(d, ctl.get("frequency"), ctl.get("amplitude"), ctl.get("m"),
                                               amp_osc=self._amp_per_osc)[0].T)
             pos += d
         self._last_end = start + duration
@@ -330,7 +325,7 @@ class _ModulatedBlit(_OscPE):
             bank.reset()
         ctl = self._controls(start, duration)
         self._last_end = start + duration
-        return bank.render_modulated_device(duration, ctl.get("frequency"), ctl.get("amplitude"),
+        return bank.render_modulated_device(duration, ctl.get("frequency"), ctl.get("amplitude"), ctl.get("m"),
                                             cuda_stream=cuda_stream, amp_osc=self._amp_per_osc)
 
     def _reset_state(self) -> None:
@@ -348,9 +343,9 @@ class BlitSawPE(_ModulatedBlit):
 
     def __init__(self, frequency, amplitude=1.0, initial_phase: float = 0.0, m=None, leak: float = 0.999,
                  channels: int = 1, *, device: int = 0):
-        self._frequency, self._amplitude = self._split_params(frequency, amplitude)
+        self._frequency, self._amplitude = self._split_params(frequency, amplitude, m)
         self._initial_phase = float(np.asarray(initial_phase, dtype=np.float64).reshape(-1)[0]) % 1.0
-        self._m = None if m is None else int(_const("m", m))
+        self._m = None if m is None else (m if "m" in self._pe_params else int(m))
         self._leak, self._channels, self._device = float(leak), int(channels), int(device)
 
     frequency = property(lambda self: self._frequency)
@@ -363,7 +358,7 @@ class BlitSawPE(_ModulatedBlit):
         return False
 
     def _make_bank(self) -> OscBank:
-        m_fixed = None if self._m is None else [max(self._m, 1)]     # blit_saw_pe.py:176-177
+        m_fixed = None if (self._m is None or "m" in self._pe_params) else [max(self._m, 1)]     # blit_saw_pe.py:176-177
         # a PE-valued frequency is used as it is (ratio 1), a PE-valued amplitude replaces the oscillator amplitude
         f = 1.0 if "frequency" in self._pe_params else self._frequency
         a = 1.0 if "amplitude" in self._pe_params else self._amplitude
@@ -372,7 +367,7 @@ class BlitSawPE(_ModulatedBlit):
                        max_pull=self._max_pull, device=self._device)
 
     def __repr__(self):
-        m = "auto" if self._m is None else str(self._m)
+        m = "auto" if self._m is None else (self._m.__class__.__name__ if "m" in self._pe_params else str(self._m))
         return (f"BlitSawPE(frequency={self._frequency}, amplitude={self._amplitude}, m={m}, "
                 f"leak={self._leak}, channels={self._channels})")
 

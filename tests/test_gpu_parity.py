@@ -552,8 +552,9 @@ def test_graph_replay_of_whole_block_pulls_is_bit_identical_to_the_streamed_sche
     n = sum(pulls)
     x = rng.uniform(-1, 1, (n, c)).astype(np.float32)
     outs = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("PGX_GRAPH", mode)
+    for mode in ("0", "1", "1f"):          # streamed schedule, graph replay, graph replay with K1+K2 as one launch
+        monkeypatch.setenv("PGX_GRAPH", mode[0])
+        monkeypatch.setenv("PGX_GRAPH_FUSE", "1" if mode == "1f" else "0")
         bank = pg.ConvolveBank(h, 1, c, block=B, single_filter_dims=True, max_pull=2 * B)
         ys, pos = [], 0
         for rnd in range(2):
@@ -566,8 +567,9 @@ def test_graph_replay_of_whole_block_pulls_is_bit_identical_to_the_streamed_sche
                 bank.reset()
         outs[mode] = np.concatenate(ys)
         info = bank.info()
-        assert (info.graph_pulls > 0) == (mode == "1"), (mode, info.graph_pulls)
+        assert (info.graph_pulls > 0) == (mode != "0"), (mode, info.graph_pulls)
         bank.close()
+    assert np.array_equal(outs["0"], outs["1f"])
     assert np.array_equal(outs["0"], outs["1"])
     ref = orc.OracleConvolve(h, c).render(x)
     assert rel_err(outs["1"][:n], ref) <= TOL

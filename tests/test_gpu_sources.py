@@ -92,13 +92,11 @@ def test_voice_mix_fused_matches_reference_golden():
     assert isinstance(mix._fused, _VoiceMix) and mix._fused.vb.bank.launches == 2 * 12
 
 
-def test_pe_valued_harmonic_count_is_rejected_loudly():
-    """Frequency and amplitude of every oscillator may be PEs (test_modulated_*); a PE-valued harmonic count `m` is
-    the one modulated parameter outside the device path, and it says so instead of falling back to anything."""
+def test_pe_valued_parameters_are_inputs_like_in_the_reference():
     assert not pg.SinePE(frequency=pg.ConstantPE(440.0)).is_pure()
     assert pg.SuperSawPE(frequency=pg.ConstantPE(440.0)).inputs()
-    with pytest.raises(NotImplementedError):
-        pg.BlitSawPE(frequency=440.0, m=pg.ConstantPE(5.0))
+    m = pg.ConstantPE(5.0)
+    assert pg.BlitSawPE(frequency=440.0, m=m).inputs() == [m]
 
 
 def test_modulated_blit_and_supersaw_match_reference_goldens():
@@ -122,6 +120,7 @@ def test_modulated_blit_and_supersaw_match_reference_goldens():
     check(_pull(pg.SuperSawPE(frequency=A("glide_freq"), amplitude=A("env_amp"), voices=5, detune_cents=35.0,
                               mix_mode="linear", channels=2, seed=4), pulls), g["ssaw_glide_env_stereo"], 0.8, "ssaw_glide")
     check(_pull(pg.SuperSawPE(frequency=110.0, amplitude=A("env_amp"), seed=5), pulls), g["ssaw_amp_only"], 0.8, "ssaw_amp")
+    check(_pull(pg.BlitSawPE(frequency=A("vib_freq"), amplitude=0.6, m=A("m_steps")), pulls), g["blit_m_pe"], 0.6, "blit_m_pe")
     pe = pg.BlitSawPE(frequency=A("vib_freq"), amplitude=A("env_amp"))
     y = np.concatenate([_pull(pe, [256, 256]), _pull(pe, [256, 256], start=1024)])
     check(y, g["blit_gap"], 0.8, "blit_gap")

@@ -109,6 +109,11 @@ def test_oracle_modulated_blit_and_supersaw_are_the_reference_bit_for_bit():
             f="ctl_glide_freq", a="ctl_env_amp")
     assert np.array_equal(np.stack([y, y], axis=1), g["ssaw_glide_env_stereo"])
     assert np.array_equal(run(osrc.OracleSuperSaw(110.0, 1.0, seed=5), a="ctl_env_amp"), g["ssaw_amp_only"][:, 0])
+    ob, out, pos = osrc.OracleBlitSaw(1.0, 0.6), [], 0
+    for d in pulls:
+        out.append(ob.render(pos, d, g["ctl_vib_freq"][pos:pos + d], None, g["ctl_m_steps"][pos:pos + d]))
+        pos += d
+    assert np.array_equal(np.concatenate(out), g["blit_m_pe"][:, 0])
     o = osrc.OracleBlitSaw(1.0, 1.0)
     a = run(o, f="ctl_vib_freq", a="ctl_env_amp", pulls=[256, 256])
     b = run(o, f="ctl_vib_freq", a="ctl_env_amp", pulls=[256, 256], start=1024, off=1024)
