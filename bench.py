@@ -315,7 +315,8 @@ def make_workload(args, w, rank, local):
             bank.set_output_gains(0.3, 0.7)
             cfg["output_stage"] = "fused ReverbPE wet/dry: y = 0.7*x + 0.3*conv (pgx_bank_set_output_gains)"
         ir_of = (lambda r, s_: wl.c2_ir(stream=r * N + s_)) if distinct else (lambda r, s_: wl.c2_ir())
-        return dict(name="c2", bank=bank, N=N, c_in=CH, c_out=CH, L=L, B=B, pull=PULL, sr=SR, distinct=distinct, mix=False,
+        gains = (0.3, 0.7) if args.reverb else None
+        return dict(name="c2", gains=gains, bank=bank, N=N, c_in=CH, c_out=CH, L=L, B=B, pull=PULL, sr=SR, distinct=distinct, mix=False,
                     config=cfg, fill_steps=bank.partitions, ir_of=ir_of)
     if w == "c1":   # 4096 mono streams x distinct 4096-tap FIRs, B = 4096 (P = 1): FFT-stage bound
         N = args.streams or 4096
@@ -451,7 +452,7 @@ def parity_leg(spec, bank, dev, stream, world, rank, do_reduce, traj_dev, traj):
 
     N, c_in, c_out, pull, mix = spec["N"], spec["c_in"], spec["c_out"], spec["pull"], spec["mix"]
     P = bank.partitions
-    n_p = P + 2 if P > 1 else 4
+    n_p = -(-spec["L"] // pull) + 2 if P > 1 else 4     # every partition (of both levels of a two-level bank) live at the end
     n = n_p * pull
     sample = sorted({0, min(1, N - 1), N // 2, N - 1})
     bank.synchronize()
@@ -518,6 +519,8 @@ def parity_leg(spec, bank, dev, stream, world, rank, do_reduce, traj_dev, traj):
             for c in range(c_out):
                 xc = xs[:, k, c if c_in > 1 else 0].reshape(-1)
                 ref = _fftconv64(xc, h[:, c if h.shape[1] > 1 else 0], n)
+                if spec.get("gains"):   # fused ReverbPE output stage: y = dry * x + wet * conv
+                    ref = spec["gains"][1] * xc.astype(np.float64) + spec["gains"][0] * ref
                 yc = y[:, s_ * c_out + c].reshape(-1)
                 worst = max(worst, float(np.max(np.abs(yc - ref)) / np.max(np.abs(ref))))
         checked = [f"streams {sample}, every channel"]

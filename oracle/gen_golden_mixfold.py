@@ -51,8 +51,41 @@ def graph(mod):
     )
 
 
+def controls():
+    """Per-sample control signals of the second graph: a tremolo gain and a pan sweep."""
+    n = 6144
+    t = np.arange(n) / SR
+    gain = (0.6 + 0.4 * np.sin(2 * np.pi * 9.0 * t)).astype(np.float32)
+    az = (80.0 * np.sin(2 * np.pi * 1.5 * t)).astype(np.float32)
+    return gain, az
+
+
+def graph_pe_controls(mod, **kw):
+    """HRTF sources the bank can hold + one whose GainPE is PE-valued (gain_pe.py:105-121: the per-sample gain applies
+    AFTER its HRTF convolution) + one panned by a PE-valued azimuth (spatial_pe.py:179-214): the un-bankable two."""
+    s = sources(mod)
+    gain, az = controls()
+    return mod.MixPE(
+        mod.DelayPE(mod.SpatialPE(s[0], method=mod.SpatialHRTF(30.0, 0.0)), 300),
+        mod.GainPE(mod.SpatialPE(s[1], method=mod.SpatialHRTF(-100.0, 20.0)), 0.5),
+        mod.GainPE(mod.SpatialPE(s[2], method=mod.SpatialHRTF(75.0, 10.0)), mod.ArrayPE(gain)),
+        mod.SpatialPE(s[3], method=mod.SpatialLinear(mod.ArrayPE(az))),
+        mod.SpatialPE(s[4], method=mod.SpatialHRTF(170.0, -10.0)),
+        mod.DelayPE(mod.SpatialPE(s[5], method=mod.SpatialConstantPower(-20.0)), 2500),
+        **kw)
+
+
 def main():
     pg.set_sample_rate(SR)
+    mix2 = graph_pe_controls(pg)
+    out, pos = [], 0
+    for d in [512] * 12:
+        out.append(mix2.render(pos, d).data.copy())
+        pos += d
+    ext2 = mix2.extent()
+    np.savez_compressed(os.path.join(GOLD, "mix_fold_pe_controls.npz"), y=np.concatenate(out), pulls=np.array([512] * 12),
+                        extent=np.array([ext2.start, ext2.end]))
+    print("wrote mix_fold_pe_controls.npz", np.concatenate(out).shape, "extent", ext2)
     mix = graph(pg)
     pulls = [512] * 12
     out, pos = [], 0

@@ -1017,6 +1017,31 @@ def test_golden_mix_fold_delay_gain_pan_and_extent_gating(fuse):
         assert not mix._fused._was_active[4]
 
 
+@pytest.mark.parametrize("fuse", [True, False])
+def test_golden_mix_with_pe_valued_gain_and_pan_azimuth(fuse):
+    """A MixPE over HRTF sources where one input is scaled by a PE-VALUED GainPE (gain_pe.py:105-121) and one is panned
+    by a PE-valued azimuth (spatial_pe.py:179-214), against outputs of the REAL reference
+    (oracle/gen_golden_mixfold.py::graph_pe_controls).  Fused: the four bank-able inputs share one HrtfMixBank, the two
+    per-sample-controlled ones are rendered beside it and added."""
+    import os
+    from conftest import ROOT
+    g = golden("mix_fold_pe_controls.npz")
+    # the generator's graph builder is module-agnostic (it takes the package as an argument): reuse its text here
+    # without importing the reference
+    src = open(os.path.join(ROOT, "oracle", "gen_golden_mixfold.py")).read()
+    ns = {"np": np, "SR": 44_100}
+    body = src[src.index("LENGTHS ="):src.index("def main():")]
+    exec(body, ns)
+    mix = ns["graph_pe_controls"](pg, fuse=fuse)
+    ext = mix.extent()
+    assert [ext.start, ext.end] == list(g["extent"])
+    y = _pull_pe(mix, g["pulls"])
+    assert y.shape == g["y"].shape and rel_err(y, g["y"]) <= TOL
+    if fuse:
+        from pygmu2_b200.hrtf_bank import HrtfMixBank
+        assert isinstance(mix.fused_bank, HrtfMixBank) and len(mix.fused_bank.sources) == 4 and len(mix._rest) == 2
+
+
 def test_mix_of_delayed_scaled_convolves_folds_into_one_bank():
     rng = np.random.default_rng(61)
     N, L = 4, 900

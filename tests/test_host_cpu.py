@@ -27,6 +27,10 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, name), name
     assert h.pgx_abi_version() == _lib.ABI_VERSION
     assert isinstance(h.pgx_last_error(), bytes)
+    # the entry-point count quoted in the documents is the header's
+    for doc in ("DESIGN.md", "INTEGRATION.md"):
+        txt = open(os.path.join(ROOT, doc)).read()
+        assert f"{len(declared)} entry points" in txt or f"all {len(declared)} prototypes" in txt, doc
 
 
 def test_struct_layouts_match_header():
