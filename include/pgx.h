@@ -294,6 +294,13 @@ PGX_API int pgx_osc_render_device(pgx_osc* osc, int64_t start, int32_t n, int32_
 /* Same pull delivered to host memory (D2H inside, returns when y is complete). */
 PGX_API int pgx_osc_render(pgx_osc* osc, int64_t start, int32_t n, int32_t flags, float* y);
 PGX_API int pgx_osc_launches(pgx_osc* osc, int64_t* launches);
+/* Speculative pulls: a consumer that has just delivered [s, s+n) may render [s+n, s+2n) right away, behind its own
+ * work on the same stream, so that the block is ready when the next contiguous pull arrives (the reference renders a
+ * block when it is asked for it, blit_saw_pe.py:150-262; the samples are the same either way).  Such a pull carries
+ * PGX_OSC_SNAPSHOT in `flags`: the oscillator state it starts from is kept, and pgx_osc_rollback restores it (enqueued
+ * on cuda_stream) when the next pull turns out to be a different one.  Any regular pull commits the speculation. */
+#define PGX_OSC_SNAPSHOT 64
+PGX_API int pgx_osc_rollback(pgx_osc* osc, void* cuda_stream);
 /* Modulated SinePE: any of frequency / amplitude / phase is a PE (sine_pe.py:134-142,188-232: the stateful branch --
  * phase[i] = cumsum(2 pi f[i] / sr)[i] + carried phase (+ phase_mod[i]), float64, np.cumsum's left-to-right order).
  * freq / amp / phase: float32 [n_voices][n], what the parameter PEs rendered for this pull (widened to float64 on the

@@ -17,6 +17,7 @@ PGX_OK, PGX_ERR_INVALID, PGX_ERR_CUDA, PGX_ERR_NO_DEVICE, PGX_ERR_NOMEM = 0, -1,
 PGX_FLAG_MIXDOWN_INPUT = 1
 PGX_PULL_MIX, PGX_PULL_INPUT_RESIDENT, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16 = 1, 2, 4, 8, 16
 PGX_PULL_REDUCE = 32
+PGX_OSC_SNAPSHOT = 64
 PGX_CTL_HOST = 1
 PGX_CTL_AMP_OSC = 2
 PGX_COMM_HANDLE_BYTES = 128
@@ -93,6 +94,7 @@ PROTOTYPES = {
                                         C.POINTER(C.c_void_p)]),
     "pgx_osc_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "pgx_osc_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "pgx_osc_rollback": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pgx_osc_render_modulated": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "pgx_bank_process_device": (C.c_int, [C.c_void_p, C.c_void_p, Layout, C.c_void_p, Layout, C.c_int32,

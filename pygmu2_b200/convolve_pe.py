@@ -44,6 +44,9 @@ class ConvolvePE(ProcessingElement):
         self._bank = None
         self._last_render_end = None
         self._out_gains = None  # (wet, dry) set by ReverbPE: fused GainPE/GainPE/MixPE tail
+        self._spec = None       # ((start, duration), DeviceBlock) of the source block rendered ahead of its pull
+        import os
+        self._speculate = os.environ.get("PGX_SPECULATE", "1") != "0"
 
     src = property(lambda self: self._src)
     fir = property(lambda self: self._fir)
@@ -84,7 +87,15 @@ class ConvolvePE(ProcessingElement):
     def _on_stop(self) -> None:
         self._reset_state()
 
+    def _drop_speculation(self) -> None:
+        if self._spec is not None:
+            self._spec = None
+            rb = getattr(self._src, "rollback_speculation", None)
+            if rb is not None and self._bank is not None:
+                rb(self._bank.stream_ptr)
+
     def _reset_state(self) -> None:
+        self._drop_speculation()
         # The reference drops _tail here but keeps _H, which makes a restart assert
         # (convolve_pe.py:152-154,186-187,252; SURVEY.md §7 "bugs not to copy").  Here the
         # prepared filter stays resident and the history is cleared on the next pull.
@@ -154,6 +165,8 @@ class ConvolvePE(ProcessingElement):
 
     def _render(self, start: int, duration: int, pcm16_out: bool = False):
         self._ensure_filter_prepared(duration)
+        if self._spec is not None and (pcm16_out or self._spec[0] != (start, duration)):
+            self._drop_speculation()     # the block rendered ahead is not the one being asked for: undo its state advance
         if duration >= 32 * self._bank.block and not getattr(self, "_warned_block", False):
             self._warned_block = True   # B is fixed at the first pull; correct, but every pull is many block steps
             log.warning("ConvolvePE: pull of %d samples on a bank partitioned at B=%d (chosen at the first pull); "
@@ -183,6 +196,25 @@ class ConvolvePE(ProcessingElement):
 
     def _render_from_device(self, dev, start: int, duration: int):
         bank = self._bank
+        if duration <= bank.max_pull:
+            # One block.  If the source rendered it ahead of time (behind the previous pull, on the bank's stream) it is
+            # already in HBM; then the NEXT contiguous block is requested right after this pull's work, so that a source
+            # whose block costs as much as the convolution itself (1024 SuperSaw voices: ~20 us) is off the latency
+            # chain of the pull that asks for it.  Same samples: the source's state is snapshotted and rolled back
+            # (_drop_speculation) whenever the next pull turns out to be a different one.
+            hit = self._spec is not None and self._spec[0] == (start, duration)
+            blk = self._spec[1] if hit else dev(start, duration, cuda_stream=bank.stream_ptr)
+            self._spec = None
+            if blk is None:
+                return None  # the source declined (e.g. pull larger than its buffer): host path
+            if blk.n_streams != 1 or blk.channels != bank.c_in:
+                raise ValueError(f"ConvolvePE src returned {blk.channels} channels, prepared for {bank.c_in}")
+            y = bank.process_device_block(blk, interleaved=True)
+            if self._speculate and getattr(self._src, "can_speculate", False):
+                nxt = dev(start + duration, duration, cuda_stream=bank.stream_ptr, speculative=True)
+                if nxt is not None:
+                    self._spec = ((start + duration, duration), nxt)
+            return y
         outs, pos = [], 0
         while pos < duration:
             d = min(bank.max_pull, duration - pos)

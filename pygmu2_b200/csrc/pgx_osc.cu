@@ -20,6 +20,9 @@ struct pgx_osc {
   double *mod_state = nullptr, *mod_scratch = nullptr;  // modulated sine: accumulated phase [V], phases [V][max_pull]
   float *ctl[3] = {nullptr, nullptr, nullptr};    // staged control vectors (host-supplied), [V][max_pull] each
   bool mod_started = false;
+  double *snap_phase = nullptr, *snap_int = nullptr;   // state before a speculative pull (PGX_OSC_SNAPSHOT)
+  int64_t snap_last_end = INT64_MIN;
+  bool snap_has_last = false, snap_valid = false;
   double* osc_freq = nullptr;                     // BLIT: per-oscillator frequency as given (the detune ratio when modulated)
   int32_t* m_fixed_dev = nullptr;                 // BLIT: fixed harmonic counts (0 = auto)
   int64_t last_end = INT64_MIN;
@@ -36,7 +39,7 @@ void free_osc(pgx_osc* h) {
   for (void* p : {(void*)h->params, (void*)h->consts, (void*)h->gain, (void*)h->amp, (void*)h->phase_init,
                   (void*)h->st_phase, (void*)h->st_int, (void*)h->out, (void*)h->mix, (void*)h->mod_state,
                   (void*)h->mod_scratch, (void*)h->ctl[0], (void*)h->ctl[1], (void*)h->ctl[2], (void*)h->osc_freq,
-                  (void*)h->m_fixed_dev})
+                  (void*)h->m_fixed_dev, (void*)h->snap_phase, (void*)h->snap_int})
     cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -61,6 +64,28 @@ int render_on(pgx_osc* h, int64_t start, int32_t n, int32_t flags, cudaStream_t 
   const pgx_osc_config& c = h->cfg;
   if (n < 1 || n > c.max_pull) return pgx_fail(PGX_ERR_INVALID, "pull of %d samples outside [1, max_pull=%d]", n, c.max_pull);
   const int C = c.channels;
+  if (flags & PGX_OSC_SNAPSHOT) {  // a speculative pull: remember the state it starts from (pgx_osc_rollback undoes it)
+    if (c.kind == PGX_OSC_BLIT) {
+      const size_t nb = (size_t)h->n_osc * sizeof(double);
+      if (!h->snap_phase) {
+        PGX_CUDA(cudaMalloc(&h->snap_phase, nb));
+        PGX_CUDA(cudaMalloc(&h->snap_int, nb));
+      }
+      if (!h->has_last || start != h->last_end) {   // the pull itself would start a new run: nothing to preserve but that
+        const int rc = reset_state(h, st);
+        if (rc != PGX_OK) return rc;
+        h->has_last = true;
+        h->last_end = start;
+      }
+      PGX_CUDA(cudaMemcpyAsync(h->snap_phase, h->st_phase, nb, cudaMemcpyDeviceToDevice, st));
+      PGX_CUDA(cudaMemcpyAsync(h->snap_int, h->st_int, nb, cudaMemcpyDeviceToDevice, st));
+    }
+    h->snap_last_end = h->last_end;
+    h->snap_has_last = h->has_last;
+    h->snap_valid = true;
+  } else {
+    h->snap_valid = false;           // a regular pull commits whatever came before it
+  }
   if (c.kind == PGX_OSC_SINE) {
     pgx::SineArgs a{};
     a.params = h->params; a.out = h->out; a.os = (int64_t)C * n; a.oc = n; a.oi = 1;
@@ -244,8 +269,25 @@ int pgx_osc_render_modulated(pgx_osc* h, int32_t n, int32_t flags, const float* 
   return PGX_OK;
 }
 
+int pgx_osc_rollback(pgx_osc* h, void* cuda_stream) {
+  if (!h) return pgx_fail(PGX_ERR_INVALID, "osc is NULL");
+  if (!h->snap_valid) return PGX_OK;   // nothing speculative outstanding
+  PGX_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  if (h->cfg.kind == PGX_OSC_BLIT) {
+    const size_t nb = (size_t)h->n_osc * sizeof(double);
+    PGX_CUDA(cudaMemcpyAsync(h->st_phase, h->snap_phase, nb, cudaMemcpyDeviceToDevice, st));
+    PGX_CUDA(cudaMemcpyAsync(h->st_int, h->snap_int, nb, cudaMemcpyDeviceToDevice, st));
+  }
+  h->last_end = h->snap_last_end;
+  h->has_last = h->snap_has_last;
+  h->snap_valid = false;
+  return PGX_OK;
+}
+
 int pgx_osc_reset(pgx_osc* h) {
   if (!h) return pgx_fail(PGX_ERR_INVALID, "osc is NULL");
+  h->snap_valid = false;
   h->mod_started = false;  // modulated sine: the next pull starts from the constant phase again (sine_pe.py:110-118)
   h->has_last = false;  // the next pull re-initialises the state on its own stream, in order
   return PGX_OK;

@@ -168,13 +168,23 @@ class MixPE(ProcessingElement):
             raise ValueError("set_trajectory needs a MixPE whose inputs are all SpatialPE(..., SpatialHRTF) sources")
         self._fused.set_trajectory(azimuth, elevation, hop=hop, start=start)
 
-    def device_block(self, start: int, duration: int, cuda_stream: int = 0):
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0, speculative: bool = False):
         """The mix left in HBM (only when the inputs are oscillator voices fused into one VoiceBank)."""
         if self._fused is None:
             self._fused = self._try_adopt(duration)
         if isinstance(self._fused, _VoiceMix):
-            return self._fused.device_block(start, duration, cuda_stream)
+            return self._fused.device_block(start, duration, cuda_stream, speculative)
         return None
+
+    @property
+    def can_speculate(self) -> bool:
+        """A voice mix depends on nothing but (start, duration) and the oscillators' carried state: its consumer may
+        render the next block ahead of the pull that asks for it."""
+        return isinstance(self._fused, _VoiceMix)
+
+    def rollback_speculation(self, cuda_stream: int = 0) -> None:
+        if isinstance(self._fused, _VoiceMix):
+            self._fused.vb.rollback(cuda_stream)
 
     def _reset_state(self) -> None:
         self._fused_pos = None
@@ -243,23 +253,8 @@ class _VoiceMix:
     def render(self, start: int, duration: int) -> np.ndarray:
         return self.vb.render(start, duration, mix=True)
 
-    @property
-    def fused_bank(self):
-        """The device bank the inputs were adopted into (None before the first pull / when the inputs are not
-        bank-able): ``HrtfMixBank``, ``ConvolveBank`` or the voice mix."""
-        return self._fused if self._fused not in (None, False) else None
-
-    def set_trajectory(self, azimuth, elevation=None, *, hop: int, start: int = 0) -> None:
-        """Moving HRTF sources without per-pull host work (extension): see ``HrtfMixBank.set_trajectory``.  Adopts
-        the inputs first if that has not happened yet (``hop`` doubles as the pull-size hint)."""
-        if self._fused is None:
-            self._fused = self._try_adopt(int(hop))
-        if not isinstance(self._fused, HrtfMixBank):
-            raise ValueError("set_trajectory needs a MixPE whose inputs are all SpatialPE(..., SpatialHRTF) sources")
-        self._fused.set_trajectory(azimuth, elevation, hop=hop, start=start)
-
-    def device_block(self, start: int, duration: int, cuda_stream: int = 0):
-        return self.vb.device_block(start, duration, mix=True, cuda_stream=cuda_stream)
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0, speculative: bool = False):
+        return self.vb.device_block(start, duration, mix=True, cuda_stream=cuda_stream, speculative=speculative)
 
     def reset(self) -> None:
         self.vb.reset()

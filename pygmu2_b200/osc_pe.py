@@ -141,11 +141,17 @@ class OscBank:
         self._modulated(duration, freq, amp, phase, False, 0, y, amp_osc)
         return y
 
-    def render_device(self, start: int, duration: int, mix: bool = False, cuda_stream: int = 0) -> DeviceBlock:
+    def rollback(self, cuda_stream: int = 0) -> None:
+        """Undo a speculative pull (``render_device(..., speculative=True)``) that turned out not to be the next one."""
+        check(lib().pgx_osc_rollback(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def render_device(self, start: int, duration: int, mix: bool = False, cuda_stream: int = 0,
+                      speculative: bool = False) -> DeviceBlock:
         """Enqueue one pull (duration <= max_pull) on ``cuda_stream``; the block lives in the handle's buffer
-        until the next render."""
+        until the next render.  ``speculative``: keep the state the pull starts from (see ``rollback``)."""
         out = C.c_void_p()
-        check(lib().pgx_osc_render_device(self._h, int(start), int(duration), 1 if mix else 0,
+        check(lib().pgx_osc_render_device(self._h, int(start), int(duration),
+                                          (1 if mix else 0) | (_lib.PGX_OSC_SNAPSHOT if speculative else 0),
                                           C.c_void_p(cuda_stream) if cuda_stream else None, C.byref(out)))
         n = int(duration)
         return DeviceBlock(int(out.value), Layout(self.channels * n, n, 1), 1 if mix else self.n_voices,
@@ -189,10 +195,16 @@ class _OscPE(ProcessingElement):
         y = self._bank().render(start, duration)           # (1, C, n)
         return Snippet(start, np.ascontiguousarray(y[0].T))
 
-    def device_block(self, start: int, duration: int, cuda_stream: int = 0) -> DeviceBlock | None:
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0, speculative: bool = False) -> DeviceBlock | None:
         if duration > self._max_pull:
             return None
-        return self._bank().render_device(start, duration, cuda_stream=cuda_stream)
+        return self._bank().render_device(start, duration, cuda_stream=cuda_stream, speculative=speculative)
+
+    def rollback_speculation(self, cuda_stream: int = 0) -> None:
+        if self._osc is not None:
+            self._osc.rollback(cuda_stream)
+
+    can_speculate = True      # constant parameters: a block depends on nothing but (start, duration) and the carried state
 
 
 class SinePE(_OscPE):
@@ -249,11 +261,15 @@ class SinePE(_OscPE):
             pos += d
         return Snippet(start, np.ascontiguousarray(outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)))
 
-    def device_block(self, start: int, duration: int, cuda_stream: int = 0) -> DeviceBlock | None:
+    can_speculate = property(lambda self: not self._pe_params)   # control PEs cannot be rendered ahead of their time
+
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0, speculative: bool = False) -> DeviceBlock | None:
         if duration > self._max_pull:
             return None
         if not self._pe_params:
-            return self._bank().render_device(start, duration, cuda_stream=cuda_stream)
+            return self._bank().render_device(start, duration, cuda_stream=cuda_stream, speculative=speculative)
+        if speculative:
+            return None
         ctl = self._controls(start, duration)
         return self._bank().render_modulated_device(duration, ctl.get("frequency"), ctl.get("amplitude"),
                                                     ctl.get("phase"), cuda_stream=cuda_stream)
@@ -315,11 +331,15 @@ class _ModulatedBlit(_OscPE):
         self._last_end = start + duration
         return Snippet(start, np.ascontiguousarray(outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)))
 
-    def device_block(self, start: int, duration: int, cuda_stream: int = 0) -> DeviceBlock | None:
+    can_speculate = property(lambda self: not self._pe_params)
+
+    def device_block(self, start: int, duration: int, cuda_stream: int = 0, speculative: bool = False) -> DeviceBlock | None:
         if duration > self._max_pull:
             return None
         if not self._pe_params:
-            return self._bank().render_device(start, duration, cuda_stream=cuda_stream)
+            return self._bank().render_device(start, duration, cuda_stream=cuda_stream, speculative=speculative)
+        if speculative:
+            return None
         bank = self._bank()
         if self._last_end is None or start != self._last_end:
             bank.reset()
@@ -500,10 +520,14 @@ class VoiceBank:
     def render(self, start: int, duration: int, mix: bool = False) -> np.ndarray:
         return self.bank.render(start, duration, mix=mix)
 
-    def device_block(self, start: int, duration: int, mix: bool = False, cuda_stream: int = 0) -> DeviceBlock | None:
+    def device_block(self, start: int, duration: int, mix: bool = False, cuda_stream: int = 0,
+                     speculative: bool = False) -> DeviceBlock | None:
         if duration > self.max_pull:
             return None
-        return self.bank.render_device(start, duration, mix=mix, cuda_stream=cuda_stream)
+        return self.bank.render_device(start, duration, mix=mix, cuda_stream=cuda_stream, speculative=speculative)
+
+    def rollback(self, cuda_stream: int = 0) -> None:
+        self.bank.rollback(cuda_stream)
 
     def close(self) -> None:
         self.bank.close()

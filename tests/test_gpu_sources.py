@@ -223,3 +223,45 @@ def test_modulated_sine_feeds_convolve_on_the_device():
     o, c = osrc.OracleSineModulated(amplitude=0.5), orc.OracleConvolve(h, 1)
     ref = np.concatenate([c.render(o.render(256, g["ctl_fm_freq"][i * 256:(i + 1) * 256])) for i in range(8)])
     assert np.max(np.abs(y - ref)) <= 1e-5 * np.max(np.abs(ref))
+
+
+def test_speculative_voice_blocks_are_invisible_in_the_output(monkeypatch):
+    """ConvolvePE over a MixPE of SuperSaw voices renders the NEXT voice block behind every pull (so that the 20 us
+    voice front end is off the latency chain of the pull that asks for it).  The oscillator state is snapshotted and
+    rolled back when the next pull is a different one: outputs must equal, BIT FOR BIT, those with speculation off --
+    through hits, a pull of another size, a non-contiguous pull, a stop/start -- and match the oracle chain."""
+    import pygmu2_oracle as orc
+    import pygmu2_oracle_sources as osrc
+    rng = np.random.default_rng(2)
+    h = (rng.standard_normal(900) / 30).astype(np.float32)
+    seq = [(0, 64), (64, 64), (128, 64), (192, 32), (224, 64), (288, 64), (1000, 64), (1064, 64), (1128, 17), (1145, 64)]
+
+    def run(spec):
+        monkeypatch.setenv("PGX_SPECULATE", spec)
+        voices = [pg.SuperSawPE(frequency=110.0 * 2 ** (i / 12.0), amplitude=1.0 / 8, seed=i) for i in range(8)]
+        pe = pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(h), block_size=64)
+        r = pg.NullRenderer(sample_rate=SR)
+        r.set_source(pe)
+        r.start()
+        ys = [pe.render(s_, d).data.copy() for s_, d in seq]
+        r.stop()
+        r.start()
+        ys += [pe.render(s_, d).data.copy() for s_, d in seq[:4]]
+        r.stop()
+        return ys, pe
+
+    y1, pe1 = run("1")
+    y0, _ = run("0")
+    for a, b in zip(y1, y0):
+        assert np.array_equal(a, b)
+    assert pe1._spec is None            # stop() dropped the outstanding block and rolled the oscillators back
+    # the oracle chain for the first contiguous run
+    vo = [osrc.OracleSuperSaw(110.0 * 2 ** (i / 12.0), 1.0 / 8, seed=i, sample_rate=SR) for i in range(8)]
+    c = orc.OracleConvolve(h, 1)
+    ref = []
+    for s_, d in seq[:6]:
+        x = osrc.oracle_mix([v.render(s_, d)[:, None] for v in vo]) if hasattr(osrc, "oracle_mix") else \
+            orc.oracle_mix([v.render(s_, d)[:, None] for v in vo])
+        ref.append(c.render(x))
+    got, want = np.concatenate(y1[:6]), np.concatenate(ref)
+    assert np.max(np.abs(got - want)) <= 1e-5 * np.max(np.abs(want))
