@@ -567,7 +567,9 @@ def test_graph_replay_of_whole_block_pulls_is_bit_identical_to_the_streamed_sche
                 bank.reset()
         outs[mode] = np.concatenate(ys)
         info = bank.info()
-        assert (info.graph_pulls > 0) == (mode != "0"), (mode, info.graph_pulls)
+        import os
+        graphable = not (os.environ.get("PGX_MAC") == "tma" and info.partitions > 16)   # no graph form of the bulk-async pass
+        assert (info.graph_pulls > 0) == (mode != "0" and graphable), (mode, info.graph_pulls)
         bank.close()
     assert np.array_equal(outs["0"], outs["1f"])
     assert np.array_equal(outs["0"], outs["1"])
