@@ -322,6 +322,14 @@ PGX_API int pgx_osc_render_modulated(pgx_osc* osc, int32_t n, int32_t flags, con
                                      const float* phase, int32_t ctl_flags, void* cuda_stream, const float** out_dev,
                                      float* y_host);
 
+/* ---- host helper: the per-pull direction -> HRTF entry search of a moving source ------------------------
+ * SpatialHRTF.hrtf_filename_for (spatial_pe.py:395-426) for n directions at once: az := min(180, |az|), least squared
+ * distance in (elevation, azimuth) over the n_tab table entries, FIRST minimum in table order; plain float64 host
+ * arithmetic in the reference's order (no device involved).  256 moving sources re-select their filters before every
+ * pull: this is the host cost of that loop. */
+PGX_API int pgx_nearest_direction(const double* tab_elev, const double* tab_az, int32_t n_tab, const double* azimuth,
+                                  const double* elevation, int32_t n, int32_t* out_index);
+
 /* ---- MixPE: replaces the float32 left-to-right sum of mix_pe.py:92-94 ------ */
 /*
  * out[e] = ((in_0[e] + in_1[e]) + in_2[e]) + ...  in float32, in input order, for

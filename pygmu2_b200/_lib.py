@@ -109,6 +109,7 @@ PROTOTYPES = {
     "pgx_comm_destroy": (C.c_int, [C.c_void_p]),
     "pgx_mix_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pgx_bank_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pgx_nearest_direction": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pgx_mix_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pgx_mix_sum_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
 }

@@ -30,10 +30,15 @@ class ConvolvePE(ProcessingElement):
         tail_block: (extension) two-level partitioning for a long filter pulled in small blocks: the first
             tail_block taps at block_size, the rest at tail_block (same result, far less delay-line traffic)
         device: (extension) CUDA device ordinal, default 0
+        speculate: (extension) render the next block of a constant-parameter device source (oscillator / voice mix)
+            right behind every pull, so that it is ready when a PACED caller (a real-time callback) asks for it; the
+            samples are the same (state snapshot + rollback on a miss).  Default: the PGX_SPECULATE environment
+            variable, else off -- in a back-to-back pull loop it only adds work to a full time line
     """
 
     def __init__(self, src: ProcessingElement, fir: ProcessingElement, *, fft_size: int | None = None,
-                 block_size: int | None = None, tail_block: int | None = None, device: int = 0):
+                 block_size: int | None = None, tail_block: int | None = None, device: int = 0,
+                 speculate: bool | None = None):
         self._src = src
         self._fir = fir
         self._fft_size = int(fft_size) if fft_size is not None else None
@@ -46,7 +51,10 @@ class ConvolvePE(ProcessingElement):
         self._out_gains = None  # (wet, dry) set by ReverbPE: fused GainPE/GainPE/MixPE tail
         self._spec = None       # ((start, duration), DeviceBlock) of the source block rendered ahead of its pull
         import os
-        self._speculate = os.environ.get("PGX_SPECULATE", "1") != "0"
+        # off by default: it pays when the caller is paced (a real-time callback: the source block is ready when the pull
+        # arrives; C5 paced at real time 45.9 -> 38.7 us per pull) and costs a few us per pull in a back-to-back loop,
+        # where the GPU's time line is full either way
+        self._speculate = (os.environ.get("PGX_SPECULATE", "0") == "1") if speculate is None else bool(speculate)
 
     src = property(lambda self: self._src)
     fir = property(lambda self: self._fir)

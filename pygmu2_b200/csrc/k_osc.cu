@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(1024) k_blit_bank(const BlitArgs a) {
     sq *= sq;
   }
   double ph0 = a.st_phase[o], y0 = a.st_int[o];               // state at the start of the pull
+  if (a.snap_phase && lane == 0) {                            // speculative pull: keep it for pgx_osc_rollback
+    a.snap_phase[o] = ph0;
+    a.snap_int[o] = y0;
+  }
   double ph_last = ph0;
 
   for (int t0 = 0; t0 < a.n; t0 += kOscTile) {

@@ -142,6 +142,8 @@ struct BlitArgs {
   int64_t os, oc, oi;
   double leak;
   int32_t n_voices, unison, channels, n, sample_rate;
+  double* snap_phase;      // speculative pull: the state this pull starts from is copied here first (or NULL)
+  double* snap_int;
 };
 void launch_blit_bank(const BlitArgs& a, cudaStream_t st);
 

@@ -634,6 +634,39 @@ int prep_filters(pgx_bank* b, const float* h_host, int first_row, int n_rows) {
 
 }  // namespace
 
+// Table entries in the outer loop, a chunk of queries in the inner one: the inner loop is a branch-free compare /
+// select over contiguous doubles that the host compiler vectorises (AVX2 clone picked at load time where the CPU
+// has it).  "d < best" strictly, entries in table order: the FIRST minimum wins, as in spatial_pe.py:413-416.
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+static void nearest_scan(const double* tab_elev, const double* tab_az, int32_t n_tab, const double* azimuth,
+                         const double* elevation, int32_t n, int32_t* out_index) {
+  constexpr int kChunk = 128;
+  double az[kChunk], best[kChunk];
+  int32_t bi[kChunk];
+  for (int32_t q0 = 0; q0 < n; q0 += kChunk) {
+    const int m = (n - q0 < kChunk) ? (n - q0) : kChunk;
+    for (int q = 0; q < m; ++q) {
+      az[q] = fmin(180.0, fabs(azimuth[q0 + q]));
+      best[q] = INFINITY;
+      bi[q] = 0;
+    }
+    const double* el = elevation + q0;
+    for (int32_t i = 0; i < n_tab; ++i) {
+      const double te = tab_elev[i], ta = tab_az[i];
+      for (int q = 0; q < m; ++q) {
+        const double de = te - el[q], da = ta - az[q];
+        const double d = de * de + da * da;
+        const bool lt = d < best[q];
+        best[q] = lt ? d : best[q];
+        bi[q] = lt ? i : bi[q];
+      }
+    }
+    for (int q = 0; q < m; ++q) out_index[q0 + q] = bi[q];
+  }
+}
+
 extern "C" {
 
 int pgx_abi_version(void) { return PGX_ABI_VERSION; }
@@ -1579,6 +1612,14 @@ int pgx_bank_profile_end(pgx_bank* b, pgx_profile* out) {
     out->ms_r2c += t.ms_r2c; out->ms_mac += t.ms_mac; out->ms_c2r += t.ms_c2r; out->ms_fold += t.ms_fold;
     out->ms_now += t.ms_now; out->ms_conv1 += t.ms_conv1; out->ms_mac_union += t.ms_mac_union; out->n_mac += t.n_mac;
   }
+  return PGX_OK;
+}
+
+int pgx_nearest_direction(const double* tab_elev, const double* tab_az, int32_t n_tab, const double* azimuth,
+                          const double* elevation, int32_t n, int32_t* out_index) {
+  if (!tab_elev || !tab_az || !azimuth || !elevation || !out_index || n_tab < 1 || n < 0)
+    return fail(PGX_ERR_INVALID, "pgx_nearest_direction: bad arguments");
+  nearest_scan(tab_elev, tab_az, n_tab, azimuth, elevation, n, out_index);
   return PGX_OK;
 }
 

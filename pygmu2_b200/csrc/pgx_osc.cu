@@ -77,8 +77,7 @@ int render_on(pgx_osc* h, int64_t start, int32_t n, int32_t flags, cudaStream_t 
         h->has_last = true;
         h->last_end = start;
       }
-      PGX_CUDA(cudaMemcpyAsync(h->snap_phase, h->st_phase, nb, cudaMemcpyDeviceToDevice, st));
-      PGX_CUDA(cudaMemcpyAsync(h->snap_int, h->st_int, nb, cudaMemcpyDeviceToDevice, st));
+      // (the kernel itself copies the state it starts from into the snapshot arrays: no extra calls on this path)
     }
     h->snap_last_end = h->last_end;
     h->snap_has_last = h->has_last;
@@ -101,6 +100,7 @@ int render_on(pgx_osc* h, int64_t start, int32_t n, int32_t flags, cudaStream_t 
     a.st_phase = h->st_phase; a.st_int = h->st_int; a.out = h->out;
     a.os = (int64_t)C * n; a.oc = n; a.oi = 1; a.channels = C;
     a.leak = c.leak; a.n_voices = c.n_voices; a.unison = c.unison; a.n = n; a.sample_rate = c.sample_rate;
+    if (flags & PGX_OSC_SNAPSHOT) { a.snap_phase = h->snap_phase; a.snap_int = h->snap_int; }
     pgx::launch_blit_bank(a, st);
   }
   h->launches += 1;

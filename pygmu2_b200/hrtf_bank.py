@@ -64,9 +64,12 @@ class HrtfMixBank:
         # while nothing moved; anything else (duck-typed methods, pan laws) is re-read on every pull
         self._dirty = [True]
         self._all_watched = all(hasattr(m, "_watchers") for m in self.methods)
-        for m in self.methods:
+        # the directions as arrays: a watched method's setter writes its new value straight into them
+        self._az = np.array([float(m.azimuth) for m in self.methods], dtype=np.float64)
+        self._el = np.array([float(getattr(m, "elevation", 0.0)) for m in self.methods], dtype=np.float64)
+        for i, m in enumerate(self.methods):
             if hasattr(m, "_watchers"):
-                m._watchers.append(self._dirty)
+                m._watchers.append((self._az, self._el, i, self._dirty))
         # [e] as measured, [E + e] ears swapped, [2E] silence: the filter of a source MixPE does not render
         both = np.concatenate([table, table[:, :, ::-1], np.zeros_like(table[:1]),
                                np.zeros((len(self.pan_index),) + table.shape[1:], np.float32)], axis=0)
@@ -102,9 +105,15 @@ class HrtfMixBank:
             return self._sel_cache.copy()
         self._dirty[0] = False
         n = len(self.methods)
-        az = np.fromiter((float(m.azimuth) for m in self.methods), dtype=np.float64, count=n)
+        if self._all_watched:
+            az = self._az.copy()
+        else:
+            az = np.fromiter((float(m.azimuth) for m in self.methods), dtype=np.float64, count=n)
         if self.n_entries == len(kemar.KEMAR_HRTF_ENTRIES):
-            el = np.fromiter((float(getattr(m, "elevation", 0.0)) for m in self.methods), dtype=np.float64, count=n)
+            if self._all_watched:
+                el = self._el.copy()
+            else:
+                el = np.fromiter((float(getattr(m, "elevation", 0.0)) for m in self.methods), dtype=np.float64, count=n)
             last = getattr(self, "_dir_cache", None)   # directions unchanged since the last pull: same rows
             if last is not None and np.array_equal(last[0], az) and np.array_equal(last[1], el):
                 e = last[2]
@@ -187,7 +196,7 @@ class HrtfMixBank:
         for m in self.methods:
             w = getattr(m, "_watchers", None)
             if w is not None:
-                w[:] = [cell for cell in w if cell is not self._dirty]   # by identity: other banks keep theirs
+                w[:] = [e for e in w if e[3] is not self._dirty]   # by identity: other banks keep theirs
         if self._resident is not None:
             self._resident.close()
             self._resident = None

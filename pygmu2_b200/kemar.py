@@ -69,6 +69,20 @@ _R_ROW = np.arange(len(_RINGS))[:, None, None]
 
 
 def nearest_indices(azimuth: np.ndarray, elevation: np.ndarray) -> np.ndarray:
+    """``nearest_index`` for arrays of directions at once, in the C library (``pgx_nearest_direction``: the plain
+    368-entry scan per direction in float64, first minimum in table order) -- the host cost of re-selecting the
+    filters of many moving sources before a pull.  ``nearest_indices_numpy`` is the vectorised numpy form of the
+    same search (4 candidates per elevation ring), kept as its cross-check."""
+    from . import _lib
+    az = np.ascontiguousarray(azimuth, dtype=np.float64).reshape(-1)
+    el = np.ascontiguousarray(np.broadcast_to(np.asarray(elevation, dtype=np.float64), az.shape)).reshape(-1)
+    out = np.empty(az.shape[0], dtype=np.int32)
+    _lib.check(_lib.lib().pgx_nearest_direction(_ELEV.ctypes.data, _AZ.ctypes.data, int(_ELEV.shape[0]),
+                                                az.ctypes.data, el.ctypes.data, int(az.shape[0]), out.ctypes.data))
+    return out.astype(np.int64)
+
+
+def nearest_indices_numpy(azimuth: np.ndarray, elevation: np.ndarray) -> np.ndarray:
     """``nearest_index`` for arrays of directions at once: same float64 arithmetic, same first-minimum rule.
     On each of the 14 elevation rings only the entries around az/step can be nearest (ring azimuths are
     round(i*step)), so 4 candidates per ring are examined instead of the whole ring: 56 distances per query

@@ -142,7 +142,8 @@ class SpatialHRTF(SpatialMethod):
                 "SpatialHRTF: azimuth and elevation must be static (float or int). "
                 "Dynamic values would switch impulse responses during rendering and cause discontinuities."
             )
-        self._watchers = []            # one-element lists owned by fused banks: [True] = "a direction changed"
+        self._watchers = []            # (az_array, el_array, index, dirty_cell) of the fused banks this method feeds: an
+                                       # assignment lands in the bank's direction arrays and raises its dirty flag
         self.azimuth = float(azimuth)
         self.elevation = float(elevation)
         self._block_size, self._device = block_size, int(device)
@@ -160,14 +161,16 @@ class SpatialHRTF(SpatialMethod):
     @azimuth.setter
     def azimuth(self, value):
         self._azimuth = value
-        for w in self._watchers:
-            w[0] = True
+        for az, _, i, cell in self._watchers:
+            az[i] = value
+            cell[0] = True
 
     @elevation.setter
     def elevation(self, value):
         self._elevation = value
-        for w in self._watchers:
-            w[0] = True
+        for _, el, i, cell in self._watchers:
+            el[i] = value
+            cell[0] = True
 
     @property
     def output_channels(self) -> int:

@@ -36,10 +36,45 @@ def run(name, pe, sr, pull, seconds, channels, before_pull=None):
                       "audio_s_ch_per_s": audio * channels / dt}), flush=True)
 
 
+def run_paced(name, pe, sr, pull, seconds):
+    """The same pull loop PACED at real time (what AudioRenderer's callback does): the latency of each render() call
+    when the caller is idle in between, not the throughput of a back-to-back loop."""
+    n_pulls = int(seconds * sr / pull)
+    period = pull / sr
+    lat = []
+    with pg.NullRenderer(sample_rate=sr) as r:
+        r.set_source(pe)
+        r.start()
+        for p in range(4):
+            r.render(p * pull, pull)
+        nxt = time.perf_counter()
+        for p in range(4, 4 + n_pulls):
+            nxt += period
+            while time.perf_counter() < nxt:
+                pass
+            t0 = time.perf_counter()
+            r.render(p * pull, pull)
+            lat.append(time.perf_counter() - t0)
+    lat = np.array(lat) * 1e6
+    print(json.dumps({"config": name + " [paced at real time]", "pull": pull, "pulls": n_pulls,
+                      "latency_us_median": float(np.median(lat)), "latency_us_p99": float(np.percentile(lat, 99)),
+                      "ms_per_pull": float(np.median(lat)) / 1e3, "x_realtime": period / (float(np.median(lat)) * 1e-6)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=2.0)
+    ap.add_argument("--paced", action="store_true", help="only the paced C5 / C2 latency measurement")
     a = ap.parse_args()
+    if a.paced:
+        pg.set_sample_rate(wl.SR_441)
+        voices = [pg.SuperSawPE(frequency=55.0 * 2.0 ** (i / 128.0), amplitude=1.0 / 32.0, seed=i) for i in range(wl.C5_VOICES)]
+        run_paced("C5 1024 SuperSaw -> MixPE -> 441000-tap IR", pg.ConvolvePE(pg.MixPE(*voices), pg.ArrayPE(wl.c5_ir()),
+                                                                             block_size=64), wl.SR_441, 64, min(a.seconds, 1.0))
+        pg.set_sample_rate(wl.SR_48)
+        x = wl.c2_input(int((a.seconds + 1) * wl.SR_48))
+        run_paced("C2 stereo reverb 132300 taps", pg.ConvolvePE(pg.ArrayPE(x), pg.ArrayPE(wl.c2_ir())), wl.SR_48, 512, a.seconds)
+        return
     S = a.seconds
     # C1: SinePE 440 Hz -> ConvolvePE with a 4096-tap FIR, mono, 44.1 kHz, default fft_size
     pg.set_sample_rate(wl.SR_441)

@@ -251,9 +251,10 @@ def test_speculative_voice_blocks_are_invisible_in_the_output(monkeypatch):
         return ys, pe
 
     y1, pe1 = run("1")
-    y0, _ = run("0")
+    y0, pe0 = run("0")
     for a, b in zip(y1, y0):
         assert np.array_equal(a, b)
+    assert pe1._speculate and not pe0._speculate
     assert pe1._spec is None            # stop() dropped the outstanding block and rolled the oscillators back
     # the oracle chain for the first contiguous run
     vo = [osrc.OracleSuperSaw(110.0 * 2 ** (i / 12.0), 1.0 / 8, seed=i, sample_rate=SR) for i in range(8)]

@@ -436,3 +436,14 @@ def test_fft16_register_model_matches_numpy_fft():
     z = rng.standard_normal(km.FFT16_N) + 1j * rng.standard_normal(km.FFT16_N)
     assert np.max(np.abs(km.fft16_forward(z) - np.fft.fft(z))) < 1e-9
     assert np.max(np.abs(km.fft16_inverse(z) - np.fft.ifft(z) * km.FFT16_N)) < 1e-9
+
+
+def test_nearest_direction_in_c_equals_numpy_and_the_scalar_rule():
+    """pgx_nearest_direction (host C: the per-pull filter selection of moving sources) against the vectorised numpy
+    search and the scalar restatement of spatial_pe.py:395-426, ties (grid points, midpoints, |az| > 180) included."""
+    rng = np.random.default_rng(3)
+    az = np.concatenate([rng.uniform(-220, 220, 4000), np.arange(-180, 181, 2.5), [0.0, 180.0, -180.0, 7.5, 172.5]])
+    el = np.concatenate([rng.uniform(-60, 100, 4000), np.resize(np.arange(-40, 91, 5.0), 145), [0.0, 90.0, 85.0, -5.0, 45.0]])
+    a = kemar.nearest_indices(az, el)
+    assert np.array_equal(a, kemar.nearest_indices_numpy(az, el))
+    assert np.array_equal(a[::37], [kemar.nearest_index(x, y) for x, y in zip(az[::37], el[::37])])
