@@ -458,12 +458,15 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
 // filter row per output channel (the HRTF pair chosen by fmap) and the G products are summed through shared
 // memory -- FFT, HRTF multiply and the MixPE sum over the CTA's sources in one kernel.  Writes one partial row per
 // (CTA, channel) that K2 folds; replaces k_r2c + k_fdl_mac<MIX> of the three-kernel step.
-template <int LOG2N>
+template <int LOG2N, bool WIDE = false>
 struct Mix1Cfg {
   using C = FftCfg<LOG2N>;
-  // sources per CTA: at most 512 threads, so that a thread may keep the filter rows of two output channels in flight
-  // in registers behind the forward transform (128 registers per thread) and a small mix spreads over more SMs
-  static constexpr int G = (512 / C::T8) < 16 ? ((512 / C::T8) < 1 ? 1 : (512 / C::T8)) : 16;
+  // sources per CTA.  Narrow (the latency case, e.g. the named 256-source mix): at most 512 threads, so that a thread
+  // may keep the filter rows of two output channels in flight in registers behind the forward transform (128 registers
+  // per thread) and a small mix spreads over more SMs.  WIDE (thousands of sources: a throughput case): up to 1024
+  // threads, half as many partial rows to write and fold, no register prefetch (64 registers per thread).
+  static constexpr int kMaxT = WIDE ? 1024 : 512;
+  static constexpr int G = (kMaxT / C::T8) < 16 ? ((kMaxT / C::T8) < 1 ? 1 : (kMaxT / C::T8)) : 16;
   static constexpr int CTA = G * C::T8;
   static constexpr int SMEM_BYTES = (C::SMEM_TW ? 2 * C::N : 0) * 8 + G * 2 * C::PADN * 8;
 };
@@ -475,11 +478,11 @@ struct Mix1Cfg {
 // the filter rows of the first two output channels are requested BEFORE the forward transform and consumed after
 // it, and the last CTA folds the partial rows with all its thread groups at once (one round trip per channel) instead
 // of two groups walking them four rows at a time.
-template <int LOG2N, bool LAST>
-__global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, const C2RArgs k, float2* __restrict__ ynow,
-                                                              unsigned int* __restrict__ ticket) {
+template <int LOG2N, bool LAST, bool WIDE = false>
+__global__ void __launch_bounds__(Mix1Cfg<LOG2N, WIDE>::CTA) k_mix1(const R2CArgs a, const C2RArgs k, float2* __restrict__ ynow,
+                                                                    unsigned int* __restrict__ ticket) {
   using C = FftCfg<LOG2N>;
-  using M = Mix1Cfg<LOG2N>;
+  using M = Mix1Cfg<LOG2N, WIDE>;
   constexpr int N = C::N, T8 = C::T8;
   extern __shared__ float2 sm[];
   const float2* tw = stage_twiddles<LOG2N>(sm, a.tw);
@@ -496,13 +499,15 @@ __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, c
   for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
   if (active) ingest_window<LOG2N>(a, f, j, v);
   // the source's filter rows of the first two output channels: in flight while the forward transform runs
-  float2 hpre[2][8];
+  float2 hpre[WIDE ? 1 : 2][8];
+  if constexpr (!WIDE) {
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int fc = (k.c_f == 1) ? 0 : c;
-    const float2* hrow = k.Hd + ((size_t)(fid * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N + j;
+    for (int c = 0; c < 2; ++c) {
+      const int fc = (k.c_f == 1) ? 0 : c;
+      const float2* hrow = k.Hd + ((size_t)(fid * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N + j;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) hpre[c][m] = (active && c < k.c_out) ? __ldg(hrow + m * T8) : make_float2(0.f, 0.f);
+      for (int m = 0; m < 8; ++m) hpre[c][m] = (active && c < k.c_out) ? __ldg(hrow + m * T8) : make_float2(0.f, 0.f);
+    }
   }
   fft_passes<LOG2N, false>(v, sA, sB, 0, j, tw);
   __syncthreads();
@@ -539,9 +544,11 @@ __global__ void __launch_bounds__(Mix1Cfg<LOG2N>::CTA) k_mix1(const R2CArgs a, c
       out[bin] = acc;
     }
   };
-  channel(0, hpre[0]);
-  if (k.c_out > 1) channel(1, hpre[1]);
-  for (int c = 2; c < k.c_out; ++c) {
+  if constexpr (!WIDE) {
+    channel(0, hpre[0]);
+    if (k.c_out > 1) channel(1, hpre[1]);
+  }
+  for (int c = WIDE ? 0 : 2; c < k.c_out; ++c) {
     const int fc = (k.c_f == 1) ? 0 : c;
     const float2* hrow = k.Hd + ((size_t)(fid * k.c_f + fc) * 2 * k.R + (k.R - 1)) * N + j;
     float2 hh[8];
@@ -758,33 +765,41 @@ void launch_conv1(const R2CArgs& a, const C2RArgs& k, cudaStream_t st) {
   launch_desc(d, params, st);
 }
 
-template <int LOG2N, bool LAST>
+template <int LOG2N, bool LAST, bool WIDE>
 static void describe_mix1_t(const R2CArgs& a, LaunchDesc* d) {
-  using M = Mix1Cfg<LOG2N>;
+  using M = Mix1Cfg<LOG2N, WIDE>;
   static bool attr_done[64] = {};
   if (M::SMEM_BYTES > 48 * 1024 && need_smem_attr(attr_done))
-    cudaFuncSetAttribute(k_mix1<LOG2N, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, M::SMEM_BYTES);
-  d->func = reinterpret_cast<const void*>(k_mix1<LOG2N, LAST>);
+    cudaFuncSetAttribute(k_mix1<LOG2N, LAST, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, M::SMEM_BYTES);
+  d->func = reinterpret_cast<const void*>(k_mix1<LOG2N, LAST, WIDE>);
   d->grid = dim3((unsigned)((a.n_fft + M::G - 1) / M::G));
   d->block = dim3(M::CTA);
   d->smem = M::SMEM_BYTES;
 }
 
-int mix1_sources_per_cta(int B) {
+// Wide CTAs from this many sources on: the mix is then a throughput problem (measured: 4096 sources 0.0348 ms wide vs
+// 0.0450 ms narrow per step; 256 sources 0.0198 ms wide vs 0.0164 ms narrow)
+static bool mix1_wide(int n_sources) { return n_sources >= 1024; }
+
+int mix1_sources_per_cta(int B, int n_sources) {
+  const bool w = mix1_wide(n_sources);
+#define PGX_G(L) (w ? Mix1Cfg<L, true>::G : Mix1Cfg<L, false>::G)
   switch (ilog2(B)) {
-    case 4: return Mix1Cfg<4>::G; case 5: return Mix1Cfg<5>::G; case 6: return Mix1Cfg<6>::G;
-    case 7: return Mix1Cfg<7>::G; case 8: return Mix1Cfg<8>::G; case 9: return Mix1Cfg<9>::G;
-    case 10: return Mix1Cfg<10>::G;
+    case 4: return PGX_G(4); case 5: return PGX_G(5); case 6: return PGX_G(6);
+    case 7: return PGX_G(7); case 8: return PGX_G(8); case 9: return PGX_G(9);
+    case 10: return PGX_G(10);
     default: return 0;  // larger transforms keep the three-kernel step
   }
+#undef PGX_G
 }
 
 bool describe_mix1(const R2CArgs& a, bool last, LaunchDesc* d) {
   d->func = nullptr;
-#define PGX_MIX1_CASE(L)                                  \
-  case L:                                                 \
-    if (last) describe_mix1_t<L, true>(a, d);             \
-    else describe_mix1_t<L, false>(a, d);                 \
+  const bool w = mix1_wide(a.n_fft);
+#define PGX_MIX1_CASE(L)                                                \
+  case L:                                                               \
+    if (last) { if (w) describe_mix1_t<L, true, true>(a, d); else describe_mix1_t<L, true, false>(a, d); }    \
+    else { if (w) describe_mix1_t<L, false, true>(a, d); else describe_mix1_t<L, false, false>(a, d); }      \
     break;
   switch (ilog2(a.B)) {
     PGX_MIX1_CASE(4) PGX_MIX1_CASE(5) PGX_MIX1_CASE(6) PGX_MIX1_CASE(7) PGX_MIX1_CASE(8) PGX_MIX1_CASE(9) PGX_MIX1_CASE(10)

@@ -174,10 +174,10 @@ void launch_copy_block(const float* src, int64_t ss, int64_t sc, int64_t si, flo
                        int64_t di, int32_t n_streams, int32_t chans, int32_t n, cudaStream_t st);
 
 // K1 + present-slot accumulate in one kernel for single-partition mixes of mono transforms (k_mix1): writes
-// ceil(n_fft / mix1_sources_per_cta(B)) partial rows per channel to ynow; 0 sources per CTA = not available for B.
-int mix1_sources_per_cta(int B);
+// ceil(n_fft / mix1_sources_per_cta(B, n_fft)) partial rows per channel to ynow; 0 sources per CTA = not available for B.
+int mix1_sources_per_cta(int B, int n_sources);
 // ticket != NULL: the last CTA to finish also does K2's work (fold, inverse transforms, emit): one launch per step.
-// Needs c_out <= mix1_sources_per_cta(B); *ticket must be 0 before the first launch (the kernel re-arms it).
+// Needs c_out <= mix1_sources_per_cta(B, n_fft); *ticket must be 0 before the first launch (the kernel re-arms it).
 void launch_mix1(const R2CArgs& a, const C2RArgs& k, float2* ynow, unsigned int* ticket, cudaStream_t st);
 
 int fft_smem_bytes(int B);

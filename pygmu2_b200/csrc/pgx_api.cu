@@ -434,7 +434,7 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
       k.fast = (whole && vec_ok(y_dev, ye)) ? 1 : 0;
     }
     // few CTAs: the last one to finish folds their rows and does the inverse transforms itself
-    const bool last = (b->mix1_rows <= 64 && c.c_out <= pgx::mix1_sources_per_cta(B));
+    const bool last = (b->mix1_rows <= 64 && c.c_out <= pgx::mix1_sources_per_cta(B, c.n_streams));
     {
       ProfScope ps(b, crit, last ? 5 : 4);
       pgx::launch_mix1(r, k, b->ynow, last ? b->mix1_ticket : nullptr, crit);
@@ -815,7 +815,7 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   if (b->ypart_bytes == 0) b->ypart_bytes = sizeof(float2);
   b->ysum_bytes = n_out_max * B * sizeof(float2) * kFoldAbove;
   {
-    const int g = pgx::mix1_sources_per_cta(B);
+    const int g = pgx::mix1_sources_per_cta(B, c.n_streams);
     b->mix1_rows = (g > 0 && P == 1 && c_x == 1) ? (c.n_streams + g - 1) / g : 0;
     const int rows = b->plan_now.n_split > b->mix1_rows ? b->plan_now.n_split : b->mix1_rows;
     b->ynow_bytes = (size_t)(rows + 1) * c.c_out * B * sizeof(float2);  // + one folded row block
@@ -1141,7 +1141,7 @@ static int graph_shape(const pgx_bank* b, bool mix) {
     return 0;
   }
   const bool mix1 = (R == 1 && b->use_mix1 && b->mix1_rows > 0);
-  if (mix1 && b->mix1_rows <= 64 && b->cfg.c_out <= pgx::mix1_sources_per_cta(b->B)) return 1;
+  if (mix1 && b->mix1_rows <= 64 && b->cfg.c_out <= pgx::mix1_sources_per_cta(b->B, b->cfg.n_streams)) return 1;
   return 0;
 }
 
