@@ -1267,33 +1267,40 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
     g = pgx_bank::PullGraph{};
   }
   if (!g.exec) {
-    PGX_CUDA(cudaGraphCreate(&g.graph, 0));
-    cudaGraphNode_t dep = nullptr;
-    if (!x_device && !zc_x) {
-      PGX_CUDA(cudaGraphAddMemcpyNode1D(&g.n_h2d, g.graph, nullptr, 0, b->x_stage[slot], b->hx_bounce[slot], xb,
-                                        cudaMemcpyHostToDevice));
+    // (a failure half-way must not leave a half-built graph behind: the next pull would build on top of it)
+    cudaError_t ge = cudaSuccess;
+    auto step = [&](cudaError_t e) { if (ge == cudaSuccess) ge = e; return ge == cudaSuccess; };
+    if (g.graph) { cudaGraphDestroy(g.graph); g = pgx_bank::PullGraph{}; }
+    cudaGraphNode_t dep = nullptr, last = nullptr;
+    cudaKernelNodeParams kp{};
+    if (step(cudaGraphCreate(&g.graph, 0)) && !x_device && !zc_x &&
+        step(cudaGraphAddMemcpyNode1D(&g.n_h2d, g.graph, nullptr, 0, b->x_stage[slot], b->hx_bounce[slot], xb,
+                                      cudaMemcpyHostToDevice)))
       dep = g.n_h2d;
-    }
-    cudaKernelNodeParams kp = knode(dA, pA);
-    PGX_CUDA(cudaGraphAddKernelNode(&g.n_a, g.graph, dep ? &dep : nullptr, dep ? 1 : 0, &kp));
-    cudaGraphNode_t last = g.n_a;
-    if (shape == 3) {
+    kp = knode(dA, pA);
+    if (step(ge) && step(cudaGraphAddKernelNode(&g.n_a, g.graph, dep ? &dep : nullptr, dep ? 1 : 0, &kp))) last = g.n_a;
+    if (shape == 3 && step(ge)) {
       if (!fuse3) {
         kp = knode(dK2, pK2);
-        PGX_CUDA(cudaGraphAddKernelNode(&g.n_k2, g.graph, &g.n_a, 1, &kp));
-        last = g.n_k2;
+        if (step(cudaGraphAddKernelNode(&g.n_k2, g.graph, &g.n_a, 1, &kp))) last = g.n_k2;
       }
       kp = knode(dMac, pMac);
-      PGX_CUDA(cudaGraphAddKernelNode(&g.n_mac, g.graph, &g.n_a, 1, &kp));
-      if (fold) {
+      step(cudaGraphAddKernelNode(&g.n_mac, g.graph, &g.n_a, 1, &kp));
+      if (fold && step(ge)) {
         kp = knode(dFold, pFold);
-        PGX_CUDA(cudaGraphAddKernelNode(&g.n_fold, g.graph, &g.n_mac, 1, &kp));
+        step(cudaGraphAddKernelNode(&g.n_fold, g.graph, &g.n_mac, 1, &kp));
       }
     }
-    if (!zc_y)
-      PGX_CUDA(cudaGraphAddMemcpyNode1D(&g.n_d2h, g.graph, &last, 1, b->hy_bounce[slot], b->y_stage[slot], yb,
-                                        cudaMemcpyDeviceToHost));
-    PGX_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+    if (!zc_y && step(ge))
+      step(cudaGraphAddMemcpyNode1D(&g.n_d2h, g.graph, &last, 1, b->hy_bounce[slot], b->y_stage[slot], yb,
+                                    cudaMemcpyDeviceToHost));
+    if (step(ge)) step(cudaGraphInstantiate(&g.exec, g.graph, 0));
+    if (ge != cudaSuccess) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      if (g.graph) cudaGraphDestroy(g.graph);
+      g = pgx_bank::PullGraph{};
+      return fail(PGX_ERR_CUDA, "graph replay: %s", cudaGetErrorString(ge));
+    }
     g.shape = shape; g.f_a = dA.func; g.f_mac = dMac.func; g.f_k2 = dK2.func; g.fold = fold; g.xb = xb; g.yb = yb;
   } else {  // refresh the arguments that move from step to step
     cudaKernelNodeParams kp = knode(dA, pA);
