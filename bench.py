@@ -627,6 +627,7 @@ def measure(args, wname, world, rank, local, numa_bound):
     ms_med = float(np.median(ms_reps))
     clocks = sampler.finish()
     info = bank.info()
+    tile = int(getattr(info, "mac_tile", 1) or 1)     # > 1: the conv pass is time-tiled (PGX_TILE)
 
     # ---- instrumented pass of the same loop: CUDA events around each kernel on its launching stream
     bank.profile_begin()
@@ -666,7 +667,9 @@ def measure(args, wname, world, rank, local, numa_bound):
     xp = PinnedArray((N_INPUT_BLOCKS, N, c_in, pull), io_dt, write_combined=args.wc)
     yp = PinnedArray((c_out, pull) if mix else (N, c_out, pull), io_dt)
     xp.array[...] = np.clip(np.rint(x_host * 32768.0), -32768, 32767).astype(np.int16) if args.pcm16 else x_host
-    E2E_DEPTH = 3  # pulls in flight: H2D of pull i+1 and D2H of pull i-1 overlap the kernels of pull i
+    # pulls in flight: H2D of pull i+1 and D2H of pull i-1 overlap the kernels of pull i; a time-tiled bank computes the
+    # past sums of `tile` blocks per pass, so it needs that many more pulls queued to keep its passes back to back
+    E2E_DEPTH = 3 if (tile <= 1 or mix) else min(8, tile + 3)
     yps = [yp] + [PinnedArray(yp.shape, io_dt) for _ in range(E2E_DEPTH - 1)]
     # steady state of the pull loop: enough pulls that the pipeline's fill and drain (one H2D + one D2H latency)
     # do not dominate a region of a few milliseconds
@@ -728,6 +731,11 @@ def measure(args, wname, world, rank, local, numa_bound):
     Kbins = Bw + 1
     xrows = N * (1 if info.c_x == 1 else c_in)
     mac_bytes = xrows * P * Kbins * 8 + (N * c_out * P * Kbins * 8 if distinct else 0) + n_out_ch * Kbins * 8
+    per_block_mac_bytes = mac_bytes
+    if tile > 1 and not mix:
+        # one tiled launch: every delay-line row once, every filter row once (the T rows a slot needs are a sliding
+        # register window), T result sets written -- for T output blocks
+        mac_bytes = xrows * P * Kbins * 8 + (N * c_out * P * Kbins * 8 if distinct else 0) + tile * info.mac_split * n_out_ch * Kbins * 8
     step_bytes = wl.bytes_per_block_step(N, c_in, c_out, Lw, Bw, distinct)
     nprof = max(prof.steps, 1)
     mac_ms_union = prof.ms_mac_union / max(prof.n_mac, 1)   # busy time per launch (union of overlapping launches)
@@ -736,7 +744,7 @@ def measure(args, wname, world, rank, local, numa_bound):
     mac_per_step = prof.n_mac / nprof                        # k_fdl_mac launches per step (1 for P > 1 banks)
     traffic, traffic_src = None, None
     tr_path = os.path.join(ROOT, "profiles", "mac_traffic.json")
-    if wname in ("c2", "c4") and os.path.exists(tr_path) and not args.streams:
+    if wname in ("c2", "c4") and os.path.exists(tr_path) and not args.streams and not (tile > 1 and not mix):
         try:
             tj = json.load(open(tr_path))
             traffic = tj.get(args.variant if wname == "c2" else wname)
@@ -756,6 +764,8 @@ def measure(args, wname, world, rank, local, numa_bound):
         # a lower bound on the kernel's own bandwidth)
         if mac_per_step > 0:
             kname, kbytes, klaunch_ms = "k_fdl_mac", mac_bytes, (ms_med / K) / mac_per_step
+            if tile > 1 and not mix:
+                kname = f"k_fdl_mac_tile (one pass per {tile} blocks)"
         elif prof.ms_conv1 > 0:
             # one fused launch IS the block step: SURVEY 8d's per-step figure (which still counts the delay-line row the
             # fused kernel never writes or re-reads: its own minimum traffic is lower, see "fused_kernel_min_bytes")
@@ -794,6 +804,8 @@ def measure(args, wname, world, rank, local, numa_bound):
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kbytes, "mean_launch_ms": klaunch_ms,
+                         "time_tile": tile,
+                         "per_block_pass_bytes": per_block_mac_bytes if tile > 1 else None,
                          "fused_kernel_min_bytes": ((N * info.c_x * Bw * 12 + N * c_out * Bw * 12) if not mix else
                                                     (N * Bw * 8 + N * c_out * Bw * 8)) if (mac_per_step == 0 and prof.ms_conv1 > 0) else None,
                          "timing": "UN-instrumented timed loop (CUDA events on the launching stream around K steps, median "
@@ -814,7 +826,9 @@ def measure(args, wname, world, rank, local, numa_bound):
                                            "k_conv1_or_mix1_fused": prof.ms_conv1 / nprof, "sum": ksum / nprof}},
                          "step": {"algorithmic_bytes": step_bytes, "ms": ms_med / K,
                                   "achieved": step_bytes / (ms_med / K * 1e-3) / 1e9,
-                                  "frac": step_bytes / (ms_med / K * 1e-3) / 1e9 / peak}},
+                                  "frac": step_bytes / (ms_med / K * 1e-3) / 1e9 / peak,
+                                  "note": ("SURVEY 8d's per-step bytes assume one delay-line read per block; the tiled pass "
+                                           f"reads it once per {tile} blocks, so this fraction can exceed 1") if tile > 1 and not mix else None}},
         }
         if reduce_info is not None:
             rec["reduce"] = reduce_info

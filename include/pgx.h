@@ -91,6 +91,9 @@ typedef struct pgx_bank_info {
   int64_t block_steps;      /* FFT->MAC->IFFT steps executed since creation */
   int32_t mac_grid, mac_split, mac_stream_tile, mac_occupancy; /* launch plan of the accumulate kernel */
   int32_t tail_block, tail_partitions; /* two-level partitioning: block and partition count of the tail level (0 = off) */
+  int32_t mac_tile;         /* time tiling of the conv pass: past sums of this many consecutive blocks per pass over the
+                               delay line (1 = one pass per block; PGX_TILE) */
+  int32_t reserved;
   int64_t graph_pulls;      /* host pulls that ran as ONE CUDA-graph replay (small whole-block pulls in the steady state:
                                copies and kernels of the pull as one launch; PGX_GRAPH=0 disables) */
 } pgx_bank_info;
@@ -201,12 +204,14 @@ PGX_API int pgx_bank_set_output_gains(pgx_bank* bank, float wet, float dry);
                                       this rank's mix is a partial one; it is summed over the ranks onto the root behind
                                       the pull's output stage (pgx_mix_reduce) and only the root delivers y */
 
+#define PGX_SUBMIT_DEPTH 8
+
 /*
  * Pipelined host-buffer pulls (the batched renderer loop, renderer.py:297-327, with more than one pull in
  * flight): submit stages x (H2D on a copy stream), enqueues the pull and the D2H of y, and returns a ticket
  * without waiting; pgx_bank_wait(ticket) returns when that pull's y is complete in host memory.  Pulls
  * execute in submission order.  x and y must stay valid (and should be pinned, pgx_host_alloc) until the
- * wait returns; at most 3 pulls are in flight - a further submit first waits for the oldest.
+ * wait returns; at most PGX_SUBMIT_DEPTH pulls are in flight - a further submit first waits for the oldest.
  * flags: PGX_PULL_MIX, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16, PGX_PULL_REDUCE (on the ranks
  * other than the root y is not written: there is no D2H copy).  pgx_bank_process[_mix] = submit + wait.
  */

@@ -15,7 +15,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libpgx.so")
-SOURCES = ["pgx_api.cu", "pgx_comm.cu", "k_fft.cu", "k_fft16.cu", "k_mac.cu", "k_mac_tma.cu", "k_osc.cu", "pgx_osc.cu"]
+SOURCES = ["pgx_api.cu", "pgx_comm.cu", "k_fft.cu", "k_fft16.cu", "k_mac.cu", "k_mac_tma.cu", "k_mac_tile_tma.cu", "k_osc.cu", "pgx_osc.cu"]
 HEADERS = ["fft.cuh", "bulk.cuh", "kernels.h", "host_util.h", os.path.join("..", "..", "include", "pgx.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -251,6 +251,26 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::CTA, FftCfg<LOG2N>::CTA == 512 
 #pragma unroll
       for (int m = 0; m < 8; ++m) v[m] = cmul(xx[m], hh[m]);
       if (j == 0) v[0] = make_float2(xx[0].x * hh[0].x, xx[0].y * hh[0].y);  // packed bin 0: two real bins
+      // time-tiled banks: the rows committed after the tiled pass that covers this block, X[head - r] * H_r
+      for (int r = 1; r <= a.n_recent; ++r) {
+        int sl = a.head - r;
+        sl += (sl < 0) ? a.R : 0;
+        const float2* xr = xrow + ((ptrdiff_t)sl - a.head) * N;
+        const float2* hr = hrow - (size_t)r * N;             // partition r lives r rows below partition 0 (row R-1)
+        float2 x2[8], h2[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          x2[m] = __ldcg(xr + j + m * T8);
+          h2[m] = __ldg(hr + j + m * T8);
+        }
+        const float2 b0 = make_float2(fmaf(x2[0].x, h2[0].x, v[0].x), fmaf(x2[0].y, h2[0].y, v[0].y));
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          v[m].x = fmaf(x2[m].x, h2[m].x, fmaf(-x2[m].y, h2[m].y, v[m].x));
+          v[m].y = fmaf(x2[m].x, h2[m].y, fmaf(x2[m].y, h2[m].x, v[m].y));
+        }
+        if (j == 0) v[0] = b0;
+      }
     }
     // split partials: 4 splits x 8 bins = 32 independent loads in flight per thread (fixed summation order)
     auto add_partials = [&](const float2* __restrict__ part, const int n) {

@@ -160,6 +160,143 @@ __global__ void __launch_bounds__(kMacThreads) k_fdl_mac(const MacArgs a) {
   }
 }
 
+// Time-tiled pass (conv layout): the past sums of T consecutive output blocks from ONE read of the delay line.
+//   S_kappa[o][k] = sum over committed rows j of X[j][k] * H[partition p0(j) + kappa][k],  kappa = 0..T-1,
+// p0(j) = (head - j) mod R = the row's partition for the first output block; a term exists while p0 >= 1 (the row is
+// committed) and p0 + kappa <= P-1 (inside the filter).  With the reversed + doubled filter rows the partition
+// p0(j) + kappa sits in row (R-1-head) + (j - kappa) (+R when negative): it depends on d = j - kappa only, so over a run
+// of consecutive slots the T filter rows a slot needs are a WINDOW that slides by one row per slot.  The kernel keeps the
+// window in registers: per slot ONE delay-line row (the HBM stream, loaded once per T output blocks) and ONE new filter
+// row, T complex MACs per loaded pair.  The committed slots are at most two runs of consecutive slots (the open slot and
+// the spare slot are skipped); each CTA walks the part of its term range that falls into each run.
+// The rows younger than the pass (at most T-1) are added by the output stage (C2RArgs.n_recent).
+// Packed bin 0 (DC and Nyquist: two real products) is lane kv = 0's first complex: that lane multiplies with three
+// operands swapped for 0 / the other component (selects on the loaded values), every lane runs the same FMAs.
+// CHECK = false: a full batch whose every (slot, kappa) term exists -- no predicates in the body.
+template <int ST, int T, int U, bool CHECK>
+__device__ __forceinline__ void mac_tile_batch(const float4* __restrict__ xp, const float4* __restrict__ hp, const size_t rs,
+                                               const size_t stream_stride, const int nst, const bool bin0, const int n_slots,
+                                               const int p0, const int P, float4 (&hw)[U + T - 1], float4 (&acc)[T][ST]) {
+  float4 xv[U][ST];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const bool in = !CHECK || u < n_slots;
+    hw[T - 1 + u] = in ? __ldg(hp + (size_t)u * rs) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < ST; ++t)
+      xv[u][t] = (in && (!CHECK || t < nst)) ? ld_stream(xp + (size_t)u * rs + (size_t)t * stream_stride)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float xim[ST], xre[ST];   // first complex: x.x as used by the imaginary sum, -x.y as used by the real sum
+#pragma unroll
+    for (int t = 0; t < ST; ++t) {
+      xim[t] = bin0 ? 0.f : xv[u][t].x;
+      xre[t] = bin0 ? 0.f : -xv[u][t].y;
+    }
+#pragma unroll
+    for (int kp = 0; kp < T; ++kp) {
+      if (!CHECK || (u < n_slots && p0 - u + kp <= P - 1)) {   // (uniform over the CTA)
+        const float4 h = hw[T - 1 + u - kp];
+        const float hsel = bin0 ? h.y : h.x;
+#pragma unroll
+        for (int t = 0; t < ST; ++t) {
+          const float4 x = xv[u][t];
+          float4& c = acc[kp][t];
+          c.x = fmaf(x.x, h.x, c.x);
+          c.x = fmaf(xre[t], h.y, c.x);
+          c.y = fmaf(xim[t], h.y, c.y);
+          c.y = fmaf(x.y, hsel, c.y);
+          c.z = fmaf(x.z, h.z, c.z);
+          c.z = fmaf(-x.w, h.w, c.z);
+          c.w = fmaf(x.z, h.w, c.w);
+          c.w = fmaf(x.w, h.z, c.w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < T - 1; ++w) hw[w] = hw[w + U];
+}
+
+template <int ST, int T, int U>
+__global__ void __launch_bounds__(kMacThreads, ST == 1 ? 5 : 4) k_fdl_mac_tile(const MacArgs a) {
+  const int ktiles = a.W4 / kMacThreads;   // tiled banks have B >= 256: a row is at least one CTA wide
+  int w = blockIdx.x;
+  const int kt = w % ktiles;
+  w /= ktiles;
+  const int ot = w % a.n_otiles;
+  const int sp = w / a.n_otiles;
+  const int kv = kt * kMacThreads + threadIdx.x;
+  const int r0 = sp * a.terms_per_split;
+  const int r1 = min(r0 + a.terms_per_split, a.n_terms);
+  const int c = ot % a.c_out;
+  const int s0 = (ot / a.c_out) * ST;
+  const int gx = (a.c_x == 1) ? 0 : c;
+  const int fc = (a.c_f == 1) ? 0 : c;
+  const bool bin0 = (kv == 0);
+  const size_t rs = (size_t)a.W4;
+  const size_t stream_stride = (size_t)a.c_x * a.R * rs;
+  const float4* xbase = a.fdl + ((size_t)(s0 * a.c_x + gx) * a.R) * rs + kv;
+  const float4* hfil = a.Hd + ((size_t)(a.fmap[s0] * a.c_f + fc) * 2 * a.R) * rs + kv;
+  const int nst = min(ST, a.N - s0);
+  const int qb = a.R - 1 - a.head;
+
+  float4 acc[T][ST];
+#pragma unroll
+  for (int kp = 0; kp < T; ++kp)
+#pragma unroll
+    for (int t = 0; t < ST; ++t) acc[kp][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // term r -> slot off + r, + nskip from slot `skip` on: terms below rsk = skip - off are the first run
+  const int rsk = a.skip - a.off;
+  for (int run = 0; run < 2; ++run) {
+    const int rb = run == 0 ? r0 : max(r0, rsk), re = run == 0 ? min(r1, rsk) : r1;
+    if (rb >= re) continue;
+    const int jbeg = a.off + rb + (run ? a.nskip : 0), jend = a.off + re + (run ? a.nskip : 0);
+    float4 hw[U + T - 1];     // hw[w] <-> d = jb - (T-1) + w
+#pragma unroll
+    for (int w2 = 0; w2 < T - 1; ++w2) {
+      int q = qb + jbeg - (T - 1) + w2;
+      q += (q < 0) ? a.R : 0;
+      hw[w2] = __ldg(hfil + (size_t)q * rs);
+    }
+    const float4* xp = xbase + (size_t)jbeg * rs;
+    const float4* hp = hfil + (size_t)(qb + jbeg) * rs;
+    int p0 = a.head - jbeg;
+    p0 += (p0 < 0) ? a.R : 0;   // the run never crosses the open slot: p0 falls by one per slot from here
+    for (int jb = jbeg; jb < jend; jb += U, p0 -= U, xp += (size_t)U * rs, hp += (size_t)U * rs) {
+      if (jb + U <= jend && p0 + T - 1 <= a.P - 1 && nst == ST)
+        mac_tile_batch<ST, T, U, false>(xp, hp, rs, stream_stride, nst, bin0, U, p0, a.P, hw, acc);
+      else
+        mac_tile_batch<ST, T, U, true>(xp, hp, rs, stream_stride, nst, bin0, jend - jb, p0, a.P, hw, acc);
+    }
+  }
+#pragma unroll
+  for (int kp = 0; kp < T; ++kp)
+#pragma unroll
+    for (int t = 0; t < ST; ++t)
+      if (t < nst) {
+        const size_t prow = (size_t)sp * a.n_out + (s0 + t) * a.c_out + c;
+        a.yspec[(size_t)((a.tile_set0 + kp) % a.tile_nsets) * a.tile_stride + prow * rs + kv] = acc[kp][t];
+      }
+}
+
+// The instantiations of the tiled pass: (streams per CTA, tile, rows in flight).  PGX_TILE_ST / PGX_TILE_U pick
+// another one than the plan's default for A/B runs.
+struct TileVariant { int st, tile, u; const void* func; };
+static const TileVariant kTileVariants[] = {
+    {1, 2, 4, reinterpret_cast<const void*>(k_fdl_mac_tile<1, 2, 4>)}, {1, 2, 8, reinterpret_cast<const void*>(k_fdl_mac_tile<1, 2, 8>)},
+    {2, 2, 4, reinterpret_cast<const void*>(k_fdl_mac_tile<2, 2, 4>)}, {4, 2, 2, reinterpret_cast<const void*>(k_fdl_mac_tile<4, 2, 2>)},
+    {1, 4, 2, reinterpret_cast<const void*>(k_fdl_mac_tile<1, 4, 2>)}, {1, 4, 4, reinterpret_cast<const void*>(k_fdl_mac_tile<1, 4, 4>)},
+    {2, 4, 2, reinterpret_cast<const void*>(k_fdl_mac_tile<2, 4, 2>)}, {2, 4, 4, reinterpret_cast<const void*>(k_fdl_mac_tile<2, 4, 4>)},
+};
+static const TileVariant* tile_variant(int st, int tile, int u) {
+  for (const TileVariant& v : kTileVariants)
+    if (v.st == st && v.tile == tile && v.u == u) return &v;
+  return nullptr;
+}
+
 template <bool MIX, int ST, int U>
 static int mac_occupancy() {
   int nb = 0;
@@ -228,9 +365,81 @@ MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_fi
   return p;
 }
 
+MacPlan mac_plan_tiled(int N, int c_out, int W4, int n_terms, bool shared_filter, int sm_count, int tile) {
+  MacPlan p{};
+  p.layout = 0;
+  p.variant = 0;
+  p.tile = tile;
+  p.st = (shared_filter && N >= 2) ? 2 : 1;
+  p.tile_u = (tile == 2 && p.st == 1) ? 8 : 4;
+  if (const char* e = getenv("PGX_TILE_ST")) {
+    const int v = atoi(e);
+    if (shared_filter && N >= v) p.st = v;
+  }
+  if (const char* e = getenv("PGX_TILE_U")) p.tile_u = atoi(e);
+  const TileVariant* tv = tile_variant(p.st, tile, p.tile_u);
+  if (!tv) {
+    p.st = (shared_filter && N >= 2) ? 2 : 1;
+    p.tile_u = (tile == 2 && p.st == 1) ? 8 : 4;
+    tv = tile_variant(p.st, tile, p.tile_u);
+  }
+  const int lanes = kMacThreads, ktiles = W4 / lanes;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tv->func, kMacThreads, 0);
+  if (occ < 1) occ = 1;
+  {
+    // rows staged through shared memory by bulk-async copies (k_mac_tile_tma.cu): PGX_TILE_TMA=0|1
+    bool tma = true;
+    if (const char* e = getenv("PGX_TILE_TMA")) tma = atoi(e) != 0;
+    int st2, tps, stages, occ2;
+    if (tma && tile_tma_supported(W4) && tile_tma_config(shared_filter, N, tile, &st2, &tps, &stages, &occ2)) {
+      p.variant = 1;
+      p.st = st2; p.tile_u = tps; p.tile_stages = stages;
+      occ = occ2;
+    }
+  }
+  p.n_otiles = ((N + p.st - 1) / p.st) * c_out;
+  const long resident = (long)sm_count * occ;
+  const long base = (long)p.n_otiles * ktiles;
+  int max_split = n_terms / 16;
+  if (max_split < 1) max_split = 1;
+  if (max_split > 8) max_split = 8;     // the output stage folds the split rows itself: keep them few (<= kFoldAbove)
+  int force_split = 0;
+  if (const char* e = getenv("PGX_TILE_SPLIT")) force_split = atoi(e);
+  if (force_split >= 1 && force_split <= max_split) max_split = force_split;
+  double best = 1e300;
+  int best_s = 1;
+  for (int s = 1; s <= max_split; ++s) {
+    const long items = base * s;
+    const long waves = (items + resident - 1) / resident;
+    const int tps = (n_terms + s - 1) / s;
+    const double cost = (double)waves * (double)(tps + 6);
+    if (cost < best * 0.995 || s == force_split) {
+      best = cost;
+      best_s = s;
+    }
+  }
+  p.terms_per_split = (n_terms + best_s - 1) / best_s;
+  p.n_split = (n_terms + p.terms_per_split - 1) / p.terms_per_split;
+  p.n_partials = p.n_split;
+  p.grid = (int)(base * p.n_split);
+  p.occupancy = occ;
+  p.persistent_ctas = (int)resident;
+  return p;
+}
+
 bool describe_fdl_mac(const MacArgs& a, LaunchDesc* d) {
   d->func = nullptr;
   if (a.variant == 1) return false;  // the bulk-async kernel has its own launcher
+  if (a.tile > 1) {
+    d->grid = dim3((unsigned)(a.n_otiles * (a.W4 / kMacThreads) * a.n_split));
+    d->block = dim3(kMacThreads);
+    d->smem = 0;
+    const TileVariant* tv = tile_variant(a.st, a.tile, a.tile_u);
+    if (!tv) return false;
+    d->func = tv->func;
+    return true;
+  }
   const int lanes = a.W4 < kMacThreads ? a.W4 : kMacThreads;
   d->grid = dim3((unsigned)(a.n_otiles * (a.W4 / lanes) * a.n_split));
   d->block = dim3(kMacThreads);
@@ -243,7 +452,8 @@ bool describe_fdl_mac(const MacArgs& a, LaunchDesc* d) {
 
 void launch_fdl_mac(const MacArgs& a, cudaStream_t st) {
   if (a.variant == 1) {
-    launch_fdl_mac_tma(a, a.persistent_ctas, st);
+    if (a.tile > 1) launch_fdl_mac_tile_tma(a, st);
+    else launch_fdl_mac_tma(a, a.persistent_ctas, st);
     return;
   }
   LaunchDesc d;

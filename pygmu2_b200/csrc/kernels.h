@@ -49,9 +49,20 @@ struct MacArgs {
   int32_t Pt, off, skip, nskip, jfix;
   int32_t variant;       // 0 = LDG kernel (k_mac.cu), 1 = bulk-async staged kernel (k_mac_tma.cu)
   int32_t persistent_ctas;
+  // time tiling (conv layout only): ONE pass over the committed rows yields the past sums of `tile` consecutive
+  // output blocks, head, head+1, ... (slot of output kappa = (head + kappa) mod R); yspec then holds `tile` result
+  // sets of tile_stride float4 each.  P = partitions of the filter, head = slot of the first output block.
+  int32_t tile, P, head;
+  int32_t tile_u;                  // rows in flight per thread / slots per stage (selects the instantiation)
+  int32_t tile_stages;             // bulk-async variant: stages of the shared-memory ring
+  int32_t tile_set0, tile_nsets;   // output kappa goes to result set (tile_set0 + kappa) % tile_nsets
+  int64_t tile_stride;
 };
 struct MacPlan {
   int32_t st, n_otiles, n_split, terms_per_split, grid, occupancy, variant, persistent_ctas;
+  int32_t tile;        // > 1: time-tiled pass (k_fdl_mac_tile): `tile` output blocks per pass
+  int32_t tile_u;      // its rows in flight per thread (LDG) / slots per stage (bulk-async)
+  int32_t tile_stages; // bulk-async variant: ring stages
   int32_t layout;      // MacArgs.mix value: 0 conv, 1 flattened mix, 2 per-stream mix
   int32_t n_partials;  // partial rows per out row that the consumer has to sum
 };
@@ -62,6 +73,12 @@ void launch_fdl_mac_tma(const MacArgs& a, int persistent_ctas, cudaStream_t st);
 // Fold split partial sums: out[o][k] = sum_sp in[sp][o][k] (rows of W4 float4), deterministic order.
 void launch_reduce_partials(const float4* in, float4* out, int n_split, int n_out, int W4, cudaStream_t st);
 MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count);
+// bulk-async staged variant of the time-tiled pass, k_mac_tile_tma.cu
+bool tile_tma_supported(int W4);
+bool tile_tma_config(bool shared_filter, int N, int tile, int* st, int* tps, int* stages, int* occupancy);
+void launch_fdl_mac_tile_tma(const MacArgs& a, cudaStream_t st);
+// same for the time-tiled pass (conv layout): tile = 2 or 4 output blocks per pass
+MacPlan mac_plan_tiled(int N, int c_out, int W4, int n_terms, bool shared_filter, int sm_count, int tile);
 void launch_fdl_mac(const MacArgs& a, cudaStream_t st);
 
 // K2: sum split partials, inverse real FFT, emit the new output samples.
@@ -95,6 +112,9 @@ struct C2RArgs {
   // fused small-P step (k_conv1<.., PAST>): the past partitions are ring slots p_off + jj (+ p_nskip from p_skip on),
   // jj < n_past, paired with filter rows q0 + slot -- the same slot walk as MacArgs
   int32_t n_past, p_off, p_skip, p_nskip, q0;
+  int32_t n_recent;      // time-tiled banks: besides the present term X[head] H_0, the output stage adds the n_recent newest
+                         // committed rows X[head - r] H_r, r = 1..n_recent (rows younger than the tiled pass that covers
+                         // this block)
   int32_t fft16;         // B = 4096 fused step: 0 radix-8 kernel, 1 radix-16 (shared-memory exchanges), 2 radix-16 + shuffles
 };
 void launch_c2r_emit(const C2RArgs& a, cudaStream_t st);

@@ -114,7 +114,7 @@ struct pgx_bank {
   cudaStream_t last_crit = nullptr;
   // host-buffer pulls: a ring of staging slots so that the H2D of pull i+1 and the D2H of pull i-1 overlap
   // the kernels of pull i (copy engines on their own streams)
-  static constexpr int kSlots = 3;
+  static constexpr int kSlots = PGX_SUBMIT_DEPTH;
   float* x_stage[kSlots] = {};
   float* y_stage[kSlots] = {};
   int16_t* xpcm_stage[kSlots] = {};  // PCM16 staging, allocated on first use
@@ -142,6 +142,18 @@ struct pgx_bank {
   int64_t last_k2_of_par[2] = {-1, -1};  // last step whose K2 read ypast[par]
   bool prev_on_crit = false;       // the previous step ran ingest + output as one kernel on the critical stream
   pgx::MacPlan plan_conv{}, plan_mix{}, plan_now{};
+  // time tiling of the conv pass (see issue_tile): one pass over the committed rows yields the past sums of `tile`
+  // consecutive blocks; result sets are indexed by (block mod 2*tile)
+  int tile = 1;
+  int n_spare = 1;                 // ring rows beyond the P partitions (R = P + n_spare)
+  pgx::MacPlan plan_tile{};
+  float2* ytile = nullptr;         // [2*tile][n_split][n_out][B]
+  size_t tile_set_elems = 0, ytile_bytes = 0;
+  int64_t tile_base = -1;          // first block covered by the newest tiled pass (-1: none valid)
+  static constexpr int kTilePasses = 4;
+  struct TilePass { int64_t base = -1; cudaEvent_t ev = nullptr; } tpass[kTilePasses];
+  int64_t n_tpass = 0;
+  int64_t last_k2_of_set[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
   int sm_count = 148;
   float wet = 1.0f, dry = 0.0f;    // fused output stage: y = dry * x + wet * conv
   // two-level partitioning (cfg.tail_block > 0): this bank convolves with the first tail_B taps at block B; `tail`
@@ -204,6 +216,9 @@ void free_bank(pgx_bank* b) {
   for (cudaStream_t s : {b->s_h2d, b->stream, b->s_in, b->s_bg, b->s_bg2, b->s_d2h})
     if (s) cudaStreamSynchronize(s);
   cudaFree(b->mix1_ticket);
+  cudaFree(b->ytile);
+  for (auto& tp : b->tpass)
+    if (tp.ev) cudaEventDestroy(tp.ev);
   cudaFree(b->xacc);
   cudaFree(b->ytail[0]);
   cudaFree(b->ytail[1]);
@@ -328,6 +343,55 @@ void issue_past(pgx_bank* b, bool mix, int64_t blk, int head, cudaEvent_t after)
   b->past_mode = mix ? 1 : 0;
 }
 
+// Time-tiled background pass: the past sums of blocks blk0 .. blk0+tile-1 (slot of blk0 = head0) from the rows
+// committed so far, i.e. every ring row except the open slot head0 and the spare slot head0+1 -- the same rows as
+// issue_past(blk0), read ONCE for `tile` outputs.  Block blk0+kappa then still lacks its kappa youngest committed
+// rows and its present term: the output stage adds them (C2RArgs.n_recent).  Passes run on one background stream
+// (they are `tile` times rarer than per-block passes), so they complete in issue order.
+void issue_tile(pgx_bank* b, int64_t blk0, int head0, cudaEvent_t after) {
+  const int T = b->tile, nsets = 2 * T;
+  cudaStream_t sbg = b->s_bg;
+  cudaStreamWaitEvent(sbg, after, 0);
+  for (int kp = 0; kp < T; ++kp) {  // WAR: the sets being overwritten were read by the output stages of blocks 2*tile earlier
+    const int64_t lk = b->last_k2_of_set[(blk0 + kp) % nsets];
+    if (lk >= 0) cudaStreamWaitEvent(sbg, b->ev_k2[lk % kRing], 0);
+  }
+  pgx::MacArgs m{};
+  fill_mac_common(b, m, false, head0);
+  const pgx::MacPlan& pl = b->plan_tile;
+  m.mix = 0;
+  m.yspec = reinterpret_cast<float4*>(b->ytile);
+  m.Pt = b->P - 1;   // the committed rows: all but the open slot head0 and the n_spare slots after it (mod R)
+  m.jfix = -1;
+  if (head0 + b->n_spare < b->R) { m.off = 0; m.skip = head0; m.nskip = 1 + b->n_spare; }
+  else                           { m.off = head0 + b->n_spare + 1 - b->R; m.skip = b->R; m.nskip = 0; }
+  m.n_terms = m.Pt;
+  m.n_split = pl.n_split; m.terms_per_split = pl.terms_per_split; m.n_otiles = pl.n_otiles; m.st = pl.st;
+  m.variant = pl.variant; m.persistent_ctas = pl.persistent_ctas;
+  m.tile = T; m.tile_u = pl.tile_u; m.tile_stages = pl.tile_stages; m.P = b->P; m.head = head0;
+  m.tile_set0 = (int)(blk0 % nsets); m.tile_nsets = nsets;
+  m.tile_stride = (int64_t)(b->tile_set_elems / 2);   // in float4
+  {
+    ProfScope ps(b, sbg, 1);
+    pgx::launch_fdl_mac(m, sbg);
+    b->launches += 1;
+  }
+  pgx_bank::TilePass& tp = b->tpass[b->n_tpass % pgx_bank::kTilePasses];
+  cudaEventRecord(tp.ev, sbg);
+  tp.base = blk0;
+  b->n_tpass += 1;
+  b->tile_base = blk0;
+}
+
+// the event of the tiled pass that covers block blk (valid coverage is the caller's business)
+cudaEvent_t tile_event_of(pgx_bank* b, int64_t blk) {
+  for (int64_t k = b->n_tpass - 1; k >= 0 && k >= b->n_tpass - pgx_bank::kTilePasses; --k) {
+    const pgx_bank::TilePass& tp = b->tpass[k % pgx_bank::kTilePasses];
+    if (tp.base >= 0 && blk >= tp.base && blk < tp.base + b->tile) return tp.ev;
+  }
+  return nullptr;
+}
+
 // One block step.  Buffers, accessors and the ordering of every cross-stream hazard:
 //   K1(i)   [ingest]     R x, hist[prev];  W hist[cur], fdl[slot(t)]
 //   PAST(t) [background] R fdl[all but slot(t), slot(t+1)], Hd, fmap;  W ypart, ypast[t&1]
@@ -395,6 +459,15 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
     if (!(b->fill > 0 || R == 1)) {
       if (i >= 2) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 2) % kRing], 0);
       if (t >= 2) cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);  // every block had its past pass issued
+      // a tiled pass with first block blk0 reads the rows of blocks blk0-P+1 .. blk0-1; this K1 overwrites the row of
+      // block t-R = t-P-n_spare: every tiled pass with blk0 <= t-n_spare-1 must be done (they complete in issue order)
+      for (int64_t kk = b->n_tpass - 1; kk >= 0 && kk >= b->n_tpass - pgx_bank::kTilePasses; --kk) {
+        const pgx_bank::TilePass& tp = b->tpass[kk % pgx_bank::kTilePasses];
+        if (tp.base >= 0 && tp.base <= t - b->n_spare - 1) {
+          cudaStreamWaitEvent(b->s_in, tp.ev, 0);
+          break;
+        }
+      }
     }
     {
       ProfScope ps(b, b->s_in, 0);
@@ -410,7 +483,20 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   // ---- background stream: past sum of the open block, if it is not in flight / valid already
   int n_split_past = 0;
   const int par = (int)(t & 1);
-  if (P > 1 && !fused1) {
+  const bool tiled = (b->tile > 1 && !mix && P > 1 && !fused1);
+  int n_recent = 0;
+  const float2* tile_set = nullptr;
+  if (tiled) {
+    if (!(b->tile_base >= 0 && t >= b->tile_base && t < b->tile_base + b->tile))
+      issue_tile(b, t, b->head, b->ev_k1[i % kRing]);    // not covered (first pull, after a reset / map change): now
+    if (cudaEvent_t e = tile_event_of(b, t)) cudaStreamWaitEvent(crit, e, 0);
+    n_recent = (int)(t - b->tile_base);
+    n_split_past = b->plan_tile.n_split;
+    const int set = (int)(t % (2 * b->tile));
+    tile_set = b->ytile + (size_t)set * b->tile_set_elems;
+    b->last_k2_of_set[set] = i;
+  } else if (P > 1 && !fused1) {
+    if (b->tile > 1) b->tile_base = -1;   // a mix pull on a tiled bank: conv coverage is recomputed when conv pulls return
     if (b->past_block != t || b->past_mode != (mix ? 1 : 0)) issue_past(b, mix, t, b->head, b->ev_k1[i % kRing]);
     cudaStreamWaitEvent(crit, b->ev_mac[t % kRing], 0);
     const int ns = (mix ? b->plan_mix : b->plan_conv).n_partials;
@@ -420,7 +506,8 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   // ---- critical stream: [NOW] + K2
   if (!fused1 && !mix1) cudaStreamWaitEvent(crit, b->ev_k1[i % kRing], 0);
   pgx::C2RArgs k{};
-  k.yspec = b->ypast[par]; k.n_split = n_split_past;
+  k.yspec = tiled ? tile_set : b->ypast[par]; k.n_split = n_split_past;
+  k.n_recent = n_recent;
   k.n_out = mix ? c.c_out : c.n_streams * c.c_out;
   bool step_done = false;  // the whole step ran inside k_mix1<LAST>: no K2 launch
   if (mix1) {
@@ -490,7 +577,10 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
 
   // the block commits with this step: its row is final once K1 has run, so the next block's past pass
   // can start now, overlapping this step's K2 and the next step's K1
-  if (completes && P > 1 && !fused1) issue_past(b, mix, t + 1, (b->head + 1) % R, b->ev_k1[i % kRing]);
+  if (completes && tiled) {
+    if (!(t + 1 >= b->tile_base && t + 1 < b->tile_base + b->tile))
+      issue_tile(b, t + 1, (b->head + 1) % R, b->ev_k1[i % kRing]);
+  } else if (completes && P > 1 && !fused1) issue_past(b, mix, t + 1, (b->head + 1) % R, b->ev_k1[i % kRing]);
   if (fused1 && P > 1) {  // past partitions summed inside the fused kernel: every ring row but the open and the spare
     k.n_past = R - 2;
     k.q0 = R - 1 - b->head;
@@ -601,6 +691,7 @@ void quiesce(pgx_bank* b) {
   cudaStreamSynchronize(b->s_d2h);
   b->past_block = -1;
   b->past_mode = -1;
+  b->tile_base = -1;
 }
 
 int check_pull_args(pgx_bank* b, const void* x, const void* y, int n) {
@@ -789,9 +880,24 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   b->c_x = c_x;
   b->B = c.block;
   b->P = (c.filter_len + c.block - 1) / c.block;
-  b->R = b->P > 1 ? b->P + 1 : 1;
-  const int B = b->B, P = b->P, R = b->R;
   const size_t n_fft = (size_t)c.n_streams * c_x;
+  {
+    // time tiling: for banks that stream a long delay line (the HBM-bound class); PGX_TILE = 1 | 2 | 4, PGX_TILE_MIN =
+    // smallest n_streams * c_x * B that qualifies
+    int want = 1;
+    long tile_min = 1L << 17;
+    if (const char* e = getenv("PGX_TILE")) want = atoi(e);
+    if (const char* e = getenv("PGX_TILE_MIN")) tile_min = atol(e);
+    if ((want == 2 || want == 4) && b->P >= 32 && b->B >= 256 && c.tail_block == 0 && (long)n_fft * b->B >= tile_min)
+      b->tile = want;
+  }
+  // ring rows: the P partitions of the open block's sum plus spare rows.  One spare lets the next block's ingest run
+  // while the open block's pass reads the other rows; a pass that covers `tile` blocks is still reading when the
+  // ingest is tile-1 blocks further, so a tiled bank keeps tile-1 spares.  Spare rows meet all-zero filter rows
+  // (partitions >= P of the filter table are never written) wherever a kernel walks them.
+  b->n_spare = b->P > 1 ? (b->tile > 2 ? b->tile - 1 : 1) : 0;
+  b->R = b->P + b->n_spare;
+  const int B = b->B, P = b->P, R = b->R;
   const size_t h_rows = (size_t)c.n_filters * c.filter_channels;
   const size_t n_out_max = (size_t)c.n_streams * c.c_out;
 
@@ -805,12 +911,17 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   }
   size_t y_conv = 0, y_mix = 0;
   if (P > 1) {  // background pass over the P-1 committed partitions
-    b->plan_conv = pgx::mac_plan(c.n_streams, c.c_out, B / 2, P - 1, false, c.n_filters == 1, b->sm_count);
-    b->plan_mix = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams * (P - 1), true, c.n_filters == 1, b->sm_count);
+    b->plan_conv = pgx::mac_plan(c.n_streams, c.c_out, B / 2, R - 2, false, c.n_filters == 1, b->sm_count);
+    b->plan_mix = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams * (R - 2), true, c.n_filters == 1, b->sm_count);
     y_conv = (size_t)b->plan_conv.n_partials * c.n_streams * c.c_out;
     y_mix = (size_t)b->plan_mix.n_partials * c.c_out;
   }
   b->plan_now = pgx::mac_plan(c.n_streams, c.c_out, B / 2, c.n_streams, true, c.n_filters == 1, b->sm_count);
+  if (b->tile > 1) {
+    b->plan_tile = pgx::mac_plan_tiled(c.n_streams, c.c_out, B / 2, P - 1, c.n_filters == 1, b->sm_count, b->tile);
+    b->tile_set_elems = (size_t)b->plan_tile.n_split * n_out_max * B;
+    b->ytile_bytes = (size_t)2 * b->tile * b->tile_set_elems * sizeof(float2);
+  }
   b->ypart_bytes = (y_conv > y_mix ? y_conv : y_mix) * B * sizeof(float2);
   if (b->ypart_bytes == 0) b->ypart_bytes = sizeof(float2);
   b->ysum_bytes = n_out_max * B * sizeof(float2) * kFoldAbove;
@@ -870,6 +981,10 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   guard(cudaMalloc(&b->ypart[0], b->ypart_bytes), "cudaMalloc(ypart)");
   guard(cudaMalloc(&b->ypart[1], b->ypart_bytes), "cudaMalloc(ypart)");
   guard(cudaMalloc(&b->ynow, b->ynow_bytes), "cudaMalloc(ynow)");
+  if (b->tile > 1) {
+    guard(cudaMalloc(&b->ytile, b->ytile_bytes), "cudaMalloc(ytile)");
+    for (auto& tp : b->tpass) guard(cudaEventCreateWithFlags(&tp.ev, cudaEventDisableTiming), "cudaEventCreate(tile)");
+  }
   guard(cudaMalloc(&b->mix1_ticket, sizeof(unsigned int)), "cudaMalloc(ticket)");
   guard(cudaMemset(b->mix1_ticket, 0, sizeof(unsigned int)), "memset ticket");
   guard(cudaMalloc(&b->tw, (size_t)2 * B * sizeof(float2)), "cudaMalloc(tw)");
@@ -947,6 +1062,7 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
     return rc;
   }
   head->tail = tail;
+  head->tile = tail->tile = 1;   // the two levels keep the per-block pass (their schedule interleaves the levels)
   head->tail_B = TB;
   head->full_filter_len = L;
   head->xacc_bytes = (size_t)cfg->n_streams * cfg->c_in * TB * sizeof(float);
@@ -991,6 +1107,12 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->mac_stream_tile = b->plan_conv.st; info->mac_occupancy = b->plan_conv.occupancy;
   info->kernel_launches = b->launches + (b->tail ? b->tail->launches : 0);
   info->graph_pulls = b->graph_pulls;
+  info->mac_tile = b->tile;
+  info->reserved = 0;
+  if (b->tile > 1) {
+    info->mac_grid = b->plan_tile.grid; info->mac_split = b->plan_tile.n_split;
+    info->mac_stream_tile = b->plan_tile.st; info->mac_occupancy = b->plan_tile.occupancy;
+  }
   return PGX_OK;
 }
 
@@ -1029,6 +1151,8 @@ int pgx_bank_reset(pgx_bank* b, const int32_t* stream_ids, int32_t k) {
     b->head = b->fill = b->half = 0;
     b->step = b->block = 0;
     b->last_k2_of_par[0] = b->last_k2_of_par[1] = -1;
+    for (auto& v : b->last_k2_of_set) v = -1;
+    for (auto& tp : b->tpass) tp.base = -1;
     b->prev_on_crit = false;
     PGX_CUDA(cudaStreamSynchronize(b->stream));
     return PGX_OK;
@@ -1087,6 +1211,7 @@ int pgx_bank_set_filter_map(pgx_bank* b, const int32_t* filter_of_stream) {
   b->fmap = b->fmap_own + (size_t)nxt * N;
   b->fmap_pending = true;
   b->past_block = -1;  // a cached past sum was computed with the previous map
+  b->tile_base = -1;
   return PGX_OK;
 }
 
@@ -1105,6 +1230,7 @@ int pgx_bank_use_filter_map_device(pgx_bank* b, const int32_t* fmap_dev) {
   if (b->tail) return fail(PGX_ERR_INVALID, "a two-level bank keeps its filter map");
   b->fmap = fmap_dev ? const_cast<int32_t*>(fmap_dev) : b->fmap_own + (size_t)b->fmap_cur * b->cfg.n_streams;
   b->past_block = -1;  // a cached past sum was computed with the previous map
+  b->tile_base = -1;
   return PGX_OK;
 }
 
@@ -1226,6 +1352,7 @@ static int graph_pull(pgx_bank* b, const float* x, const pgx_layout& xl, int slo
   *done = false;
   const pgx_bank_config& c = b->cfg;
   if (!b->use_graph || b->tail || b->profiling || b->serial || b->fill != 0 || n != b->B) return PGX_OK;
+  if (b->tile > 1 && !mix) return PGX_OK;   // time-tiled conv banks are throughput banks: the streamed schedule
   if ((size_t)c.n_streams * b->c_x * b->B > (size_t)(1 << 18)) return PGX_OK;   // big banks: the streamed schedule overlaps better
   const int shape = graph_shape(b, mix);
   if (shape == 0) return PGX_OK;

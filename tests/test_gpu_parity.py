@@ -371,7 +371,7 @@ def test_full_plan_c2_256_streams_shared_ir_every_partition():
     L, N, pull = ir.shape[0], 256, 512
     bank = pg.ConvolveBank(ir, N, 2, block=512, single_filter_dims=True, max_pull=pull)
     info = bank.info()
-    assert info.partitions == 259 and info.mac_stream_tile == 4          # the plan bench.py times
+    assert info.partitions == 259 and info.mac_stream_tile == (4 if info.mac_tile == 1 else 2)   # the plan bench.py times
     pulls = 259 + 3
     n = pulls * pull
     rng = np.random.default_rng(77)
@@ -568,8 +568,8 @@ def test_graph_replay_of_whole_block_pulls_is_bit_identical_to_the_streamed_sche
         outs[mode] = np.concatenate(ys)
         info = bank.info()
         import os
-        if os.environ.get("PGX_MAC") == "tma" and info.partitions > 16:
-            assert mode != "0" or info.graph_pulls == 0     # (the bulk-async pass has no graph form: either way is fine)
+        if (os.environ.get("PGX_MAC") == "tma" and info.partitions > 16) or info.mac_tile > 1:
+            assert mode != "0" or info.graph_pulls == 0     # (the bulk-async and the time-tiled pass have no graph form: either way is fine)
         else:
             assert (info.graph_pulls > 0) == (mode != "0"), (mode, info.graph_pulls)
         bank.close()
@@ -1401,3 +1401,86 @@ def test_fused_hrtf_mix_host_gather_equals_resident_sources():
     yr, yh = _pull_pe(res, [512] * 6), _pull_pe(host, [512] * 6)
     assert res._fused._resident is not None and host._fused._resident is None
     np.testing.assert_array_equal(yr, yh)
+
+
+# ---------------------------------------------------------------------------
+# time-tiled accumulate passes (PGX_TILE): one pass over the delay line per `tile` blocks
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile", ["2", "4"])
+@pytest.mark.parametrize("shared", [True, False])
+def test_time_tiled_pass_matches_per_block_pass_and_float64(tile, shared, monkeypatch):
+    """The same bank with the per-block pass and with the tiled pass (forced on a small bank), pulled in ragged
+    chunks: the tiled outputs against the float64 convolution, and against the per-block schedule far below the
+    parity tolerance."""
+    pg.set_sample_rate(wl.SR_48)
+    rng = np.random.default_rng(int(tile) * 10 + shared)
+    B, P, N, c = 256, 37, 5, 2
+    L = B * P - 19
+    nf = 1 if shared else 3
+    h = (rng.standard_normal((nf, L, c)) * np.exp(-np.arange(L) / (L / 5))[None, :, None]).astype(np.float32)
+    fmap0 = np.zeros(N, np.int32) if shared else (np.arange(N) % nf).astype(np.int32)
+    pulls = [256, 256, 100, 156, 512, 700, 68, 256] + [256] * 44 + [1024, 33, 223] + [256] * 12
+    n = sum(pulls)
+    x = rng.uniform(-1, 1, (N, c, n)).astype(np.float32)
+
+    def run(env_tile):
+        monkeypatch.setenv("PGX_TILE", env_tile)
+        monkeypatch.setenv("PGX_TILE_MIN", "0")
+        bank = pg.ConvolveBank(h[0] if shared else h, N, c, block=B, single_filter_dims=shared, max_pull=1024,
+                               filter_of_stream=None if shared else fmap0)
+        assert bank.info().mac_tile == int(env_tile)
+        out, pos = [], 0
+        for d in pulls:
+            out.append(bank.process(np.ascontiguousarray(x[:, :, pos:pos + d])).copy())
+            pos += d
+        bank.close()
+        return np.concatenate(out, axis=2)
+
+    y1 = run("1")
+    yt = run(tile)
+    for s in range(N):
+        for ch in range(c):
+            ref = _fftconv64(x[s, ch], h[fmap0[s], :, ch], n)
+            assert rel_err(yt[s, ch], ref) <= TOL, (s, ch)
+    assert rel_err(yt, y1) <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile", ["2", "4"])
+def test_time_tiled_pass_random_operation_sequence(tile, monkeypatch):
+    """Resets, filter-map changes, filter reloads and conv/mix switches at arbitrary points of a tiled bank: the
+    outputs equal those of the per-block schedule driven through the same sequence."""
+    pg.set_sample_rate(wl.SR_48)
+    B, P, N, c = 256, 33, 4, 1
+    L = B * P
+    rng0 = np.random.default_rng(5)
+    h = (rng0.standard_normal((3, L, c)) * np.exp(-np.arange(L) / (L / 4))[None, :, None]).astype(np.float32)
+    h2 = (rng0.standard_normal((L, c)) * 0.05).astype(np.float32)
+
+    def run(env_tile):
+        monkeypatch.setenv("PGX_TILE", env_tile)
+        monkeypatch.setenv("PGX_TILE_MIN", "0")
+        rng = np.random.default_rng(99)
+        bank = pg.ConvolveBank(h, N, c, block=B, max_pull=600, filter_of_stream=np.arange(N, dtype=np.int32) % 3)
+        assert bank.info().mac_tile == int(env_tile)
+        outs = []
+        for step in range(140):
+            op = rng.integers(0, 12)
+            if op == 0:
+                bank.reset([int(rng.integers(0, N))])
+            elif op == 1:
+                bank.set_filter_map(rng.integers(0, 3, N).astype(np.int32))
+            elif op == 2 and step > 60:
+                bank.load_filter(1, h2)
+            d = int(rng.choice([256, 256, 256, 512, 600, 17, 239, 100]))
+            xx = rng.uniform(-1, 1, (N, c, d)).astype(np.float32)
+            if op == 3:
+                outs.append(bank.process_mix(xx).copy().ravel())
+            else:
+                outs.append(bank.process(xx).copy().ravel())
+        bank.close()
+        return np.concatenate(outs)
+
+    y1 = run("1")
+    yt = run(tile)
+    assert rel_err(yt, y1) <= 2e-6
