@@ -744,11 +744,14 @@ def measure(args, wname, world, rank, local, numa_bound):
     mac_per_step = prof.n_mac / nprof                        # k_fdl_mac launches per step (1 for P > 1 banks)
     traffic, traffic_src = None, None
     tr_path = os.path.join(ROOT, "profiles", "mac_traffic.json")
-    if wname in ("c2", "c4") and os.path.exists(tr_path) and not args.streams and not (tile > 1 and not mix):
+    if wname in ("c2", "c4") and os.path.exists(tr_path) and not args.streams:
         try:
             tj = json.load(open(tr_path))
-            traffic = tj.get(args.variant if wname == "c2" else wname)
-            traffic_src = ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one k_fdl_mac launch "
+            key = args.variant if wname == "c2" else wname
+            if tile > 1 and not mix:
+                key = f"{key}_tile{tile}"
+            traffic = tj.get(key)
+            traffic_src = None if traffic is None else ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one k_fdl_mac[_tile] launch "
                            f"from the committed `ncu --set full` capture ({tj.get('source', 'profiles/')})")
         except Exception:
             traffic = None

@@ -383,19 +383,26 @@ MacPlan mac_plan_tiled(int N, int c_out, int W4, int n_terms, bool shared_filter
     p.tile_u = (tile == 2 && p.st == 1) ? 8 : 4;
     tv = tile_variant(p.st, tile, p.tile_u);
   }
-  const int lanes = kMacThreads, ktiles = W4 / lanes;
+  const int lanes = kMacThreads;
+  int ktiles = W4 / lanes;
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tv->func, kMacThreads, 0);
   if (occ < 1) occ = 1;
   {
     // rows staged through shared memory by bulk-async copies (k_mac_tile_tma.cu): PGX_TILE_TMA=0|1
-    bool tma = true;
+    bool tma = false;
     if (const char* e = getenv("PGX_TILE_TMA")) tma = atoi(e) != 0;
     int st2, tps, stages, occ2;
-    if (tma && tile_tma_supported(W4) && tile_tma_config(shared_filter, N, tile, &st2, &tps, &stages, &occ2)) {
+    if (tma && tile_tma_supported(W4) && tile_tma_config(shared_filter, N, W4, tile, &st2, &tps, &stages, &occ2)) {
       p.variant = 1;
       p.st = st2; p.tile_u = tps; p.tile_stages = stages;
       occ = occ2;
+      ktiles = tile_tma_ktiles(W4);
+      // persistent CTAs per SM: fewer than fit, so that the ingest / output kernels of the blocks in flight find room
+      // beside the pass (PGX_TILE_CTAS)
+      int cap = 2;
+      if (const char* e = getenv("PGX_TILE_CTAS")) cap = atoi(e);
+      if (cap >= 1 && cap < occ) occ = cap;
     }
   }
   p.n_otiles = ((N + p.st - 1) / p.st) * c_out;

@@ -5,8 +5,8 @@
 // committed delay-line rows, the T filter rows of a slot a register window that slides by one row per slot.  What
 // changes is how the rows reach the SM: the tiled pass does T times the arithmetic per loaded byte, so the LDG kernel
 // needs its registers for accumulators and cannot also keep enough loads in flight to fill HBM.  Here a persistent
-// CTA = 1 producer warp + 4 consumer warps walks a static list of work items (out tile x bin tile x term split); the
-// producer streams 2 KB row segments into a ring of stages with cp.async.bulk (SASS: UBLKCP), completion counted in
+// CTA = 1 producer warp + SEG/32 consumer warps walks a static list of work items (out tile x bin tile x term split);
+// the producer streams row segments into a ring of stages with cp.async.bulk (SASS: UBLKCP), completion counted in
 // bytes on an mbarrier per stage, and the bytes in flight live in shared memory (STAGES x stage bytes per CTA).
 // A stage = TPS consecutive slots x (ST delay-line rows + the slot's one new filter row); the first stage of a run of
 // consecutive slots also carries the T-1 older filter rows that seed the window.
@@ -19,10 +19,9 @@
 
 namespace pgx {
 
-static constexpr int kTtConsumers = 128;              // 4 consumer warps, one float4 column each
-static constexpr int kTtThreads = kTtConsumers + 32;
-static constexpr int kTtSegF4 = 128;                  // float4 per row segment (2 KB)
-static constexpr int kTtSegBytes = kTtSegF4 * 16;
+// SEG = float4 per row segment = consumer threads (one float4 column each): 128 (2 KB) or 256 (4 KB).  When a segment is
+// the whole row (W4 == SEG) the rows of consecutive slots are contiguous in HBM and a stage's TPS rows of one stream (or
+// of the filter) travel as ONE bulk copy; otherwise one copy per row segment.
 
 struct TtItem {
   int kt, ot, sp, r0, r1, c, s0, gx, fc, nst;
@@ -55,8 +54,9 @@ __device__ __forceinline__ bool tt_run(const MacArgs& a, const TtItem& it, int r
   return true;
 }
 
-template <int ST, int T, int TPS, int STAGES>
-__global__ void __launch_bounds__(kTtThreads) k_fdl_mac_tile_tma(const MacArgs a, const int n_items) {
+template <int ST, int T, int TPS, int STAGES, int SEG>
+__global__ void __launch_bounds__(SEG + 32) k_fdl_mac_tile_tma(const MacArgs a, const int n_items) {
+  constexpr int kTtConsumers = SEG, kTtSegF4 = SEG, kTtSegBytes = SEG * 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int ROWS = TPS * (ST + 1) + (T - 1);       // + the window seed rows (first stage of a run)
   constexpr int STAGE_F4 = ROWS * kTtSegF4;
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kTtThreads) k_fdl_mac_tile_tma(const MacArgs a
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ktiles = a.W4 / kTtSegF4;
+  const bool contig = (ktiles == 1);
   const size_t rs = (size_t)a.W4;
   const size_t stream_stride = (size_t)a.c_x * a.R * rs;
   const int qb = a.R - 1 - a.head;
@@ -102,8 +103,21 @@ __global__ void __launch_bounds__(kTtThreads) k_fdl_mac_tile_tma(const MacArgs a
           }
           __syncwarp();
           float4* sb = stage_base + (size_t)stage * STAGE_F4;
-          if (lane < TPS * (ST + 1)) {
-            const int u = lane / (ST + 1), q = lane - u * (ST + 1);   // slot within the stage, row within the slot (ST = H)
+          // stage layout: [q = 0..ST-1 delay-line rows of stream q | q = ST filter rows][slot u], then the window seed
+          if (contig) {
+            if (lane <= ST && (lane == ST || lane < it.nst)) {
+              const float4* src = (lane == ST) ? hfil + (size_t)(qb + jb) * rs
+                                               : xbase + (size_t)jb * rs + (size_t)lane * stream_stride;
+              bulk_g2s(sb + (size_t)lane * TPS * kTtSegF4, src, (uint32_t)(nterm * kTtSegBytes), &full[stage],
+                       lane == ST ? pol_h : pol_x);
+            } else if (first && lane == ST + 1) {
+              int q = qb + jbeg - (T - 1);
+              q += (q < 0) ? a.R : 0;      // rows q and q + R hold the same partition: shift the whole seed run
+              bulk_g2s(sb + (size_t)(ST + 1) * TPS * kTtSegF4, hfil + (size_t)q * rs, (uint32_t)((T - 1) * kTtSegBytes),
+                       &full[stage], pol_h);
+            }
+          } else if (lane < TPS * (ST + 1)) {
+            const int q = lane / TPS, u = lane - q * TPS;   // row kind, slot within the stage
             if (u < nterm) {
               const int j = jb + u;
               if (q == ST) bulk_g2s(sb + (size_t)lane * kTtSegF4, hfil + (size_t)(qb + j) * rs, kTtSegBytes, &full[stage], pol_h);
@@ -113,9 +127,9 @@ __global__ void __launch_bounds__(kTtThreads) k_fdl_mac_tile_tma(const MacArgs a
             }
           } else if (first && lane < ROWS) {
             const int w2 = lane - TPS * (ST + 1);                      // window seed: d = jbeg - (T-1) + w2
-            int q = qb + jbeg - (T - 1) + w2;
+            int q = qb + jbeg - (T - 1);
             q += (q < 0) ? a.R : 0;
-            bulk_g2s(sb + (size_t)lane * kTtSegF4, hfil + (size_t)q * rs, kTtSegBytes, &full[stage], pol_h);
+            bulk_g2s(sb + (size_t)lane * kTtSegF4, hfil + (size_t)(q + w2) * rs, kTtSegBytes, &full[stage], pol_h);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -156,12 +170,12 @@ __global__ void __launch_bounds__(kTtThreads) k_fdl_mac_tile_tma(const MacArgs a
 #pragma unroll
           for (int u = 0; u < TPS; ++u) {
             if (fast || u < nterm) {
-              hw[T - 1 + u] = sb[(size_t)(u * (ST + 1) + ST) * kTtSegF4];
+              hw[T - 1 + u] = sb[(size_t)(ST * TPS + u) * kTtSegF4];
               float4 x[ST];
               float xim[ST], xre[ST];   // first complex: x.x as the imaginary sum uses it, -x.y as the real sum does
 #pragma unroll
               for (int t = 0; t < ST; ++t) {
-                x[t] = (fast || t < it.nst) ? sb[(size_t)(u * (ST + 1) + t) * kTtSegF4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[t] = (fast || t < it.nst) ? sb[(size_t)(t * TPS + u) * kTtSegF4] : make_float4(0.f, 0.f, 0.f, 0.f);
                 xim[t] = bin0 ? 0.f : x[t].x;   // packed bin 0 (lane kv = 0): two real products
                 xre[t] = bin0 ? 0.f : -x[t].y;
               }
@@ -209,59 +223,72 @@ __global__ void __launch_bounds__(kTtThreads) k_fdl_mac_tile_tma(const MacArgs a
 }
 
 struct TtVariant {
-  int st, tile, tps, stages;
+  int st, tile, tps, stages, seg;
   const void* func;
   int smem;
 };
-#define TT_V(ST, T, TPS, STAGES)                                                            \
-  {ST, T, TPS, STAGES, reinterpret_cast<const void*>(k_fdl_mac_tile_tma<ST, T, TPS, STAGES>), \
-   STAGES * (TPS * (ST + 1) + (T - 1)) * kTtSegBytes + 2 * STAGES * (int)sizeof(uint64_t)}
+#define TT_V(ST, T, TPS, STAGES, SEG)                                                                 \
+  {ST, T, TPS, STAGES, SEG, reinterpret_cast<const void*>(k_fdl_mac_tile_tma<ST, T, TPS, STAGES, SEG>), \
+   STAGES * (TPS * (ST + 1) + (T - 1)) * SEG * 16 + 2 * STAGES * (int)sizeof(uint64_t)}
 static const TtVariant kTtVariants[] = {
-    TT_V(2, 4, 2, 3), TT_V(2, 4, 2, 4), TT_V(2, 4, 4, 3), TT_V(4, 4, 2, 3), TT_V(4, 4, 2, 4),
-    TT_V(1, 4, 2, 4), TT_V(1, 4, 4, 3), TT_V(1, 4, 4, 4),
-    TT_V(2, 2, 2, 4), TT_V(2, 2, 4, 3), TT_V(4, 2, 2, 4), TT_V(1, 2, 4, 4), TT_V(1, 2, 4, 3),
+    TT_V(2, 4, 2, 3, 128), TT_V(2, 4, 2, 4, 128), TT_V(2, 4, 4, 3, 128), TT_V(1, 4, 4, 3, 128), TT_V(1, 4, 4, 4, 128),
+    TT_V(2, 2, 2, 4, 128), TT_V(1, 2, 4, 4, 128),
+    TT_V(2, 4, 2, 3, 256), TT_V(2, 4, 4, 2, 256), TT_V(2, 4, 4, 3, 256), TT_V(1, 4, 4, 3, 256), TT_V(1, 4, 4, 4, 256),
+    TT_V(1, 4, 8, 2, 256), TT_V(2, 2, 4, 3, 256), TT_V(1, 2, 4, 4, 256),
 };
 
-static const TtVariant* tt_variant(int st, int tile, int tps, int stages) {
+static const TtVariant* tt_variant(int st, int tile, int tps, int stages, int seg) {
   for (const TtVariant& v : kTtVariants)
-    if (v.st == st && v.tile == tile && v.tps == tps && v.stages == stages) return &v;
+    if (v.st == st && v.tile == tile && v.tps == tps && v.stages == stages && v.seg == seg) return &v;
   return nullptr;
 }
 
-bool tile_tma_supported(int W4) { return W4 >= kTtSegF4 && (W4 % kTtSegF4) == 0; }
+bool tile_tma_supported(int W4) { return W4 >= 128 && (W4 % 128) == 0; }
 
-// default configuration per (shared filter?, tile); PGX_TILE_ST / PGX_TILE_TPS / PGX_TILE_STAGES override for A/B runs
-bool tile_tma_config(bool shared_filter, int N, int tile, int* st, int* tps, int* stages, int* occupancy) {
-  int s = (shared_filter && N >= 2) ? 2 : 1, p = s == 1 ? 4 : 2, g = s == 1 ? 3 : (tile == 4 ? 3 : 4);
+static int tt_seg(int W4) {
+  int seg = (W4 % 256) == 0 ? 256 : 128;
+  if (const char* e = getenv("PGX_TILE_SEG")) {
+    const int v = atoi(e);
+    if ((v == 128 || v == 256) && (W4 % v) == 0) seg = v;
+  }
+  return seg;
+}
+
+// default configuration per (shared filter?, tile); PGX_TILE_ST / PGX_TILE_TPS / PGX_TILE_STAGES / PGX_TILE_SEG override
+bool tile_tma_config(bool shared_filter, int N, int W4, int tile, int* st, int* tps, int* stages, int* occupancy) {
+  const int seg = tt_seg(W4);
+  const int s0 = (shared_filter && N >= 2) ? 2 : 1, p0 = 4, g0 = 3;
+  int s = s0, p = p0, g = g0;
   if (const char* e = getenv("PGX_TILE_ST")) {
     const int v = atoi(e);
     if (v == 1 || (shared_filter && N >= v)) s = v;
   }
   if (const char* e = getenv("PGX_TILE_TPS")) p = atoi(e);
   if (const char* e = getenv("PGX_TILE_STAGES")) g = atoi(e);
-  const TtVariant* v = tt_variant(s, tile, p, g);
+  const TtVariant* v = tt_variant(s, tile, p, g, seg);
   if (!v) {
-    s = (shared_filter && N >= 2) ? 2 : 1; p = s == 1 ? 4 : 2; g = s == 1 ? 3 : (tile == 4 ? 3 : 4);
-    v = tt_variant(s, tile, p, g);
+    s = s0; p = p0; g = g0;
+    v = tt_variant(s, tile, p, g, seg);
   }
   if (!v) return false;
   cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, v->smem);
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v->func, kTtThreads, v->smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v->func, seg + 32, v->smem);
   *st = s; *tps = p; *stages = g; *occupancy = nb > 0 ? nb : 1;
   return true;
 }
 
-int tile_tma_ktiles(int W4) { return W4 / kTtSegF4; }
+int tile_tma_ktiles(int W4) { return W4 / tt_seg(W4); }
 
 bool describe_fdl_mac_tile_tma(const MacArgs& a, LaunchDesc* d, int* n_items) {
-  const TtVariant* v = tt_variant(a.st, a.tile, a.tile_u, a.tile_stages);
+  const int seg = tt_seg(a.W4);
+  const TtVariant* v = tt_variant(a.st, a.tile, a.tile_u, a.tile_stages, seg);
   if (!v) return false;
-  *n_items = a.n_otiles * (a.W4 / kTtSegF4) * a.n_split;
+  *n_items = a.n_otiles * (a.W4 / seg) * a.n_split;
   const int grid = *n_items < a.persistent_ctas ? *n_items : a.persistent_ctas;
   d->func = v->func;
   d->grid = dim3((unsigned)grid);
-  d->block = dim3(kTtThreads);
+  d->block = dim3(seg + 32);
   d->smem = (size_t)v->smem;
   return true;
 }

@@ -75,7 +75,8 @@ void launch_reduce_partials(const float4* in, float4* out, int n_split, int n_ou
 MacPlan mac_plan(int N, int c_out, int W4, int n_terms, bool mix, bool shared_filter, int sm_count);
 // bulk-async staged variant of the time-tiled pass, k_mac_tile_tma.cu
 bool tile_tma_supported(int W4);
-bool tile_tma_config(bool shared_filter, int N, int tile, int* st, int* tps, int* stages, int* occupancy);
+bool tile_tma_config(bool shared_filter, int N, int W4, int tile, int* st, int* tps, int* stages, int* occupancy);
+int tile_tma_ktiles(int W4);
 void launch_fdl_mac_tile_tma(const MacArgs& a, cudaStream_t st);
 // same for the time-tiled pass (conv layout): tile = 2 or 4 output blocks per pass
 MacPlan mac_plan_tiled(int N, int c_out, int W4, int n_terms, bool shared_filter, int sm_count, int tile);

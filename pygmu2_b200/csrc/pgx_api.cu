@@ -76,7 +76,7 @@ bool layout_dense(const pgx_layout& l, int64_t S, int64_t C, int64_t n) {
 // K2 folds up to this many split partials itself; beyond that a fold kernel runs right after the
 // background pass, off the critical path.
 constexpr int kFoldAbove = 8;
-constexpr int kRing = 4;  // event ring depth (steps / blocks in flight)
+constexpr int kRing = 8;  // event ring depth (steps / blocks in flight)
 
 }  // namespace
 
@@ -353,8 +353,10 @@ void issue_tile(pgx_bank* b, int64_t blk0, int head0, cudaEvent_t after) {
   cudaStream_t sbg = b->s_bg;
   cudaStreamWaitEvent(sbg, after, 0);
   for (int kp = 0; kp < T; ++kp) {  // WAR: the sets being overwritten were read by the output stages of blocks 2*tile earlier
-    const int64_t lk = b->last_k2_of_set[(blk0 + kp) % nsets];
-    if (lk >= 0) cudaStreamWaitEvent(sbg, b->ev_k2[lk % kRing], 0);
+    int64_t lk = b->last_k2_of_set[(blk0 + kp) % nsets];
+    if (lk < 0) continue;
+    if (lk < b->step - kRing) lk = b->step - kRing + 1;   // its event was reused: the oldest one still valid is later
+    cudaStreamWaitEvent(sbg, b->ev_k2[lk % kRing], 0);
   }
   pgx::MacArgs m{};
   fill_mac_common(b, m, false, head0);
@@ -457,7 +459,12 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
       if (i >= 1) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 1) % kRing], 0);
     }
     if (!(b->fill > 0 || R == 1)) {
-      if (i >= 2) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - 2) % kRing], 0);
+      // (a step far enough back stands in for the output stages that read this ring row R blocks ago.  On a tiled bank
+      // the output stages of the last `tile` blocks wait for a pass that may still be running, and the next pass cannot
+      // start before this K1: look further back than they reach -- R >= 35 there, so tile + 2 steps back is still
+      // younger than every reader of the row)
+      const int back = b->tile > 1 ? b->tile + 2 : 2;
+      if (i >= back) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - back) % kRing], 0);
       if (t >= 2) cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);  // every block had its past pass issued
       // a tiled pass with first block blk0 reads the rows of blocks blk0-P+1 .. blk0-1; this K1 overwrites the row of
       // block t-R = t-P-n_spare: every tiled pass with blk0 <= t-n_spare-1 must be done (they complete in issue order)
@@ -882,9 +889,9 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   b->P = (c.filter_len + c.block - 1) / c.block;
   const size_t n_fft = (size_t)c.n_streams * c_x;
   {
-    // time tiling: for banks that stream a long delay line (the HBM-bound class); PGX_TILE = 1 | 2 | 4, PGX_TILE_MIN =
-    // smallest n_streams * c_x * B that qualifies
-    int want = 1;
+    // time tiling: for banks that stream a long delay line (the HBM-bound class); PGX_TILE = 1 (off) | 2 | 4,
+    // PGX_TILE_MIN = smallest n_streams * c_x * B that qualifies
+    int want = 4;
     long tile_min = 1L << 17;
     if (const char* e = getenv("PGX_TILE")) want = atoi(e);
     if (const char* e = getenv("PGX_TILE_MIN")) tile_min = atol(e);
