@@ -669,7 +669,7 @@ def measure(args, wname, world, rank, local, numa_bound):
     xp.array[...] = np.clip(np.rint(x_host * 32768.0), -32768, 32767).astype(np.int16) if args.pcm16 else x_host
     # pulls in flight: H2D of pull i+1 and D2H of pull i-1 overlap the kernels of pull i; a time-tiled bank computes the
     # past sums of `tile` blocks per pass, so it needs that many more pulls queued to keep its passes back to back
-    E2E_DEPTH = 3 if (tile <= 1 or mix) else min(8, tile + 3)
+    E2E_DEPTH = 3 if (tile <= 1 or mix) else min(int(getattr(info, 'submit_depth', 0)) or 8, tile + 3)
     yps = [yp] + [PinnedArray(yp.shape, io_dt) for _ in range(E2E_DEPTH - 1)]
     # steady state of the pull loop: enough pulls that the pipeline's fill and drain (one H2D + one D2H latency)
     # do not dominate a region of a few milliseconds
@@ -823,6 +823,7 @@ def measure(args, wname, world, rank, local, numa_bound):
                              "k_fdl_mac_busy_ms_per_launch": mac_ms_union, "k_fdl_mac_start_to_end_ms": mac_ms_each,
                              "k_fdl_mac_gbs_busy": (mac_bytes / (mac_ms_union * 1e-3) / 1e9) if mac_ms_union > 0 else None,
                              "launches_timed": int(prof.n_mac), "share_of_step": prof.ms_mac / max(ksum, 1e-12),
+                             "k_fdl_mac_busy_fraction_of_step": mac_ms_union * mac_per_step / (ms_med / K),
                              "kernel_ms": {"k_r2c_ingest": prof.ms_r2c / nprof, "k_fdl_mac": mac_ms_union,
                                            "k_c2r_emit": prof.ms_c2r / nprof, "k_reduce_partials": prof.ms_fold / nprof,
                                            "k_fdl_mac_present_slot": prof.ms_now / nprof,

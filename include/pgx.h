@@ -93,7 +93,7 @@ typedef struct pgx_bank_info {
   int32_t tail_block, tail_partitions; /* two-level partitioning: block and partition count of the tail level (0 = off) */
   int32_t mac_tile;         /* time tiling of the conv pass: past sums of this many consecutive blocks per pass over the
                                delay line (1 = one pass per block; PGX_TILE) */
-  int32_t reserved;
+  int32_t submit_depth;     /* host-buffer pulls this bank keeps in flight (pgx_bank_submit): 3, PGX_SUBMIT_DEPTH when tiled */
   int64_t graph_pulls;      /* host pulls that ran as ONE CUDA-graph replay (small whole-block pulls in the steady state:
                                copies and kernels of the pull as one launch; PGX_GRAPH=0 disables) */
 } pgx_bank_info;
@@ -211,7 +211,8 @@ PGX_API int pgx_bank_set_output_gains(pgx_bank* bank, float wet, float dry);
  * flight): submit stages x (H2D on a copy stream), enqueues the pull and the D2H of y, and returns a ticket
  * without waiting; pgx_bank_wait(ticket) returns when that pull's y is complete in host memory.  Pulls
  * execute in submission order.  x and y must stay valid (and should be pinned, pgx_host_alloc) until the
- * wait returns; at most PGX_SUBMIT_DEPTH pulls are in flight - a further submit first waits for the oldest.
+ * wait returns; at most pgx_bank_info.submit_depth pulls are in flight (3; PGX_SUBMIT_DEPTH on a time-tiled bank,
+ * whose passes cover several blocks) - a further submit first waits for the oldest.
  * flags: PGX_PULL_MIX, PGX_PULL_X_DEVICE, PGX_PULL_X_PCM16, PGX_PULL_Y_PCM16, PGX_PULL_REDUCE (on the ranks
  * other than the root y is not written: there is no D2H copy).  pgx_bank_process[_mix] = submit + wait.
  */

@@ -41,7 +41,7 @@ class BankInfo(C.Structure):
                                           "fill")] + \
                [(n, C.c_int64) for n in ("state_bytes", "kernel_launches", "block_steps")] + \
                [(n, C.c_int32) for n in ("mac_grid", "mac_split", "mac_stream_tile", "mac_occupancy",
-                                          "tail_block", "tail_partitions", "mac_tile", "reserved")] + \
+                                          "tail_block", "tail_partitions", "mac_tile", "submit_depth")] + \
                [("graph_pulls", C.c_int64)]
 
 

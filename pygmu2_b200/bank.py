@@ -227,7 +227,7 @@ class ConvolveBank:
     def submit(self, x: np.ndarray, out: np.ndarray, *, mix: bool = False, reduce: bool = False) -> int:
         """Enqueue one pull: x (N, C_in, n) -> out (N, C_out, n), or (C_out, n) when ``mix``.  Returns a
         ticket for ``wait``.  x and out must be C-contiguous float32 (pinned for real overlap: ``PinnedArray``)
-        and must not be touched until the wait returns; at most 8 pulls (PGX_SUBMIT_DEPTH) are in flight."""
+        and must not be touched until the wait returns; at most `info().submit_depth` pulls are in flight (3; 8 on a time-tiled bank)."""
         if x.dtype not in (np.float32, np.int16) or out.dtype not in (np.float32, np.int16) \
                 or not x.flags.c_contiguous or not out.flags.c_contiguous:
             raise ValueError("submit needs C-contiguous float32 (or int16 PCM) arrays")

@@ -115,6 +115,7 @@ struct pgx_bank {
   // host-buffer pulls: a ring of staging slots so that the H2D of pull i+1 and the D2H of pull i-1 overlap
   // the kernels of pull i (copy engines on their own streams)
   static constexpr int kSlots = PGX_SUBMIT_DEPTH;
+  int n_slots = 3;                 // pulls in flight on this bank: 3, kSlots on a time-tiled bank (its passes cover `tile` blocks)
   float* x_stage[kSlots] = {};
   float* y_stage[kSlots] = {};
   int16_t* xpcm_stage[kSlots] = {};  // PCM16 staging, allocated on first use
@@ -996,9 +997,12 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
   guard(cudaMemset(b->mix1_ticket, 0, sizeof(unsigned int)), "memset ticket");
   guard(cudaMalloc(&b->tw, (size_t)2 * B * sizeof(float2)), "cudaMalloc(tw)");
   guard(cudaMalloc(&b->fmap_own, (size_t)pgx_bank::kMapSlots * c.n_streams * sizeof(int32_t)), "cudaMalloc(fmap)");
+  b->n_slots = b->tile > 1 ? pgx_bank::kSlots : 3;
   for (int i = 0; i < pgx_bank::kSlots; ++i) {
-    guard(cudaMalloc(&b->x_stage[i], b->xs_bytes), "cudaMalloc(x_stage)");
-    guard(cudaMalloc(&b->y_stage[i], b->ys_bytes), "cudaMalloc(y_stage)");
+    if (i < b->n_slots) {
+      guard(cudaMalloc(&b->x_stage[i], b->xs_bytes), "cudaMalloc(x_stage)");
+      guard(cudaMalloc(&b->y_stage[i], b->ys_bytes), "cudaMalloc(y_stage)");
+    }
     guard(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming), "cudaEventCreate");
     guard(cudaEventCreateWithFlags(&b->ev_y[i], cudaEventDisableTiming), "cudaEventCreate");
     guard(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming), "cudaEventCreate");
@@ -1101,7 +1105,7 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->block = b->B; info->partitions = b->P; info->max_pull = c.max_pull; info->device = c.device;
   info->head = b->head; info->fill = b->fill;
   info->state_bytes = (int64_t)(b->hist_bytes + b->fdl_bytes + b->Hd_bytes + 2 * b->ypart_bytes + 2 * b->ysum_bytes +
-                                b->ynow_bytes + pgx_bank::kSlots * (b->xs_bytes + b->ys_bytes));
+                                b->ynow_bytes + b->ytile_bytes + b->n_slots * (b->xs_bytes + b->ys_bytes));
   info->block_steps = b->steps;
   info->tail_block = b->tail ? b->tail_B : 0;
   info->tail_partitions = b->tail ? b->tail->P : 0;
@@ -1115,7 +1119,7 @@ int pgx_bank_get_info(pgx_bank* b, pgx_bank_info* info) {
   info->kernel_launches = b->launches + (b->tail ? b->tail->launches : 0);
   info->graph_pulls = b->graph_pulls;
   info->mac_tile = b->tile;
-  info->reserved = 0;
+  info->submit_depth = b->n_slots;
   if (b->tile > 1) {
     info->mac_grid = b->plan_tile.grid; info->mac_split = b->plan_tile.n_split;
     info->mac_stream_tile = b->plan_tile.st; info->mac_occupancy = b->plan_tile.occupancy;
@@ -1513,9 +1517,9 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
   const size_t xb = (size_t)c.n_streams * c.c_in * n * sizeof(float);
   const size_t yb = (size_t)(mix ? 1 : c.n_streams) * c.c_out * n * sizeof(float);
   const int64_t tk = b->next_ticket;
-  const int slot = (int)(tk % pgx_bank::kSlots);
+  const int slot = (int)(tk % b->n_slots);
   // the slot's previous pull is over once its D2H has completed (its K1s read x_stage before that)
-  if (tk >= pgx_bank::kSlots) PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
+  if (tk >= b->n_slots) PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
   if (b->y_user[slot]) {  // that pull was never waited for: its result still has to reach the caller's array
     memcpy(b->y_user[slot], b->hy_bounce[slot], b->y_user_bytes[slot]);
     b->y_user[slot] = nullptr;
@@ -1601,9 +1605,9 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
 static int submit_wait(pgx_bank* b, int64_t ticket) {
   if (!b) return fail(PGX_ERR_INVALID, "bank is NULL");
   if (ticket < 0 || ticket >= b->next_ticket) return fail(PGX_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
-  if (ticket + pgx_bank::kSlots < b->next_ticket) return PGX_OK;  // its slot was recycled: long complete
+  if (ticket + b->n_slots < b->next_ticket) return PGX_OK;  // its slot was recycled: long complete
   PGX_CUDA(cudaSetDevice(b->cfg.device));
-  const int slot = (int)(ticket % pgx_bank::kSlots);
+  const int slot = (int)(ticket % b->n_slots);
   PGX_CUDA(cudaEventSynchronize(b->ev_done[slot]));
   if (b->y_user[slot]) {  // small result: out of the bank's pinned bounce buffer into the caller's array
     memcpy(b->y_user[slot], b->hy_bounce[slot], b->y_user_bytes[slot]);

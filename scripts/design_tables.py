@@ -22,12 +22,16 @@ def fmt_k(v):
 
 
 def bench_table():
-    rows = [("C2 shared IR, driver-shaped run (`--steps 20`, burst) — headline", "r02b_bench_c2_k20.json"),
-            ("C2 shared IR, sustained (`--steps 2000`, software power cap)", "r02b_bench_c2.json"),
-            ("C1 4096 streams × 4096-tap FIR (P=1, `k_conv1_r16`)", "r02b_bench_c1.json"),
-            ("C3 256 moving HRTF sources × 2 ears → stereo mix (one `k_mix1` launch per step)", "r02b_bench_c3.json"),
-            ("C4 512 mono streams × 88 200 taps, fused mix (one GPU's share)", "r02b_bench_c4.json"),
-            ("C5 single stream, 441 000 taps at 64-sample blocks (latency-bound)", "r02b_bench_c5.json")]
+    rows = [("C2 shared IR, driver-shaped run (`--steps 20`, burst) — headline (time tile 4)", "r02c_bench_c2_k20.json"),
+            ("C2 shared IR, sustained (`--steps 2000`, software power cap)", "r02c_bench_c2.json"),
+            ("C2 shared IR, per-block pass (`PGX_TILE=1`: the round-1 schedule), same box, sustained", "r02c_bench_c2_untiled.json"),
+            ("C2 shared IR, time tile 2 (`PGX_TILE=2`), same box", "r02c_bench_c2_tile2.json"),
+            ("C2 distinct IRs (one per stream), time tile 4", "r02c_bench_c2_distinct.json"),
+            ("C2 distinct IRs, per-block pass (`PGX_TILE=1`), same box", "r02c_bench_c2_distinct_untiled.json"),
+            ("C1 4096 streams × 4096-tap FIR (P=1, `k_conv1_r16`)", "r02c_bench_c1.json"),
+            ("C3 256 moving HRTF sources × 2 ears → stereo mix (one `k_mix1` launch per step)", "r02c_bench_c3.json"),
+            ("C4 512 mono streams × 88 200 taps, fused mix (one GPU's share)", "r02c_bench_c4.json"),
+            ("C5 single stream, 441 000 taps at 64-sample blocks (latency-bound)", "r02c_bench_c5.json")]
     out = ["| workload | ms/step (min…max over reps) | value (audio-s·ch/s) | e2e (of value) | dominant kernel: GB/s (frac of measured peak) | step-level frac | parity (max rel err, pulls) | SM MHz, reasons |",
            "|---|---|---|---|---|---|---|---|"]
     for label, f in rows:
@@ -45,7 +49,7 @@ def multi_table():
     out = ["| GPUs | C2 ms/step | C2 value | C2 e2e (of value; copy GB/s per rank min…max) | C4 ms/step | C4 value | C4 e2e (of value) | cross-GPU sum: exposed µs per pull | parity C2 / C4 |",
            "|---|---|---|---|---|---|---|---|---|"]
     for n in (1, 2, 4, 8):
-        d = line(f"r02b_scale_n{n}_k20.json")
+        d = line(f"r02c_scale_n{n}_k20.json") or line(f"r02b_scale_n{n}_k20.json")
         if d is None:
             continue
         e = d["e2e"]
@@ -61,7 +65,7 @@ def multi_table():
     d = line("r02b_scale_n8_k20_nccl.json")
     if d and "c4" in d:
         c = d["c4"]
-        out.append(f"| 8, NCCL `dist.reduce` baseline | {d['ms_per_step']:.4f} | {fmt_k(d['value'])} | — | {c['ms_per_step']:.4f} | {fmt_k(c['value'])} | "
+        out.append(f"| 8, NCCL `dist.reduce` baseline (earlier visit, per-block pass) | {d['ms_per_step']:.4f} | {fmt_k(d['value'])} | — | {c['ms_per_step']:.4f} | {fmt_k(c['value'])} | "
                    f"{fmt_k(c['e2e']['value'])} ({c['e2e']['frac_of_value']:.2f}) | {c['reduce']['exposed_us_per_pull']:.2f} (NCCL) | — |")
     extra = []
     for tag, what in (("plain", "float32 staging"), ("wc", "write-combined input buffers"), ("pcm16", "int16 PCM staging (§7 rank 4)")):
@@ -77,7 +81,7 @@ R1 = {"C1": 52, "C2 stereo": 54, "C2 as": 62, "C3 256 HRTF": 67, "C3 256 MOVING 
 
 
 def named_table():
-    path = os.path.join(P, "r02b_named_configs.jsonl")
+    path = os.path.join(P, "r02c_named_configs.jsonl")
     if not os.path.exists(path):
         return ""
     out = ["| named configuration | pull | µs per pull (round 1) | × real time |", "|---|---|---|---|"]
