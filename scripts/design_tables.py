@@ -81,7 +81,7 @@ R1 = {"C1": 52, "C2 stereo": 54, "C2 as": 62, "C3 256 HRTF": 67, "C3 256 MOVING 
 
 
 def named_table():
-    path = os.path.join(P, "r02c_named_configs.jsonl")
+    path = os.path.join(P, "r02d_named_configs.jsonl")
     if not os.path.exists(path):
         return ""
     out = ["| named configuration | pull | µs per pull (round 1) | × real time |", "|---|---|---|---|"]
