@@ -97,6 +97,10 @@ class ConvolveBank:
                                     h_planar.ctypes.data_as(C.POINTER(C.c_float)),
                                     fmap.ctypes.data_as(C.POINTER(C.c_int32)) if fmap is not None else None))
         self.sources = None
+        self._inflight = {}
+        self._submit_layouts = {}
+        self._submit_ticket = C.c_int64(-1)
+        self._submit_fn = lib().pgx_bank_submit
 
     # -- lifetime ------------------------------------------------------------
     def close(self) -> None:
@@ -237,19 +241,22 @@ class ConvolveBank:
         want = (self.c_out, n) if mix else (self.n_streams, self.c_out, n)
         if out.shape != want:
             raise ValueError(f"out must be {want}, got {out.shape}")
-        tk = C.c_int64(-1)
-        check(lib().pgx_bank_submit(self._h, _lib.f32_ptr(x), Layout(self.c_in * n, n, 1), _lib.f32_ptr(out),
-                                    Layout(0 if mix else self.c_out * n, n, 1), n,
-                                    (1 if mix else 0) | (_lib.PGX_PULL_REDUCE if reduce else 0)
-                                    | (_lib.PGX_PULL_X_PCM16 if x.dtype == np.int16 else 0)
-                                    | (_lib.PGX_PULL_Y_PCM16 if out.dtype == np.int16 else 0), C.byref(tk)))
-        self._inflight = getattr(self, "_inflight", {})
-        self._inflight[tk.value] = (x, out)  # keep the buffers alive until waited
-        return int(tk.value)
+        key = (n, mix)
+        lay = self._submit_layouts.get(key)
+        if lay is None:   # (the two layout structs of a pull shape are built once: this call is on the per-pull path)
+            lay = self._submit_layouts[key] = (Layout(self.c_in * n, n, 1), Layout(0 if mix else self.c_out * n, n, 1))
+        tk = self._submit_ticket
+        check(self._submit_fn(self._h, _lib.f32_ptr(x), lay[0], _lib.f32_ptr(out), lay[1], n,
+                              (1 if mix else 0) | (_lib.PGX_PULL_REDUCE if reduce else 0)
+                              | (_lib.PGX_PULL_X_PCM16 if x.dtype == np.int16 else 0)
+                              | (_lib.PGX_PULL_Y_PCM16 if out.dtype == np.int16 else 0), C.byref(tk)))
+        t = int(tk.value)
+        self._inflight[t] = (x, out)  # keep the buffers alive until waited
+        return t
 
     def wait(self, ticket: int) -> None:
         check(lib().pgx_bank_wait(self._h, int(ticket)))
-        infl = getattr(self, "_inflight", {})
+        infl = self._inflight
         for t in [t for t in infl if t <= ticket]:
             del infl[t]
 

@@ -155,6 +155,11 @@ struct pgx_bank {
   struct TilePass { int64_t base = -1; cudaEvent_t ev = nullptr; } tpass[kTilePasses];
   int64_t n_tpass = 0;
   int64_t last_k2_of_set[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  // waits a stream has already made need not be repeated (streams are in-order): the newest tiled pass (by issue
+  // count) the ingest stream / the critical stream of the last pull has waited for
+  int64_t sin_waited_tpass = -1, crit_waited_tpass = -1;
+  cudaStream_t crit_waited_stream = nullptr;
+  int64_t last_past_issue_block = -1;   // newest block a per-block pass (issue_past) was issued for
   int sm_count = 148;
   float wet = 1.0f, dry = 0.0f;    // fused output stage: y = dry * x + wet * conv
   // two-level partitioning (cfg.tail_block > 0): this bank convolves with the first tail_B taps at block B; `tail`
@@ -340,6 +345,7 @@ void issue_past(pgx_bank* b, bool mix, int64_t blk, int head, cudaEvent_t after)
     b->launches += 1;
   }
   cudaEventRecord(b->ev_mac[blk % kRing], sbg);
+  if (blk > b->last_past_issue_block) b->last_past_issue_block = blk;
   b->past_block = blk;
   b->past_mode = mix ? 1 : 0;
 }
@@ -386,13 +392,13 @@ void issue_tile(pgx_bank* b, int64_t blk0, int head0, cudaEvent_t after) {
   b->tile_base = blk0;
 }
 
-// the event of the tiled pass that covers block blk (valid coverage is the caller's business)
-cudaEvent_t tile_event_of(pgx_bank* b, int64_t blk) {
+// the tiled pass that covers block blk (valid coverage is the caller's business): its issue count, or -1
+int64_t tile_pass_of(pgx_bank* b, int64_t blk) {
   for (int64_t k = b->n_tpass - 1; k >= 0 && k >= b->n_tpass - pgx_bank::kTilePasses; --k) {
     const pgx_bank::TilePass& tp = b->tpass[k % pgx_bank::kTilePasses];
-    if (tp.base >= 0 && blk >= tp.base && blk < tp.base + b->tile) return tp.ev;
+    if (tp.base >= 0 && blk >= tp.base && blk < tp.base + b->tile) return k;
   }
-  return nullptr;
+  return -1;
 }
 
 // One block step.  Buffers, accessors and the ordering of every cross-stream hazard:
@@ -466,13 +472,18 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
       // younger than every reader of the row)
       const int back = b->tile > 1 ? b->tile + 2 : 2;
       if (i >= back) cudaStreamWaitEvent(b->s_in, b->ev_k2[(i - back) % kRing], 0);
-      if (t >= 2) cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);  // every block had its past pass issued
+      // (per-block passes: every block had one issued.  A tiled bank only issues them for mix pulls)
+      if (t >= 2 && (b->tile == 1 || b->last_past_issue_block >= t - 2))
+        cudaStreamWaitEvent(b->s_in, b->ev_mac[(t - 2) % kRing], 0);
       // a tiled pass with first block blk0 reads the rows of blocks blk0-P+1 .. blk0-1; this K1 overwrites the row of
       // block t-R = t-P-n_spare: every tiled pass with blk0 <= t-n_spare-1 must be done (they complete in issue order)
       for (int64_t kk = b->n_tpass - 1; kk >= 0 && kk >= b->n_tpass - pgx_bank::kTilePasses; --kk) {
         const pgx_bank::TilePass& tp = b->tpass[kk % pgx_bank::kTilePasses];
         if (tp.base >= 0 && tp.base <= t - b->n_spare - 1) {
-          cudaStreamWaitEvent(b->s_in, tp.ev, 0);
+          if (kk > b->sin_waited_tpass || b->serial) {   // (else: the ingest stream is already behind that pass)
+            cudaStreamWaitEvent(b->s_in, tp.ev, 0);
+            if (!b->serial) b->sin_waited_tpass = kk;
+          }
           break;
         }
       }
@@ -497,7 +508,12 @@ int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev
   if (tiled) {
     if (!(b->tile_base >= 0 && t >= b->tile_base && t < b->tile_base + b->tile))
       issue_tile(b, t, b->head, b->ev_k1[i % kRing]);    // not covered (first pull, after a reset / map change): now
-    if (cudaEvent_t e = tile_event_of(b, t)) cudaStreamWaitEvent(crit, e, 0);
+    const int64_t kk = tile_pass_of(b, t);
+    if (kk >= 0 && !(crit == b->crit_waited_stream && kk == b->crit_waited_tpass)) {
+      cudaStreamWaitEvent(crit, b->tpass[kk % pgx_bank::kTilePasses].ev, 0);
+      b->crit_waited_stream = crit;
+      b->crit_waited_tpass = kk;
+    }
     n_recent = (int)(t - b->tile_base);
     n_split_past = b->plan_tile.n_split;
     const int set = (int)(t % (2 * b->tile));
@@ -1567,7 +1583,9 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
     PGX_CUDA(cudaMemcpyAsync(b->x_stage[slot], x_src, xb, cudaMemcpyHostToDevice, b->s_h2d));
     PGX_CUDA(cudaEventRecord(b->ev_h2d[slot], b->s_h2d));
     PGX_CUDA(cudaStreamWaitEvent(b->s_in, b->ev_h2d[slot], 0));
-    PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
+    // kernels on the bank's stream that read x themselves (fused single-partition steps, the dry path of the output
+    // stage) need the copy too; on a tiled conv bank without dry gain only K1 (ingest stream) reads x
+    if (!(b->tile > 1 && !mix && b->dry == 0.0f && !b->serial)) PGX_CUDA(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0));
     rc = run_pull(b, b->x_stage[slot], xl, b->y_stage[slot], yd, n, mix, true, b->stream);
   }
   if (rc != PGX_OK) {  // part of the pull may be enqueued and reading x_stage[slot]: drain before the slot is reused
@@ -1585,8 +1603,12 @@ static int submit_host(pgx_bank* b, const float* x, pgx_layout xl, float* y, pgx
     pgx::launch_f32_to_pcm16(b->y_stage[slot], b->ypcm_stage[slot], (int64_t)(yb / sizeof(float)), b->stream);
     b->launches += 1;
   }
-  PGX_CUDA(cudaEventRecord(b->ev_y[slot], b->stream));
-  PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_y[slot], 0));
+  if (reduce || y_pcm || b->tail || b->step < 1) {
+    PGX_CUDA(cudaEventRecord(b->ev_y[slot], b->stream));
+    PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_y[slot], 0));
+  } else {  // the pull's last operation on the bank's stream is its last output stage, which recorded ev_k2
+    PGX_CUDA(cudaStreamWaitEvent(b->s_d2h, b->ev_k2[(b->step - 1) % kRing], 0));
+  }
   if (deliver) {
     if (y_pcm) PGX_CUDA(cudaMemcpyAsync(y_dst, b->ypcm_stage[slot], yb / 2, cudaMemcpyDeviceToHost, b->s_d2h));
     else

@@ -279,3 +279,57 @@ def fft16_inverse(Wk):
     z=np.empty(N,complex)
     for n2 in range(16): z[j+256*n2]=v[:,P(n2)]
     return z
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Time-tiled accumulate pass: the index algebra of issue_tile (pgx_api.cu), k_fdl_mac_tile (k_mac.cu) and the recent-row
+# loop of k_c2r (k_fft.cu), on plain complex rows.  Ring of R = P + n_spare rows, block t in slot t % R; filter table of 2R
+# rows with partition p at rows R-1-p and 2R-1-p (the others stay zero).
+def tiled_pass_terms(P: int, T: int, head0: int):
+    """(off, skip, nskip, n_terms) exactly as issue_tile sets them for a pass whose first block sits in slot head0."""
+    n_spare = (T - 1 if T > 2 else 1) if P > 1 else 0
+    R = P + n_spare
+    if head0 + n_spare < R:
+        off, skip, nskip = 0, head0, 1 + n_spare
+    else:
+        off, skip, nskip = head0 + n_spare + 1 - R, R, 0
+    return R, n_spare, off, skip, nskip, P - 1
+
+
+def tiled_pass(ring: np.ndarray, Hd: np.ndarray, P: int, T: int, head0: int, n_split: int = 1) -> np.ndarray:
+    """The T result sets of one pass: S[kappa] = sum over committed slots j of ring[j] * Hd[row(j - kappa)], walked the
+    way the kernel walks them (term range per split, at most two runs of consecutive slots, sliding filter window)."""
+    R, n_spare, off, skip, nskip, n_terms = tiled_pass_terms(P, T, head0)
+    qb = R - 1 - head0
+    S = np.zeros((T,) + ring.shape[1:], complex)
+    tps = -(-n_terms // n_split)
+    rsk = skip - off
+    for sp in range(n_split):
+        r0, r1 = sp * tps, min((sp + 1) * tps, n_terms)
+        for run in range(2):
+            rb, re = (r0, min(r1, rsk)) if run == 0 else (max(r0, rsk), r1)
+            if rb >= re:
+                continue
+            jbeg, jend = off + rb + (nskip if run else 0), off + re + (nskip if run else 0)
+            window = {}                                    # d = j - kappa -> filter row, as the register window holds it
+            for w in range(T - 1):
+                d = jbeg - (T - 1) + w
+                q = qb + d
+                window[d] = Hd[q + R if q < 0 else q]
+            p0 = (head0 - jbeg) % R
+            for j in range(jbeg, jend):
+                assert p0 == (head0 - j) % R and 1 <= p0 <= P - 1, "a run never crosses the open or a spare slot"
+                window[j] = Hd[qb + j]                     # the slot's one new filter row
+                for kp in range(T):
+                    if p0 + kp <= P - 1:
+                        S[kp] += ring[j] * window[j - kp]
+                p0 -= 1
+    return S
+
+
+def tiled_output(ring: np.ndarray, Hd: np.ndarray, S_kappa: np.ndarray, R: int, head_u: int, n_recent: int) -> np.ndarray:
+    """k_c2r on a tiled bank: the result set of the block + its present term + the n_recent rows committed after the pass."""
+    y = S_kappa + ring[head_u] * Hd[R - 1]
+    for r in range(1, n_recent + 1):
+        y = y + ring[(head_u - r) % R] * Hd[R - 1 - r]
+    return y

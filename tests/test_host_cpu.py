@@ -447,3 +447,32 @@ def test_nearest_direction_in_c_equals_numpy_and_the_scalar_rule():
     a = kemar.nearest_indices(az, el)
     assert np.array_equal(a, kemar.nearest_indices_numpy(az, el))
     assert np.array_equal(a[::37], [kemar.nearest_index(x, y) for x, y in zip(az[::37], el[::37])])
+
+
+@pytest.mark.parametrize("P,T", [(2, 2), (5, 2), (5, 4), (8, 4), (33, 4), (33, 2)])
+def test_time_tiled_pass_index_model_equals_the_partitioned_sum(P, T):
+    """The index algebra of the time-tiled pass (tests/kernel_model.py restates issue_tile, k_fdl_mac_tile's two runs and
+    sliding filter window, and k_c2r's recent rows): for every ring position, with passes issued every T blocks and
+    re-issued on demand at arbitrary blocks, every block's output equals sum_p X[t-p] * H[p]."""
+    import kernel_model as km
+    rng = np.random.default_rng(P * 10 + T)
+    K = 3
+    R, n_spare, *_ = km.tiled_pass_terms(P, T, 0)
+    H = rng.standard_normal((P, K)) + 1j * rng.standard_normal((P, K))
+    Hd = np.zeros((2 * R, K), complex)
+    for p in range(P):
+        Hd[R - 1 - p] = Hd[2 * R - 1 - p] = H[p]
+    n_blocks = 3 * R + 7
+    X = rng.standard_normal((n_blocks, K)) + 1j * rng.standard_normal((n_blocks, K))
+    ring = np.zeros((R, K), complex)
+    base, S = None, None
+    invalidate_at = set(rng.integers(1, n_blocks, 6).tolist())      # resets of the coverage (map change, reload, ...)
+    for t in range(n_blocks):
+        head = t % R
+        if base is None or not (base <= t < base + T) or t in invalidate_at:
+            S = km.tiled_pass(ring, Hd, P, T, head, n_split=1 + (t % 3))   # rows committed so far: blocks < t
+            base = t
+        ring[head] = X[t]                                            # K1 of block t
+        y = km.tiled_output(ring, Hd, S[t - base], R, head, t - base)
+        ref = sum(X[t - p] * H[p] for p in range(P) if t - p >= 0)
+        np.testing.assert_allclose(y, ref, atol=1e-9, err_msg=f"block {t}")
