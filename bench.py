@@ -303,9 +303,11 @@ def make_workload(args, w, rank, local):
         N = args.streams or STREAMS_PER_GPU
         if distinct:
             irs = np.stack([wl.c2_ir(stream=rank * N + s) for s in range(N)])
-            bank = pg.ConvolveBank(irs, N, CH, block=B, max_pull=PULL, device=local, tail_block=args.tail_block or None)
+            bank = pg.ConvolveBank(irs, N, CH, block=B, max_pull=PULL * max(1, args.e2e_blocks), device=local,
+                                   tail_block=args.tail_block or None)
         else:
-            bank = pg.ConvolveBank(wl.c2_ir(), N, CH, block=B, max_pull=PULL, device=local, single_filter_dims=True,
+            bank = pg.ConvolveBank(wl.c2_ir(), N, CH, block=B, max_pull=PULL * max(1, args.e2e_blocks), device=local,
+                                   single_filter_dims=True,
                                    tail_block=args.tail_block or None)
         cfg = _config(args)
         if args.tail_block:  # NOT the named configuration (uniform partitions): an extra data point
@@ -707,6 +709,50 @@ def measure(args, wname, world, rank, local, numa_bound):
         e2e_drain(tk)
         torch.cuda.synchronize(dev)
         dts.append(time.perf_counter() - t0)
+    # ---- supplementary: the same host API with M blocks per submit (--e2e-blocks M): one H2D and one D2H of M MiB
+    multi = None
+    M = int(args.e2e_blocks or 1)
+    if M > 1 and wname == "c2" and vb is None and traj is None and not args.pcm16 and not do_reduce:
+        try:
+            xm = PinnedArray((2, N, c_in, M * pull), np.float32)
+            for b_ in range(2):
+                xm.array[b_] = np.concatenate([x_host[(b_ * M + j) % N_INPUT_BLOCKS] for j in range(M)], axis=2)
+            depth_m = 3
+            yms = [PinnedArray((N, c_out, M * pull), np.float32) for _ in range(depth_m)]
+            kem = max(ke // M, 60)
+
+            def mstep(i):
+                tkm = bank.submit(xm.array[i % 2], yms[i % depth_m].array)
+                bank.wait(tkm - (depth_m - 1))
+                return tkm
+
+            tkm = None
+            for i in range(4):
+                tkm = mstep(i)
+            for t_ in range(tkm - (depth_m - 2), tkm + 1):
+                bank.wait(t_)
+            mdts = []
+            for _ in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                for i in range(kem):
+                    tkm = mstep(i)
+                for t_ in range(tkm - (depth_m - 2), tkm + 1):
+                    bank.wait(t_)
+                torch.cuda.synchronize(dev)
+                mdts.append(time.perf_counter() - t0)
+            tm = torch.tensor(mdts, dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dtm = float(np.median(tm.cpu().numpy()))
+            multi = {"blocks_per_submit": M, "submits": kem, "submits_in_flight": depth_m,
+                     "seconds": dtm, "bytes_per_submit_each_way": N * c_in * M * pull * 4,
+                     "copy_gbs_per_direction": N * c_in * M * pull * 4 * kem / dtm / 1e9}
+            xm.free()
+            for a_ in yms:
+                a_.free()
+        except Exception as exc:  # a supplementary leg never takes the line down
+            multi = {"blocks_per_submit": M, "error": repr(exc)}
     te = torch.tensor(dts, dtype=torch.float64, device=dev)
     per_rank = [te.clone() for _ in range(world)]
     if world > 1:
@@ -801,7 +847,10 @@ def measure(args, wname, world, rank, local, numa_bound):
                             f"{E2E_DEPTH} pulls in flight, every pull's H2D and D2H inside the timed region"
                             + ("; PGX_PULL_REDUCE: the mix is summed over the ranks on the device, D2H on rank 0 only" if do_reduce else "")),
                     "host_affinity_bound": numa_bound, "x_write_combined": bool(args.wc),
-                    "checksum_mean_abs_y": checksum},
+                    "checksum_mean_abs_y": checksum,
+                    "multi_block": (dict(multi, value=(world * N * c_out * pull / sr) * M * multi["submits"] / multi["seconds"],
+                                         frac_of_value=(world * N * c_out * pull / sr) * M * multi["submits"] / multi["seconds"] / value)
+                                    if multi and "seconds" in multi else multi)},
             "gpu_launches": launches, "host_enqueue_ms_per_step": float(np.median(host_reps)),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
@@ -902,6 +951,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--wc", action="store_true", help="e2e leg: input staging buffers in write-combined pinned memory")
     ap.add_argument("--reps", type=int, default=0, help="repetitions of the K-step timed loop (default: ~4 s worth, 5..60)")
+    ap.add_argument("--e2e-blocks", type=int, default=1,
+                    help="c2: also time the host API with this many 512-sample blocks per submit (fewer, larger copies); "
+                         "reported as e2e.multi_block beside the named one-block-per-pull e2e")
     ap.add_argument("--no-c4", action="store_true", help="--gpus N>1: skip the sharded-mix (c4) sub-record")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
                     help="c4 under torchrun: the cross-GPU sum through pgx_mix_reduce (NVLink peer memory, default) or "
