@@ -857,6 +857,11 @@ def measure(args, wname, world, rank, local, numa_bound):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kbytes, "mean_launch_ms": klaunch_ms,
                          "time_tile": tile,
+                         "note": (f"time-tiled pass: one launch serves {tile} block steps and moves every delay-line row once, so "
+                                  f"its algorithmic bytes per STEP are 1/{tile} of the per-block schedule's (per_block_pass_bytes) "
+                                  "that SURVEY 8d's ceiling assumes; frac is this launch's own bytes over its own time. The "
+                                  "per-block kernel (PGX_TILE=1) sits at frac ~1.0 and ~2.9x lower throughput "
+                                  "(profiles/r02c_bench_c2_untiled.json)") if tile > 1 and not mix else None,
                          "per_block_pass_bytes": per_block_mac_bytes if tile > 1 else None,
                          "fused_kernel_min_bytes": ((N * info.c_x * Bw * 12 + N * c_out * Bw * 12) if not mix else
                                                     (N * Bw * 8 + N * c_out * Bw * 8)) if (mac_per_step == 0 and prof.ms_conv1 > 0) else None,

@@ -4,10 +4,12 @@
 //   hist  [N*c_x][2][B]       float   previous block / open block (time domain)
 //   fdl   [N*c_x][R][B]       float2  frequency-domain delay line: packed spectra of the last windows,
 //                                     a ring of R = P+1 rows (R = 1 when P = 1): P live rows + one spare
+//                                     (R = P+T-1 on a time-tiled bank: T-1 spares)
 //   Hd    [F*c_f][2R][B]      float2  filter partition spectra, reversed + doubled, scaled 1/B
 //   ypast [2][<=8][n_out][B]  float2  sums over the past partitions of the open block (by block parity)
 //   ypart [n_split][n_out][B] float2  split partials of the background pass in flight
 //   ynow  [n_split][c_out][B] float2  present-slot partials (mix mode)
+//   ytile [2T][n_split][n_out][B] float2  time-tiled banks: result sets of the tiled passes (by block mod 2T)
 // and advances them one "block step" at a time.  A pull of n samples is cut at block boundaries; a
 // partially filled block is transformed with zeros in the not-yet-known positions (causality makes the
 // emitted samples exact) and re-transformed when more samples arrive, so any (start, duration) pull
@@ -24,6 +26,11 @@
 // The spare ring row lets K1 of block t+1 run while the background pass of block t is still reading, so
 // in a back-to-back queue of pulls the step time is the accumulate kernel alone.  Hazards and the event
 // that orders each one are listed at run_step().
+//
+// Time tiling (conv pulls of banks whose pass is HBM-bound, bank->tile = T > 1): the background pass runs once per T
+// blocks and yields the past sums of blocks t0 .. t0+T-1 from one read of the committed rows (issue_tile); K2 of block
+// t0+kappa adds the kappa rows committed since (C2RArgs.n_recent).  Coverage is dropped by anything that changes what a
+// past sum would be (reset, filter map, filter reload, a mix pull) and re-established on demand by the next pull.
 #include <cuda_runtime.h>
 
 #include <cmath>
