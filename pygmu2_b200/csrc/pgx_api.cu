@@ -422,6 +422,18 @@ int64_t tile_pass_of(pgx_bank* b, int64_t blk) {
 //        present term, by K2/NOW of block t-R ..................... ingest waits ev_mac[t-2] and ev_k2[i-2]
 //   WAR  PAST(t+1) overwrites ypast[(t+1)&1] read by K2 of block t-1 . background waits that K2's event
 //   same-stream order covers hist halves (K1 only), ypart (background only), ynow (critical only).
+// Time-tiled banks (conv pulls) replace PAST(t) by TILE(t0), one per `tile` blocks, on one background stream:
+//   TILE(t0) [background] R fdl[all but slot(t0) and the n_spare slots after it], Hd, fmap;  W ytile[set(t0 .. t0+tile-1)]
+//   K2(i)    [critical]   R ytile[set(t)], fdl[slot(t), slot(t-1) .. slot(t-(t-t0))], Hd, fmap;  W y
+//   RAW  TILE(t0) <- K1 of the step completing block t0-1 ........ wait ev_k1                (issue_tile `after`)
+//   RAW  K2(i) <- TILE(t0) covering block t ...................... critical waits the pass's event (once per pass and stream)
+//   WAR  K1 of a new block t overwrites slot(t) = block t-R, which TILE(t0) reads while t0-P+1 <= t-R, i.e. for
+//        every pass with t0 <= t-n_spare-1 ....................... ingest waits that pass's event (once per pass)
+//   WAR  K1 of a new block t vs the output stages that read slot(t) R blocks ago: a step tile+2 back stands in for
+//        them (a nearer one would wait for the pass that is still running and stall the next pass behind this K1)
+//   WAR  TILE(t0) overwrites the sets of blocks t0-2*tile .. t0-tile-1 ... background waits the last K2 of each set
+//   Coverage (tile_base) is dropped by reset / filter map / filter reload / a mix pull; the next conv step issues a
+//   pass on demand for its own block, like the per-block schedule does.
 int run_step(pgx_bank* b, const float* x_dev, const pgx_layout& xl, float* y_dev, const pgx_layout& yl, int pos,
              int take, bool mix, cudaStream_t crit) {
   struct StreamSwap {  // PGX_DEBUG_SERIAL=1: run all three roles on the critical stream
