@@ -476,3 +476,17 @@ def test_time_tiled_pass_index_model_equals_the_partitioned_sum(P, T):
         y = km.tiled_output(ring, Hd, S[t - base], R, head, t - base)
         ref = sum(X[t - p] * H[p] for p in range(P) if t - p >= 0)
         np.testing.assert_allclose(y, ref, atol=1e-9, err_msg=f"block {t}")
+
+
+def test_design_tables_match_the_committed_bench_records():
+    """The measured tables of DESIGN.md are generated from profiles/*.json by scripts/design_tables.py: regenerating them
+    must reproduce the committed text (a table edited by hand, or a refreshed record without its table, fails here)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("design_tables", os.path.join(root, "scripts", "design_tables.py"))
+    dt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dt)
+    text = open(os.path.join(root, "DESIGN.md")).read()
+    for key, fn in (("BENCH_TABLE", dt.bench_table), ("MULTIGPU_NUMBERS", dt.multi_table), ("NAMED_TABLE", dt.named_table)):
+        block = f"<!-- BEGIN {key} -->\n{fn()}\n<!-- END {key} -->"
+        assert block in text, key
