@@ -879,7 +879,8 @@ int pgx_device_zero(int32_t device, void* dst_dev, int64_t bytes) {
   return PGX_OK;
 }
 
-static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float* h, const int32_t* filter_of_stream) {
+static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float* h, const int32_t* filter_of_stream,
+                         bool allow_tile = true) {
   if (!out || !cfg || !h) return fail(PGX_ERR_INVALID, "pgx_bank_create: NULL argument");
   *out = nullptr;
   const pgx_bank_config& c = *cfg;
@@ -931,7 +932,8 @@ static int create_single(pgx_bank** out, const pgx_bank_config* cfg, const float
     long tile_min = 1L << 17;
     if (const char* e = getenv("PGX_TILE")) want = atoi(e);
     if (const char* e = getenv("PGX_TILE_MIN")) tile_min = atol(e);
-    if ((want == 2 || want == 4) && b->P >= 32 && b->B >= 256 && c.tail_block == 0 && (long)n_fft * b->B >= tile_min)
+    if (allow_tile && (want == 2 || want == 4) && b->P >= 32 && b->B >= 256 && c.tail_block == 0 &&
+        (long)n_fft * b->B >= tile_min)
       b->tile = want;
   }
   // ring rows: the P partitions of the open block's sum plus spare rows.  One spare lets the next block's ingest run
@@ -1100,15 +1102,15 @@ int pgx_bank_create(pgx_bank** out, const pgx_bank_config* cfg, const float* h, 
   ch.filter_len = TB; ch.tail_block = 0;
   ct.filter_len = Lt; ct.block = TB; ct.max_pull = TB; ct.tail_block = 0;
   pgx_bank *head = nullptr, *tail = nullptr;
-  int rc = create_single(&head, &ch, hh.data(), filter_of_stream);
+  // (the two levels keep the per-block pass: their schedule interleaves the levels)
+  int rc = create_single(&head, &ch, hh.data(), filter_of_stream, false);
   if (rc != PGX_OK) return rc;
-  rc = create_single(&tail, &ct, ht.data(), filter_of_stream);
+  rc = create_single(&tail, &ct, ht.data(), filter_of_stream, false);
   if (rc != PGX_OK) {
     free_bank(head);
     return rc;
   }
   head->tail = tail;
-  head->tile = tail->tile = 1;   // the two levels keep the per-block pass (their schedule interleaves the levels)
   head->tail_B = TB;
   head->full_filter_len = L;
   head->xacc_bytes = (size_t)cfg->n_streams * cfg->c_in * TB * sizeof(float);
