@@ -393,6 +393,14 @@ void issue_tile(pgx_bank* b, int64_t blk0, int head0, cudaEvent_t after) {
     b->launches += 1;
   }
   pgx_bank::TilePass& tp = b->tpass[b->n_tpass % pgx_bank::kTilePasses];
+  // the entry this one replaces leaves the ring K1's WAR scan looks at: if the ingest stream has not waited for that
+  // pass yet (several passes per block: coverage dropped again and again inside ragged pulls) it does so now, before
+  // the event is reused -- in the regular cadence that pass was waited for long ago and nothing is enqueued
+  const int64_t evicted = b->n_tpass - pgx_bank::kTilePasses;
+  if (evicted >= 0 && tp.base >= 0 && evicted > b->sin_waited_tpass) {
+    cudaStreamWaitEvent(b->s_in, tp.ev, 0);
+    if (!b->serial) b->sin_waited_tpass = evicted;
+  }
   cudaEventRecord(tp.ev, sbg);
   tp.base = blk0;
   b->n_tpass += 1;
