@@ -490,3 +490,30 @@ def test_design_tables_match_the_committed_bench_records():
     for key, fn in (("BENCH_TABLE", dt.bench_table), ("MULTIGPU_NUMBERS", dt.multi_table), ("NAMED_TABLE", dt.named_table)):
         block = f"<!-- BEGIN {key} -->\n{fn()}\n<!-- END {key} -->"
         assert block in text, key
+
+
+def test_committed_headline_record_carries_the_bench_contract():
+    """The headline bench line as committed (profiles/r02c_bench_c2_k20.json: the driver-shaped default run on a B200) has
+    every key of the bench contract, on the BASELINE metric and the named workload, with a green parity leg."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = [l for l in open(os.path.join(root, "profiles", "r02c_bench_c2_k20.json")).read().splitlines() if l.startswith("{")]
+    d = json.loads(txt[-1])
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity"):
+        assert k in d, k
+    assert d["metric"].startswith("ConvolvePE audio-sec") and base["metric"].startswith("ConvolvePE audio-sec")
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] > 0
+    assert d["parity"]["ok"] and d["parity"]["max_rel_err"] <= 1e-5
