@@ -12,7 +12,7 @@ the built library or without a CUDA device raises.
 from .core import (ErrorMode, ExtendMode, Extent, ProcessingElement, Snippet, SourcePE,
                    diagnostics_report, enable_diagnostics, get_error_mode, get_sample_rate,
                    handle_error, set_error_mode, set_sample_rate)
-from .sources import ArrayPE, CachePE, ConstantPE, CropPE, DelayPE, GainPE
+from .sources import ArrayPE, CachePE, ConstantPE, CropPE, DelayPE, GainPE, InterpolationMode
 from .osc_pe import BlitSawPE, DeviceBlock, OscBank, SinePE, SuperSawPE, VoiceBank
 from .renderer import AudioRenderer, BankRenderer, CallbackStop, NullRenderer, Renderer
 from .bank import ConvolveBank, choose_block
@@ -28,7 +28,7 @@ __all__ = [
     "ErrorMode", "ExtendMode", "Extent", "ProcessingElement", "Snippet", "SourcePE",
     "set_sample_rate", "get_sample_rate", "set_error_mode", "get_error_mode", "handle_error",
     "enable_diagnostics", "diagnostics_report",
-    "ArrayPE", "CachePE", "ConstantPE", "CropPE", "DelayPE", "GainPE", "SinePE", "BlitSawPE", "SuperSawPE",
+    "ArrayPE", "CachePE", "ConstantPE", "CropPE", "DelayPE", "GainPE", "InterpolationMode", "SinePE", "BlitSawPE", "SuperSawPE",
     "OscBank", "VoiceBank", "DeviceBlock",
     "Renderer", "NullRenderer", "AudioRenderer", "BankRenderer", "CallbackStop", "ReverbPE",
     "ConvolveBank", "HrtfMixBank", "choose_block",

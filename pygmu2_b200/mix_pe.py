@@ -225,7 +225,7 @@ def _unwrap(pe):
     -> (core PE, total delay in samples, combined float32 gain or None)."""
     delay, gain = 0, None
     while True:
-        if type(pe) is DelayPE:
+        if type(pe) is DelayPE and pe.mode == "int":
             delay += pe.delay
             pe = pe.source
         elif type(pe) is GainPE and not isinstance(pe.gain, ProcessingElement):

@@ -5,10 +5,12 @@ feed ConvolvePE / SpatialPE / MixPE.  They are *not* accelerated (SURVEY.md §2b
 out of scope) and exist so graphs can be built on a machine without pygmu2.
 
 ArrayPE   array_pe.py:17-133     ConstantPE constant_pe.py:15-72
-GainPE    gain_pe.py:60-155                        DelayPE delay_pe.py:153-160 (integer delay)
+GainPE    gain_pe.py:60-155      DelayPE    delay_pe.py:19-231 (integer: folded into fused mixes; float / PE: interpolated)
 CropPE    crop_pe.py:18-96       CachePE    cache_pe.py:17-84
 """
 from __future__ import annotations
+
+import enum
 
 import numpy as np
 
@@ -116,22 +118,90 @@ class GainPE(_Unary):
         return Snippet(start, x * g)
 
 
+class InterpolationMode(enum.Enum):
+    """wavetable_pe.py:19-22 (the reference keeps it there; DelayPE is its user on this path)."""
+    LINEAR = "linear"
+    CUBIC = "cubic"
+
+
+def _interpolate(source: ProcessingElement, out_start: int, where: np.ndarray, mode, silent: np.ndarray | None) -> Snippet:
+    """Sample ``source`` at the fractional positions ``where`` (interpolated_lookup.py:89-145): ONE render of the
+    window that covers every tap, taps clamped to that window, float64 weights on the float32 samples, rounded to
+    float32 at the end; positions flagged in ``silent`` (outside a finite source extent) give 0."""
+    where = np.asarray(where, dtype=np.float64).reshape(-1)
+    if where.size == 0:
+        return Snippet.from_zeros(out_start, 0, source.channel_count() or 1)
+    cubic = str(getattr(mode, "value", mode)).lower() == "cubic"
+    reach = 2 if cubic else 1                                   # taps below / above the bracketing pair
+    lo = int(np.floor(where.min())) - (reach - 1)
+    hi = int(np.ceil(where.max())) + reach
+    window = source.render(lo, hi - lo).data
+    base = np.floor(where).astype(np.int64)
+    f = (where - base).reshape(-1, 1)
+    last = window.shape[0] - 1
+
+    def tap(offset):
+        return window[np.clip(base - lo + offset, 0, last)]
+
+    if cubic:   # Catmull-Rom through the four neighbours, in the reference's grouping (its float32 sub-sums included)
+        a, b_, c, d = tap(-1), tap(0), tap(1), tap(2)
+        f2 = f * f
+        f3 = f2 * f
+        y = 0.5 * ((2.0 * b_) + (-a + c) * f + (2.0 * a - 5.0 * b_ + 4.0 * c - d) * f2 + (-a + 3.0 * b_ - 3.0 * c + d) * f3)
+    else:
+        y = (1.0 - f) * tap(0) + f * tap(1)
+    if silent is not None and silent.any():
+        y = np.array(y, copy=True)
+        y[silent] = 0.0
+    return Snippet(out_start, y.astype(np.float32, copy=False))
+
+
 class DelayPE(_Unary):
-    def __init__(self, source: ProcessingElement, delay: int):
-        if int(delay) != delay:
-            raise NotImplementedError("pygmu2_b200.DelayPE supports integer delays only")
+    """delay_pe.py:19-231.  An integer delay pulls the source earlier (and is what a fused MixPE folds into its bank);
+    a fractional or PE-valued delay reads the source at ``t - delay[t]`` with linear or cubic interpolation.  The
+    interpolated modes are host-side input vehicles (numpy), like PE-valued GainPE."""
+
+    def __init__(self, source: ProcessingElement, delay, interpolation=InterpolationMode.LINEAR):
         super().__init__(source)
-        self._delay = int(delay)
+        self._interpolation = interpolation
+        if isinstance(delay, ProcessingElement):
+            self._mode, self._delay = "pe", delay
+        elif isinstance(delay, float) and not delay.is_integer():
+            self._mode, self._delay = "float", delay
+        else:
+            self._mode, self._delay = "int", int(delay)
 
     delay = property(lambda self: self._delay)
+    mode = property(lambda self: self._mode)
+    interpolation = property(lambda self: self._interpolation)
+
+    def inputs(self) -> list:
+        return [self._source, self._delay] if self._mode == "pe" else [self._source]
 
     def _compute_extent(self) -> Extent:
         e = self._source.extent()
-        return Extent(None if e.start is None else e.start + self._delay,
-                      None if e.end is None else e.end + self._delay)
+        if self._mode == "pe":                       # defined where both the source and the control are
+            return e.intersection(self._delay.extent())
+        lo = None if e.start is None else e.start + self._delay
+        hi = None if e.end is None else e.end + self._delay
+        if self._mode == "float":                    # extents are integer: round outwards
+            lo = None if lo is None else int(np.floor(lo))
+            hi = None if hi is None else int(np.ceil(hi))
+        return Extent(lo, hi)
 
     def _render(self, start: int, duration: int) -> Snippet:
-        return Snippet(start, self._source.render(start - self._delay, duration).data)
+        if self._mode == "int":
+            return Snippet(start, self._source.render(start - self._delay, duration).data)
+        t = np.arange(start, start + duration, dtype=np.float64)
+        if self._mode == "float":
+            where = t - self._delay
+        else:                                         # the control's first channel, per sample
+            where = t - self._delay.render(start, duration).data[:, 0].astype(np.float64)
+        e = self._source.extent()
+        silent = None
+        if e.start is not None and e.end is not None:
+            silent = (where < e.start) | (where >= e.end)
+        return _interpolate(self._source, start, where, self._interpolation, silent)
 
 
 class CropPE(_Unary):

@@ -517,3 +517,28 @@ def test_committed_headline_record_carries_the_bench_contract():
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] > 0
     assert d["parity"]["ok"] and d["parity"]["max_rel_err"] <= 1e-5
+
+
+def test_delay_pe_fractional_and_pe_valued_delays_match_the_reference_golden():
+    """DelayPE's interpolated modes (delay_pe.py:163-228, interpolated_lookup.py:89-145) against outputs of the REAL
+    reference (oracle/gen_golden_delay.py -> tests/golden/delay_interp.npz): fractional delays of either sign and a
+    PE-valued vibrato, linear and cubic, ragged pulls from before the source starts to after it ends, and the extents."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_golden_delay", os.path.join(root, "oracle", "gen_golden_delay.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(root, "tests", "golden", "delay_interp.npz"))
+    pg.set_sample_rate(44_100)
+    cases = gen.cases(pg, lambda n: pg.InterpolationMode(n))
+    assert len(cases) == 6
+    for name, pe in cases.items():
+        y = gen.pull(pe)
+        assert y.dtype == np.float32 and y.shape == gold[name].shape
+        np.testing.assert_array_equal(y, gold[name], err_msg=name)          # same arithmetic in numpy: bit for bit
+        e = pe.extent()
+        assert [e.start, e.end] == gold[name + "_extent"].tolist(), name
+    # whole-number floats are integer delays (delay_pe.py:72-78) and stay foldable into a fused mix
+    assert pg.DelayPE(pg.ArrayPE(np.ones(8)), 4.0).mode == "int" and pg.DelayPE(pg.ArrayPE(np.ones(8)), 4.5).mode == "float"
+    ctl = pg.DelayPE(pg.ArrayPE(np.ones(8)), pg.ConstantPE(2.0))
+    assert ctl.mode == "pe" and len(ctl.inputs()) == 2
