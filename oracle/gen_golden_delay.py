@@ -20,8 +20,6 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = os.environ.get("PYGMU2_REFERENCE", "/root/reference")
-sys.path.insert(0, os.path.join(HERE, "stubs"))
-sys.path.insert(0, os.path.join(REF, "src"))
 
 PULLS = (100, 37, 512, 1, 255, 1024, 700, 300, 171)
 START = -64
@@ -57,6 +55,8 @@ def pull(pe):
 
 
 def main():
+    sys.path.insert(0, os.path.join(HERE, "stubs"))      # (only here: the tests import this module for cases() / pull())
+    sys.path.insert(0, os.path.join(REF, "src"))
     import pygmu2 as ref  # noqa: E402  (the real reference)
     from pygmu2.wavetable_pe import InterpolationMode
     ref.set_sample_rate(44_100)
